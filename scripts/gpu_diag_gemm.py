@@ -1,0 +1,195 @@
+"""GEMM bring-up diagnostics for the B200 box: every variant in its own subprocess (a trapped launch
+poisons the CUDA context), bounded by a timeout, with an error-structure dump on mismatch.
+
+    python scripts/gpu_diag_gemm.py            # run all variants, write gpurun_out/diag_gemm.log
+    python scripts/gpu_diag_gemm.py <variant>  # one variant in-process
+"""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+VARIANTS = [
+    "nk_small", "nk_ragged", "nk_bn64", "nk_bn128", "nk_bn192", "nk_bn256", "nk_big",
+    "nk_f16", "gelu", "resid", "dgelu", "acc32", "store32",
+    "kn_dgrad", "kn_dgrad_256", "wgrad", "wgrad_split", "wgrad_192",
+    "s2d_w128", "s2d_w32", "s2d_c48", "d2s", "d2s_c48", "perf",
+]
+
+
+def report(name, got, ref, tol):
+    import torch
+    got = got.float()
+    ref = ref.float()
+    err = (got - ref).abs()
+    denom = ref.abs().max().clamp_min(1e-6)
+    rel = float(err.max() / denom)
+    ok = rel < tol and bool(torch.isfinite(got).all())
+    print(f"[{name}] max|err|/max|ref| = {rel:.3e}  (tol {tol})  {'OK' if ok else 'MISMATCH'}", flush=True)
+    if not ok:
+        bad = err > tol * denom
+        rows = bad.any(dim=1).nonzero().flatten()
+        cols = bad.any(dim=0).nonzero().flatten()
+        print(f"   bad rows: {rows.numel()}/{got.shape[0]} first {rows[:16].tolist()}")
+        print(f"   bad cols: {cols.numel()}/{got.shape[1]} first {cols[:16].tolist()}")
+        print("   got[:4,:8] ", got[:4, :8].tolist())
+        print("   ref[:4,:8] ", ref[:4, :8].tolist())
+        nz = float((got != 0).float().mean())
+        print(f"   nonzero fraction of output {nz:.3f}; ratio got/ref median "
+              f"{float((got / ref.clamp_min(1e-3)).median()):.3f}")
+    return ok
+
+
+def run_variant(v):
+    import torch
+    from bubbleformer_b200 import _lib as L, ops
+    torch.manual_seed(0)
+    dev = "cuda"
+    dt = torch.float16 if v == "nk_f16" else torch.bfloat16
+
+    def rnd(*s, scale=1.0):
+        return (torch.randn(*s, device=dev) * scale).to(dt)
+
+    ok = True
+    if v.startswith("nk_") or v in ("gelu", "resid", "dgelu", "acc32", "store32"):
+        shapes = {"nk_small": (128, 128, 64), "nk_ragged": (300, 200, 104), "nk_bn64": (256, 64, 128),
+                  "nk_bn128": (4096, 384, 384), "nk_bn192": (4096, 1152, 384), "nk_bn256": (4096, 1536, 384),
+                  "nk_big": (40960, 1152, 384), "nk_f16": (1024, 96, 384)}
+        M, N, K = shapes.get(v, (1000, 384, 256))
+        bn = {"nk_bn64": 64, "nk_bn128": 128, "nk_bn192": 192, "nk_bn256": 256}.get(v, 0)
+        A, B = rnd(M, K), rnd(N, K, scale=K ** -0.5)
+        bias = torch.randn(N, device=dev)
+        ref = A.float() @ B.float().t() + bias
+        if v.startswith("nk_"):
+            out = torch.zeros(M, N, device=dev, dtype=dt)
+            ops.gemm(A, B, M, N, K, epilogue=L.EPI_STORE16, bias=bias, out16=out, bn=bn)
+            ok &= report(v, out, ref, 1e-2)
+        elif v == "store32":
+            out = torch.zeros(M, N, device=dev)
+            ops.gemm(A, B, M, N, K, epilogue=L.EPI_STORE32, bias=bias, out32=out)
+            ok &= report(v, out, ref, 1e-5)
+        elif v == "gelu":
+            out = torch.zeros(M, N, device=dev, dtype=dt)
+            pre = torch.zeros(M, N, device=dev, dtype=dt)
+            ops.gemm(A, B, M, N, K, epilogue=L.EPI_GELU, bias=bias, out16=out, out16b=pre)
+            ok &= report(v + ".pre", pre, ref, 1e-2)
+            ok &= report(v + ".act", out, torch.nn.functional.gelu(ref), 1e-2)
+        elif v == "resid":
+            xin = torch.randn(M, N, device=dev)
+            cs, ch, cg = torch.randn(N, device=dev), torch.randn(N, device=dev), torch.randn(N, device=dev)
+            rpg = 100
+            rs = torch.rand((M + rpg - 1) // rpg, device=dev)
+            out32 = torch.zeros(M, N, device=dev)
+            out16 = torch.zeros(M, N, device=dev, dtype=dt)
+            z = torch.zeros(M, N, device=dev, dtype=dt)
+            ops.gemm(A, B, M, N, K, epilogue=L.EPI_RESID, bias=bias, col_scale=cs, col_shift=ch, col_gamma=cg,
+                     row_scale=rs, rows_per_group=rpg, in32=xin, out32=out32, out16=out16, out16b=z)
+            rsx = rs.repeat_interleave(rpg)[:M, None]
+            want = xin + rsx * cg * (ref * cs + ch)
+            ok &= report(v + ".z", z, ref, 1e-2)
+            ok &= report(v + ".x32", out32, want, 1e-5)
+            ok &= report(v + ".x16", out16, want, 1e-2)
+        elif v == "dgelu":
+            pre = rnd(M, N)
+            out = torch.zeros(M, N, device=dev, dtype=dt)
+            ops.gemm(A, B, M, N, K, epilogue=L.EPI_DGELU, aux16=pre, out16=out)
+            p32 = pre.float().requires_grad_(True)
+            torch.nn.functional.gelu(p32).sum().backward()
+            ok &= report(v, out, (A.float() @ B.float().t()) * p32.grad, 1e-2)
+        elif v == "acc32":
+            g = torch.randn(M, N, device=dev)
+            out = torch.zeros(M, N, device=dev)
+            ops.gemm(A, B, M, N, K, epilogue=L.EPI_ACC32, in32=g, out32=out)
+            ok &= report(v, out, g + A.float() @ B.float().t(), 1e-5)
+    elif v.startswith("kn_dgrad"):
+        M, N, K = (4096, 384, 1536) if v == "kn_dgrad" else (2048, 1536, 384)
+        A, Bkn = rnd(M, K), rnd(K, N, scale=K ** -0.5)          # B stored (K, N)
+        out = torch.zeros(M, N, device=dev, dtype=dt)
+        ops.gemm(A, Bkn, M, N, K, epilogue=L.EPI_STORE16, b_mode=L.B_KN, out16=out)
+        ok &= report(v, out, A.float() @ Bkn.float(), 1e-2)
+    elif v.startswith("wgrad"):
+        T = 4096                                                  # tokens = contraction
+        Mw, Nw = (384, 1152) if v == "wgrad_192" else (384, 384)
+        dY, X = rnd(T, Mw), rnd(T, Nw, scale=T ** -0.5)
+        out = torch.zeros(Mw, Nw, device=dev)
+        ops.gemm(dY, X, Mw, Nw, T, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
+                 split_k=8 if v == "wgrad_split" else 1, out32=out,
+                 bn=192 if v == "wgrad_192" else 0)
+        ok &= report(v, out, dY.float().t() @ X.float(), 1e-4)
+    elif v.startswith("s2d"):
+        I, Hin, Win, Cin, N = {"s2d_w128": (2, 8, 256, 96, 96), "s2d_w32": (3, 64, 64, 96, 384),
+                               "s2d_c48": (2, 16, 32, 48, 48)}[v]
+        img = rnd(I, Hin, Win, Cin)
+        Wt = rnd(N, 4 * Cin, scale=(4 * Cin) ** -0.5)            # K order (ky, kx, ci)
+        M = I * (Hin // 2) * (Win // 2)
+        out = torch.zeros(M, N, device=dev, dtype=dt)
+        ops.gemm(img, Wt, M, N, 4 * Cin, epilogue=L.EPI_STORE16, a_mode=L.A_S2D, ldb=4 * Cin,
+                 s2d=(I, Hin, Win, Cin), out16=out)
+        g = img.float().reshape(I, Hin // 2, 2, Win // 2, 2, Cin).permute(0, 1, 3, 2, 4, 5).reshape(M, 4 * Cin)
+        ok &= report(v, out, g @ Wt.float().t(), 1e-2)
+    elif v.startswith("d2s"):
+        I, h, w, Cin, co = (2, 8, 16, 384, 96) if v == "d2s" else (1, 4, 8, 192, 48)
+        X = rnd(I * h * w, Cin)
+        Wt = rnd(4 * co, Cin, scale=Cin ** -0.5)                  # rows ordered (ky, kx, co)
+        out = torch.zeros(I, 2 * h, 2 * w, co, device=dev, dtype=dt)
+        ops.gemm(X, Wt, I * h * w, 4 * co, Cin, epilogue=L.EPI_D2S, d2s=(h, w, co), out16=out, ldo=4 * co)
+        y = (X.float() @ Wt.float().t()).reshape(I, h, w, 2, 2, co).permute(0, 1, 3, 2, 4, 5).reshape(I, 2 * h, 2 * w, co)
+        ok &= report(v, out.reshape(-1, co), y.reshape(-1, co), 1e-2)
+    elif v == "perf":
+        for (M, N, K, bn) in [(40960, 1152, 384, 192), (40960, 1152, 384, 128), (40960, 1536, 384, 256),
+                              (40960, 1536, 384, 128), (40960, 384, 1536, 192), (40960, 384, 1536, 128),
+                              (40960, 384, 384, 192), (40960, 384, 384, 128), (163840, 2304, 768, 256)]:
+            A, B = rnd(M, K), rnd(N, K, scale=K ** -0.5)
+            out = torch.zeros(M, N, device=dev, dtype=dt)
+            for _ in range(3):
+                ops.gemm(A, B, M, N, K, epilogue=L.EPI_STORE16, out16=out, bn=bn)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                ops.gemm(A, B, M, N, K, epilogue=L.EPI_STORE16, out16=out, bn=bn)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 20
+            print(f"[perf] M={M} N={N} K={K} bn={bn}: {ms*1e3:.1f} us  {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
+            ref = torch.matmul(A, B.t())
+            for _ in range(3):
+                torch.matmul(A, B.t(), out=ref)
+            e0.record()
+            for _ in range(20):
+                torch.matmul(A, B.t(), out=ref)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 20
+            print(f"[perf]   cuBLAS same shape: {ms*1e3:.1f} us  {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
+    else:
+        raise SystemExit(f"unknown variant {v}")
+    torch.cuda.synchronize()
+    return ok
+
+
+def main():
+    if len(sys.argv) > 1:
+        ok = run_variant(sys.argv[1])
+        sys.exit(0 if ok else 3)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    log = open(os.path.join(ROOT, "gpurun_out", "diag_gemm.log"), "w")
+    summary = []
+    for v in VARIANTS:
+        try:
+            r = subprocess.run([sys.executable, __file__, v], capture_output=True, text=True, timeout=180)
+            out, code = r.stdout + r.stderr, r.returncode
+        except subprocess.TimeoutExpired as e:
+            out, code = (e.stdout or b"").decode() + (e.stderr or b"").decode() + "\nTIMEOUT", -9
+        tail = "\n".join(out.strip().splitlines()[-14:])
+        log.write(f"==== {v} (exit {code})\n{out}\n")
+        log.flush()
+        print(f"==== {v} (exit {code})\n{tail}", flush=True)
+        summary.append((v, code))
+    print("SUMMARY " + " ".join(f"{v}:{c}" for v, c in summary))
+    log.write("SUMMARY " + " ".join(f"{v}:{c}" for v, c in summary) + "\n")
+
+
+if __name__ == "__main__":
+    main()
