@@ -60,3 +60,83 @@ def check(status: int, what: str = "") -> None:
 
 def launch_count() -> int:
     return int(lib.bf_launch_count())
+
+
+BF_F32 = 2
+
+
+class InormApplyArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("x_dtype", C.c_int32), ("out_dtype", C.c_int32),
+        ("ldx", C.c_int64), ("ldo", C.c_int64),
+        ("I", C.c_int32), ("P", C.c_int32), ("C", C.c_int32), ("gelu", C.c_int32),
+        ("stats", C.c_void_p), ("weight", C.c_void_p), ("bias", C.c_void_p),
+        ("film_gamma", C.c_void_p), ("film_beta", C.c_void_p),
+        ("film_T", C.c_int32), ("reserved0", C.c_int32),
+        ("resid_in", C.c_void_p), ("row_scale", C.c_void_p), ("col_gamma", C.c_void_p),
+        ("out", C.c_void_p),
+    ]
+
+
+class InormBwdArgs(C.Structure):
+    _fields_ = [
+        ("phase", C.c_int32), ("gelu", C.c_int32),
+        ("gin", C.c_void_p), ("g_dtype", C.c_int32), ("x_dtype", C.c_int32),
+        ("x", C.c_void_p),
+        ("ldg", C.c_int64), ("ldx", C.c_int64), ("ldo", C.c_int64),
+        ("I", C.c_int32), ("P", C.c_int32), ("C", C.c_int32), ("out_dtype", C.c_int32),
+        ("stats", C.c_void_p), ("weight", C.c_void_p), ("bias", C.c_void_p),
+        ("red", C.c_void_p),
+        ("row_scale", C.c_void_p), ("col_scale", C.c_void_p), ("film_gamma", C.c_void_p),
+        ("film_T", C.c_int32), ("reserved0", C.c_int32),
+        ("add32", C.c_void_p), ("out", C.c_void_p),
+    ]
+
+
+class InormBwdParamsArgs(C.Structure):
+    _fields_ = [
+        ("red", C.c_void_p),
+        ("I", C.c_int32), ("P", C.c_int32), ("C", C.c_int32), ("film_T", C.c_int32),
+        ("row_scale", C.c_void_p), ("col_scale", C.c_void_p), ("film_gamma", C.c_void_p),
+        ("weight", C.c_void_p), ("bias", C.c_void_p),
+        ("dweight", C.c_void_p), ("dbias", C.c_void_p), ("dcol_scale", C.c_void_p),
+        ("dfilm_gamma", C.c_void_p), ("dfilm_beta", C.c_void_p),
+    ]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("qkv", C.c_void_p), ("ld_qkv", C.c_int64),
+        ("out", C.c_void_p), ("ld_out", C.c_int64),
+        ("dout", C.c_void_p), ("ld_dout", C.c_int64),
+        ("heads", C.c_int32), ("head_dim", C.c_int32), ("L", C.c_int32), ("accumulate", C.c_int32),
+        ("n_seq", C.c_int64), ("inner", C.c_int64), ("outer_stride", C.c_int64),
+        ("inner_stride", C.c_int64), ("tok_stride", C.c_int64),
+        ("qn_w", C.c_void_p), ("qn_b", C.c_void_p), ("kn_w", C.c_void_p), ("kn_b", C.c_void_p),
+        ("bias_emb", C.c_void_p), ("bucket", C.c_void_p), ("scale_factor", C.c_void_p),
+        ("out_scale", C.c_float), ("reserved0", C.c_int32),
+        ("d_qn_w", C.c_void_p), ("d_qn_b", C.c_void_p), ("d_kn_w", C.c_void_p), ("d_kn_b", C.c_void_p),
+        ("d_bias_emb", C.c_void_p), ("d_scale_factor", C.c_void_p),
+    ]
+
+
+EXPORTS = ["bf_last_error", "bf_version", "bf_launch_count", "bf_gemm", "bf_inorm_stats", "bf_inorm_apply",
+           "bf_inorm_bwd", "bf_inorm_bwd_params", "bf_resid_bwd", "bf_colsum16", "bf_attention_fwd",
+           "bf_attention_bwd", "bf_patch_in", "bf_patch_out", "bf_patch_wgrad", "bf_s2d_gather", "bf_cast16", "bf_convert16"]
+
+_vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
+lib.bf_gemm.argtypes = [C.POINTER(GemmArgs), _vp]
+lib.bf_inorm_stats.argtypes = [_vp, _i, _i, _i, _i, _i64, _vp, _vp]
+lib.bf_inorm_apply.argtypes = [C.POINTER(InormApplyArgs), _vp]
+lib.bf_inorm_bwd.argtypes = [C.POINTER(InormBwdArgs), _vp]
+lib.bf_inorm_bwd_params.argtypes = [C.POINTER(InormBwdParamsArgs), _vp]
+lib.bf_resid_bwd.argtypes = [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]
+lib.bf_colsum16.argtypes = [_vp, _i, _i64, _i, _i64, _vp, _vp]
+lib.bf_attention_fwd.argtypes = [C.POINTER(AttnArgs), _vp]
+lib.bf_attention_bwd.argtypes = [C.POINTER(AttnArgs), _vp]
+lib.bf_patch_in.argtypes = [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp]
+lib.bf_patch_out.argtypes = [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp]
+lib.bf_patch_wgrad.argtypes = [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp]
+lib.bf_s2d_gather.argtypes = [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp]
+lib.bf_convert16.argtypes = [_vp, _i, _vp, _i, _i64, _vp]
+lib.bf_cast16.argtypes = [_vp, _vp, _i, _i64, _vp]

@@ -616,6 +616,7 @@ extern "C" int bf_inorm_bwd(const bf_inorm_bwd_args* a, void* stream) {
     else if (gd == BF_BF16 && xd == BF_F32) BF_RED(__nv_bfloat16, float);
     else if (gd == BF_BF16 && xd == BF_BF16) BF_RED(__nv_bfloat16, __nv_bfloat16);
     else if (gd == BF_F16 && xd == BF_F16) BF_RED(__half, __half);
+    else if (gd == BF_BF16 && xd == BF_F16) BF_RED(__nv_bfloat16, __half);
     else BF_REQUIRE(false, "bf_inorm_bwd: unsupported dtype pair g=%d x=%d", gd, xd);
 #undef BF_RED
     count_launch();
@@ -632,6 +633,8 @@ extern "C" int bf_inorm_bwd(const bf_inorm_bwd_args* a, void* stream) {
   else if (gd == BF_BF16 && xd == BF_F32 && od == BF_F32) BF_APP(__nv_bfloat16, float, float);
   else if (gd == BF_BF16 && xd == BF_BF16 && od == BF_BF16) BF_APP(__nv_bfloat16, __nv_bfloat16, __nv_bfloat16);
   else if (gd == BF_F16 && xd == BF_F16 && od == BF_F16) BF_APP(__half, __half, __half);
+  else if (gd == BF_BF16 && xd == BF_F16 && od == BF_BF16) BF_APP(__nv_bfloat16, __half, __nv_bfloat16);
+  else if (gd == BF_F32 && xd == BF_F16 && od == BF_BF16) BF_APP(float, __half, __nv_bfloat16);
   else BF_REQUIRE(false, "bf_inorm_bwd: unsupported dtype triple g=%d x=%d out=%d", gd, xd, od);
 #undef BF_APP
   count_launch();

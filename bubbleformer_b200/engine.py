@@ -1,0 +1,492 @@
+"""Forward / backward orchestration of the FiLMAViT hot path over the C-ABI kernels.
+
+Everything here is host-side sequencing: which kernel runs on which buffer.  All device work is done by
+libbubbleformer_b200.so (bubbleformer_b200.ops); torch supplies memory, streams and autograd plumbing.
+
+Data layout: activations are token-major.  One *image* is a (b, t) frame of P = h*w tokens; the
+residual stream X is an fp32 (I*P, E) matrix, GEMM operands are bf16 copies (fp16 inside the patch
+embed / unembed, whose errors are amplified by the InstanceNorms that follow them; their gradients are
+bf16 again so they cannot underflow).
+
+Reference behaviour restated here (upstream paths):
+  temporal block   bubbleformer/layers/attention.py:66-124
+  spatial block    bubbleformer/layers/attention.py:199-319
+  embed / debed    bubbleformer/layers/patching.py:30-58, 86-115
+  FiLM             bubbleformer/layers/linear_layers.py:56-77
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+F32, BF16, F16 = torch.float32, torch.bfloat16, torch.float16
+
+
+@dataclass(frozen=True)
+class Geom:
+    B: int
+    T: int
+    h: int
+    w: int
+
+    @property
+    def I(self) -> int:  # noqa: E743
+        return self.B * self.T
+
+    @property
+    def P(self) -> int:
+        return self.h * self.w
+
+    @property
+    def N(self) -> int:
+        return self.B * self.T * self.h * self.w
+
+
+# ---------------------------------------------------------------------------------------------
+# T5 relative-position buckets (upstream layers/positional_encoding.py:76-129), host computed once per L
+# ---------------------------------------------------------------------------------------------
+_BUCKETS: Dict[tuple, torch.Tensor] = {}
+
+
+def relpos_bucket_vector(Ln: int, device) -> torch.Tensor:
+    """int32 (2L-1,): bucket of rel = key - query for rel in [-(L-1), L-1].
+
+    Bidirectional, 32 buckets, max_distance 32 (the static default that upstream actually runs with);
+    the logarithmic branch is evaluated in float32 exactly like upstream so bucket edges agree.
+    """
+    key = (Ln, str(device))
+    if key not in _BUCKETS:
+        rel = torch.arange(-(Ln - 1), Ln, dtype=torch.long)
+        n = -rel
+        ret = (n < 0).to(torch.long) * 16
+        n = n.abs()
+        large = 8 + (torch.log(n.float() / 8) / math.log(32 / 8) * 8).to(torch.long)
+        large = torch.minimum(large, torch.full_like(large, 15))
+        ret = ret + torch.where(n < 8, n, large)
+        _BUCKETS[key] = ret.to(torch.int32).to(device)
+    return _BUCKETS[key]
+
+
+def pick_split(k_tokens: int, m: int, n: int) -> int:
+    """Split-K factor for a token-contraction (wgrad) GEMM: fill ~2 waves of SMs, divide ceil(K/64)."""
+    k_total = (k_tokens + 63) // 64
+    tiles = ((m + 127) // 128) * ((n + 127) // 128)
+    s = max(1, min(k_total, (2 * 148) // max(tiles, 1)))
+    while k_total % s:
+        s -= 1
+    return s
+
+
+def _empty(shape, dtype, like):
+    return torch.empty(shape, dtype=dtype, device=like.device)
+
+
+def _zeros(shape, like, dtype=F32):
+    return torch.zeros(shape, dtype=dtype, device=like.device)
+
+
+def _axis(g: Geom, axis: str) -> dict:
+    P = g.P
+    if axis == "t":
+        return dict(L_=g.T, n_seq=g.B * P, inner=P, outer_stride=g.T * P, inner_stride=1, tok_stride=P)
+    if axis == "x":
+        return dict(L_=g.w, n_seq=g.I * g.h, inner=g.h, outer_stride=P, inner_stride=g.w, tok_stride=1)
+    return dict(L_=g.h, n_seq=g.I * g.w, inner=g.w, outer_stride=P, inner_stride=1, tok_stride=g.w)
+
+
+# ---------------------------------------------------------------------------------------------
+# shared pieces: IN -> QKV -> attention(s) -> IN -> out-projection with residual epilogue
+# ---------------------------------------------------------------------------------------------
+def _attn_branch_fwd(X, g: Geom, p: Dict[str, torch.Tensor], w16, heads: int, axes: List[str], scale_keys,
+                     mask_img, col_scale, col_shift, gamma, want_x16: bool, save: bool):
+    I, P, N, E = g.I, g.P, g.N, X.shape[1]
+    st1 = _zeros((I, E, 2), X)
+    ops.inorm_stats(X, I, P, st1)
+    Xn = _empty((N, E), BF16, X)
+    ops.inorm_apply(X, Xn, I, P, st1, p["norm1.weight"], p["norm1.bias"])
+    QKV = _empty((N, 3 * E), BF16, X)
+    ops.gemm(Xn, w16("input_head.weight"), N, 3 * E, E, epilogue=L.EPI_STORE16, bias=p["input_head.bias"], out16=QKV)
+    O = _empty((N, E), BF16, X)
+    oscale = 1.0 / len(axes)
+    for i, ax in enumerate(axes):
+        geo = _axis(g, ax)
+        sf = p[scale_keys[i]].reshape(-1) if scale_keys is not None else None
+        ops.attention(QKV, O, heads=heads, qn_w=p["qnorm.weight"], qn_b=p["qnorm.bias"], kn_w=p["knorm.weight"],
+                      kn_b=p["knorm.bias"], bias_emb=p["rel_pos_bias.relative_attention_bias.weight"],
+                      bucket=relpos_bucket_vector(geo["L_"], X.device), scale_factor=sf, out_scale=oscale,
+                      accumulate=i > 0, **geo)
+    st2 = _zeros((I, E, 2), X)
+    ops.inorm_stats(O, I, P, st2)
+    On = _empty((N, E), BF16, X)
+    ops.inorm_apply(O, On, I, P, st2, p["norm2.weight"], p["norm2.bias"])
+    Xout = _empty((N, E), F32, X)
+    Z = _empty((N, E), BF16, X) if save else None
+    X16 = _empty((N, E), BF16, X) if want_x16 else None
+    ops.gemm(On, w16("output_head.weight"), N, E, E, epilogue=L.EPI_RESID, bias=p["output_head.bias"],
+             col_scale=col_scale, col_shift=col_shift, col_gamma=gamma, row_scale=mask_img, rows_per_group=P,
+             in32=X, out32=Xout, out16=X16, out16b=Z)
+    saved = dict(X=X, st1=st1, Xn=Xn, QKV=QKV, O=O, st2=st2, On=On, Z=Z) if save else None
+    return Xout, X16, saved
+
+
+def _attn_branch_bwd(dXout, g: Geom, p, w16, heads: int, axes, scale_keys, mask_img, coef, sv, grads):
+    """Backward of X_out = X + mask*gamma*(Z*c1 + c0) through out-proj, IN, attention(s), QKV, IN.
+
+    `coef` = gamma*c1 (the factor between dX_out and dZ).  Returns (dX, S0, S1) with
+    S0[c] = sum mask*dX_out, S1[c] = sum mask*dX_out*Z for the caller's gamma / feature-scale gradients.
+    Accumulates the gradients of norm1/2, input_head, output_head.weight, qnorm/knorm, bias table, scales.
+    """
+    I, P, N = g.I, g.P, g.N
+    E = dXout.shape[1]
+    X, st1, Xn, QKV, O, st2, On, Z = (sv[k] for k in ("X", "st1", "Xn", "QKV", "O", "st2", "On", "Z"))
+    S0, S1 = _zeros((E,), dXout), _zeros((E,), dXout)
+    dZ = _empty((N, E), BF16, dXout)
+    ops.resid_bwd(dXout, Z, dZ, I, P, mask_img, coef, S0, S1)
+    # output_head: dgrad reads W (E_out, E_in) as the (K, N) operand, wgrad contracts over tokens
+    dOn = _empty((N, E), BF16, dXout)
+    ops.gemm(dZ, w16("output_head.weight"), N, E, E, epilogue=L.EPI_STORE16, b_mode=L.B_KN, out16=dOn)
+    ops.gemm(dZ, On, E, E, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN, split_k=pick_split(N, E, E),
+             out32=grads["output_head.weight"].view(E, E))
+    # norm2
+    red2 = _zeros((I, E, 2), dXout)
+    ops.inorm_bwd(1, dOn, O, I, P, st2, p["norm2.weight"], p["norm2.bias"], red2)
+    dO = _empty((N, E), BF16, dXout)
+    ops.inorm_bwd(2, dOn, O, I, P, st2, p["norm2.weight"], p["norm2.bias"], red2, out=dO)
+    ops.inorm_bwd_params(red2, I, P, E, p["norm2.weight"], p["norm2.bias"], dweight=grads["norm2.weight"],
+                         dbias=grads["norm2.bias"])
+    # attention(s)
+    dQKV = _empty((N, 3 * E), BF16, dXout)
+    oscale = 1.0 / len(axes)
+    for i, ax in enumerate(axes):
+        geo = _axis(g, ax)
+        sf = p[scale_keys[i]].reshape(-1) if scale_keys is not None else None
+        gr = dict(d_qn_w=grads["qnorm.weight"], d_qn_b=grads["qnorm.bias"], d_kn_w=grads["knorm.weight"],
+                  d_kn_b=grads["knorm.bias"], d_bias_emb=grads["rel_pos_bias.relative_attention_bias.weight"],
+                  d_scale_factor=grads[scale_keys[i]].view(-1) if scale_keys is not None else None)
+        ops.attention(QKV, dQKV, heads=heads, qn_w=p["qnorm.weight"], qn_b=p["qnorm.bias"], kn_w=p["knorm.weight"],
+                      kn_b=p["knorm.bias"], bias_emb=p["rel_pos_bias.relative_attention_bias.weight"],
+                      bucket=relpos_bucket_vector(geo["L_"], dXout.device), scale_factor=sf, out_scale=oscale,
+                      accumulate=i > 0, dout=dO, grads=gr, **geo)
+    ops.colsum16(dQKV, grads["input_head.bias"])
+    # input_head
+    dXn = _empty((N, E), BF16, dXout)
+    ops.gemm(dQKV, w16("input_head.weight"), N, E, 3 * E, epilogue=L.EPI_STORE16, b_mode=L.B_KN, out16=dXn)
+    ops.gemm(dQKV, Xn, 3 * E, E, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
+             split_k=pick_split(N, 3 * E, E), out32=grads["input_head.weight"].view(3 * E, E))
+    # norm1 (+ the identity path of the residual)
+    red1 = _zeros((I, E, 2), dXout)
+    ops.inorm_bwd(1, dXn, X, I, P, st1, p["norm1.weight"], p["norm1.bias"], red1)
+    dX = _empty((N, E), F32, dXout)
+    ops.inorm_bwd(2, dXn, X, I, P, st1, p["norm1.weight"], p["norm1.bias"], red1, out=dX, add32=dXout)
+    ops.inorm_bwd_params(red1, I, P, E, p["norm1.weight"], p["norm1.bias"], dweight=grads["norm1.weight"],
+                         dbias=grads["norm1.bias"])
+    return dX, S0, S1
+
+
+# ---------------------------------------------------------------------------------------------
+# temporal block
+# ---------------------------------------------------------------------------------------------
+def temporal_forward(X, g: Geom, p, w16, heads: int, attn_scale: bool, mask_img, save: bool):
+    keys = ["attn_scale_factor"] if attn_scale else None
+    Xout, _, saved = _attn_branch_fwd(X, g, p, w16, heads, ["t"], keys, mask_img, None, None, p["gamma"], False, save)
+    return Xout, saved
+
+
+def temporal_backward(dXout, g: Geom, p, w16, heads: int, attn_scale: bool, mask_img, sv, grads):
+    keys = ["attn_scale_factor"] if attn_scale else None
+    dX, S0, S1 = _attn_branch_bwd(dXout, g, p, w16, heads, ["t"], keys, mask_img, p["gamma"], sv, grads)
+    grads["gamma"] += S1                        # d/dgamma of mask*gamma*Z
+    grads["output_head.bias"] += p["gamma"] * S0
+    return dX
+
+
+# ---------------------------------------------------------------------------------------------
+# spatial block (axial attention + MLP)
+# ---------------------------------------------------------------------------------------------
+def _feat_consts(p, feat_scale: bool):
+    """Feature scaling  z + mean_img(z)*low + (z - mean_img(z))*high  (attention.py:302-307).
+
+    mean_img(z) over an image of z = IN(o) W^T + b is exactly W b_norm2 + b_out =: c (the normalised part of
+    IN has zero mean per image and channel), so the op is the per-channel affine z*(1+high) + c*(low-high).
+    """
+    if not feat_scale:
+        return None, None, None
+    Wm = p["output_head.weight"].reshape(p["output_head.weight"].shape[0], -1)
+    c = (Wm * p["norm2.bias"][None, :]).sum(dim=1) + p["output_head.bias"]
+    c1 = (1.0 + p["high_freq_scalar"]).contiguous()
+    c0 = (c * (p["low_freq_scalar"] - p["high_freq_scalar"])).contiguous()
+    return c, c1, c0
+
+
+def spatial_forward(X, g: Geom, p, w16, heads: int, attn_scale: bool, feat_scale: bool, mask_att, mask_mlp, save: bool):
+    I, P, N, E = g.I, g.P, g.N, X.shape[1]
+    keys = ["attn_scale_factor_x", "attn_scale_factor_y"] if attn_scale else None
+    c, c1, c0 = _feat_consts(p, feat_scale)
+    Xmid, Xb, sv = _attn_branch_fwd(X, g, p, w16, heads, ["x", "y"], keys, mask_att, c1, c0, p["gamma_att"], True, save)
+    G = _empty((N, 4 * E), BF16, X)
+    Hpre = _empty((N, 4 * E), BF16, X) if save else None
+    ops.gemm(Xb, w16("mlp.fc1.weight"), N, 4 * E, E, epilogue=L.EPI_GELU, bias=p["mlp.fc1.bias"], out16=G, out16b=Hpre)
+    Y2 = _empty((N, E), BF16, X)
+    ops.gemm(G, w16("mlp.fc2.weight"), N, E, 4 * E, epilogue=L.EPI_STORE16, bias=p["mlp.fc2.bias"], out16=Y2)
+    st3 = _zeros((I, E, 2), X)
+    ops.inorm_stats(Y2, I, P, st3)
+    Xout = _empty((N, E), F32, X)
+    ops.inorm_apply(Y2, Xout, I, P, st3, p["mlp_norm.weight"], p["mlp_norm.bias"], resid_in=Xmid, row_scale=mask_mlp,
+                    col_gamma=p["gamma_mlp"])
+    if save:
+        sv.update(Xb=Xb, G=G, Hpre=Hpre, Y2=Y2, st3=st3)
+    return Xout, sv
+
+
+def spatial_backward(dXout, g: Geom, p, w16, heads: int, attn_scale: bool, feat_scale: bool, mask_att, mask_mlp, sv,
+                     grads):
+    I, P, N = g.I, g.P, g.N
+    E = dXout.shape[1]
+    Xb, G, Hpre, Y2, st3 = (sv[k] for k in ("Xb", "G", "Hpre", "Y2", "st3"))
+    # ---- MLP branch: X_out = X_mid + mask*gamma_mlp*IN(Y2) ----
+    red3 = _zeros((I, E, 2), dXout)
+    ops.inorm_bwd(1, dXout, Y2, I, P, st3, p["mlp_norm.weight"], p["mlp_norm.bias"], red3)
+    dY2 = _empty((N, E), BF16, dXout)
+    ops.inorm_bwd(2, dXout, Y2, I, P, st3, p["mlp_norm.weight"], p["mlp_norm.bias"], red3, out=dY2,
+                  row_scale=mask_mlp, col_scale=p["gamma_mlp"])
+    ops.inorm_bwd_params(red3, I, P, E, p["mlp_norm.weight"], p["mlp_norm.bias"], row_scale=mask_mlp,
+                         col_scale=p["gamma_mlp"], dweight=grads["mlp_norm.weight"], dbias=grads["mlp_norm.bias"],
+                         dcol_scale=grads["gamma_mlp"])
+    # fc2 (its bias feeds an InstanceNorm, so its gradient is identically zero and stays zero)
+    dH = _empty((N, 4 * E), BF16, dXout)
+    ops.gemm(dY2, w16("mlp.fc2.weight"), N, 4 * E, E, epilogue=L.EPI_DGELU, b_mode=L.B_KN, aux16=Hpre, out16=dH)
+    ops.gemm(dY2, G, E, 4 * E, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
+             split_k=pick_split(N, E, 4 * E), out32=grads["mlp.fc2.weight"])
+    ops.colsum16(dH, grads["mlp.fc1.bias"])
+    # fc1: the input gradient joins the residual-stream gradient in the epilogue
+    dXmid = _empty((N, E), F32, dXout)
+    ops.gemm(dH, w16("mlp.fc1.weight"), N, E, 4 * E, epilogue=L.EPI_ACC32, b_mode=L.B_KN, in32=dXout, out32=dXmid)
+    ops.gemm(dH, Xb, 4 * E, E, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
+             split_k=pick_split(N, 4 * E, E), out32=grads["mlp.fc1.weight"])
+    # ---- attention branch ----
+    keys = ["attn_scale_factor_x", "attn_scale_factor_y"] if attn_scale else None
+    c, c1, c0 = _feat_consts(p, feat_scale)
+    ga = p["gamma_att"]
+    coef = (ga * c1).contiguous() if feat_scale else ga
+    dX, S0, S1 = _attn_branch_bwd(dXmid, g, p, w16, heads, ["x", "y"], keys, mask_att, coef, sv, grads)
+    if feat_scale:
+        lo, hi = p["low_freq_scalar"], p["high_freq_scalar"]
+        grads["gamma_att"] += c1 * S1 + c0 * S0
+        grads["high_freq_scalar"] += ga * (S1 - c * S0)
+        grads["low_freq_scalar"] += ga * c * S0
+        dc = ga * (lo - hi) * S0                     # gradient reaching c = W b_norm2 + b_out
+        Wm = p["output_head.weight"].reshape(E, E)
+        grads["output_head.weight"].view(E, E).add_(dc[:, None] * p["norm2.bias"][None, :])
+        grads["norm2.bias"] += (Wm * dc[:, None]).sum(dim=0)
+        grads["output_head.bias"] += coef * S0 + dc
+    else:
+        grads["gamma_att"] += S1
+        grads["output_head.bias"] += ga * S0
+    return dX
+
+
+# ---------------------------------------------------------------------------------------------
+# hierarchical patch embed (+ FiLM) and unembed
+# ---------------------------------------------------------------------------------------------
+def _conv_w_fwd(w: torch.Tensor, dtype) -> torch.Tensor:
+    """(Cout, Cin, 2, 2) -> (Cout, (ky, kx, ci)) operand copy."""
+    return w.detach().permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(dtype).contiguous()
+
+
+def _s2d_ok(wo: int) -> bool:
+    return (wo % 128 == 0) if wo >= 128 else (128 % wo == 0)
+
+
+def embed_forward(x, g_in, p, n_layers: int, film_gb: Optional[torch.Tensor], T: int, save: bool):
+    """x: (I, F, H, W) fp32.  p: embed params keyed 'in_proj.k.weight/bias'.  Returns X (I*h*w, E) fp32."""
+    I, Fd, H, W = x.shape
+    sv = dict(x=x, Y=[], st=[], A=[], dims=[], film_gb=film_gb) if save else None
+    A = None
+    h_, w_ = H, W
+    X = None
+    for i in range(n_layers):
+        last = i == n_layers - 1
+        wt = p[f"in_proj.{3 * i}.weight"]
+        Cout, Cin = wt.shape[0], wt.shape[1]
+        ho, wo = h_ // 2, w_ // 2
+        M = I * ho * wo
+        st = _zeros((I, Cout, 2), x)
+        Y = _empty((M, Cout), F16, x)
+        if i == 0:
+            Wkn = wt.detach().reshape(Cout, 4 * Fd).t().contiguous()
+            ops.patch_in(x, Wkn, Y.view(I, ho, wo, Cout), st)
+        else:
+            W16 = _conv_w_fwd(wt, F16)
+            if _s2d_ok(wo):
+                ops.gemm(A, W16, M, Cout, 4 * Cin, epilogue=L.EPI_STORE16, a_mode=L.A_S2D, ldb=4 * Cin,
+                         s2d=(I, h_, w_, Cin), out16=Y)
+            else:
+                Ag = _empty((M, 4 * Cin), F16, x)
+                ops.s2d_gather(A.view(I, h_, w_, Cin), Ag)
+                ops.gemm(Ag, W16, M, Cout, 4 * Cin, epilogue=L.EPI_STORE16, out16=Y)
+            ops.inorm_stats(Y, I, ho * wo, st)
+        nw, nb = p[f"in_proj.{3 * i + 1}.weight"], p[f"in_proj.{3 * i + 1}.bias"]
+        if not last:
+            An = _empty((M, Cout), F16, x)
+            ops.inorm_apply(Y, An, I, ho * wo, st, nw, nb, gelu=True)
+        else:
+            X = _empty((M, Cout), F32, x)
+            if film_gb is not None:
+                E = Cout
+                fg, fb = film_gb[:, :E].contiguous(), film_gb[:, E:].contiguous()
+                ops.inorm_apply(Y, X, I, ho * wo, st, nw, nb, film_gamma=fg, film_beta=fb, film_T=T)
+            else:
+                ops.inorm_apply(Y, X, I, ho * wo, st, nw, nb)
+            An = None
+        if save:
+            sv["Y"].append(Y); sv["st"].append(st); sv["A"].append(A); sv["dims"].append((h_, w_, Cin, Cout))
+        A = An
+        h_, w_ = ho, wo
+    return X, sv
+
+
+def embed_backward(dX, p, n_layers: int, film_gb, T: int, sv, grads, need_dx: bool):
+    """Returns (dx or None, d_film_gb or None).  Gradients inside the stem are bf16 (range), activations fp16."""
+    x = sv["x"]
+    I, Fd, H, W = x.shape
+    dfilm = None
+    gin = dX                      # gradient w.r.t. the output of stage i's IN(+GELU / +FiLM)
+    for i in reversed(range(n_layers)):
+        last = i == n_layers - 1
+        h_, w_, Cin, Cout = sv["dims"][i]
+        ho, wo = h_ // 2, w_ // 2
+        M = I * ho * wo
+        Y, st = sv["Y"][i], sv["st"][i]
+        nw, nb = p[f"in_proj.{3 * i + 1}.weight"], p[f"in_proj.{3 * i + 1}.bias"]
+        red = _zeros((I, Cout, 2), dX)
+        ops.inorm_bwd(1, gin, Y, I, ho * wo, st, nw, nb, red, gelu=not last)
+        dY = _empty((M, Cout), BF16, dX)
+        kw = {}
+        if last and film_gb is not None:
+            fg = film_gb[:, :Cout].contiguous()
+            kw = dict(film_gamma=fg, film_T=T)
+        ops.inorm_bwd(2, gin, Y, I, ho * wo, st, nw, nb, red, gelu=not last, out=dY, **kw)
+        pk = dict(dweight=grads[f"in_proj.{3 * i + 1}.weight"], dbias=grads[f"in_proj.{3 * i + 1}.bias"])
+        if last and film_gb is not None:
+            dfg, dfb = _empty((I // T, Cout), F32, dX), _empty((I // T, Cout), F32, dX)
+            ops.inorm_bwd_params(red, I, ho * wo, Cout, nw, nb, film_gamma=kw["film_gamma"], film_T=T,
+                                 dfilm_gamma=dfg, dfilm_beta=dfb, **pk)
+            dfilm = torch.cat([dfg, dfb], dim=1)
+        else:
+            ops.inorm_bwd_params(red, I, ho * wo, Cout, nw, nb, **pk)
+        wt = p[f"in_proj.{3 * i}.weight"]
+        if i == 0:
+            ops.patch_wgrad(dY.view(I, ho, wo, Cout), x, grads[f"in_proj.0.weight"])
+            if need_dx:
+                dx = _empty((I, Fd, H, W), F32, dX)
+                ops.patch_out(dY.view(I, ho, wo, Cout), wt.detach().reshape(Cout, 4 * Fd).contiguous(), dx)
+                return dx, dfilm
+            return None, dfilm
+        # GEMM stage: wgrad over the gathered (bf16) patches, dgrad scattered back depth-to-space
+        A = sv["A"][i]
+        Ag = _empty((M, 4 * Cin), BF16, dX)
+        ops.s2d_gather(A.view(I, h_, w_, Cin), Ag)
+        dWp = _zeros((Cout, 4 * Cin), dX)
+        ops.gemm(dY, Ag, Cout, 4 * Cin, M, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
+                 split_k=pick_split(M, Cout, 4 * Cin), out32=dWp)
+        grads[f"in_proj.{3 * i}.weight"] += dWp.view(Cout, 2, 2, Cin).permute(0, 3, 1, 2)
+        del Ag
+        dA = _empty((I * h_ * w_, Cin), BF16, dX)
+        ops.gemm(dY, _conv_w_fwd(wt, BF16), M, 4 * Cin, Cout, epilogue=L.EPI_D2S, b_mode=L.B_KN, d2s=(ho, wo, Cin),
+                 out16=dA, ldo=4 * Cin)
+        gin = dA
+    raise AssertionError("unreachable")
+
+
+def _convT_w(w: torch.Tensor, dtype) -> torch.Tensor:
+    """(Cin, Cout, 2, 2) -> (Cin, (ky, kx, co)) operand copy."""
+    return w.detach().permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(dtype).contiguous()
+
+
+def debed_forward(X, g: Geom, p, n_layers: int, out_fields: int, save: bool):
+    """X: (I*h*w, E) fp32 -> (I, F, H, W) fp32."""
+    I = g.I
+    h_, w_ = g.h, g.w
+    Xh = _empty(tuple(X.shape), F16, X)
+    ops.cast16(X, Xh)
+    A = Xh
+    sv = dict(A=[], Z=[], st=[], dims=[]) if save else None
+    out = None
+    for i in range(n_layers):
+        last = i == n_layers - 1
+        wt = p[f"out_proj.{3 * i}.weight"]
+        Cin, Cout = wt.shape[0], wt.shape[1]
+        M = I * h_ * w_
+        if last:
+            out = _empty((I, Cout, 2 * h_, 2 * w_), F32, X)
+            ops.patch_out(A.view(I, h_, w_, Cin), wt.detach().reshape(Cin, 4 * Cout).contiguous(), out)
+            if save:
+                sv["A"].append(A); sv["dims"].append((h_, w_, Cin, Cout))
+            break
+        Z = _empty((4 * M, Cout), F16, X)
+        ops.gemm(A, _convT_w(wt, F16), M, 4 * Cout, Cin, epilogue=L.EPI_D2S, b_mode=L.B_KN, d2s=(h_, w_, Cout),
+                 out16=Z, ldo=4 * Cout)
+        st = _zeros((I, Cout, 2), X)
+        ops.inorm_stats(Z, I, 4 * h_ * w_, st)
+        An = _empty((4 * M, Cout), F16, X)
+        ops.inorm_apply(Z, An, I, 4 * h_ * w_, st, p[f"out_proj.{3 * i + 1}.weight"], p[f"out_proj.{3 * i + 1}.bias"],
+                        gelu=True)
+        if save:
+            sv["A"].append(A); sv["Z"].append(Z); sv["st"].append(st); sv["dims"].append((h_, w_, Cin, Cout))
+        A = An
+        h_, w_ = 2 * h_, 2 * w_
+    return out, sv
+
+
+def debed_backward(dOut, g: Geom, p, n_layers: int, sv, grads):
+    """dOut: (I, F, H, W) fp32 -> dX (I*h*w, E) fp32."""
+    I = g.I
+    dOut = dOut.contiguous()
+    gin = None
+    dX = None
+    for i in reversed(range(n_layers)):
+        last = i == n_layers - 1
+        h_, w_, Cin, Cout = sv["dims"][i]
+        M = I * h_ * w_
+        A = sv["A"][i]
+        wt = p[f"out_proj.{3 * i}.weight"]
+        if last:
+            ops.patch_wgrad(A.view(I, h_, w_, Cin), dOut, grads[f"out_proj.{3 * i}.weight"])
+            dA = _empty((M, Cin), BF16, dOut)
+            ops.patch_in(dOut, wt.detach().reshape(Cin, 4 * Cout).t().contiguous(), dA.view(I, h_, w_, Cin), None)
+            if n_layers == 1:
+                return dA.float()
+            gin = dA
+            continue
+        Z, st = sv["Z"][i], sv["st"][i]
+        nw, nb = p[f"out_proj.{3 * i + 1}.weight"], p[f"out_proj.{3 * i + 1}.bias"]
+        red = _zeros((I, Cout, 2), dOut)
+        ops.inorm_bwd(1, gin, Z, I, 4 * h_ * w_, st, nw, nb, red, gelu=True)
+        dZ = _empty((4 * M, Cout), BF16, dOut)
+        ops.inorm_bwd(2, gin, Z, I, 4 * h_ * w_, st, nw, nb, red, gelu=True, out=dZ)
+        ops.inorm_bwd_params(red, I, 4 * h_ * w_, Cout, nw, nb, dweight=grads[f"out_proj.{3 * i + 1}.weight"],
+                             dbias=grads[f"out_proj.{3 * i + 1}.bias"])
+        # gather dZ (I, 2h, 2w, Cout) into (M, (ky, kx, co)): A operand of the dgrad and B operand of the wgrad
+        dZg = _empty((M, 4 * Cout), BF16, dOut)
+        ops.s2d_gather(dZ.view(I, 2 * h_, 2 * w_, Cout), dZg)
+        Ab = _empty(tuple(A.shape), BF16, dOut)
+        ops.convert16(A, Ab)
+        dWp = _zeros((Cin, 4 * Cout), dOut)
+        ops.gemm(Ab, dZg, Cin, 4 * Cout, M, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
+                 split_k=pick_split(M, Cin, 4 * Cout), out32=dWp)
+        grads[f"out_proj.{3 * i}.weight"] += dWp.view(Cin, 2, 2, Cout).permute(0, 3, 1, 2)
+        Wb = _convT_w(wt, BF16)                                   # (Cin, 4*Cout) = (N, K) of the dgrad
+        if i == 0:
+            dX = _empty((M, Cin), F32, dOut)
+            ops.gemm(dZg, Wb, M, Cin, 4 * Cout, epilogue=L.EPI_STORE32, out32=dX)
+            return dX
+        dA = _empty((M, Cin), BF16, dOut)
+        ops.gemm(dZg, Wb, M, Cin, 4 * Cout, epilogue=L.EPI_STORE16, out16=dA)
+        gin = dA
+    return dX

@@ -81,3 +81,193 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, epilogue: 
         ld32 = ref.stride(0) if (ref is not None and ref.dim() == 2) else N
     a.ldo, a.ld32 = ldo, ld32
     L.check(L.lib.bf_gemm(C.byref(a), _stream()), "bf_gemm")
+
+
+# ---------------------------------------------------------------------------------------------
+# InstanceNorm family
+# ---------------------------------------------------------------------------------------------
+_DT3 = {torch.bfloat16: L.BF_BF16, torch.float16: L.BF_F16, torch.float32: L.BF_F32}
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype not in _DT3:
+        raise L.BubbleformerB200Error(f"unsupported dtype {t.dtype}")
+    return _DT3[t.dtype]
+
+
+def _mat(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise L.BubbleformerB200Error(f"{name}: expected a row-major 2-D matrix, got {tuple(t.shape)} / {t.stride()}")
+    return t
+
+
+def inorm_stats(x: torch.Tensor, I: int, P: int, stats: torch.Tensor) -> None:
+    """stats[img, c] += (sum x, sum x^2); `stats` (I, C, 2) fp32 must be zeroed by the caller."""
+    _mat(x, "x")
+    C_ = x.shape[1]
+    assert x.shape[0] == I * P and stats.shape == (I, C_, 2) and stats.dtype == torch.float32
+    L.check(L.lib.bf_inorm_stats(_ptr(x), _dt(x), I, P, C_, x.stride(0), _ptr(stats), _stream()), "bf_inorm_stats")
+
+
+def inorm_apply(x, out, I, P, stats, weight, bias, *, gelu=False, film_gamma=None, film_beta=None, film_T=0,
+                resid_in=None, row_scale=None, col_gamma=None) -> None:
+    _mat(x, "x"); _mat(out, "out")
+    C_ = x.shape[1]
+    a = L.InormApplyArgs()
+    a.x, a.x_dtype, a.out_dtype = _ptr(x), _dt(x), _dt(out)
+    a.ldx, a.ldo = x.stride(0), out.stride(0)
+    a.I, a.P, a.C, a.gelu = I, P, C_, int(gelu)
+    a.stats = _f32(stats, I * C_ * 2, "stats")
+    a.weight, a.bias = _f32(weight, C_, "weight"), _f32(bias, C_, "bias")
+    a.film_gamma = _f32(film_gamma, 1, "film_gamma")
+    a.film_beta = _f32(film_beta, 1, "film_beta")
+    a.film_T = film_T
+    if resid_in is not None:
+        _mat(resid_in, "resid_in")
+        assert resid_in.dtype == torch.float32 and resid_in.stride(0) == out.stride(0)
+    a.resid_in = _ptr(resid_in)
+    a.row_scale = _f32(row_scale, I, "row_scale")
+    a.col_gamma = _f32(col_gamma, C_, "col_gamma")
+    a.out = _ptr(out)
+    L.check(L.lib.bf_inorm_apply(C.byref(a), _stream()), "bf_inorm_apply")
+
+
+def inorm_bwd(phase, gin, x, I, P, stats, weight, bias, red, *, gelu=False, out=None, row_scale=None,
+              col_scale=None, film_gamma=None, film_T=0, add32=None) -> None:
+    _mat(gin, "gin"); _mat(x, "x")
+    C_ = x.shape[1]
+    a = L.InormBwdArgs()
+    a.phase, a.gelu = phase, int(gelu)
+    a.gin, a.g_dtype, a.x_dtype, a.x = _ptr(gin), _dt(gin), _dt(x), _ptr(x)
+    a.ldg, a.ldx = gin.stride(0), x.stride(0)
+    a.I, a.P, a.C = I, P, C_
+    a.stats = _f32(stats, I * C_ * 2, "stats")
+    a.weight, a.bias = _f32(weight, C_, "weight"), _f32(bias, C_, "bias")
+    a.red = _f32(red, I * C_ * 2, "red")
+    a.row_scale = _f32(row_scale, I, "row_scale")
+    a.col_scale = _f32(col_scale, C_, "col_scale")
+    a.film_gamma = _f32(film_gamma, 1, "film_gamma")
+    a.film_T = film_T
+    if out is not None:
+        _mat(out, "out")
+        a.out, a.out_dtype, a.ldo = _ptr(out), _dt(out), out.stride(0)
+    if add32 is not None:
+        assert add32.dtype == torch.float32 and add32.stride(0) == out.stride(0)
+        a.add32 = _ptr(add32)
+    L.check(L.lib.bf_inorm_bwd(C.byref(a), _stream()), "bf_inorm_bwd")
+
+
+def inorm_bwd_params(red, I, P, Cn, weight, bias, *, row_scale=None, col_scale=None, film_gamma=None, film_T=0,
+                     dweight=None, dbias=None, dcol_scale=None, dfilm_gamma=None, dfilm_beta=None) -> None:
+    a = L.InormBwdParamsArgs()
+    a.red = _f32(red, I * Cn * 2, "red")
+    a.I, a.P, a.C, a.film_T = I, P, Cn, film_T
+    a.row_scale = _f32(row_scale, I, "row_scale")
+    a.col_scale = _f32(col_scale, Cn, "col_scale")
+    a.film_gamma = _f32(film_gamma, 1, "film_gamma")
+    a.weight, a.bias = _f32(weight, Cn, "weight"), _f32(bias, Cn, "bias")
+    a.dweight, a.dbias = _f32(dweight, Cn, "dweight"), _f32(dbias, Cn, "dbias")
+    a.dcol_scale = _f32(dcol_scale, Cn, "dcol_scale")
+    a.dfilm_gamma, a.dfilm_beta = _f32(dfilm_gamma, 1, "dfilm_gamma"), _f32(dfilm_beta, 1, "dfilm_beta")
+    L.check(L.lib.bf_inorm_bwd_params(C.byref(a), _stream()), "bf_inorm_bwd_params")
+
+
+def resid_bwd(dx, z16, dz16, I, P, row_scale, coef, S0, S1) -> None:
+    _mat(dx, "dx")
+    Cn = dx.shape[1]
+    ref = z16 if z16 is not None else dz16
+    dt = _DT[ref.dtype]
+    L.check(L.lib.bf_resid_bwd(_ptr(dx), dx.stride(0), _ptr(z16), _ptr(dz16), ref.stride(0), dt, I, P, Cn,
+                               _f32(row_scale, I, "row_scale"), _f32(coef, Cn, "coef"), _f32(S0, Cn, "S0"),
+                               _f32(S1, Cn, "S1"), _stream()), "bf_resid_bwd")
+
+
+def colsum16(x, out) -> None:
+    _mat(x, "x")
+    L.check(L.lib.bf_colsum16(_ptr(x), _DT[x.dtype], x.shape[0], x.shape[1], x.stride(0),
+                              _f32(out, x.shape[1], "out"), _stream()), "bf_colsum16")
+
+
+# ---------------------------------------------------------------------------------------------
+# attention
+# ---------------------------------------------------------------------------------------------
+def attention(qkv, out, *, heads, L_, n_seq, inner, outer_stride, inner_stride, tok_stride, qn_w, qn_b, kn_w, kn_b,
+              bias_emb, bucket, scale_factor=None, out_scale=1.0, accumulate=False, dout=None, grads=None) -> None:
+    """Forward (dout is None): out (tokens, E).  Backward: out is dqkv (tokens, 3E); grads = dict of fp32
+    accumulators d_qn_w, d_qn_b, d_kn_w, d_kn_b, d_bias_emb, d_scale_factor."""
+    _mat(qkv, "qkv"); _mat(out, "out")
+    if qkv.dtype != torch.bfloat16 or out.dtype != torch.bfloat16:
+        raise L.BubbleformerB200Error("attention: bf16 tensors required")
+    E3 = qkv.shape[1]
+    d = E3 // (3 * heads)
+    a = L.AttnArgs()
+    a.qkv, a.ld_qkv = _ptr(qkv), qkv.stride(0)
+    a.out, a.ld_out = _ptr(out), out.stride(0)
+    a.heads, a.head_dim, a.L, a.accumulate = heads, d, L_, int(accumulate)
+    a.n_seq, a.inner, a.outer_stride, a.inner_stride, a.tok_stride = n_seq, inner, outer_stride, inner_stride, tok_stride
+    a.qn_w, a.qn_b, a.kn_w, a.kn_b = (_f32(t, d, "ln") for t in (qn_w, qn_b, kn_w, kn_b))
+    a.bias_emb = _f32(bias_emb, 32 * heads, "bias_emb")
+    if bucket.dtype != torch.int32 or bucket.numel() != 2 * L_ - 1:
+        raise L.BubbleformerB200Error("attention: bucket must be int32 of length 2L-1")
+    a.bucket = _ptr(bucket)
+    a.scale_factor = _f32(scale_factor, heads, "scale_factor")
+    a.out_scale = out_scale
+    if dout is None:
+        L.check(L.lib.bf_attention_fwd(C.byref(a), _stream()), "bf_attention_fwd")
+        return
+    _mat(dout, "dout")
+    a.dout, a.ld_dout = _ptr(dout), dout.stride(0)
+    a.d_qn_w, a.d_qn_b = _f32(grads["d_qn_w"], d, "d_qn_w"), _f32(grads["d_qn_b"], d, "d_qn_b")
+    a.d_kn_w, a.d_kn_b = _f32(grads["d_kn_w"], d, "d_kn_w"), _f32(grads["d_kn_b"], d, "d_kn_b")
+    a.d_bias_emb = _f32(grads.get("d_bias_emb"), 32 * heads, "d_bias_emb")
+    a.d_scale_factor = _f32(grads.get("d_scale_factor"), heads, "d_scale_factor")
+    L.check(L.lib.bf_attention_bwd(C.byref(a), _stream()), "bf_attention_bwd")
+
+
+# ---------------------------------------------------------------------------------------------
+# patch boundary + casts
+# ---------------------------------------------------------------------------------------------
+def patch_in(x, Wkn, out, stats) -> None:
+    """x (I, F, H, W) fp32 -> out (I, H/2, W/2, N) 16-bit; stats (I, N, 2) fp32 accumulated if given."""
+    I, F, H, W = x.shape
+    N = out.shape[-1]
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous()
+    assert Wkn.shape == (4 * F, N) and Wkn.dtype == torch.float32 and Wkn.is_contiguous()
+    L.check(L.lib.bf_patch_in(_ptr(x), _ptr(Wkn), _ptr(out), _DT[out.dtype], _ptr(stats), I, F, H, W, N, _stream()),
+            "bf_patch_in")
+
+
+def patch_out(a, Wck, out) -> None:
+    """a (I, h, w, C) 16-bit -> out (I, F, 2h, 2w) fp32."""
+    I, h, w, Cn = a.shape
+    F = out.shape[1]
+    assert out.dtype == torch.float32 and out.is_contiguous() and a.is_contiguous()
+    assert Wck.shape == (Cn, 4 * F) and Wck.dtype == torch.float32 and Wck.is_contiguous()
+    L.check(L.lib.bf_patch_out(_ptr(a), _DT[a.dtype], _ptr(Wck), _ptr(out), I, F, h, w, Cn, _stream()), "bf_patch_out")
+
+
+def patch_wgrad(a, x, dW) -> None:
+    """dW (N, 4F) fp32 += sum_pix a[pix, n] * patch(x)[pix, (f, ky, kx)];  a (I, H/2, W/2, N), x (I, F, H, W)."""
+    I, F, H, W = x.shape
+    N = a.shape[-1]
+    assert x.dtype == torch.float32 and x.is_contiguous() and a.is_contiguous()
+    assert dW.dtype == torch.float32 and dW.is_contiguous() and dW.numel() == N * 4 * F
+    L.check(L.lib.bf_patch_wgrad(_ptr(a), _DT[a.dtype], _ptr(x), _ptr(dW), I, F, H, W, N, _stream()), "bf_patch_wgrad")
+
+
+def s2d_gather(img, out) -> None:
+    I, H, W, Cn = img.shape
+    assert img.is_contiguous() and out.is_contiguous() and out.numel() == img.numel()
+    L.check(L.lib.bf_s2d_gather(_ptr(img), _DT[img.dtype], _ptr(out), _DT[out.dtype], I, H, W, Cn, _stream()),
+            "bf_s2d_gather")
+
+
+def convert16(src, dst) -> None:
+    assert src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel()
+    L.check(L.lib.bf_convert16(_ptr(src), _DT[src.dtype], _ptr(dst), _DT[dst.dtype], src.numel(), _stream()),
+            "bf_convert16")
+
+
+def cast16(src, dst) -> None:
+    assert src.dtype == torch.float32 and src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel()
+    L.check(L.lib.bf_cast16(_ptr(src), _ptr(dst), _DT[dst.dtype], src.numel(), _stream()), "bf_cast16")

@@ -37,6 +37,7 @@ extern "C" {
 
 #define BF_BF16 0
 #define BF_F16 1
+#define BF_F32 2
 
 /* ---- library ------------------------------------------------------------------------------- */
 BF_API const char* bf_last_error(void);
@@ -106,6 +107,130 @@ typedef struct bf_gemm_args {
 } bf_gemm_args;
 
 BF_API int bf_gemm(const bf_gemm_args* args, void* stream);
+
+/* ---- InstanceNorm over the token grid (per image, per channel) -------------------------------
+ * Token-major tensors (I*P, C).  Statistics are raw sums: stats[img][c] = (sum x, sum x^2), fp32,
+ * ACCUMULATED with atomics -- the caller zeroes the buffer first (cudaMemsetAsync).
+ * Replaces nn.InstanceNorm2d(affine=True) (upstream layers/attention.py:39-40,153-154,197 and
+ * layers/patching.py:45,102; eps 1e-5, biased variance) and the elementwise ops fused around it.
+ */
+BF_API int bf_inorm_stats(const void* x, int x_dtype, int I, int P, int C, int64_t ldx, float* stats, void* stream);
+
+typedef struct bf_inorm_apply_args {
+  const void* x;  int32_t x_dtype;  int32_t out_dtype;   /* BF_BF16 | BF_F16 | BF_F32 */
+  int64_t ldx, ldo;
+  int32_t I, P, C;
+  int32_t gelu;               /* 1: y = gelu_erf(y)   (layers/patching.py:47,103)                       */
+  const float* stats;         /* [I][C][2] */
+  const float* weight;        /* [C] */
+  const float* bias;          /* [C] */
+  const float* film_gamma;    /* [I/film_T][C] or NULL: y = film_gamma*y + film_beta (linear_layers.py:77) */
+  const float* film_beta;
+  int32_t film_T;  int32_t reserved0;
+  const float* resid_in;      /* fp32 (I*P, C) ld = ldo or NULL: out = resid_in + row_scale[img]*col_gamma[c]*y
+                                 (layer scale * drop-path + residual, layers/attention.py:317)           */
+  const float* row_scale;     /* [I] or NULL */
+  const float* col_gamma;     /* [C] (with resid_in) */
+  void* out;
+} bf_inorm_apply_args;
+BF_API int bf_inorm_apply(const bf_inorm_apply_args* args, void* stream);
+
+/* Backward of y = [gelu](IN(x)) given gin = dL/dy (times an optional per-(image, channel) scale
+ * cs = row_scale[img]*col_scale[c]*film_gamma[img/film_T][c] that sat between y and the consumer).
+ * phase 1: red[img][c] += (sum g, sum g*xhat), g = gin [* gelu'(.)]         (red zeroed by the caller)
+ * phase 2: out = rstd*w*cs*(g - R1/P - xhat*R2/P) [+ add32]                                            */
+typedef struct bf_inorm_bwd_args {
+  int32_t phase;  int32_t gelu;
+  const void* gin;  int32_t g_dtype;  int32_t x_dtype;
+  const void* x;
+  int64_t ldg, ldx, ldo;
+  int32_t I, P, C;  int32_t out_dtype;
+  const float* stats;  const float* weight;  const float* bias;
+  float* red;                 /* [I][C][2] */
+  const float* row_scale;  const float* col_scale;  const float* film_gamma;
+  int32_t film_T;  int32_t reserved0;
+  const float* add32;         /* fp32 (I*P, C) ld = ldo or NULL */
+  void* out;
+} bf_inorm_bwd_args;
+BF_API int bf_inorm_bwd(const bf_inorm_bwd_args* args, void* stream);
+
+/* Parameter gradients from red (tiny): dweight[c] += sum_img cs*R2, dbias[c] += sum_img cs*R1,
+ * dcol_scale[c] += sum_img row_scale[img]*(w*R2 + b*R1), dfilm_gamma[b][c] = sum_t (w*R2 + b*R1),
+ * dfilm_beta[b][c] = sum_t R1.  NULL outputs are skipped.                                              */
+typedef struct bf_inorm_bwd_params_args {
+  const float* red;
+  int32_t I, P, C, film_T;
+  const float* row_scale;  const float* col_scale;  const float* film_gamma;
+  const float* weight;  const float* bias;
+  float* dweight;  float* dbias;  float* dcol_scale;  float* dfilm_gamma;  float* dfilm_beta;
+} bf_inorm_bwd_params_args;
+BF_API int bf_inorm_bwd_params(const bf_inorm_bwd_params_args* args, void* stream);
+
+/* Residual-branch backward (layers/attention.py:123,309 reversed): one pass over the fp32 gradient stream
+ *   dz16[m,c] = row_scale[img]*coef[c]*dx[m,c];  S0[c] += sum_m rs*dx;  S1[c] += sum_m rs*dx*z16[m,c]   */
+BF_API int bf_resid_bwd(const float* dx, int64_t lddx, const void* z16, void* dz16, int64_t ldz, int dtype,
+                        int I, int P, int C, const float* row_scale, const float* coef, float* S0, float* S1,
+                        void* stream);
+
+/* out[c] += sum_rows x[r, c] for a 16-bit matrix (bias gradients of the 1x1 convs / linears) */
+BF_API int bf_colsum16(const void* x, int dtype, int64_t rows, int C, int64_t ldx, float* out, void* stream);
+
+/* ---- fused 1-D attention along one axis of the token grid -----------------------------------
+ * Replaces upstream layers/attention.py:80-101 (temporal) and :212-238 / :258-277 (axial x / y):
+ * head split of the (tokens, 3E) QKV matrix (column = head*3d + [q | k | v]), LayerNorm(d) on q and k,
+ * T5 relative-position bias (layers/positional_encoding.py:134-162), softmax(q k^T d^-1/2 + bias),
+ * attn = 1/L + (softmax - 1/L)*scale_factor[head], attn @ v, written back token-major (tokens, E).
+ * Sequence `s` (0 <= s < n_seq) consists of the L tokens
+ *     base(s) + i*tok_stride,  base(s) = (s / inner)*outer_stride + (s % inner)*inner_stride
+ * so that time / row / column attention need no permuted copies:
+ *     temporal (B,T,P): n_seq = B*P, inner = P, outer_stride = T*P, inner_stride = 1, tok_stride = P, L = T
+ *     x axis  (I,h,w):  n_seq = I*h, inner = h, outer_stride = P,   inner_stride = w, tok_stride = 1, L = w
+ *     y axis  (I,h,w):  n_seq = I*w, inner = w, outer_stride = P,   inner_stride = 1, tok_stride = w, L = h
+ * bucket[r], r = (j - i) + L - 1, is the T5 bucket index of key j relative to query i (host computed).
+ * forward : out(tokens, E)    = out_scale * attention            (+= if accumulate)
+ * backward: out(tokens, 3E)   = d qkv given dout(tokens, E)*out_scale (+= if accumulate); parameter
+ *           gradients are atomically ACCUMULATED into d_* (fp32).  bf16 only, L <= 64, d in {32,48,64,96,128}.
+ */
+typedef struct bf_attn_args {
+  const void* qkv;  int64_t ld_qkv;
+  void* out;        int64_t ld_out;
+  const void* dout; int64_t ld_dout;
+  int32_t heads, head_dim, L, accumulate;
+  int64_t n_seq, inner, outer_stride, inner_stride, tok_stride;
+  const float* qn_w;  const float* qn_b;  const float* kn_w;  const float* kn_b;  /* [d] */
+  const float* bias_emb;       /* [32][heads] */
+  const int32_t* bucket;       /* [2L-1] */
+  const float* scale_factor;   /* [heads] or NULL (attn_scale=False) */
+  float out_scale;  int32_t reserved0;
+  float* d_qn_w;  float* d_qn_b;  float* d_kn_w;  float* d_kn_b;
+  float* d_bias_emb;  float* d_scale_factor;
+} bf_attn_args;
+BF_API int bf_attention_fwd(const bf_attn_args* args, void* stream);
+BF_API int bf_attention_bwd(const bf_attn_args* args, void* stream);
+
+/* ---- patch boundary: fp32 NCHW fields <-> 16-bit channels-last tokens -------------------------
+ * bf_patch_in : out(I, H/2, W/2, N) = 2x2/stride-2 conv of x(I, F, H, W) with Wkn[(f,ky,kx)][n] (fp32, K x N);
+ *               optional stats[img][n] += (sum, sum^2) of the stored values (feeds the following IN).
+ *               First Conv2d of HMLPEmbed (upstream layers/patching.py:37-44); also d(input) of the last
+ *               ConvTranspose2d of HMLPDebed.
+ * bf_patch_out: out(I, F, 2h, 2w) fp32 = 2x2/stride-2 conv-transpose of a(I, h, w, C) with Wck[c][(f,ky,kx)].
+ *               Last ConvTranspose2d of HMLPDebed (layers/patching.py:93-99); also d(input) of the first Conv2d.
+ * bf_patch_wgrad: dW[n][(f,ky,kx)] += sum_pix a[pix][n] * x[img, f, 2y+ky, 2x+kx]  (weight gradient of both).
+ * bf_s2d_gather: explicit im2col (I, Hin, Win, C) -> (I*Hin/2*Win/2, 4C), K order (ky, kx, ci), with optional
+ *               fp16 <-> bf16 conversion on the way.
+ * bf_cast16   : flat fp32 -> bf16/fp16 (operand copies of the fp32 master weights).
+ */
+BF_API int bf_patch_in(const float* x, const float* Wkn, void* out, int dtype, float* stats, int I, int F, int H,
+                       int W, int N, void* stream);
+BF_API int bf_patch_out(const void* a, int dtype, const float* Wck, float* out, int I, int F, int h, int w, int C,
+                        void* stream);
+BF_API int bf_patch_wgrad(const void* a, int dtype, const float* x, float* dW, int I, int F, int H, int W, int N,
+                          void* stream);
+BF_API int bf_s2d_gather(const void* in, int in_dtype, void* out, int out_dtype, int I, int Hin, int Win, int C,
+                         void* stream);
+/* fp16 <-> bf16 (the fp16 stem/head activations become bf16 operands of the backward GEMMs) */
+BF_API int bf_convert16(const void* in, int in_dtype, void* out, int out_dtype, int64_t n, void* stream);
+BF_API int bf_cast16(const float* in, void* out, int dtype, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,297 @@
+"""Bring-up diagnostics for the non-GEMM kernels on the B200 box (each group in its own subprocess).
+
+    python scripts/gpu_diag_kernels.py            # all groups -> gpurun_out/diag_kernels.log
+    python scripts/gpu_diag_kernels.py <group>
+References are torch fp32 evaluations of the oracle's formulas (oracle/filmavit_oracle.py) on the GPU.
+"""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+GROUPS = ["stats", "apply", "inorm_bwd", "resid_colsum", "attn_x", "attn_y", "attn_t", "attn_d48", "attn_l64",
+          "attn_noscale", "patch", "misc"]
+
+
+def rel(got, ref):
+    import torch
+    got, ref = got.double(), ref.double()
+    return float((got - ref).norm() / ref.norm().clamp_min(1e-30))
+
+
+def report(name, got, ref, tol):
+    import torch
+    r = rel(got, ref)
+    finite = bool(torch.isfinite(got.float()).all())
+    ok = r < tol and finite
+    print(f"[{name}] rel-L2 {r:.3e} (tol {tol}) finite={finite} {'OK' if ok else 'MISMATCH'}", flush=True)
+    if not ok:
+        g, f = got.float().flatten(), ref.float().flatten()
+        idx = (g - f).abs().argmax()
+        print(f"   worst idx {int(idx)} got {float(g[idx]):.5f} ref {float(f[idx]):.5f}; got[:6] {g[:6].tolist()} ref[:6] {f[:6].tolist()}")
+    return ok
+
+
+def run(group):
+    import torch
+    import torch.nn.functional as F
+    from bubbleformer_b200 import ops
+    from oracle import filmavit_oracle as O
+    torch.manual_seed(0)
+    dev = "cuda"
+    ok = True
+
+    def inorm_ref(x, I, P, w, b):
+        xi = x.float().reshape(I, P, 1, -1)
+        return O.instance_norm(xi, w, b).reshape(I * P, -1)
+
+    if group == "stats":
+        for (I, P, Cn, dt) in [(3, 1024, 384, torch.float32), (3, 1024, 384, torch.bfloat16),
+                               (2, 4096, 96, torch.float16), (5, 16, 128, torch.float32), (1, 24, 24, torch.float16)]:
+            x = (torch.randn(I * P, Cn, device=dev) * 2 + 0.5).to(dt)
+            st = torch.zeros(I, Cn, 2, device=dev)
+            ops.inorm_stats(x, I, P, st)
+            xi = x.float().reshape(I, P, Cn)
+            ref = torch.stack([xi.sum(1), (xi * xi).sum(1)], dim=-1)
+            ok &= report(f"stats {I}x{P}x{Cn} {dt}", st, ref, 1e-5)
+    elif group == "apply":
+        I, P, Cn, T = 4, 1024, 384, 2
+        w, b = torch.randn(Cn, device=dev), torch.randn(Cn, device=dev)
+        for (din, dout, gelu, film, resid) in [(torch.float32, torch.bfloat16, False, False, False),
+                                               (torch.bfloat16, torch.bfloat16, False, False, False),
+                                               (torch.float16, torch.float16, True, False, False),
+                                               (torch.float16, torch.float32, False, True, False),
+                                               (torch.bfloat16, torch.float32, False, False, True),
+                                               (torch.float32, torch.float32, False, False, False)]:
+            x = (torch.randn(I * P, Cn, device=dev) * 1.7 + 0.3).to(din)
+            st = torch.zeros(I, Cn, 2, device=dev)
+            ops.inorm_stats(x, I, P, st)
+            out = torch.zeros(I * P, Cn, device=dev, dtype=dout)
+            y = inorm_ref(x, I, P, w, b)
+            kw = {}
+            if gelu:
+                y = F.gelu(y); kw["gelu"] = True
+            if film:
+                fg, fb = torch.randn(I // T, Cn, device=dev), torch.randn(I // T, Cn, device=dev)
+                y = y * fg.repeat_interleave(T * P, 0) + fb.repeat_interleave(T * P, 0)
+                kw.update(film_gamma=fg, film_beta=fb, film_T=T)
+            if resid:
+                xin = torch.randn(I * P, Cn, device=dev)
+                rs, cg = torch.rand(I, device=dev), torch.randn(Cn, device=dev)
+                y = xin + rs.repeat_interleave(P)[:, None] * cg * y
+                kw.update(resid_in=xin, row_scale=rs, col_gamma=cg)
+            ops.inorm_apply(x, out, I, P, st, w, b, **kw)
+            ok &= report(f"apply {din}->{dout} gelu={gelu} film={film} resid={resid}", out, y,
+                         1e-5 if dout == torch.float32 else 6e-3)
+    elif group == "inorm_bwd":
+        I, P, Cn, T = 4, 256, 96, 2
+        for (dx_, dg_, dout_, gelu, mode) in [(torch.float32, torch.bfloat16, torch.float32, False, "add"),
+                                              (torch.bfloat16, torch.float32, torch.bfloat16, False, "scale"),
+                                              (torch.float16, torch.float16, torch.float16, True, "plain"),
+                                              (torch.float16, torch.float32, torch.float16, False, "film"),
+                                              (torch.float32, torch.float32, torch.float32, False, "plain")]:
+            x = (torch.randn(I * P, Cn, device=dev) * 1.5 + 0.2).to(dx_)
+            w = (1 + 0.1 * torch.randn(Cn, device=dev)).requires_grad_(True)
+            b = (0.1 * torch.randn(Cn, device=dev)).requires_grad_(True)
+            gin = torch.randn(I * P, Cn, device=dev).to(dg_)
+            x32 = x.float().requires_grad_(True)
+            y = inorm_ref(x32, I, P, w, b)
+            if gelu:
+                y = F.gelu(y)
+            kw, kwp = {}, {}
+            rs = cs = fg = None
+            if mode == "scale" or mode == "add":
+                rs = torch.rand(I, device=dev)
+                cs = torch.randn(Cn, device=dev).requires_grad_(True)
+                y = rs.repeat_interleave(P)[:, None] * cs * y
+                kw.update(row_scale=rs, col_scale=cs.detach())
+            if mode == "film":
+                fg = torch.randn(I // T, Cn, device=dev).requires_grad_(True)
+                fb = torch.randn(I // T, Cn, device=dev).requires_grad_(True)
+                y = y * fg.repeat_interleave(T * P, 0) + fb.repeat_interleave(T * P, 0)
+                kw.update(film_gamma=fg.detach(), film_T=T)
+            (y * gin.float()).sum().backward()
+            st = torch.zeros(I, Cn, 2, device=dev)
+            ops.inorm_stats(x, I, P, st)
+            red = torch.zeros(I, Cn, 2, device=dev)
+            ops.inorm_bwd(1, gin, x, I, P, st, w.detach(), b.detach(), red, gelu=gelu)
+            out = torch.zeros(I * P, Cn, device=dev, dtype=dout_)
+            add = torch.randn(I * P, Cn, device=dev) if mode == "add" else None
+            ops.inorm_bwd(2, gin, x, I, P, st, w.detach(), b.detach(), red, gelu=gelu, out=out, add32=add, **kw)
+            want = x32.grad + (add if add is not None else 0)
+            tol = 1e-4 if dout_ == torch.float32 and dx_ == torch.float32 and dg_ == torch.float32 else 1e-2
+            ok &= report(f"inorm_bwd dx x={dx_} g={dg_} gelu={gelu} {mode}", out, want, tol)
+            dw, db = torch.zeros(Cn, device=dev), torch.zeros(Cn, device=dev)
+            dcs = torch.zeros(Cn, device=dev)
+            dfg = torch.zeros(I // T, Cn, device=dev)
+            dfb = torch.zeros(I // T, Cn, device=dev)
+            ops.inorm_bwd_params(red, I, P, Cn, w.detach(), b.detach(), dweight=dw, dbias=db,
+                                 dcol_scale=dcs if cs is not None else None,
+                                 dfilm_gamma=dfg if fg is not None else None,
+                                 dfilm_beta=dfb if fg is not None else None,
+                                 row_scale=rs, col_scale=cs.detach() if cs is not None else None,
+                                 film_gamma=fg.detach() if fg is not None else None, film_T=T if fg is not None else 0)
+            ok &= report(f"   dweight {mode}", dw, w.grad, 1e-2)
+            ok &= report(f"   dbias {mode}", db, b.grad, 1e-2)
+            if cs is not None:
+                ok &= report(f"   dcol_scale {mode}", dcs, cs.grad, 1e-2)
+            if fg is not None:
+                ok &= report(f"   dfilm_gamma", dfg, fg.grad, 1e-2)
+                ok &= report(f"   dfilm_beta", dfb, fb.grad, 1e-2)
+    elif group == "resid_colsum":
+        I, P, Cn = 5, 1024, 384
+        dx = torch.randn(I * P, Cn, device=dev)
+        z = torch.randn(I * P, Cn, device=dev).bfloat16()
+        rs, coef = torch.rand(I, device=dev), torch.randn(Cn, device=dev)
+        dz = torch.zeros_like(z)
+        S0, S1 = torch.zeros(Cn, device=dev), torch.zeros(Cn, device=dev)
+        ops.resid_bwd(dx, z, dz, I, P, rs, coef, S0, S1)
+        rsx = rs.repeat_interleave(P)[:, None]
+        ok &= report("resid dz", dz, rsx * coef * dx, 6e-3)
+        ok &= report("resid S0", S0, (rsx * dx).sum(0), 1e-4)
+        ok &= report("resid S1", S1, (rsx * dx * z.float()).sum(0), 1e-4)
+        for (R, Cn2) in [(5120, 1152), (1000, 1536), (77, 24)]:
+            x = torch.randn(R, Cn2, device=dev).bfloat16()
+            out = torch.zeros(Cn2, device=dev)
+            ops.colsum16(x, out)
+            ok &= report(f"colsum {R}x{Cn2}", out, x.float().sum(0), 1e-4)
+    elif group.startswith("attn"):
+        cfg = {"attn_x": dict(I=6, h=8, w=32, E=384, he=6, axis="x"), "attn_y": dict(I=6, h=32, w=8, E=384, he=6, axis="y"),
+               "attn_t": dict(I=10, h=4, w=8, E=384, he=6, axis="t", T=5), "attn_d48": dict(I=4, h=4, w=20, E=192, he=4, axis="x"),
+               "attn_l64": dict(I=2, h=3, w=64, E=128, he=2, axis="x"), "attn_noscale": dict(I=3, h=12, w=6, E=128, he=2, axis="y", noscale=True)}[group]
+        I, h, w, E, he, axis = cfg["I"], cfg["h"], cfg["w"], cfg["E"], cfg["he"], cfg["axis"]
+        d = E // he
+        P = h * w
+        tokens = I * P
+        qkv = torch.randn(tokens, 3 * E, device=dev).bfloat16()
+        ln = [(1 + 0.1 * torch.randn(d, device=dev)), 0.1 * torch.randn(d, device=dev),
+              (1 + 0.1 * torch.randn(d, device=dev)), 0.1 * torch.randn(d, device=dev)]
+        emb = torch.randn(32, he, device=dev)
+        sf = None if cfg.get("noscale") else (1 + 0.3 * torch.randn(he, device=dev))
+        if axis == "x":
+            Ls, geo = w, dict(n_seq=I * h, inner=h, outer_stride=P, inner_stride=w, tok_stride=1)
+        elif axis == "y":
+            Ls, geo = h, dict(n_seq=I * w, inner=w, outer_stride=P, inner_stride=1, tok_stride=w)
+        else:
+            T = cfg["T"]; B = I // T
+            Ls, geo = T, dict(n_seq=B * P, inner=P, outer_stride=T * P, inner_stride=1, tok_stride=P)
+        bucket = O.relpos_bucket_table(Ls)
+        bvec = torch.tensor([int(bucket[0, r - (Ls - 1)]) if r >= Ls - 1 else int(bucket[(Ls - 1) - r, 0])
+                             for r in range(2 * Ls - 1)], dtype=torch.int32, device=dev)
+
+        def to_seq(t, width):
+            t = t.reshape(I, h, w, width)
+            if axis == "x":
+                return t.reshape(I * h, w, width)
+            if axis == "y":
+                return t.permute(0, 2, 1, 3).reshape(I * w, h, width)
+            return t.reshape(B, T, P, width).permute(0, 2, 1, 3).reshape(B * P, T, width)
+
+        def from_seq(t, width):
+            if axis == "x":
+                return t.reshape(tokens, width)
+            if axis == "y":
+                return t.reshape(I, w, h, width).permute(0, 2, 1, 3).reshape(tokens, width)
+            return t.reshape(B, P, T, width).permute(0, 2, 1, 3).reshape(tokens, width)
+
+        params = [p.clone().requires_grad_(True) for p in ln] + [emb.clone().requires_grad_(True)]
+        sfp = sf.clone().requires_grad_(True) if sf is not None else None
+        q32 = qkv.float().requires_grad_(True)
+        ref = O.attention_1d(to_seq(q32, 3 * E), he, params[0], params[1], params[2], params[3], params[4].cpu().to(dev), sfp)
+        ref = from_seq(ref, E) * 0.5
+        out = torch.zeros(tokens, E, device=dev, dtype=torch.bfloat16)
+        common = dict(heads=he, L_=Ls, qn_w=ln[0], qn_b=ln[1], kn_w=ln[2], kn_b=ln[3], bias_emb=emb, bucket=bvec,
+                      scale_factor=sf, out_scale=0.5, **geo)
+        ops.attention(qkv, out, **common)
+        ok &= report(f"{group} fwd", out, ref, 1.5e-2)
+        out2 = out.clone()
+        ops.attention(qkv, out2, accumulate=True, **common)
+        ok &= report(f"{group} fwd accumulate", out2, 2 * ref, 1.5e-2)
+        dout = torch.randn(tokens, E, device=dev).bfloat16()
+        (ref * dout.float()).sum().backward()          # includes the 0.5
+        dqkv = torch.zeros(tokens, 3 * E, device=dev, dtype=torch.bfloat16)
+        grads = dict(d_qn_w=torch.zeros(d, device=dev), d_qn_b=torch.zeros(d, device=dev), d_kn_w=torch.zeros(d, device=dev),
+                     d_kn_b=torch.zeros(d, device=dev), d_bias_emb=torch.zeros(32, he, device=dev),
+                     d_scale_factor=torch.zeros(he, device=dev) if sf is not None else None)
+        ops.attention(qkv, dqkv, dout=dout, grads=grads, **common)
+        dq_ref = q32.grad.reshape(tokens, he, 3, d)
+        got = dqkv.float().reshape(tokens, he, 3, d)
+        for i, nm in enumerate("qkv"):
+            ok &= report(f"{group} d{nm}", got[:, :, i], dq_ref[:, :, i], 3e-2)
+        ok &= report(f"{group} d_qn_w", grads["d_qn_w"], params[0].grad, 3e-2)
+        ok &= report(f"{group} d_qn_b", grads["d_qn_b"], params[1].grad, 3e-2)
+        ok &= report(f"{group} d_kn_w", grads["d_kn_w"], params[2].grad, 3e-2)
+        kb = float((grads["d_kn_b"] - params[3].grad).abs().max() / params[2].grad.abs().max())
+        print(f"[{group} d_kn_b] (true gradient is 0) |err|/|d_kn_w|max = {kb:.3e}")
+        ok &= kb < 3e-2
+        ok &= report(f"{group} d_bias_emb", grads["d_bias_emb"], params[4].grad, 3e-2)
+        if sf is not None:
+            ok &= report(f"{group} d_scale_factor", grads["d_scale_factor"], sfp.grad, 3e-2)
+    elif group == "patch":
+        for (I, Fd, H, W, N, dt) in [(2, 4, 64, 64, 96, torch.float16), (3, 2, 32, 48, 24, torch.float16),
+                                     (1, 1, 16, 16, 384, torch.bfloat16)]:
+            x = torch.randn(I, Fd, H, W, device=dev)
+            Wc = torch.randn(N, Fd, 2, 2, device=dev) / (4 * Fd) ** 0.5
+            out = torch.zeros(I, H // 2, W // 2, N, device=dev, dtype=dt)
+            st = torch.zeros(I, N, 2, device=dev)
+            ops.patch_in(x, Wc.reshape(N, 4 * Fd).t().contiguous(), out, st)
+            ref = F.conv2d(x, Wc, stride=2).permute(0, 2, 3, 1)
+            ok &= report(f"patch_in {I},{Fd},{H},{W}->{N}", out, ref, 2e-3 if dt == torch.float16 else 6e-3)
+            of = out.float().reshape(I, -1, N)
+            ok &= report("   fused stats", st, torch.stack([of.sum(1), (of * of).sum(1)], -1), 1e-4)
+            # conv-transpose out: a (I,h,w,C) -> (I,F,2h,2w)
+            a = torch.randn(I, H // 2, W // 2, N, device=dev).to(dt)
+            Wt = torch.randn(N, Fd, 2, 2, device=dev) / N ** 0.5
+            o2 = torch.zeros(I, Fd, H, W, device=dev)
+            ops.patch_out(a, Wt.reshape(N, 4 * Fd).contiguous(), o2)
+            ref2 = F.conv_transpose2d(a.float().permute(0, 3, 1, 2), Wt, stride=2)
+            ok &= report(f"patch_out {N}->{Fd}", o2, ref2, 1e-5)
+            dW = torch.zeros(N, Fd, 2, 2, device=dev)
+            ops.patch_wgrad(a, x, dW)
+            xs = x.reshape(I, Fd, H // 2, 2, W // 2, 2).permute(0, 2, 4, 1, 3, 5).reshape(-1, 4 * Fd)
+            refw = a.float().reshape(-1, N).t() @ xs
+            ok &= report(f"patch_wgrad", dW.reshape(N, 4 * Fd), refw, 1e-4)
+    elif group == "misc":
+        for (I, H, W, Cn) in [(2, 8, 12, 24), (3, 64, 64, 96)]:
+            img = torch.randn(I, H, W, Cn, device=dev).half()
+            out = torch.zeros(I * (H // 2) * (W // 2), 4 * Cn, device=dev, dtype=torch.float16)
+            ops.s2d_gather(img, out)
+            ref = img.reshape(I, H // 2, 2, W // 2, 2, Cn).permute(0, 1, 3, 2, 4, 5).reshape(-1, 4 * Cn)
+            ok &= report(f"s2d_gather {I},{H},{W},{Cn}", out, ref, 1e-7)
+        for n in (1000003, 8, 5):
+            src = torch.randn(n, device=dev)
+            for dt in (torch.bfloat16, torch.float16):
+                dst = torch.zeros(n, device=dev, dtype=dt)
+                ops.cast16(src, dst)
+                ok &= report(f"cast16 {n} {dt}", dst, src.to(dt), 1e-7)
+    else:
+        raise SystemExit(f"unknown group {group}")
+    torch.cuda.synchronize()
+    return ok
+
+
+def main():
+    if len(sys.argv) > 1:
+        sys.exit(0 if run(sys.argv[1]) else 3)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    log = open(os.path.join(ROOT, "gpurun_out", "diag_kernels.log"), "w")
+    summary = []
+    for g in GROUPS:
+        try:
+            r = subprocess.run([sys.executable, __file__, g], capture_output=True, text=True, timeout=240)
+            out, code = r.stdout + r.stderr, r.returncode
+        except subprocess.TimeoutExpired as e:
+            out, code = (e.stdout or b"").decode() + (e.stderr or b"").decode() + "\nTIMEOUT", -9
+        log.write(f"==== {g} (exit {code})\n{out}\n")
+        log.flush()
+        print(f"==== {g} (exit {code})\n" + "\n".join(out.strip().splitlines()[-40:]), flush=True)
+        summary.append((g, code))
+    s = "SUMMARY " + " ".join(f"{g}:{c}" for g, c in summary)
+    print(s)
+    log.write(s + "\n")
+
+
+if __name__ == "__main__":
+    main()
