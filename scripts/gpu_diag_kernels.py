@@ -40,6 +40,8 @@ def run(group):
     from bubbleformer_b200 import ops
     from oracle import filmavit_oracle as O
     torch.manual_seed(0)
+    torch.backends.cudnn.allow_tf32 = False          # the references must be true fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
     dev = "cuda"
     ok = True
 
