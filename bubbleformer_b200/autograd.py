@@ -11,6 +11,9 @@ import torch
 from . import ops
 
 
+ACTIVE_SINK = None      # set by bubbleformer_b200.parallel.GradSink
+
+
 class KernelFn(torch.autograd.Function):
     """Generic bridge.  `spec` provides
 
@@ -30,6 +33,8 @@ class KernelFn(torch.autograd.Function):
         ctx.spec, ctx.pd, ctx.saved = spec, pd, saved
         ctx.need_dx = ctx.needs_input_grad[1]
         ctx.has_aux = aux is not None
+        sink = ACTIVE_SINK
+        ctx.sink = sink if (sink is not None and save and params and sink.owns(params[0])) else None
         return out
 
     @staticmethod
@@ -38,6 +43,14 @@ class KernelFn(torch.autograd.Function):
         if saved is None:
             raise RuntimeError("bubbleformer_b200: backward called twice or without saved activations")
         names = spec.names
+        dout = dout.contiguous()
+        if ctx.sink is not None:
+            # gradients accumulate straight into the persistent flat buffer; its segment is all-reduced from here
+            grads = ctx.sink.views(pd)
+            dx, daux = spec.backward(dout, pd, saved, grads, ctx.need_dx)
+            ctx.sink.segment_done(pd)
+            ctx.saved = None
+            return (None, dx, daux if ctx.has_aux else None) + (None,) * len(names)
         sizes = [pd[n].numel() for n in names]
         offs, tot = [], 0
         for s in sizes:
@@ -45,7 +58,6 @@ class KernelFn(torch.autograd.Function):
             tot += (s + 7) // 8 * 8          # keep every view 32-byte aligned
         flat = torch.zeros(max(tot, 1), dtype=torch.float32, device=dout.device)
         grads = {n: flat[o:o + s].view(pd[n].shape) for n, o, s in zip(names, offs, sizes)}
-        dout = dout.contiguous()
         dx, daux = spec.backward(dout, pd, saved, grads, ctx.need_dx)
         ctx.saved = None
         return (None, dx, daux if ctx.has_aux else None) + tuple(grads[n] for n in names)

@@ -22,6 +22,7 @@ struct AttnParams {
   bf16* out; long ld_out;            // fwd: (tokens, E).  bwd: dqkv (tokens, 3E)
   const bf16* dout; long ld_dout;    // bwd: (tokens, E)
   int heads, L;
+  int G;                             // sequences packed per warp tile (block-diagonal attention), G*L <= LP
   long n_seq;
   long inner;                        // seq -> base token = (seq / inner) * outer_stride + (seq % inner) * inner_stride
   long outer_stride, inner_stride, tok_stride;
@@ -105,19 +106,35 @@ struct AttnSmem {
   static constexpr int LS = LP + 8;
   static constexpr int kTile = LP * DS;          // elements of one (LP x D) tile
   static constexpr int kSq = LP * LS;            // elements of one (LP x LP) tile
-  // forward: q, k, v, p (bf16) + meanv[D], brel[2*LP], stat[2][LP][2] (fp32)
-  static constexpr int kFwdBytes = (3 * kTile + kSq) * 2 + (D + 2 * LP + 4 * LP) * 4;
-  // backward: q, k, v, do (bf16), p, ds (bf16) + meanv/cdo[D], brel[2*LP], stat[2][LP][2] (fp32)
-  static constexpr int kBwdBytes = (4 * kTile + 2 * kSq) * 2 + (D + 2 * LP + 4 * LP) * 4;
+  static constexpr int kMaxG = 8;                // sequences per tile
+  // per-warp tables: meanv/cdo[kMaxG][D], brel[2*LP], stat[2][LP][2] (fp32), rowtok[LP] (int64), rowgp[LP] (int32)
+  static constexpr int kMiscBytes = (kMaxG * D + 2 * LP + 4 * LP) * 4 + LP * 8 + LP * 4;
+  // forward: q, k, v, p (bf16)
+  static constexpr int kFwdBytes = (3 * kTile + kSq) * 2 + kMiscBytes;
+  // backward: q, k, v, do (bf16), p, ds (bf16)
+  static constexpr int kBwdBytes = (4 * kTile + 2 * kSq) * 2 + kMiscBytes;
 };
 
 __device__ __forceinline__ long seq_base(const AttnParams& p, long seq) {
   return (seq / p.inner) * p.outer_stride + (seq % p.inner) * p.inner_stride;
 }
 
-// Stage raw q, k, v rows of one (sequence, head) into shared memory; rows >= L are zeroed.
+// Row tables of one work item: tile row r holds token rowtok[r] (or -1), belonging to packed sequence
+// rowgp[r] >> 8 at position rowgp[r] & 255 (group 255 = unused row).
+template <int LP>
+__device__ __forceinline__ void fill_row_tables(const AttnParams& p, long seq0, long* rowtok, int* rowgp, int lane) {
+  for (int r = lane; r < LP; r += 32) {
+    const int g = r / p.L, i = r - g * p.L;
+    const long sq = seq0 + g;
+    const bool ok = g < p.G && sq < p.n_seq;
+    rowtok[r] = ok ? seq_base(p, sq) + (long)i * p.tok_stride : -1;
+    rowgp[r] = ok ? ((g << 8) | i) : (255 << 8);
+  }
+}
+
+// Stage raw q, k, v rows of one (tile, head) into shared memory; unused rows are zeroed.
 template <int D, int LP>
-__device__ __forceinline__ void stage_qkv(const AttnParams& p, long base, int head, bf16* sQ, bf16* sK, bf16* sV,
+__device__ __forceinline__ void stage_qkv(const AttnParams& p, const long* rowtok, int head, bf16* sQ, bf16* sK, bf16* sV,
                                           int lane) {
   constexpr int DS = D + 8;
   constexpr int CPR = 3 * D / 8;                   // 16-byte chunks per row
@@ -126,7 +143,8 @@ __device__ __forceinline__ void stage_qkv(const AttnParams& p, long base, int he
     const int r = idx / CPR, ch = idx - r * CPR;
     const int which = ch / (D / 8), off = (ch - which * (D / 8)) * 8;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (r < p.L) v = *reinterpret_cast<const uint4*>(src + (base + (long)r * p.tok_stride) * p.ld_qkv + ch * 8);
+    const long tok = rowtok[r];
+    if (tok >= 0) v = *reinterpret_cast<const uint4*>(src + tok * p.ld_qkv + ch * 8);
     bf16* dst = (which == 0 ? sQ : (which == 1 ? sK : sV)) + r * DS + off;
     *reinterpret_cast<uint4*>(dst) = v;
   }
@@ -135,7 +153,8 @@ __device__ __forceinline__ void stage_qkv(const AttnParams& p, long base, int he
 // LayerNorm over D of the q rows then the k rows in place (4 lanes per row); q is also multiplied by
 // D^-1/2.  Row statistics (mean, rstd) of the raw rows go to stat[which][row][2].
 template <int D, int LP>
-__device__ __forceinline__ void layernorm_qk(const AttnParams& p, bf16* sQ, bf16* sK, float* stat, int lane) {
+__device__ __forceinline__ void layernorm_qk(const AttnParams& p, bf16* sQ, bf16* sK, float* stat, const long* rowtok,
+                                             int lane) {
   constexpr int DS = D + 8;
   constexpr int EPL = D / 4;                       // elements per lane
   const float qscale = rsqrtf((float)D);
@@ -162,7 +181,7 @@ __device__ __forceinline__ void layernorm_qk(const AttnParams& p, bf16* sQ, bf16
     const float rstd = rsqrtf(quad_sum(q) * (1.f / D) + 1e-5f);
     if (sub == 0) { stat[(which * LP + r) * 2] = mean; stat[(which * LP + r) * 2 + 1] = rstd; }
     const float post = which ? 1.f : qscale;
-    if (r < p.L) {
+    if (rowtok[r] >= 0) {
 #pragma unroll
       for (int j = 0; j < EPL; j += 2) {
         const float y0 = ((v[j] - mean) * rstd * __ldg(w + j) + __ldg(b + j)) * post;
@@ -175,21 +194,25 @@ __device__ __forceinline__ void layernorm_qk(const AttnParams& p, bf16* sQ, bf16
 
 // scores of one 16-row tile -> probabilities in place (fp32 fragments)
 template <int LP>
-__device__ __forceinline__ void softmax_tile(float (&acc)[LP / 8][4], const float* brel, int L, int mt, int lane) {
+__device__ __forceinline__ void softmax_tile(float (&acc)[LP / 8][4], const float* brel, const int* rowgp, int L, int mt,
+                                             int lane) {
   constexpr int NT = LP / 8;
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int i = mt * 16 + g + half * 8;
+    const int gi = rowgp[i];
     float mx = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int j = nt * 8 + 2 * t + e;
+        const int gj = rowgp[j];
         float s = acc[nt][half * 2 + e];
-        if (j < L) { if (i < L) s += brel[j - i + L - 1]; }
-        else s = -INFINITY;
+        if ((gi >> 8) == 255) s = 0.f;                                   // unused query row: harmless uniform row
+        else if ((gj >> 8) == (gi >> 8)) s += brel[(gj & 255) - (gi & 255) + L - 1];
+        else s = -INFINITY;                                              // other sequence / padding
         acc[nt][half * 2 + e] = s;
         mx = fmaxf(mx, s);
       }
@@ -226,13 +249,15 @@ __device__ __forceinline__ void store_tile_bf16(bf16* S, int ld, int m0, const f
 
 // coalesced copy of L rows x D columns from shared memory to a strided global destination
 template <int D>
-__device__ __forceinline__ void store_rows(const bf16* S, int ld, bf16* dst, long ld_dst, long base, long tok_stride,
-                                           int L, int accumulate, int lane) {
+__device__ __forceinline__ void store_rows(const bf16* S, int ld, bf16* dst, long ld_dst, const long* rowtok, int rows,
+                                           int accumulate, int lane) {
   constexpr int CPR = D / 8;
-  for (int idx = lane; idx < L * CPR; idx += 32) {
+  for (int idx = lane; idx < rows * CPR; idx += 32) {
     const int r = idx / CPR, ch = idx - r * CPR;
+    const long tok = rowtok[r];
+    if (tok < 0) continue;
     uint4 v = *reinterpret_cast<const uint4*>(S + r * ld + ch * 8);
-    bf16* gp = dst + (base + (long)r * tok_stride) * ld_dst + ch * 8;
+    bf16* gp = dst + tok * ld_dst + ch * 8;
     if (accumulate) {
       uint4 o = *reinterpret_cast<const uint4*>(gp);
       uint32_t* vv = reinterpret_cast<uint32_t*>(&v);
@@ -262,34 +287,40 @@ attn_fwd_kernel(AttnParams p) {
   bf16* sK = sQ + SM::kTile;
   bf16* sV = sK + SM::kTile;
   bf16* sP = sV + SM::kTile;
-  float* meanv = reinterpret_cast<float*>(sP + SM::kSq);
-  float* brel = meanv + D;
+  long* rowtok = reinterpret_cast<long*>(sP + SM::kSq);
+  float* meanv = reinterpret_cast<float*>(rowtok + LP);     // [G][D]
+  float* brel = meanv + SM::kMaxG * D;
   float* stat = brel + 2 * LP;
-  const int L = p.L;
-  const long n_work = p.n_seq * p.heads;
-  const int g = lane >> 2, t = lane & 3;
+  int* rowgp = reinterpret_cast<int*>(stat + 4 * LP);
+  const int L = p.L, G = p.G;
+  const int rows = G * L;
+  const long n_tiles = (p.n_seq + G - 1) / G;
+  const long n_work = n_tiles * p.heads;
+  const int t = lane & 3, g8 = lane >> 2;
 
   for (long wi = (long)blockIdx.x * WARPS + warp; wi < n_work; wi += (long)gridDim.x * WARPS) {
-    const long seq = wi / p.heads;
-    const int head = (int)(wi - seq * p.heads);
-    const long base = seq_base(p, seq);
-    stage_qkv<D, LP>(p, base, head, sQ, sK, sV, lane);
+    const long tile = wi / p.heads;
+    const int head = (int)(wi - tile * p.heads);
+    fill_row_tables<LP>(p, tile * G, rowtok, rowgp, lane);
     for (int r = lane; r < 2 * L - 1; r += 32) brel[r] = __ldg(p.bias_emb + __ldg(p.bucket + r) * p.heads + head);
     __syncwarp();
-    layernorm_qk<D, LP>(p, sQ, sK, stat, lane);
-    for (int c = lane; c < D; c += 32) {
+    stage_qkv<D, LP>(p, rowtok, head, sQ, sK, sV, lane);
+    __syncwarp();
+    layernorm_qk<D, LP>(p, sQ, sK, stat, rowtok, lane);
+    for (int idx = lane; idx < G * D; idx += 32) {
+      const int gq = idx / D, c = idx - gq * D;
       float s = 0.f;
-      for (int r = 0; r < L; ++r) s += __bfloat162float(sV[r * DS + c]);
-      meanv[c] = s / (float)L;
+      for (int i = 0; i < L; ++i) s += __bfloat162float(sV[(gq * L + i) * DS + c]);
+      meanv[idx] = s / (float)L;
     }
     __syncwarp();
     const float sf = p.scale_factor != nullptr ? __ldg(p.scale_factor + head) : 1.f;
-    for (int mt = 0; mt * 16 < L; ++mt) {
+    for (int mt = 0; mt * 16 < rows; ++mt) {
       float acc[NT][4];
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
       warp_gemm<NT, D / 16, false, false>(acc, sQ, DS, mt * 16, sK, DS, lane);
-      softmax_tile<LP>(acc, brel, L, mt, lane);
+      softmax_tile<LP>(acc, brel, rowgp, L, mt, lane);
       store_tile_bf16<NT>(sP, LS, mt * 16, acc, lane);
       __syncwarp();
       float o[D / 8][4];
@@ -297,19 +328,21 @@ attn_fwd_kernel(AttnParams p) {
       for (int nt = 0; nt < D / 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
       warp_gemm<D / 8, LP / 16, false, true>(o, sP, LS, mt * 16, sV, DS, lane);
       // attn = 1/L + (P - 1/L) * s  =>  out = s * (P V) + (1 - s) * mean_L(V)
+      const int ga = min(rowgp[mt * 16 + g8] >> 8, G - 1), gb = min(rowgp[mt * 16 + g8 + 8] >> 8, G - 1);
 #pragma unroll
       for (int nt = 0; nt < D / 8; ++nt) {
-        const float m0 = (1.f - sf) * meanv[nt * 8 + 2 * t], m1 = (1.f - sf) * meanv[nt * 8 + 2 * t + 1];
-        o[nt][0] = (sf * o[nt][0] + m0) * p.out_scale; o[nt][1] = (sf * o[nt][1] + m1) * p.out_scale;
-        o[nt][2] = (sf * o[nt][2] + m0) * p.out_scale; o[nt][3] = (sf * o[nt][3] + m1) * p.out_scale;
+        const int c = nt * 8 + 2 * t;
+        o[nt][0] = (sf * o[nt][0] + (1.f - sf) * meanv[ga * D + c]) * p.out_scale;
+        o[nt][1] = (sf * o[nt][1] + (1.f - sf) * meanv[ga * D + c + 1]) * p.out_scale;
+        o[nt][2] = (sf * o[nt][2] + (1.f - sf) * meanv[gb * D + c]) * p.out_scale;
+        o[nt][3] = (sf * o[nt][3] + (1.f - sf) * meanv[gb * D + c + 1]) * p.out_scale;
       }
       store_tile_bf16<D / 8>(sQ, DS, mt * 16, o, lane);     // the Q rows of this tile are dead
     }
     __syncwarp();
-    store_rows<D>(sQ, DS, p.out + (long)head * D, p.ld_out, base, p.tok_stride, L, p.accumulate, lane);
+    store_rows<D>(sQ, DS, p.out + (long)head * D, p.ld_out, rowtok, rows, p.accumulate, lane);
     __syncwarp();
   }
-  (void)g;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -370,14 +403,14 @@ __device__ __forceinline__ void ln_bwd_tile(float (&acc)[D / 8][4], float pre, c
 }
 
 template <int D, int LP>
-__device__ __forceinline__ void stage_rows(const bf16* src, long ld_src, long base, long tok_stride, int L, bf16* S,
-                                           float mul, int lane) {
+__device__ __forceinline__ void stage_rows(const bf16* src, long ld_src, const long* rowtok, bf16* S, float mul, int lane) {
   constexpr int DS = D + 8, CPR = D / 8;
   for (int idx = lane; idx < LP * CPR; idx += 32) {
     const int r = idx / CPR, ch = idx - r * CPR;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (r < L) {
-      v = *reinterpret_cast<const uint4*>(src + (base + (long)r * tok_stride) * ld_src + ch * 8);
+    const long tok = rowtok[r];
+    if (tok >= 0) {
+      v = *reinterpret_cast<const uint4*>(src + tok * ld_src + ch * 8);
       if (mul != 1.f) {
         uint32_t* vv = reinterpret_cast<uint32_t*>(&v);
 #pragma unroll
@@ -414,28 +447,34 @@ attn_bwd_kernel(AttnParams p) {
   bf16* sG = sV + SM::kTile;       // dO, later the raw k / q rows
   bf16* sP = sG + SM::kTile;
   bf16* sS = sP + SM::kSq;         // dS
-  float* cdo = reinterpret_cast<float*>(sS + SM::kSq);   // column sums of dO
-  float* brel = cdo + D;
+  long* rowtok = reinterpret_cast<long*>(sS + SM::kSq);
+  float* cdo = reinterpret_cast<float*>(rowtok + LP);    // [G][D] column sums of dO per packed sequence
+  float* brel = cdo + SM::kMaxG * D;
   float* stat = brel + 2 * LP;
-  const int L = p.L;
+  int* rowgp = reinterpret_cast<int*>(stat + 4 * LP);
+  const int L = p.L, G = p.G;
+  const int rows = G * L;
   const float invL = 1.f / (float)L;
-  const long n_work = p.n_seq * p.heads;
-  const int g = lane >> 2, t = lane & 3;
+  const long n_tiles = (p.n_seq + G - 1) / G;
+  const long n_work = n_tiles * p.heads;
+  const int g8 = lane >> 2, t = lane & 3;
   const float qscale = rsqrtf((float)D);
 
   for (long wi = (long)blockIdx.x * WARPS + warp; wi < n_work; wi += (long)gridDim.x * WARPS) {
-    const long seq = wi / p.heads;
-    const int head = (int)(wi - seq * p.heads);
-    const long base = seq_base(p, seq);
-    stage_qkv<D, LP>(p, base, head, sQ, sK, sV, lane);
-    stage_rows<D, LP>(p.dout + (long)head * D, p.ld_dout, base, p.tok_stride, L, sG, p.out_scale, lane);
+    const long tile = wi / p.heads;
+    const int head = (int)(wi - tile * p.heads);
+    fill_row_tables<LP>(p, tile * G, rowtok, rowgp, lane);
     for (int r = lane; r < 2 * L - 1; r += 32) brel[r] = __ldg(p.bias_emb + __ldg(p.bucket + r) * p.heads + head);
     __syncwarp();
-    layernorm_qk<D, LP>(p, sQ, sK, stat, lane);
-    for (int c = lane; c < D; c += 32) {
+    stage_qkv<D, LP>(p, rowtok, head, sQ, sK, sV, lane);
+    stage_rows<D, LP>(p.dout + (long)head * D, p.ld_dout, rowtok, sG, p.out_scale, lane);
+    __syncwarp();
+    layernorm_qk<D, LP>(p, sQ, sK, stat, rowtok, lane);
+    for (int idx = lane; idx < G * D; idx += 32) {
+      const int gq = idx / D, c = idx - gq * D;
       float s = 0.f;
-      for (int r = 0; r < L; ++r) s += __bfloat162float(sG[r * DS + c]);
-      cdo[c] = s;
+      for (int i = 0; i < L; ++i) s += __bfloat162float(sG[(gq * L + i) * DS + c]);
+      cdo[idx] = s;
     }
     __syncwarp();
     const float sf = p.scale_factor != nullptr ? __ldg(p.scale_factor + head) : 1.f;
@@ -448,21 +487,25 @@ attn_bwd_kernel(AttnParams p) {
         acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
         dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
       }
-      if (mt * 16 < L) {
+      if (mt * 16 < rows) {
         warp_gemm<NT, D / 16, false, false>(acc, sQ, DS, mt * 16, sK, DS, lane);
-        softmax_tile<LP>(acc, brel, L, mt, lane);
+        softmax_tile<LP>(acc, brel, rowgp, L, mt, lane);
         warp_gemm<NT, D / 16, false, false>(dp, sG, DS, mt * 16, sV, DS, lane);   // dP_raw = dO V^T
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          const int i = mt * 16 + g + half * 8;
+          const int i = mt * 16 + g8 + half * 8;
+          const int gi = rowgp[i] >> 8;
           float dot = 0.f;
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int j = nt * 8 + 2 * t + e;
-              const float pv = acc[nt][half * 2 + e], d = dp[nt][half * 2 + e];
-              if (i < L && j < L) dsf = fmaf(d, pv - invL, dsf);
+              const bool valid = gi != 255 && (rowgp[j] >> 8) == gi;
+              const float pv = valid ? acc[nt][half * 2 + e] : 0.f;
+              const float d = dp[nt][half * 2 + e];
+              acc[nt][half * 2 + e] = pv;               // probabilities outside the sequence's block are zero
+              if (valid) dsf = fmaf(d, pv - invL, dsf);
               dot = fmaf(pv, d, dot);
             }
           }
@@ -470,14 +513,8 @@ attn_bwd_kernel(AttnParams p) {
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int j = nt * 8 + 2 * t + e;
-              const float pv = acc[nt][half * 2 + e];
-              float ds = sf * pv * (dp[nt][half * 2 + e] - dot);
-              if (!(i < L && j < L)) ds = 0.f;
-              dp[nt][half * 2 + e] = ds;
-              if (!(i < L)) acc[nt][half * 2 + e] = 0.f;     // padded query rows carry no probability mass
-            }
+            for (int e = 0; e < 2; ++e)
+              dp[nt][half * 2 + e] = sf * acc[nt][half * 2 + e] * (dp[nt][half * 2 + e] - dot);
           }
         }
       }
@@ -489,9 +526,11 @@ attn_bwd_kernel(AttnParams p) {
     if (p.d_bias_emb != nullptr) {
       for (int r = lane; r < 2 * L - 1; r += 32) {
         float s = 0.f;
-        for (int i = 0; i < L; ++i) {
-          const int j = i + r - (L - 1);
-          if (j >= 0 && j < L) s += __bfloat162float(sS[i * LS + j]);
+        for (int gq = 0; gq < G; ++gq) {
+          for (int i = 0; i < L; ++i) {
+            const int j = i + r - (L - 1);
+            if (j >= 0 && j < L) s += __bfloat162float(sS[(gq * L + i) * LS + gq * L + j]);
+          }
         }
         atomicAdd(s_demb + __ldg(p.bucket + r) * p.heads + head, s);
       }
@@ -501,28 +540,29 @@ attn_bwd_kernel(AttnParams p) {
       if (lane == 0) atomicAdd(s_dsf + head, dsf);
     }
     // ---- phase 2a: dV = s * P^T dO + (1 - s)/L * colsum(dO)  -> staged in sV ----
-    for (int mt = 0; mt * 16 < L; ++mt) {
+    for (int mt = 0; mt * 16 < rows; ++mt) {
       float o[D / 8][4];
 #pragma unroll
       for (int nt = 0; nt < D / 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
       warp_gemm<D / 8, LP / 16, true, true>(o, sP, LS, mt * 16, sG, DS, lane);
+      const int ga = min(rowgp[mt * 16 + g8] >> 8, G - 1), gb = min(rowgp[mt * 16 + g8 + 8] >> 8, G - 1);
+      const float k1 = (1.f - sf) * invL;
 #pragma unroll
       for (int nt = 0; nt < D / 8; ++nt) {
-        const float m0 = (1.f - sf) * invL * cdo[nt * 8 + 2 * t], m1 = (1.f - sf) * invL * cdo[nt * 8 + 2 * t + 1];
-        o[nt][0] = sf * o[nt][0] + m0; o[nt][1] = sf * o[nt][1] + m1;
-        o[nt][2] = sf * o[nt][2] + m0; o[nt][3] = sf * o[nt][3] + m1;
+        const int c = nt * 8 + 2 * t;
+        o[nt][0] = sf * o[nt][0] + k1 * cdo[ga * D + c]; o[nt][1] = sf * o[nt][1] + k1 * cdo[ga * D + c + 1];
+        o[nt][2] = sf * o[nt][2] + k1 * cdo[gb * D + c]; o[nt][3] = sf * o[nt][3] + k1 * cdo[gb * D + c + 1];
       }
-      __syncwarp();
-      store_tile_bf16<D / 8>(sV, DS, mt * 16, o, lane);
+      store_tile_bf16<D / 8>(sV, DS, mt * 16, o, lane);    // V is dead once every dP tile has been formed
     }
     __syncwarp();
-    store_rows<D>(sV, DS, p.out + (long)head * 3 * D + 2 * D, p.ld_out, base, p.tok_stride, L, p.accumulate, lane);
+    store_rows<D>(sV, DS, p.out + (long)head * 3 * D + 2 * D, p.ld_out, rowtok, rows, p.accumulate, lane);
     // raw k rows -> sG (dO is dead now)
     __syncwarp();
-    stage_rows<D, LP>(p.qkv + (long)head * 3 * D + D, p.ld_qkv, base, p.tok_stride, L, sG, 1.f, lane);
+    stage_rows<D, LP>(p.qkv + (long)head * 3 * D + D, p.ld_qkv, rowtok, sG, 1.f, lane);
     __syncwarp();
     // ---- phase 2b: dK^ = dS^T Q^  -> LN backward -> sV ----
-    for (int mt = 0; mt * 16 < L; ++mt) {
+    for (int mt = 0; mt * 16 < rows; ++mt) {
       float o[D / 8][4];
 #pragma unroll
       for (int nt = 0; nt < D / 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
@@ -531,12 +571,12 @@ attn_bwd_kernel(AttnParams p) {
       store_tile_bf16<D / 8>(sV, DS, mt * 16, o, lane);
     }
     __syncwarp();
-    store_rows<D>(sV, DS, p.out + (long)head * 3 * D + D, p.ld_out, base, p.tok_stride, L, p.accumulate, lane);
+    store_rows<D>(sV, DS, p.out + (long)head * 3 * D + D, p.ld_out, rowtok, rows, p.accumulate, lane);
     __syncwarp();
-    stage_rows<D, LP>(p.qkv + (long)head * 3 * D, p.ld_qkv, base, p.tok_stride, L, sG, 1.f, lane);
+    stage_rows<D, LP>(p.qkv + (long)head * 3 * D, p.ld_qkv, rowtok, sG, 1.f, lane);
     __syncwarp();
     // ---- phase 2c: dQ^ = dS K^ (w.r.t. the pre-scaled q^) -> LN backward -> sV ----
-    for (int mt = 0; mt * 16 < L; ++mt) {
+    for (int mt = 0; mt * 16 < rows; ++mt) {
       float o[D / 8][4];
 #pragma unroll
       for (int nt = 0; nt < D / 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
@@ -545,7 +585,7 @@ attn_bwd_kernel(AttnParams p) {
       store_tile_bf16<D / 8>(sV, DS, mt * 16, o, lane);
     }
     __syncwarp();
-    store_rows<D>(sV, DS, p.out + (long)head * 3 * D, p.ld_out, base, p.tok_stride, L, p.accumulate, lane);
+    store_rows<D>(sV, DS, p.out + (long)head * 3 * D, p.ld_out, rowtok, rows, p.accumulate, lane);
     __syncwarp();
   }
   __syncthreads();
@@ -566,9 +606,9 @@ template <int D, int LP, bool BWD>
 static int launch_attn(const AttnParams& p, cudaStream_t st) {
   using SM = AttnSmem<D, LP>;
   constexpr int per_warp = BWD ? SM::kBwdBytes : SM::kFwdBytes;
-  constexpr int budget = 200 * 1024;
+  constexpr int budget = 220 * 1024;
   constexpr int w_fit = budget / per_warp;
-  constexpr int WARPS = w_fit >= 8 ? 8 : (w_fit >= 4 ? 4 : (w_fit >= 2 ? 2 : 1));
+  constexpr int WARPS = w_fit >= 4 ? 4 : (w_fit >= 2 ? 2 : 1);     // small blocks: several co-reside per SM
   static_assert(w_fit >= 1, "attention tile does not fit in shared memory");
   const size_t smem = (size_t)WARPS * per_warp + (BWD ? (size_t)(4 * D + 33 * p.heads) * sizeof(float) : 0);
   void (*kern)(AttnParams);
@@ -582,10 +622,10 @@ static int launch_attn(const AttnParams& p, cudaStream_t st) {
     attr_done = true;
   }
   BF_REQUIRE(smem <= 227 * 1024, "attention: shared memory %zu too large (heads=%d)", smem, p.heads);
-  const long n_work = p.n_seq * p.heads;
-  const int per_sm = (int)((227 * 1024) / smem) > 0 ? (int)((227 * 1024) / smem) : 1;
+  const long n_work = ((p.n_seq + p.G - 1) / p.G) * p.heads;
+  const int per_sm = (int)((227 * 1024) / (smem + 1024)) > 0 ? (int)((227 * 1024) / (smem + 1024)) : 1;
   long blocks = (n_work + WARPS - 1) / WARPS;
-  const long cap = (long)num_sms() * (per_sm > 4 ? 4 : per_sm);
+  const long cap = (long)num_sms() * (per_sm > 8 ? 8 : per_sm);
   if (blocks > cap) blocks = cap;
   kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(p);
   count_launch();
@@ -595,11 +635,11 @@ static int launch_attn(const AttnParams& p, cudaStream_t st) {
 template <bool BWD>
 static int dispatch_attn(int D, int LP, const AttnParams& p, cudaStream_t st) {
 #define BF_CASE(D_, LP_) if (D == D_ && LP == LP_) return launch_attn<D_, LP_, BWD>(p, st);
-  BF_CASE(32, 16) BF_CASE(32, 32) BF_CASE(32, 64)
-  BF_CASE(48, 16) BF_CASE(48, 32) BF_CASE(48, 64)
-  BF_CASE(64, 16) BF_CASE(64, 32) BF_CASE(64, 64)
-  BF_CASE(96, 16) BF_CASE(96, 32) BF_CASE(96, 64)
-  BF_CASE(128, 16) BF_CASE(128, 32) BF_CASE(128, 64)
+  BF_CASE(32, 32) BF_CASE(32, 64)
+  BF_CASE(48, 32) BF_CASE(48, 64)
+  BF_CASE(64, 32) BF_CASE(64, 64)
+  BF_CASE(96, 32) BF_CASE(96, 64)
+  BF_CASE(128, 32) BF_CASE(128, 64)
 #undef BF_CASE
   set_error("bf_attention: unsupported head_dim %d (supported: 32, 48, 64, 96, 128)", D);
   return BF_ERR_INVALID;
@@ -623,8 +663,12 @@ static int attn_common(const bf_attn_args* a, AttnParams& p, int& LP, bool bwd) 
     BF_REQUIRE(a->dout && a->ld_dout % 8 == 0, "bf_attention_bwd: dout");
     BF_REQUIRE(a->d_qn_w && a->d_qn_b && a->d_kn_w && a->d_kn_b, "bf_attention_bwd: LayerNorm gradient buffers");
   }
-  LP = a->L <= 16 ? 16 : (a->L <= 32 ? 32 : 64);
+  // short sequences are packed G per tile (block-diagonal attention): L <= 16 -> 32-row tiles holding 32/L of them
+  LP = a->L <= 32 ? 32 : 64;
   p = AttnParams{};
+  p.G = LP / a->L;
+  if (p.G > 8) p.G = 8;
+  if (p.G < 1) p.G = 1;
   p.qkv = static_cast<const bf16*>(a->qkv); p.ld_qkv = a->ld_qkv;
   p.out = static_cast<bf16*>(a->out); p.ld_out = a->ld_out;
   p.dout = static_cast<const bf16*>(a->dout); p.ld_dout = a->ld_dout;

@@ -56,163 +56,221 @@ struct SmemLayout {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN <= 128) ? 6 : (BN <= 192 ? 5 : 4);
+  static constexpr int kStages = (BN <= 128) ? 5 : 4;
   static constexpr int kTileBytes = kStages * kStageBytes;
+  static constexpr int kScratchBytes = kEpiWarps * 32 * 33 * 4;  // per-warp 32x33 fp32 transpose scratch
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kTotal = kTileBytes + kBarBytes + 1024;  // + slack for manual 1 KiB alignment
+  static constexpr int kTotal = kTileBytes + kScratchBytes + kBarBytes + 1024;  // + slack for 1 KiB alignment
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
 };
 
 // ---------------------------------------------------------------------------------------------
-// epilogue on one 32-column chunk of one row
+// Epilogue on one 32-row x 32-column chunk owned by one warp.
+//
+// tcgen05.ld hands every thread one ROW of the chunk (32 consecutive fp32 columns).  Touching global
+// memory in that shape makes each warp instruction hit 32 different rows, so all global traffic goes
+// through a per-warp 32x33 fp32 shared-memory transpose instead: with 8 lanes per row (fp32) or 4 lanes
+// per row (16-bit) every instruction reads / writes whole 128-byte / 64-byte row segments.
+// The +1 padding makes both the row-wise and the transposed accesses bank-conflict free.
 // ---------------------------------------------------------------------------------------------
-template <typename T16>
-__device__ __forceinline__ void store16_chunk(T16* dst, const float (&v)[32], int ncols, bool vec_ok) {
-  if (vec_ok && ncols == 32) {
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
+struct ChunkCtx {
+  float* scratch;      // this warp's [32][33] floats
+  int lane;
+  int rows_valid;      // rows of the chunk inside the matrix (0..32), warp uniform
+  int ncols;           // columns of the chunk inside the matrix (1..32), warp uniform
+};
+
+__device__ __forceinline__ void regs_to_scratch(const ChunkCtx& c, const float (&v)[32]) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint4 u;
-      u.x = pack2<T16>(v[8 * q + 0], v[8 * q + 1]);
-      u.y = pack2<T16>(v[8 * q + 2], v[8 * q + 3]);
-      u.z = pack2<T16>(v[8 * q + 4], v[8 * q + 5]);
-      u.w = pack2<T16>(v[8 * q + 6], v[8 * q + 7]);
-      d4[q] = u;
+  for (int j = 0; j < 32; ++j) c.scratch[c.lane * 33 + j] = v[j];
+  __syncwarp();
+}
+__device__ __forceinline__ void scratch_to_regs(const ChunkCtx& c, float (&v)[32]) {
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = c.scratch[c.lane * 33 + j];
+  __syncwarp();
+}
+
+// global (rows at base + r*ld) fp32 -> thread-row registers
+__device__ __forceinline__ void coop_load32(const ChunkCtx& c, const float* base, long ld, float (&v)[32]) {
+  const bool vec = (c.ncols == 32) && (ld % 4 == 0);
+  if (vec) {
+    const int cc = (c.lane & 7) * 4;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const int r = p * 4 + (c.lane >> 3);
+      float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < c.rows_valid) u = *reinterpret_cast<const float4*>(base + (long)r * ld + cc);
+      float* s = c.scratch + r * 33 + cc;
+      s[0] = u.x; s[1] = u.y; s[2] = u.z; s[3] = u.w;
     }
   } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < ncols) dst[j] = from_f32<T16>(v[j]);
+    for (int r = 0; r < c.rows_valid; ++r)
+      c.scratch[r * 33 + c.lane] = (c.lane < c.ncols) ? base[(long)r * ld + c.lane] : 0.f;
   }
+  scratch_to_regs(c, v);
+}
+
+__device__ __forceinline__ void coop_store32(const ChunkCtx& c, float* base, long ld, const float (&v)[32]) {
+  regs_to_scratch(c, v);
+  const bool vec = (c.ncols == 32) && (ld % 4 == 0);
+  if (vec) {
+    const int cc = (c.lane & 7) * 4;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const int r = p * 4 + (c.lane >> 3);
+      const float* s = c.scratch + r * 33 + cc;
+      if (r < c.rows_valid) *reinterpret_cast<float4*>(base + (long)r * ld + cc) = make_float4(s[0], s[1], s[2], s[3]);
+    }
+  } else {
+    for (int r = 0; r < c.rows_valid; ++r)
+      if (c.lane < c.ncols) base[(long)r * ld + c.lane] = c.scratch[r * 33 + c.lane];
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void coop_atomic32(const ChunkCtx& c, float* base, long ld, const float (&v)[32]) {
+  regs_to_scratch(c, v);
+  for (int r = 0; r < c.rows_valid; ++r)
+    if (c.lane < c.ncols) atomicAdd(base + (long)r * ld + c.lane, c.scratch[r * 33 + c.lane]);
+  __syncwarp();
+}
+
+// 16-bit rows; row r of the chunk lives at rowptr(r)
+template <typename T16, typename RowPtr>
+__device__ __forceinline__ void coop_store16(const ChunkCtx& c, RowPtr rowptr, bool aligned, const float (&v)[32]) {
+  regs_to_scratch(c, v);
+  if (aligned && c.ncols == 32) {
+    const int cc = (c.lane & 3) * 8;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int r = p * 8 + (c.lane >> 2);
+      const float* s = c.scratch + r * 33 + cc;
+      if (r < c.rows_valid) {
+        uint4 u;
+        u.x = pack2<T16>(s[0], s[1]); u.y = pack2<T16>(s[2], s[3]);
+        u.z = pack2<T16>(s[4], s[5]); u.w = pack2<T16>(s[6], s[7]);
+        *reinterpret_cast<uint4*>(rowptr(r) + cc) = u;
+      }
+    }
+  } else {
+    for (int r = 0; r < c.rows_valid; ++r)
+      if (c.lane < c.ncols) rowptr(r)[c.lane] = from_f32<T16>(c.scratch[r * 33 + c.lane]);
+  }
+  __syncwarp();
 }
 
 template <typename T16>
-__device__ __forceinline__ void load16_chunk(const T16* src, float (&v)[32], int ncols, bool vec_ok) {
-  if (vec_ok && ncols == 32) {
-    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+__device__ __forceinline__ void coop_load16(const ChunkCtx& c, const T16* base, long ld, float (&v)[32]) {
+  if ((ld % 8 == 0) && c.ncols == 32) {
+    const int cc = (c.lane & 3) * 8;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint4 u = s4[q];
-      float2 a = unpack2<T16>(u.x), b = unpack2<T16>(u.y), c = unpack2<T16>(u.z), d = unpack2<T16>(u.w);
-      v[8 * q + 0] = a.x; v[8 * q + 1] = a.y; v[8 * q + 2] = b.x; v[8 * q + 3] = b.y;
-      v[8 * q + 4] = c.x; v[8 * q + 5] = c.y; v[8 * q + 6] = d.x; v[8 * q + 7] = d.y;
+    for (int p = 0; p < 4; ++p) {
+      const int r = p * 8 + (c.lane >> 2);
+      uint4 u = make_uint4(0u, 0u, 0u, 0u);
+      if (r < c.rows_valid) u = *reinterpret_cast<const uint4*>(base + (long)r * ld + cc);
+      const float2 a = unpack2<T16>(u.x), b = unpack2<T16>(u.y), d = unpack2<T16>(u.z), e = unpack2<T16>(u.w);
+      float* s = c.scratch + r * 33 + cc;
+      s[0] = a.x; s[1] = a.y; s[2] = b.x; s[3] = b.y; s[4] = d.x; s[5] = d.y; s[6] = e.x; s[7] = e.y;
     }
   } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = (j < ncols) ? to_f32<T16>(src[j]) : 0.f;
+    for (int r = 0; r < c.rows_valid; ++r)
+      c.scratch[r * 33 + c.lane] = (c.lane < c.ncols) ? to_f32<T16>(base[(long)r * ld + c.lane]) : 0.f;
   }
+  scratch_to_regs(c, v);
 }
 
-__device__ __forceinline__ void load32_chunk(const float* src, float (&v)[32], int ncols, bool vec_ok) {
-  if (vec_ok && ncols == 32) {
-    const float4* s4 = reinterpret_cast<const float4*>(src);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      float4 u = s4[q];
-      v[4 * q + 0] = u.x; v[4 * q + 1] = u.y; v[4 * q + 2] = u.z; v[4 * q + 3] = u.w;
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = (j < ncols) ? src[j] : 0.f;
-  }
-}
-
-__device__ __forceinline__ void store32_chunk(float* dst, const float (&v)[32], int ncols, bool vec_ok) {
-  if (vec_ok && ncols == 32) {
-    float4* d4 = reinterpret_cast<float4*>(dst);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) d4[q] = make_float4(v[4 * q + 0], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < ncols) dst[j] = v[j];
-  }
-}
-
+// m_base: first global row of the chunk (warp uniform), n: first global column.  Thread `lane` holds row m_base+lane.
 template <typename T16>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int m, int n, float (&acc)[32]) {
-  // m: global row (< M guaranteed by the caller), n: first global column of the chunk
-  const int ncols = min(32, p.N - n);
-  if (ncols <= 0) return;
-  const bool v16 = (p.ldo % 8 == 0);
-  const bool v32 = (p.ld32 % 4 == 0);
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const ChunkCtx& c, int m_base, int n, float (&acc)[32]) {
+  const bool a16 = (p.ldo % 8 == 0);
   if (p.bias != nullptr) {
 #pragma unroll
     for (int j = 0; j < 32; ++j)
-      if (j < ncols) acc[j] += __ldg(p.bias + n + j);
+      if (j < c.ncols) acc[j] += __ldg(p.bias + n + j);
   }
+  auto row16 = [&](void* ptr) {
+    T16* b = reinterpret_cast<T16*>(ptr) + (long)m_base * p.ldo + n;
+    const long ld = p.ldo;
+    return [b, ld](int r) { return b + (long)r * ld; };
+  };
   switch (p.epilogue) {
     case BF_EPI_STORE16: {
-      store16_chunk<T16>(reinterpret_cast<T16*>(p.out16) + (long)m * p.ldo + n, acc, ncols, v16);
+      coop_store16<T16>(c, row16(p.out16), a16, acc);
       break;
     }
     case BF_EPI_STORE32: {
-      store32_chunk(p.out32 + (long)m * p.ld32 + n, acc, ncols, v32);
+      coop_store32(c, p.out32 + (long)m_base * p.ld32 + n, p.ld32, acc);
       break;
     }
     case BF_EPI_GELU: {
-      if (p.out16b != nullptr)
-        store16_chunk<T16>(reinterpret_cast<T16*>(p.out16b) + (long)m * p.ldo + n, acc, ncols, v16);
+      if (p.out16b != nullptr) coop_store16<T16>(c, row16(p.out16b), a16, acc);
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[j] = gelu_erf(acc[j]);
-      store16_chunk<T16>(reinterpret_cast<T16*>(p.out16) + (long)m * p.ldo + n, acc, ncols, v16);
+      coop_store16<T16>(c, row16(p.out16), a16, acc);
       break;
     }
     case BF_EPI_RESID: {
-      if (p.out16b != nullptr)
-        store16_chunk<T16>(reinterpret_cast<T16*>(p.out16b) + (long)m * p.ldo + n, acc, ncols, v16);
-      const float rs = (p.row_scale != nullptr) ? __ldg(p.row_scale + m / p.rows_per_group) : 1.f;
+      if (p.out16b != nullptr) coop_store16<T16>(c, row16(p.out16b), a16, acc);
+      const int m = m_base + c.lane;
+      const float rs = (p.row_scale != nullptr && c.lane < c.rows_valid) ? __ldg(p.row_scale + m / p.rows_per_group) : 1.f;
       float xin[32];
-      load32_chunk(p.in32 + (long)m * p.ld32 + n, xin, ncols, v32);
+      coop_load32(c, p.in32 + (long)m_base * p.ld32 + n, p.ld32, xin);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        if (j < ncols) {
+        if (j < c.ncols) {
           float v = acc[j];
           if (p.col_scale != nullptr) v = fmaf(v, __ldg(p.col_scale + n + j), __ldg(p.col_shift + n + j));
           acc[j] = fmaf(rs * __ldg(p.col_gamma + n + j), v, xin[j]);
         }
       }
-      store32_chunk(p.out32 + (long)m * p.ld32 + n, acc, ncols, v32);
-      if (p.out16 != nullptr)
-        store16_chunk<T16>(reinterpret_cast<T16*>(p.out16) + (long)m * p.ldo + n, acc, ncols, v16);
+      coop_store32(c, p.out32 + (long)m_base * p.ld32 + n, p.ld32, acc);
+      if (p.out16 != nullptr) coop_store16<T16>(c, row16(p.out16), a16, acc);
       break;
     }
     case BF_EPI_DGELU: {
       float pre[32];
-      load16_chunk<T16>(reinterpret_cast<const T16*>(p.aux16) + (long)m * p.ldo + n, pre, ncols, v16);
+      coop_load16<T16>(c, reinterpret_cast<const T16*>(p.aux16) + (long)m_base * p.ldo + n, p.ldo, pre);
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[j] *= gelu_erf_grad(pre[j]);
-      store16_chunk<T16>(reinterpret_cast<T16*>(p.out16) + (long)m * p.ldo + n, acc, ncols, v16);
+      coop_store16<T16>(c, row16(p.out16), a16, acc);
       break;
     }
     case BF_EPI_ACC32: {
       float g[32];
-      load32_chunk(p.in32 + (long)m * p.ld32 + n, g, ncols, v32);
+      coop_load32(c, p.in32 + (long)m_base * p.ld32 + n, p.ld32, g);
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[j] += g[j];
-      store32_chunk(p.out32 + (long)m * p.ld32 + n, acc, ncols, v32);
+      coop_store32(c, p.out32 + (long)m_base * p.ld32 + n, p.ld32, acc);
       break;
     }
     case BF_EPI_ATOMIC32: {
-      float* dst = p.out32 + (long)m * p.ld32 + n;
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols) atomicAdd(dst + j, acc[j]);
+      coop_atomic32(c, p.out32 + (long)m_base * p.ld32 + n, p.ld32, acc);
       break;
     }
     case BF_EPI_D2S: {
+      // m = (img, y, x), n = (ky, kx, co) -> out[((img*2h + 2y+ky)*2w + 2x+kx)*cout + co]
       const int w = p.d2s_w, h = p.d2s_h, co = p.d2s_cout;
-      const int x = m % w, y = (m / w) % h, img = m / (w * h);
       T16* out = reinterpret_cast<T16*>(p.out16);
       if (co % 32 == 0) {
         const int q = n / co, c0 = n - q * co;
-        const long pix = ((long)(img * 2 * h + 2 * y + (q >> 1)) * (2 * w) + 2 * x + (q & 1));
-        store16_chunk<T16>(out + pix * co + c0, acc, ncols, true);
-      } else {
-        for (int j = 0; j < ncols; ++j) {
-          const int q = (n + j) / co, c0 = (n + j) - q * co;
+        auto rowptr = [=](int r) {
+          const int m = m_base + r;
+          const int x = m % w, y = (m / w) % h, img = m / (w * h);
           const long pix = ((long)(img * 2 * h + 2 * y + (q >> 1)) * (2 * w) + 2 * x + (q & 1));
-          out[pix * co + c0] = from_f32<T16>(acc[j]);
+          return out + pix * co + c0;
+        };
+        coop_store16<T16>(c, rowptr, true, acc);
+      } else {
+        const int m = m_base + c.lane;
+        if (c.lane < c.rows_valid) {
+          const int x = m % w, y = (m / w) % h, img = m / (w * h);
+          for (int j = 0; j < c.ncols; ++j) {
+            const int q = (n + j) / co, c0 = (n + j) - q * co;
+            const long pix = ((long)(img * 2 * h + 2 * y + (q >> 1)) * (2 * w) + 2 * x + (q & 1));
+            out[pix * co + c0] = from_f32<T16>(acc[j]);
+          }
         }
       }
       break;
@@ -232,7 +290,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kTileBytes);
+  float* scratch_all = reinterpret_cast<float*>(smem + L::kTileBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kTileBytes + L::kScratchBytes);
   uint64_t* empty_bar = full_bar + L::kStages;
   uint64_t* tmem_full = empty_bar + L::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -346,7 +405,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int ew = warp - 2;
     const int quad = warp & 3;              // TMEM lane quadrant this warp may access
     const int half = ew >> 2;               // which half of the tile's columns
-    const int row_in_tile = quad * 32 + lane;
+    ChunkCtx cc;
+    cc.scratch = scratch_all + ew * (32 * 33);
+    cc.lane = lane;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -354,8 +415,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int mn = tile - ks * tiles_mn;
       const int m_blk = mn / p.num_n_blocks;
       const int n_blk = mn - m_blk * p.num_n_blocks;
-      const int m = m_blk * BM + row_in_tile;
+      const int m_base = m_blk * BM + quad * 32;
       const int n0 = n_blk * BN;
+      cc.rows_valid = min(32, max(0, p.M - m_base));
       mbar_wait(tmem_full + as, aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN);
@@ -364,9 +426,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         float acc[32];
         tmem_ld_32x32(t_row + static_cast<uint32_t>(c), acc);
         tmem_ld_wait();
-        if (m < p.M) {
-          if (p.is_f16) epilogue_chunk<__half>(p, m, n0 + c, acc);
-          else          epilogue_chunk<__nv_bfloat16>(p, m, n0 + c, acc);
+        cc.ncols = min(32, p.N - (n0 + c));
+        if (cc.rows_valid > 0 && cc.ncols > 0) {
+          if (p.is_f16) epilogue_chunk<__half>(p, cc, m_base, n0 + c, acc);
+          else          epilogue_chunk<__nv_bfloat16>(p, cc, m_base, n0 + c, acc);
         }
       }
       tc_fence_before();

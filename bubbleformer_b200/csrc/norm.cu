@@ -52,6 +52,26 @@ __device__ __forceinline__ void store_vec(T* p, const float (&v)[N], bool vec) {
   }
 }
 
+// 8 consecutive channels per thread regardless of the storage type (16 B for 16-bit, 2 x 16 B for fp32)
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&v)[8]) {
+  if constexpr (sizeof(T) == 4) {
+    const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    load_vec<T, 8>(p, v, true);
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float (&v)[8]) {
+  if constexpr (sizeof(T) == 4) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    store_vec<T, 8>(p, v, true);
+  }
+}
+
 // Thread geometry shared by all row-streaming kernels: a block covers `tx_n` vector columns and
 // `ty_n` rows at a time; grid = (column chunks, row splits, images).
 struct RowGeom {
@@ -69,7 +89,7 @@ static RowGeom make_geom(int C, int vecn, int P, int I) {
   g.ty_n = kNormThreads / g.tx_n;
   const int want_blocks = 4 * num_sms();
   int splits = (want_blocks + I * g.chunks - 1) / (I * g.chunks);
-  const int max_splits = (P + 4 * g.ty_n - 1) / (4 * g.ty_n);     // keep >= 4 rows per thread
+  const int max_splits = (P + 8 * g.ty_n - 1) / (8 * g.ty_n);     // keep >= 8 rows per thread (unrolled loops)
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   g.splits = splits;
@@ -103,11 +123,23 @@ inorm_stats_kernel(const T* __restrict__ x, NormCommon nc, float* __restrict__ s
   for (int j = 0; j < N; ++j) { s[j] = 0.f; q[j] = 0.f; }
   if (active) {
     const T* base = x + ((long)img * nc.P) * nc.ldx + (long)vcol * N;
-    for (int r = r0 + ty; r < r1; r += g.ty_n) {
-      float v[N];
-      load_vec<T, N>(base + (long)r * nc.ldx, v, true);
+    constexpr int UN = 4;
+    for (int r = r0 + ty; r < r1; r += UN * g.ty_n) {
+      float v[UN][N];
 #pragma unroll
-      for (int j = 0; j < N; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
+      for (int u = 0; u < UN; ++u) {
+        const int rr = r + u * g.ty_n;
+        if (rr < r1) load_vec<T, N>(base + (long)rr * nc.ldx, v[u], true);
+        else {
+#pragma unroll
+          for (int j = 0; j < N; ++j) v[u][j] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) { s[j] += v[u][j]; q[j] = fmaf(v[u][j], v[u][j], q[j]); }
+      }
     }
     float* my = red + ((long)ty * g.tx_n + tx) * 2 * N;
 #pragma unroll
@@ -187,35 +219,50 @@ inorm_apply_kernel(const TI* __restrict__ x, TO* __restrict__ out, ApplyParams p
   const TI* xb = x + ((long)img * p.nc.P) * p.nc.ldx + c0;
   TO* ob = out + ((long)img * p.nc.P) * p.ldo + c0;
   const float* rb = p.resid_in != nullptr ? p.resid_in + ((long)img * p.nc.P) * p.ldo + c0 : nullptr;
-  for (int r = r0 + ty; r < r1; r += g.ty_n) {
-    float v[N];
-    load_vec<TI, N>(xb + (long)r * p.nc.ldx, v, true);
+  constexpr int UN = 2;
+  for (int r = r0 + ty; r < r1; r += UN * g.ty_n) {
+    float vv[UN][N];
+    float xr[UN][N];
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-      float y = fmaf(v[j], a[j], b[j]);
-      if (p.gelu) y = gelu_erf(y);
-      if (p.film_gamma != nullptr) y = fmaf(fg[j], y, fb[j]);
-      v[j] = y;
-    }
-    if (rb != nullptr) {
+    for (int u = 0; u < UN; ++u) {
+      const int rr = r + u * g.ty_n;
+      if (rr < r1) {
+        load_vec<TI, N>(xb + (long)rr * p.nc.ldx, vv[u], true);
+        if (rb != nullptr) {
 #pragma unroll
-      for (int h = 0; h < N / 4; ++h) {
-        float xr[4];
-        load_vec<float, 4>(rb + (long)r * p.ldo + 4 * h, xr, true);
+          for (int h = 0; h < N / 4; ++h) {
+            float t4[4];
+            load_vec<float, 4>(rb + (long)rr * p.ldo + 4 * h, t4, true);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[4 * h + j] = fmaf(cg[4 * h + j], v[4 * h + j], xr[j]);
+            for (int j = 0; j < 4; ++j) xr[u][4 * h + j] = t4[j];
+          }
+        }
       }
     }
-    if constexpr (sizeof(TO) == 4 && N == 8) {
-      float lo[4] = {v[0], v[1], v[2], v[3]}, hi[4] = {v[4], v[5], v[6], v[7]};
-      store_vec<float, 4>(reinterpret_cast<float*>(ob + (long)r * p.ldo), lo, true);
-      store_vec<float, 4>(reinterpret_cast<float*>(ob + (long)r * p.ldo) + 4, hi, true);
-    } else if constexpr (sizeof(TO) == 2 && N == 4) {
-      uint2 u;
-      u.x = pack2<TO>(v[0], v[1]); u.y = pack2<TO>(v[2], v[3]);
-      *reinterpret_cast<uint2*>(ob + (long)r * p.ldo) = u;
-    } else {
-      store_vec<TO, N>(ob + (long)r * p.ldo, v, true);
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int rr = r + u * g.ty_n;
+      if (rr >= r1) continue;
+      float (&v)[N] = vv[u];
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        float y = fmaf(v[j], a[j], b[j]);
+        if (p.gelu) y = gelu_erf(y);
+        if (p.film_gamma != nullptr) y = fmaf(fg[j], y, fb[j]);
+        if (rb != nullptr) y = fmaf(cg[j], y, xr[u][j]);
+        v[j] = y;
+      }
+      if constexpr (sizeof(TO) == 4 && N == 8) {
+        float lo[4] = {v[0], v[1], v[2], v[3]}, hi[4] = {v[4], v[5], v[6], v[7]};
+        store_vec<float, 4>(reinterpret_cast<float*>(ob + (long)rr * p.ldo), lo, true);
+        store_vec<float, 4>(reinterpret_cast<float*>(ob + (long)rr * p.ldo) + 4, hi, true);
+      } else if constexpr (sizeof(TO) == 2 && N == 4) {
+        uint2 u2;
+        u2.x = pack2<TO>(v[0], v[1]); u2.y = pack2<TO>(v[2], v[3]);
+        *reinterpret_cast<uint2*>(ob + (long)rr * p.ldo) = u2;
+      } else {
+        store_vec<TO, N>(ob + (long)rr * p.ldo, v, true);
+      }
     }
   }
 }
@@ -243,7 +290,8 @@ struct BwdParams {
 template <typename TG, typename TX>
 __global__ void __launch_bounds__(kNormThreads)
 inorm_bwd_reduce_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, BwdParams p) {
-  constexpr int N = 4;                 // 4 channels per thread for every dtype combination
+  constexpr int N = 8;                 // 8 channels per thread for every dtype combination
+  constexpr int UN = 2;
   extern __shared__ float red[];       // [ty_n][tx_n][2N]
   const RowGeom& g = p.nc.g;
   const int tx = threadIdx.x % g.tx_n, ty = threadIdx.x / g.tx_n;
@@ -267,21 +315,27 @@ inorm_bwd_reduce_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, Bw
     const int r1 = min(p.nc.P, r0 + rows_per_split);
     const TG* gb = gin + ((long)img * p.nc.P) * p.ldg + c0;
     const TX* xb = x + ((long)img * p.nc.P) * p.nc.ldx + c0;
-    for (int r = r0 + ty; r < r1; r += g.ty_n) {
-      float gv[N], xv[N];
-      if constexpr (sizeof(TG) == 4) load_vec<float, 4>(reinterpret_cast<const float*>(gb + (long)r * p.ldg), gv, true);
-      else { uint2 u = *reinterpret_cast<const uint2*>(gb + (long)r * p.ldg);
-             float2 a2 = unpack2<TG>(u.x), b2 = unpack2<TG>(u.y); gv[0] = a2.x; gv[1] = a2.y; gv[2] = b2.x; gv[3] = b2.y; }
-      if constexpr (sizeof(TX) == 4) load_vec<float, 4>(reinterpret_cast<const float*>(xb + (long)r * p.nc.ldx), xv, true);
-      else { uint2 u = *reinterpret_cast<const uint2*>(xb + (long)r * p.nc.ldx);
-             float2 a2 = unpack2<TX>(u.x), b2 = unpack2<TX>(u.y); xv[0] = a2.x; xv[1] = a2.y; xv[2] = b2.x; xv[3] = b2.y; }
+    for (int r = r0 + ty; r < r1; r += UN * g.ty_n) {
+      float gv[UN][N], xv[UN][N];
 #pragma unroll
-      for (int j = 0; j < N; ++j) {
-        const float xh = (xv[j] - mean[j]) * rstd[j];
-        float gg = gv[j];
-        if (p.gelu) gg *= gelu_erf_grad(fmaf(xh, w[j], b[j]));
-        s[j] += gg;
-        q[j] = fmaf(gg, xh, q[j]);
+      for (int u = 0; u < UN; ++u) {
+        const int rr = r + u * g.ty_n;
+        if (rr < r1) {
+          load8<TG>(gb + (long)rr * p.ldg, gv[u]);
+          load8<TX>(xb + (long)rr * p.nc.ldx, xv[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        if (r + u * g.ty_n >= r1) continue;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          const float xh = (xv[u][j] - mean[j]) * rstd[j];
+          float gg = gv[u][j];
+          if (p.gelu) gg *= gelu_erf_grad(fmaf(xh, w[j], b[j]));
+          s[j] += gg;
+          q[j] = fmaf(gg, xh, q[j]);
+        }
       }
     }
     float* my = red + ((long)ty * g.tx_n + tx) * 2 * N;
@@ -308,7 +362,8 @@ inorm_bwd_reduce_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, Bw
 template <typename TG, typename TX, typename TO>
 __global__ void __launch_bounds__(kNormThreads)
 inorm_bwd_apply_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, TO* __restrict__ out, BwdParams p) {
-  constexpr int N = 4;
+  constexpr int N = 8;
+  constexpr int UN = 2;
   const RowGeom& g = p.nc.g;
   const int tx = threadIdx.x % g.tx_n, ty = threadIdx.x / g.tx_n;
   const int vcol = blockIdx.x * g.tx_n + tx;
@@ -338,39 +393,36 @@ inorm_bwd_apply_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, TO*
   const TX* xb = x + ((long)img * p.nc.P) * p.nc.ldx + c0;
   TO* ob = out + ((long)img * p.nc.P) * p.ldo + c0;
   const float* ab = p.add32 != nullptr ? p.add32 + ((long)img * p.nc.P) * p.ldo + c0 : nullptr;
-  for (int r = r0 + ty; r < r1; r += g.ty_n) {
-    float gv[N], xv[N];
-    if constexpr (sizeof(TG) == 4) load_vec<float, 4>(reinterpret_cast<const float*>(gb + (long)r * p.ldg), gv, true);
-    else { uint2 u = *reinterpret_cast<const uint2*>(gb + (long)r * p.ldg);
-           float2 a2 = unpack2<TG>(u.x), b2 = unpack2<TG>(u.y); gv[0] = a2.x; gv[1] = a2.y; gv[2] = b2.x; gv[3] = b2.y; }
-    if constexpr (sizeof(TX) == 4) load_vec<float, 4>(reinterpret_cast<const float*>(xb + (long)r * p.nc.ldx), xv, true);
-    else { uint2 u = *reinterpret_cast<const uint2*>(xb + (long)r * p.nc.ldx);
-           float2 a2 = unpack2<TX>(u.x), b2 = unpack2<TX>(u.y); xv[0] = a2.x; xv[1] = a2.y; xv[2] = b2.x; xv[3] = b2.y; }
-    float o[N];
+  for (int r = r0 + ty; r < r1; r += UN * g.ty_n) {
+    float gv[UN][N], xv[UN][N], av[UN][N];
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-      const float xh = (xv[j] - mean[j]) * rstd[j];
-      float gg = gv[j];
-      if (p.gelu) gg *= gelu_erf_grad(fmaf(xh, w[j], b[j]));
-      o[j] = k[j] * (gg - m1[j] - xh * m2[j]);
+    for (int u = 0; u < UN; ++u) {
+      const int rr = r + u * g.ty_n;
+      if (rr < r1) {
+        load8<TG>(gb + (long)rr * p.ldg, gv[u]);
+        load8<TX>(xb + (long)rr * p.nc.ldx, xv[u]);
+        if (ab != nullptr) load8<float>(ab + (long)rr * p.ldo, av[u]);
+      }
     }
-    if (ab != nullptr) {
-      float av[4];
-      load_vec<float, 4>(ab + (long)r * p.ldo, av, true);
 #pragma unroll
-      for (int j = 0; j < N; ++j) o[j] += av[j];
-    }
-    if constexpr (sizeof(TO) == 4) {
-      store_vec<float, 4>(reinterpret_cast<float*>(ob + (long)r * p.ldo), o, true);
-    } else {
-      uint2 u;
-      u.x = pack2<TO>(o[0], o[1]); u.y = pack2<TO>(o[2], o[3]);
-      *reinterpret_cast<uint2*>(ob + (long)r * p.ldo) = u;
+    for (int u = 0; u < UN; ++u) {
+      const int rr = r + u * g.ty_n;
+      if (rr >= r1) continue;
+      float o[N];
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const float xh = (xv[u][j] - mean[j]) * rstd[j];
+        float gg = gv[u][j];
+        if (p.gelu) gg *= gelu_erf_grad(fmaf(xh, w[j], b[j]));
+        o[j] = k[j] * (gg - m1[j] - xh * m2[j]);
+        if (ab != nullptr) o[j] += av[u][j];
+      }
+      store8<TO>(ob + (long)rr * p.ldo, o);
     }
   }
 }
 
-// parameter gradients from the per-(image, channel) reductions (tiny)
+// parameter gradients from the per-(image, channel) reductions: 32 channels x 8 image lanes per block
 struct BwdParamArgs {
   const float* red; const float* stats;
   int I, P, C;
@@ -378,38 +430,46 @@ struct BwdParamArgs {
   const float* weight; const float* bias;
   float* dweight; float* dbias; float* dcol_scale; float* dfilm_gamma; float* dfilm_beta;
 };
-__global__ void inorm_bwd_params_kernel(BwdParamArgs a) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= a.C) return;
-  const float w = a.weight[c], b = a.bias[c];
+__global__ void __launch_bounds__(256) inorm_bwd_params_kernel(BwdParamArgs a) {
+  __shared__ float sh[3][8][33];
+  const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   float dw = 0.f, db = 0.f, dcs = 0.f;
-  const int nb = a.film_T > 0 ? a.I / a.film_T : 0;
-  for (int img = 0; img < a.I; ++img) {
-    const long idx = (long)img * a.C + c;
-    const float R1 = a.red[2 * idx], R2 = a.red[2 * idx + 1];
-    float cs = 1.f;
-    const float rs = a.row_scale != nullptr ? a.row_scale[img] : 1.f;
-    cs *= rs;
-    if (a.col_scale != nullptr) cs *= a.col_scale[c];
-    if (a.film_gamma != nullptr) cs *= a.film_gamma[(long)(img / a.film_T) * a.C + c];
-    dw = fmaf(cs, R2, dw);
-    db = fmaf(cs, R1, db);
-    dcs = fmaf(rs, fmaf(w, R2, b * R1), dcs);
+  float w = 0.f, b = 0.f;
+  if (c < a.C) {
+    w = a.weight[c]; b = a.bias[c];
+    for (int img = grp; img < a.I; img += 8) {
+      const long idx = (long)img * a.C + c;
+      const float R1 = a.red[2 * idx], R2 = a.red[2 * idx + 1];
+      const float rs = a.row_scale != nullptr ? a.row_scale[img] : 1.f;
+      float cs = rs;
+      if (a.col_scale != nullptr) cs *= a.col_scale[c];
+      if (a.film_gamma != nullptr) cs *= a.film_gamma[(long)(img / a.film_T) * a.C + c];
+      dw = fmaf(cs, R2, dw);
+      db = fmaf(cs, R1, db);
+      dcs = fmaf(rs, fmaf(w, R2, b * R1), dcs);
+    }
   }
-  if (a.dweight) a.dweight[c] += dw;
-  if (a.dbias) a.dbias[c] += db;
-  if (a.dcol_scale) a.dcol_scale[c] += dcs;
-  if (a.dfilm_gamma) {
-    for (int bi = 0; bi < nb; ++bi) {
-      float dg = 0.f, dbt = 0.f;
-      for (int t = 0; t < a.film_T; ++t) {
-        const long idx = (long)(bi * a.film_T + t) * a.C + c;
-        const float R1 = a.red[2 * idx], R2 = a.red[2 * idx + 1];
-        dg += fmaf(w, R2, b * R1);
-        dbt += R1;
+  sh[0][grp][cl] = dw; sh[1][grp][cl] = db; sh[2][grp][cl] = dcs;
+  __syncthreads();
+  if (grp == 0 && c < a.C) {
+    for (int t = 1; t < 8; ++t) { dw += sh[0][t][cl]; db += sh[1][t][cl]; dcs += sh[2][t][cl]; }
+    if (a.dweight) a.dweight[c] += dw;
+    if (a.dbias) a.dbias[c] += db;
+    if (a.dcol_scale) a.dcol_scale[c] += dcs;
+    if (a.dfilm_gamma) {
+      const int nb = a.I / a.film_T;
+      for (int bi = 0; bi < nb; ++bi) {
+        float dg = 0.f, dbt = 0.f;
+        for (int t = 0; t < a.film_T; ++t) {
+          const long idx = (long)(bi * a.film_T + t) * a.C + c;
+          const float R1 = a.red[2 * idx], R2 = a.red[2 * idx + 1];
+          dg += fmaf(w, R2, b * R1);
+          dbt += R1;
+        }
+        a.dfilm_gamma[(long)bi * a.C + c] = dg;
+        a.dfilm_beta[(long)bi * a.C + c] = dbt;
       }
-      a.dfilm_gamma[(long)bi * a.C + c] = dg;
-      a.dfilm_beta[(long)bi * a.C + c] = dbt;
     }
   }
 }
@@ -431,7 +491,8 @@ struct ResidBwdParams {
 template <typename T16>
 __global__ void __launch_bounds__(kNormThreads)
 resid_bwd_kernel(ResidBwdParams p) {
-  constexpr int N = 4;
+  constexpr int N = 8;
+  constexpr int UN = 2;
   extern __shared__ float red[];
   const RowGeom& g = p.nc.g;
   const int tx = threadIdx.x % g.tx_n, ty = threadIdx.x / g.tx_n;
@@ -453,23 +514,28 @@ resid_bwd_kernel(ResidBwdParams p) {
     const float* db = p.dx + ((long)img * p.nc.P) * p.nc.ldx + c0;
     const T16* zb = p.z16 ? reinterpret_cast<const T16*>(p.z16) + ((long)img * p.nc.P) * p.ldz + c0 : nullptr;
     T16* ob = p.dz16 ? reinterpret_cast<T16*>(p.dz16) + ((long)img * p.nc.P) * p.ldz + c0 : nullptr;
-    for (int r = r0 + ty; r < r1; r += g.ty_n) {
-      float dv[N];
-      load_vec<float, 4>(db + (long)r * p.nc.ldx, dv, true);
-      if (zb != nullptr) {
-        uint2 u = *reinterpret_cast<const uint2*>(zb + (long)r * p.ldz);
-        float2 a2 = unpack2<T16>(u.x), b2 = unpack2<T16>(u.y);
-        const float zv[4] = {a2.x, a2.y, b2.x, b2.y};
+    for (int r = r0 + ty; r < r1; r += UN * g.ty_n) {
+      float dv[UN][N], zv[UN][N];
 #pragma unroll
-        for (int j = 0; j < N; ++j) q[j] = fmaf(rs * dv[j], zv[j], q[j]);
+      for (int u = 0; u < UN; ++u) {
+        const int rr = r + u * g.ty_n;
+        if (rr < r1) {
+          load8<float>(db + (long)rr * p.nc.ldx, dv[u]);
+          if (zb != nullptr) load8<T16>(zb + (long)rr * p.ldz, zv[u]);
+        }
       }
 #pragma unroll
-      for (int j = 0; j < N; ++j) s[j] = fmaf(rs, dv[j], s[j]);
-      if (ob != nullptr) {
-        uint2 u;
-        u.x = pack2<T16>(cf[0] * dv[0], cf[1] * dv[1]);
-        u.y = pack2<T16>(cf[2] * dv[2], cf[3] * dv[3]);
-        *reinterpret_cast<uint2*>(ob + (long)r * p.ldz) = u;
+      for (int u = 0; u < UN; ++u) {
+        const int rr = r + u * g.ty_n;
+        if (rr >= r1) continue;
+        float o[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          if (zb != nullptr) q[j] = fmaf(rs * dv[u][j], zv[u][j], q[j]);
+          s[j] = fmaf(rs, dv[u][j], s[j]);
+          o[j] = cf[j] * dv[u][j];
+        }
+        if (ob != nullptr) store8<T16>(ob + (long)rr * p.ldz, o);
       }
     }
     float* my = red + ((long)ty * g.tx_n + tx) * 2 * N;
@@ -509,11 +575,23 @@ colsum16_kernel(const T16* __restrict__ x, NormCommon nc, float* __restrict__ ou
     const int r0 = blockIdx.y * rows_per_split;
     const int r1 = min(nc.P, r0 + rows_per_split);
     const T16* base = x + (long)vcol * N;
-    for (int r = r0 + ty; r < r1; r += g.ty_n) {
-      float v[N];
-      load_vec<T16, N>(base + (long)r * nc.ldx, v, true);
+    constexpr int UN = 4;
+    for (int r = r0 + ty; r < r1; r += UN * g.ty_n) {
+      float v[UN][N];
 #pragma unroll
-      for (int j = 0; j < N; ++j) s[j] += v[j];
+      for (int u = 0; u < UN; ++u) {
+        const int rr = r + u * g.ty_n;
+        if (rr < r1) load_vec<T16, N>(base + (long)rr * nc.ldx, v[u], true);
+        else {
+#pragma unroll
+          for (int j = 0; j < N; ++j) v[u][j] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) s[j] += v[u][j];
+      }
     }
     float* my = red + ((long)ty * g.tx_n + tx) * N;
 #pragma unroll
@@ -596,16 +674,16 @@ extern "C" int bf_inorm_apply(const bf_inorm_apply_args* a, void* stream) {
 
 extern "C" int bf_inorm_bwd(const bf_inorm_bwd_args* a, void* stream) {
   BF_REQUIRE(a && a->gin && a->x && a->stats && a->weight && a->bias && a->red, "bf_inorm_bwd: null pointer");
-  if (int st = check_common("bf_inorm_bwd", a->I, a->P, a->C, a->ldx, 4, a->x)) return st;
-  BF_REQUIRE(a->ldg >= a->C && a->ldg % 4 == 0, "bf_inorm_bwd: ldg");
+  if (int st = check_common("bf_inorm_bwd", a->I, a->P, a->C, a->ldx, 8, a->x)) return st;
+  BF_REQUIRE(a->ldg >= a->C && a->ldg % 8 == 0, "bf_inorm_bwd: ldg");
   BF_REQUIRE(a->phase == 1 || a->phase == 2, "bf_inorm_bwd: phase %d", a->phase);
   BwdParams p{};
-  p.nc = NormCommon{a->I, a->P, a->C, a->ldx, make_geom(a->C, 4, a->P, a->I)};
+  p.nc = NormCommon{a->I, a->P, a->C, a->ldx, make_geom(a->C, 8, a->P, a->I)};
   p.stats = a->stats; p.weight = a->weight; p.bias = a->bias; p.gelu = a->gelu; p.ldg = a->ldg; p.red = a->red;
   p.row_scale = a->row_scale; p.col_scale = a->col_scale; p.film_gamma = a->film_gamma;
   p.film_T = a->film_T > 0 ? a->film_T : 1; p.add32 = a->add32; p.ldo = a->ldo;
   dim3 grid(p.nc.g.chunks, p.nc.g.splits, a->I);
-  const size_t sm = (size_t)p.nc.g.ty_n * p.nc.g.tx_n * 8 * sizeof(float);
+  const size_t sm = (size_t)p.nc.g.ty_n * p.nc.g.tx_n * 16 * sizeof(float);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int gd = a->g_dtype, xd = a->x_dtype, od = a->out_dtype;
   if (a->phase == 1) {
@@ -624,7 +702,7 @@ extern "C" int bf_inorm_bwd(const bf_inorm_bwd_args* a, void* stream) {
     return BF_OK;
   }
   BF_REQUIRE(a->out, "bf_inorm_bwd: out required in phase 2");
-  BF_REQUIRE(a->ldo >= a->C && a->ldo % 4 == 0, "bf_inorm_bwd: ldo");
+  BF_REQUIRE(a->ldo >= a->C && a->ldo % 8 == 0, "bf_inorm_bwd: ldo");
   BF_REQUIRE(a->add32 == nullptr || od == BF_F32, "bf_inorm_bwd: add32 needs f32 out");
 #define BF_APP(TG, TX, TO) inorm_bwd_apply_kernel<TG, TX, TO><<<grid, kNormThreads, 0, s>>>((const TG*)a->gin, (const TX*)a->x, (TO*)a->out, p)
   if (gd == BF_F32 && xd == BF_F32 && od == BF_F32) BF_APP(float, float, float);
@@ -650,7 +728,7 @@ extern "C" int bf_inorm_bwd_params(const bf_inorm_bwd_params_args* a, void* stre
   BwdParamArgs k{a->red, nullptr, a->I, a->P, a->C, a->row_scale, a->col_scale, a->film_gamma,
                  a->film_T > 0 ? a->film_T : 1, a->weight, a->bias, a->dweight, a->dbias, a->dcol_scale,
                  a->dfilm_gamma, a->dfilm_beta};
-  inorm_bwd_params_kernel<<<(a->C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(k);
+  inorm_bwd_params_kernel<<<(a->C + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(k);
   count_launch();
   BF_LAUNCH_CHECK("inorm_bwd_params_kernel");
   return BF_OK;
@@ -662,13 +740,13 @@ extern "C" int bf_resid_bwd(const float* dx, int64_t lddx, const void* z16, void
   BF_REQUIRE(dx && coef && S0, "bf_resid_bwd: null pointer");
   BF_REQUIRE(z16 == nullptr || S1 != nullptr, "bf_resid_bwd: S1 required with z16");
   BF_REQUIRE(dtype == BF_BF16 || dtype == BF_F16, "bf_resid_bwd: dtype");
-  if (int st = check_common("bf_resid_bwd", I, P, C, lddx, 4, dx)) return st;
-  BF_REQUIRE((z16 == nullptr && dz16 == nullptr) || (ldz >= C && ldz % 4 == 0), "bf_resid_bwd: ldz");
+  if (int st = check_common("bf_resid_bwd", I, P, C, lddx, 8, dx)) return st;
+  BF_REQUIRE((z16 == nullptr && dz16 == nullptr) || (ldz >= C && ldz % 8 == 0), "bf_resid_bwd: ldz");
   ResidBwdParams p{};
-  p.nc = NormCommon{I, P, C, lddx, make_geom(C, 4, P, I)};
+  p.nc = NormCommon{I, P, C, lddx, make_geom(C, 8, P, I)};
   p.dx = dx; p.z16 = z16; p.ldz = ldz; p.row_scale = row_scale; p.coef = coef; p.dz16 = dz16; p.S0 = S0; p.S1 = S1;
   dim3 grid(p.nc.g.chunks, p.nc.g.splits, I);
-  const size_t sm = (size_t)p.nc.g.ty_n * p.nc.g.tx_n * 8 * sizeof(float);
+  const size_t sm = (size_t)p.nc.g.ty_n * p.nc.g.tx_n * 16 * sizeof(float);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == BF_BF16) resid_bwd_kernel<__nv_bfloat16><<<grid, kNormThreads, sm, s>>>(p);
   else resid_bwd_kernel<__half><<<grid, kNormThreads, sm, s>>>(p);

@@ -19,16 +19,15 @@ constexpr int kMaxF = 8;     // fields
 
 // ---------------------------------------------------------------------------------------------
 // (I, F, H, W) fp32  ->  (I, H/2, W/2, N) 16-bit,  out[pix][n] = sum_k patch[pix][k] * Wkn[k][n], k = (f, ky, kx)
+// Each thread owns 8 output channels and keeps their 4F x 8 weights in registers (F <= 4), so the inner loop
+// is pure FMA: 16 coalesced input floats in, one 16-byte store out.
 // ---------------------------------------------------------------------------------------------
-template <typename T16>
+template <typename T16, int FMAX>
 __global__ void __launch_bounds__(256)
 patch_in_kernel(const float* __restrict__ x, const float* __restrict__ Wkn, T16* __restrict__ out, float* stats,
                 int I, int F, int H, int W, int N, int pix_per_block) {
   extern __shared__ float sm[];
-  const int K = 4 * F;
-  float* sW = sm;                    // [K][N]
-  float* sStat = sW + K * N;         // [N][2]
-  for (int i = threadIdx.x; i < K * N; i += blockDim.x) sW[i] = Wkn[i];
+  float* sStat = sm;                 // [N][2]
   for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) sStat[i] = 0.f;
   __syncthreads();
   const int groups = N / 8;
@@ -39,6 +38,12 @@ patch_in_kernel(const float* __restrict__ x, const float* __restrict__ Wkn, T16*
   const int img = blockIdx.y;
   const long p0 = (long)blockIdx.x * pix_per_block;
   const long p1 = min(pix_img, p0 + pix_per_block);
+  float wreg[4 * FMAX][8];
+#pragma unroll
+  for (int k = 0; k < 4 * FMAX; ++k) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wreg[k][j] = (k < 4 * F) ? __ldg(Wkn + (long)k * N + cg * 8 + j) : 0.f;
+  }
   float ssum[8], ssq[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { ssum[j] = 0.f; ssq[j] = 0.f; }
@@ -48,19 +53,18 @@ patch_in_kernel(const float* __restrict__ x, const float* __restrict__ Wkn, T16*
       float acc[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-      for (int f = 0; f < F; ++f) {
-        const float* xp = x + (((long)img * F + f) * H + 2 * yo) * W + 2 * xo;
-        const float2 r0 = *reinterpret_cast<const float2*>(xp);
-        const float2 r1 = *reinterpret_cast<const float2*>(xp + W);
-        const float v[4] = {r0.x, r0.y, r1.x, r1.y};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float* wr = sW + (f * 4 + q) * N + cg * 8;
-          const float4 w0 = *reinterpret_cast<const float4*>(wr), w1 = *reinterpret_cast<const float4*>(wr + 4);
-          acc[0] = fmaf(v[q], w0.x, acc[0]); acc[1] = fmaf(v[q], w0.y, acc[1]);
-          acc[2] = fmaf(v[q], w0.z, acc[2]); acc[3] = fmaf(v[q], w0.w, acc[3]);
-          acc[4] = fmaf(v[q], w1.x, acc[4]); acc[5] = fmaf(v[q], w1.y, acc[5]);
-          acc[6] = fmaf(v[q], w1.z, acc[6]); acc[7] = fmaf(v[q], w1.w, acc[7]);
+      for (int f = 0; f < FMAX; ++f) {
+        if (f < F) {
+          const float* xp = x + (((long)img * F + f) * H + 2 * yo) * W + 2 * xo;
+          const float2 r0 = *reinterpret_cast<const float2*>(xp);
+          const float2 r1 = *reinterpret_cast<const float2*>(xp + W);
+          const float v[4] = {r0.x, r0.y, r1.x, r1.y};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[q], wreg[f * 4 + q][j], acc[j]);
+          }
         }
       }
       uint4 u;
@@ -91,41 +95,63 @@ patch_in_kernel(const float* __restrict__ x, const float* __restrict__ Wkn, T16*
 
 // ---------------------------------------------------------------------------------------------
 // (I, h, w, C) 16-bit  ->  (I, F, 2h, 2w) fp32,  out[img][f][2y+ky][2x+kx] = sum_c a[pix][c] * Wck[c][(f,ky,kx)]
+// One thread per input pixel computes all 4F outputs; the activation row is read from a conflict-free
+// (odd word stride) shared tile, the weights are warp-broadcast from shared memory.
 // ---------------------------------------------------------------------------------------------
-template <typename T16>
+template <typename T16, int FMAX>
 __global__ void __launch_bounds__(256)
 patch_out_kernel(const T16* __restrict__ a, const float* __restrict__ Wck, float* __restrict__ out,
                  int I, int F, int h, int w, int C, int tile_px) {
   extern __shared__ float sm[];
   const int K = 4 * F;
-  float* sW = sm;                                       // [C][K]
-  T16* sA = reinterpret_cast<T16*>(sW + C * K);          // [tile_px][C + 8]
-  const int CS = C + 8;
-  for (int i = threadIdx.x; i < C * K; i += blockDim.x) sW[i] = Wck[i];
-  const int tiles_x = (w + tile_px - 1) / tile_px;
-  const int xt = blockIdx.x % tiles_x, y = blockIdx.x / tiles_x, img = blockIdx.y;
-  const int x0 = xt * tile_px;
-  const int npx = min(tile_px, w - x0);
-  const T16* src = a + (((long)img * h + y) * w + x0) * C;
-  const int cpr = C / 8;
-  for (int i = threadIdx.x; i < npx * cpr; i += blockDim.x) {
-    const int px = i / cpr, ch = i - px * cpr;
-    *reinterpret_cast<uint4*>(sA + px * CS + ch * 8) = *reinterpret_cast<const uint4*>(src + (long)px * C + ch * 8);
+  float* sW = sm;                                               // [C][4*FMAX] (zero padded)
+  uint32_t* sA = reinterpret_cast<uint32_t*>(sW + C * 4 * FMAX);  // [tile_px][C/2 + 1] channel pairs
+  const int CW = C / 2 + 1;
+  for (int i = threadIdx.x; i < C * 4 * FMAX; i += blockDim.x) {
+    const int c = i / (4 * FMAX), k = i - c * (4 * FMAX);
+    sW[i] = k < K ? Wck[(long)c * K + k] : 0.f;
+  }
+  const long pix_img = (long)h * w;
+  const int img = blockIdx.y;
+  const long p0 = (long)blockIdx.x * tile_px;
+  const int npx = (int)min((long)tile_px, pix_img - p0);
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(a + ((long)img * pix_img + p0) * C);
+  const int wpp = C / 2;                                        // 32-bit words per pixel
+  for (int i = threadIdx.x; i < npx * wpp; i += blockDim.x) {
+    const int px = i / wpp, cw = i - px * wpp;
+    sA[px * CW + cw] = src[i];
   }
   __syncthreads();
-  const int f = threadIdx.x % F, px = threadIdx.x / F;
+  const int px = threadIdx.x;
   if (px < npx) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const T16* ar = sA + px * CS;
-    for (int c = 0; c < C; ++c) {
-      const float av = to_f32<T16>(ar[c]);
-      const float4 wv = *reinterpret_cast<const float4*>(sW + c * K + f * 4);
-      acc[0] = fmaf(av, wv.x, acc[0]); acc[1] = fmaf(av, wv.y, acc[1]);
-      acc[2] = fmaf(av, wv.z, acc[2]); acc[3] = fmaf(av, wv.w, acc[3]);
+    float acc[4 * FMAX];
+#pragma unroll
+    for (int k = 0; k < 4 * FMAX; ++k) acc[k] = 0.f;
+    const uint32_t* ar = sA + px * CW;
+    for (int cw = 0; cw < wpp; ++cw) {
+      const float2 av = unpack2<T16>(ar[cw]);
+      const float* w0 = sW + (2 * cw) * 4 * FMAX;
+      const float* w1 = w0 + 4 * FMAX;
+#pragma unroll
+      for (int k4 = 0; k4 < FMAX; ++k4) {
+        const float4 u0 = *reinterpret_cast<const float4*>(w0 + 4 * k4);
+        const float4 u1 = *reinterpret_cast<const float4*>(w1 + 4 * k4);
+        acc[4 * k4 + 0] = fmaf(av.x, u0.x, fmaf(av.y, u1.x, acc[4 * k4 + 0]));
+        acc[4 * k4 + 1] = fmaf(av.x, u0.y, fmaf(av.y, u1.y, acc[4 * k4 + 1]));
+        acc[4 * k4 + 2] = fmaf(av.x, u0.z, fmaf(av.y, u1.z, acc[4 * k4 + 2]));
+        acc[4 * k4 + 3] = fmaf(av.x, u0.w, fmaf(av.y, u1.w, acc[4 * k4 + 3]));
+      }
     }
-    float* op = out + (((long)img * F + f) * (2 * h) + 2 * y) * (2 * w) + 2 * (x0 + px);
-    *reinterpret_cast<float2*>(op) = make_float2(acc[0], acc[1]);
-    *reinterpret_cast<float2*>(op + 2 * w) = make_float2(acc[2], acc[3]);
+    const long pix = p0 + px;
+    const int y = (int)(pix / w), xx = (int)(pix - (long)y * w);
+#pragma unroll
+    for (int f = 0; f < FMAX; ++f) {
+      if (f < F) {
+        float* op = out + (((long)img * F + f) * (2 * h) + 2 * y) * (2 * w) + 2 * xx;
+        *reinterpret_cast<float2*>(op) = make_float2(acc[4 * f + 0], acc[4 * f + 1]);
+        *reinterpret_cast<float2*>(op + 2 * w) = make_float2(acc[4 * f + 2], acc[4 * f + 3]);
+      }
+    }
   }
 }
 
@@ -247,17 +273,38 @@ extern "C" int bf_patch_in(const float* x, const float* Wkn, void* out, int dtyp
   BF_REQUIRE(N % 8 == 0 && N >= 8 && N <= 2048, "bf_patch_in: N=%d must be a multiple of 8 in [8, 2048]", N);
   BF_REQUIRE((reinterpret_cast<uintptr_t>(x) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "bf_patch_in: alignment");
   const long pix_img = (long)(H / 2) * (W / 2);
-  const int ppi = 256 / (N / 8) > 0 ? 256 / (N / 8) : 1;
-  BF_REQUIRE(N / 8 <= 256, "bf_patch_in: N too large");
-  long ppb = (long)ppi * 32;
-  if (ppb > pix_img) ppb = ((pix_img + ppi - 1) / ppi) * ppi;
+  const int ppi = 256 / (N / 8);
+  long ppb = (long)ppi * 64;                         // 64 pixels per thread amortise the register-resident weights
+  while (ppb > ppi && ((pix_img + ppb - 1) / ppb) * I < 2L * num_sms()) ppb /= 2;
+  if (ppb < ppi) ppb = ppi;
   dim3 grid((unsigned)((pix_img + ppb - 1) / ppb), I);
-  const size_t sm = ((size_t)4 * F * N + 2 * N) * sizeof(float);
+  const size_t sm = (size_t)2 * N * sizeof(float);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (dtype == BF_BF16) patch_in_kernel<__nv_bfloat16><<<grid, 256, sm, s>>>(x, Wkn, (__nv_bfloat16*)out, stats, I, F, H, W, N, (int)ppb);
-  else patch_in_kernel<__half><<<grid, 256, sm, s>>>(x, Wkn, (__half*)out, stats, I, F, H, W, N, (int)ppb);
+#define BF_PIN(T, FM) patch_in_kernel<T, FM><<<grid, 256, sm, s>>>(x, Wkn, (T*)out, stats, I, F, H, W, N, (int)ppb)
+  if (dtype == BF_BF16) { if (F <= 4) BF_PIN(__nv_bfloat16, 4); else BF_PIN(__nv_bfloat16, 8); }
+  else                  { if (F <= 4) BF_PIN(__half, 4); else BF_PIN(__half, 8); }
+#undef BF_PIN
   count_launch();
   BF_LAUNCH_CHECK("patch_in_kernel");
+  return BF_OK;
+}
+
+template <typename T16, int FM>
+static int launch_patch_out(const void* a, const float* Wck, float* out, int I, int F, int h, int w, int C, cudaStream_t s) {
+  const long pix_img = (long)h * w;
+  int tile_px = pix_img < 256 ? (int)pix_img : 256;
+  const size_t sm = (size_t)C * 4 * FM * sizeof(float) + (size_t)tile_px * (C / 2 + 1) * 4;
+  BF_REQUIRE(sm <= 220 * 1024, "bf_patch_out: C=%d too large for the shared-memory tile", C);
+  static bool done = false;
+  if (!done) {
+    if (int e = check_cuda(cudaFuncSetAttribute(patch_out_kernel<T16, FM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                220 * 1024), "cudaFuncSetAttribute(patch_out)")) return e;
+    done = true;
+  }
+  dim3 grid((unsigned)((pix_img + tile_px - 1) / tile_px), I);
+  patch_out_kernel<T16, FM><<<grid, 256, sm, s>>>((const T16*)a, Wck, out, I, F, h, w, C, tile_px);
+  count_launch();
+  BF_LAUNCH_CHECK("patch_out_kernel");
   return BF_OK;
 }
 
@@ -267,25 +314,11 @@ extern "C" int bf_patch_out(const void* a, int dtype, const float* Wck, float* o
   BF_REQUIRE(dtype == BF_BF16 || dtype == BF_F16, "bf_patch_out: dtype");
   BF_REQUIRE(I > 0 && F > 0 && F <= kMaxF && h > 0 && w > 0 && C % 8 == 0 && C > 0, "bf_patch_out: geometry");
   BF_REQUIRE((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0, "bf_patch_out: alignment");
-  int tile_px = 256 / F;
-  if (tile_px > w) tile_px = w;
-  const size_t sm = (size_t)C * 4 * F * sizeof(float) + (size_t)tile_px * (C + 8) * 2;
-  BF_REQUIRE(sm <= 200 * 1024, "bf_patch_out: C=%d too large for the shared-memory tile", C);
-  const int tiles_x = (w + tile_px - 1) / tile_px;
-  dim3 grid((unsigned)(tiles_x * h), I);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (dtype == BF_BF16) {
-    static bool done = false;
-    if (!done) { cudaFuncSetAttribute(patch_out_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); done = true; }
-    patch_out_kernel<__nv_bfloat16><<<grid, 256, sm, s>>>((const __nv_bfloat16*)a, Wck, out, I, F, h, w, C, tile_px);
-  } else {
-    static bool done = false;
-    if (!done) { cudaFuncSetAttribute(patch_out_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); done = true; }
-    patch_out_kernel<__half><<<grid, 256, sm, s>>>((const __half*)a, Wck, out, I, F, h, w, C, tile_px);
-  }
-  count_launch();
-  BF_LAUNCH_CHECK("patch_out_kernel");
-  return BF_OK;
+  if (dtype == BF_BF16) return F <= 4 ? launch_patch_out<__nv_bfloat16, 4>(a, Wck, out, I, F, h, w, C, s)
+                                      : launch_patch_out<__nv_bfloat16, 8>(a, Wck, out, I, F, h, w, C, s);
+  return F <= 4 ? launch_patch_out<__half, 4>(a, Wck, out, I, F, h, w, C, s)
+                : launch_patch_out<__half, 8>(a, Wck, out, I, F, h, w, C, s);
 }
 
 extern "C" int bf_patch_wgrad(const void* a, int dtype, const float* x, float* dW, int I, int F, int H, int W, int N,

@@ -271,3 +271,49 @@ def convert16(src, dst) -> None:
 def cast16(src, dst) -> None:
     assert src.dtype == torch.float32 and src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel()
     L.check(L.lib.bf_cast16(_ptr(src), _ptr(dst), _DT[dst.dtype], src.numel(), _stream()), "bf_cast16")
+
+
+# ---------------------------------------------------------------------------------------------
+# optional per-launch timing (bench.py roofline, scripts/profile_step.py); zero overhead when off
+# ---------------------------------------------------------------------------------------------
+GEMM_TIMING = None      # list of (start_event, end_event, flops) when enabled
+PROFILE = None          # list of (name, tag, start_event, end_event) when enabled
+
+
+def _instrument(name, fn, tagger):
+    def wrapped(*a, **k):
+        if PROFILE is None and not (GEMM_TIMING is not None and name == "gemm"):
+            return fn(*a, **k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn(*a, **k)
+        e1.record()
+        if PROFILE is not None:
+            PROFILE.append((name, tagger(a, k), e0, e1))
+        if GEMM_TIMING is not None and name == "gemm":
+            GEMM_TIMING.append((e0, e1, 2.0 * a[2] * a[3] * a[4]))
+        return r
+    wrapped.__name__, wrapped.__doc__ = fn.__name__, fn.__doc__
+    return wrapped
+
+
+def _gemm_tag(a, k):
+    return f"M{a[2]} N{a[3]} K{a[4]} epi{k.get('epilogue')} a{k.get('a_mode', 0)} b{k.get('b_mode', 0)} s{k.get('split_k', 1)}"
+
+
+def _shape_tag(a, k):
+    for t in a:
+        if isinstance(t, torch.Tensor):
+            return "x".join(str(s) for s in t.shape) + f" {str(t.dtype)[6:]}"
+    return ""
+
+
+def _attn_tag(a, k):
+    return f"L{k.get('L_')} nseq{k.get('n_seq')} {'bwd' if k.get('dout') is not None else 'fwd'}"
+
+
+gemm = _instrument("gemm", gemm, _gemm_tag)
+attention = _instrument("attention", attention, _attn_tag)
+for _n in ("inorm_stats", "inorm_apply", "inorm_bwd", "inorm_bwd_params", "resid_bwd", "colsum16", "patch_in",
+           "patch_out", "patch_wgrad", "s2d_gather", "cast16", "convert16"):
+    globals()[_n] = _instrument(_n, globals()[_n], _shape_tag)

@@ -1,0 +1,109 @@
+"""Data-parallel plumbing: flat gradient sink + bucketed NCCL all-reduce overlapped with backward.
+
+Mirrors what upstream gets from Lightning's `strategy="ddp"` (scripts/train.py:158-163): one process per GPU,
+gradients averaged over ranks each step.  Here every autograd Function of the model (embed, each temporal /
+spatial block, debed) accumulates its parameter gradients straight into one persistent flat fp32 buffer laid
+out like the weight bank, and as soon as a Function's backward has finished its contiguous segment is
+all-reduced on a side stream while the remaining backward kernels keep running.  `finish()` joins the
+streams.  With world size 1 the sink still removes the per-backward gradient allocations and zero fills.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class GradSink:
+    def __init__(self, model: torch.nn.Module, process_group=None, bucket_bytes: int = 8 << 20):
+        self.model = model
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        params = list(model.parameters())
+        self.offsets: Dict[int, int] = {}
+        tot = 0
+        for p in params:
+            self.offsets[id(p)] = tot
+            tot += (p.numel() + 7) // 8 * 8
+        dev = params[0].device
+        self.flat = torch.zeros(tot, dtype=torch.float32, device=dev)
+        for p in params:
+            o = self.offsets[id(p)]
+            p.grad = self.flat[o:o + p.numel()].view(p.shape)
+        self.params = params
+        self.bucket_elems = bucket_bytes // 4
+        self.comm_stream = torch.cuda.Stream(device=dev) if (self.world > 1 and dev.type == "cuda") else None
+        self._pending: List = []
+        self._lo: Optional[int] = None
+        self._hi: Optional[int] = None
+        model._grad_sink = self
+        from . import autograd
+        autograd.ACTIVE_SINK = self
+
+    def owns(self, p: torch.Tensor) -> bool:
+        g = p.grad
+        if g is None:
+            return False
+        o = g.data_ptr() - self.flat.data_ptr()
+        return 0 <= o < 4 * self.flat.numel()
+
+    def close(self) -> None:
+        from . import autograd
+        if autograd.ACTIVE_SINK is self:
+            autograd.ACTIVE_SINK = None
+
+    # -- per step -------------------------------------------------------------------------------
+    def begin_step(self) -> None:
+        """Zero the flat gradient buffer (one memset) before backward."""
+        self.flat.zero_()
+        self._pending.clear()
+        self._lo = self._hi = None
+
+    def views(self, named: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Gradient views for the parameters of one autograd Function."""
+        out = {}
+        for n, p in named.items():
+            o = self._offset_of(p)
+            out[n] = self.flat[o:o + p.numel()].view(p.shape)
+        return out
+
+    def _offset_of(self, p: torch.Tensor) -> int:
+        g = p.grad
+        if g is None:
+            raise RuntimeError("GradSink: parameter lost its gradient view (use sink.begin_step(), not zero_grad())")
+        return (g.data_ptr() - self.flat.data_ptr()) // 4
+
+    def segment_done(self, named: Dict[str, torch.Tensor]) -> None:
+        """Called when one Function's backward kernels have been enqueued: maybe launch a bucket all-reduce."""
+        if self.world == 1:
+            return
+        lo = min(self._offset_of(p) for p in named.values())
+        hi = max(self._offset_of(p) + p.numel() for p in named.values())
+        self._lo = lo if self._lo is None else min(self._lo, lo)
+        self._hi = hi if self._hi is None else max(self._hi, hi)
+        # the Function owning offset 0 (the embed) runs last, and the FiLM MLP's gradients (plain torch autograd,
+        # laid out right after it) only arrive once it has returned: leave that bucket to finish()
+        if lo > 0 and self._hi - self._lo >= self.bucket_elems:
+            self._flush()
+
+    def _flush(self) -> None:
+        if self._lo is None:
+            return
+        seg = self.flat[self._lo:self._hi]
+        if self.comm_stream is not None:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(seg, op=dist.ReduceOp.AVG, group=self.group)
+        else:                                   # gloo (CPU tests): no AVG
+            dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.group)
+            seg.div_(self.world)
+        self._lo = self._hi = None
+
+    def finish(self) -> None:
+        """Flush the last bucket and make the compute stream wait for all reductions."""
+        if self.world == 1:
+            return
+        self._flush()
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)

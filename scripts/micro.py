@@ -1,0 +1,106 @@
+"""Micro-benchmark of individual kernels at config-2 shapes (for CUDA-event timing and ncu captures).
+
+    python scripts/micro.py [gemm_qkv gemm_fc1 gemm_resid attn_fwd attn_bwd attn_t inorm_bwd inorm_apply ...] [--iters 5]
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    from bubbleformer_b200 import _lib as L, engine, ops
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("names", nargs="*")
+    ap.add_argument("--iters", type=int, default=5)
+    args = ap.parse_args()
+    names, iters = args.names, args.iters
+    dev = "cuda"
+    N, E, I, P, he = 40960, 384, 40, 1024, 6
+    g = engine.Geom(8, 5, 32, 32)
+    bf = torch.bfloat16
+    X32 = torch.randn(N, E, device=dev)
+    Xb = torch.randn(N, E, device=dev).to(bf)
+    QKV = torch.randn(N, 3 * E, device=dev).to(bf)
+    H = torch.randn(N, 4 * E, device=dev).to(bf)
+    Win = (torch.randn(3 * E, E, device=dev) * E ** -0.5).to(bf)
+    W1 = (torch.randn(4 * E, E, device=dev) * E ** -0.5).to(bf)
+    W2 = (torch.randn(E, 4 * E, device=dev) * (4 * E) ** -0.5).to(bf)
+    Wo = (torch.randn(E, E, device=dev) * E ** -0.5).to(bf)
+    vE = torch.randn(E, device=dev)
+    v3E = torch.randn(3 * E, device=dev)
+    v4E = torch.randn(4 * E, device=dev)
+    rs = torch.ones(I, device=dev)
+    st = torch.zeros(I, E, 2, device=dev)
+    ops.inorm_stats(X32, I, P, st)
+    ln = [torch.ones(64, device=dev), torch.zeros(64, device=dev), torch.ones(64, device=dev), torch.zeros(64, device=dev)]
+    emb = torch.randn(32, he, device=dev)
+    sf = torch.ones(he, device=dev)
+    O = torch.empty(N, E, device=dev, dtype=bf)
+    O2 = torch.empty(N, E, device=dev, dtype=bf)
+    out3 = torch.empty(N, 3 * E, device=dev, dtype=bf)
+    out4 = torch.empty(N, 4 * E, device=dev, dtype=bf)
+    out4b = torch.empty(N, 4 * E, device=dev, dtype=bf)
+    o32 = torch.empty(N, E, device=dev)
+    red = torch.zeros(I, E, 2, device=dev)
+    gr = dict(d_qn_w=torch.zeros(64, device=dev), d_qn_b=torch.zeros(64, device=dev), d_kn_w=torch.zeros(64, device=dev),
+              d_kn_b=torch.zeros(64, device=dev), d_bias_emb=torch.zeros(32, he, device=dev),
+              d_scale_factor=torch.zeros(he, device=dev))
+
+    def attn(axis, bwd):
+        geo = engine._axis(g, axis)
+        kw = dict(heads=he, qn_w=ln[0], qn_b=ln[1], kn_w=ln[2], kn_b=ln[3], bias_emb=emb,
+                  bucket=engine.relpos_bucket_vector(geo["L_"], dev), scale_factor=sf, out_scale=0.5, **geo)
+        if bwd:
+            ops.attention(QKV, out3, dout=Xb, grads=gr, **kw)
+        else:
+            ops.attention(QKV, O, **kw)
+
+    table = {
+        "gemm_qkv": (lambda: ops.gemm(Xb, Win, N, 3 * E, E, epilogue=L.EPI_STORE16, bias=v3E, out16=out3), 2.0 * N * 3 * E * E, (N * E + N * 3 * E) * 2),
+        "gemm_fc1": (lambda: ops.gemm(Xb, W1, N, 4 * E, E, epilogue=L.EPI_GELU, bias=v4E, out16=out4, out16b=out4b), 2.0 * N * 4 * E * E, (N * E + 2 * N * 4 * E) * 2),
+        "gemm_fc2": (lambda: ops.gemm(H, W2, N, E, 4 * E, epilogue=L.EPI_STORE16, bias=vE, out16=O), 2.0 * N * 4 * E * E, (N * 4 * E + N * E) * 2),
+        "gemm_resid": (lambda: ops.gemm(Xb, Wo, N, E, E, epilogue=L.EPI_RESID, bias=vE, col_gamma=vE, row_scale=rs, rows_per_group=P,
+                                        in32=X32, out32=o32, out16=O, out16b=O2), 2.0 * N * E * E, N * E * (2 + 4 + 4 + 2 + 2)),
+        "gemm_dgelu": (lambda: ops.gemm(Xb, W2, N, 4 * E, E, epilogue=L.EPI_DGELU, b_mode=L.B_KN, aux16=H, out16=out4), 2.0 * N * 4 * E * E, (N * E + 2 * N * 4 * E) * 2),
+        "gemm_wgrad": (lambda: ops.gemm(H, Xb, 4 * E, E, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN, split_k=8,
+                                        out32=torch.zeros(4 * E, E, device=dev)), 2.0 * N * 4 * E * E, (N * 4 * E + N * E) * 2),
+        "attn_fwd": (lambda: attn("x", False), 0, N * 4 * E * 2),
+        "attn_fwd_y": (lambda: attn("y", False), 0, N * 4 * E * 2),
+        "attn_bwd": (lambda: attn("x", True), 0, N * 7 * E * 2),
+        "attn_t": (lambda: attn("t", False), 0, N * 4 * E * 2),
+        "attn_t_bwd": (lambda: attn("t", True), 0, N * 7 * E * 2),
+        "inorm_stats": (lambda: ops.inorm_stats(X32, I, P, st), 0, N * E * 4),
+        "inorm_apply": (lambda: ops.inorm_apply(X32, O, I, P, st, vE, vE), 0, N * E * 6),
+        "inorm_apply_resid": (lambda: ops.inorm_apply(Xb, o32, I, P, st, vE, vE, resid_in=X32, row_scale=rs, col_gamma=vE), 0, N * E * 10),
+        "inorm_bwd1": (lambda: ops.inorm_bwd(1, Xb, O, I, P, st, vE, vE, red), 0, N * E * 4),
+        "inorm_bwd2": (lambda: ops.inorm_bwd(2, Xb, O, I, P, st, vE, vE, red, out=O2), 0, N * E * 6),
+        "inorm_bwd2_add": (lambda: ops.inorm_bwd(2, Xb, X32, I, P, st, vE, vE, red, out=o32, add32=X32), 0, N * E * 14),
+        "resid_bwd": (lambda: ops.resid_bwd(X32, Xb, O, I, P, rs, vE, torch.zeros(E, device=dev), torch.zeros(E, device=dev)), 0, N * E * 8),
+        "colsum": (lambda: ops.colsum16(QKV, torch.zeros(3 * E, device=dev)), 0, N * 3 * E * 2),
+    }
+    if not names:
+        names = list(table)
+    for n in names:
+        fn, flops, nbytes = table[n]
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / iters * 1e3
+        msg = f"[micro] {n:18s} {us:8.1f} us   {nbytes / us / 1e3:7.1f} GB/s (algorithmic bytes)"
+        if flops:
+            msg += f"   {flops / us / 1e6:7.1f} TFLOP/s"
+        print(msg, flush=True)
+
+
+if __name__ == "__main__":
+    main()
