@@ -34,6 +34,7 @@ class GemmArgs(C.Structure):
         ("row_scale", C.c_void_p), ("in32", C.c_void_p), ("aux16", C.c_void_p),
         ("out16", C.c_void_p), ("out16b", C.c_void_p), ("out32", C.c_void_p),
         ("ldo", C.c_int64), ("ld32", C.c_int64),
+        ("stats_out", C.c_void_p),
     ]
 
 

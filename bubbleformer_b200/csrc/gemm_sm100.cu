@@ -2,15 +2,21 @@
 // FiLMAViT hot path (see include/bubbleformer_b200.h, bf_gemm).
 //
 // Structure (one CTA per SM, persistent over output tiles, 128 x BN tile, BK = 64):
-//   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
-//   warp 1      : MMA issuer     (tcgen05.mma cta_group::1 kind::f16, fp32 accumulators in TMEM,
-//                                 tcgen05.commit releases smem slots / publishes accumulators)
-//   warps 2..9  : epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
-// TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   warp 0      : TMA producer of the A / B operand ring (cp.async.bulk.tensor, 128B swizzle, mbarrier tx)
+//   warp 1      : MMA issuer (tcgen05.mma cta_group::1 kind::f16, fp32 accumulators in TMEM;
+//                 tcgen05.commit releases smem slots / publishes accumulators)
+//   warp 2      : TMA producer of the epilogue *input* tile (fp32 residual stream / saved pre-activation),
+//                 prefetched while the tile's MMAs run
+//   warp 3      : idle (keeps the epilogue warps aligned to the TMEM lane quadrants)
+//   warps 4..11 : epilogue: tcgen05.ld -> registers -> fused math -> swizzled smem -> TMA store
+//                 (cp.async.bulk.tensor shared -> global, or cp.reduce.async.bulk.tensor .add for split-K)
+// TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.  No epilogue
+// warp ever touches global memory with ld/st: inputs arrive by TMA into smem, outputs leave by TMA from
+// per-warp 32 x 32 slabs, so every DRAM transaction is a full, coalesced line and nothing waits on it.
 //
 // Operand layouts: K-major (row-major (rows, K)) or MN-major (row-major (K, rows)) for both A and B,
-// so forward, dgrad (B = W read K x N) and wgrad (A = dY^T, B = X, contraction over tokens, split-K
-// with fp32 atomics) all run through this kernel without any transposed copy in HBM.
+// so forward, dgrad (B = W read K x N) and wgrad (A = dY^T, B = X, contraction over tokens, split-K)
+// all run through this kernel without any transposed copy in HBM.
 // A can also be an implicit 2x2/stride-2 patch gather expressed purely as a 4-D TMA tensor map.
 #include <cstdarg>
 #include <cstdio>
@@ -23,7 +29,11 @@ namespace bf {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kFirstEpiWarp = 4;
+constexpr int kThreads = 32 * (kFirstEpiWarp + kEpiWarps);
+constexpr int kMaxStages = 8;
+constexpr int kSlabBytes = 8192;          // per epilogue warp: output staging (see epilogue)
+constexpr int kSmemBudget = 227 * 1024;
 
 struct GemmParams {
   int M, N, K;
@@ -38,244 +48,80 @@ struct GemmParams {
   int epilogue;
   int rows_per_group;
   int d2s_h, d2s_w, d2s_cout;
+  // shared-memory plan (bytes from the 1 KiB aligned base)
+  int stages;
+  int in_kind;        // 0: no epilogue input tile, 1: 16-bit (aux16), 2: fp32 (in32)
+  int in_bufs;        // 1 or 2
+  int in_bytes;       // bytes of one input tile buffer
+  int in_off, slab_off, bar_off;
   const float* bias;
   const float* col_scale;
   const float* col_shift;
   const float* col_gamma;
   const float* row_scale;
-  const float* in32;
-  const void* aux16;
-  void* out16;
-  void* out16b;
-  float* out32;
-  long ldo, ld32;
-};
-
-template <int BN>
-struct SmemLayout {
-  static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN <= 128) ? 5 : 4;
-  static constexpr int kTileBytes = kStages * kStageBytes;
-  static constexpr int kScratchBytes = kEpiWarps * 32 * 33 * 4;  // per-warp 32x33 fp32 transpose scratch
-  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kTotal = kTileBytes + kScratchBytes + kBarBytes + 1024;  // + slack for 1 KiB alignment
-  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  void* out16;        // D2S only (direct stores)
+  int has_out16, has_out16b;
+  float* stats_out;   // RESID: stats_out[(m / rows_per_group)][n][2] += (sum, sum^2) of out32 (may be null)
+  long ldo;
 };
 
 // ---------------------------------------------------------------------------------------------
-// Epilogue on one 32-row x 32-column chunk owned by one warp.
-//
-// tcgen05.ld hands every thread one ROW of the chunk (32 consecutive fp32 columns).  Touching global
-// memory in that shape makes each warp instruction hit 32 different rows, so all global traffic goes
-// through a per-warp 32x33 fp32 shared-memory transpose instead: with 8 lanes per row (fp32) or 4 lanes
-// per row (16-bit) every instruction reads / writes whole 128-byte / 64-byte row segments.
-// The +1 padding makes both the row-wise and the transposed accesses bank-conflict free.
+// swizzled shared-memory rows.  `base` is the (1 KiB aligned) start of a TMA box whose rows are
+// 128 B (fp32, SWIZZLE_128B) or 64 B (16-bit, SWIZZLE_64B) wide; `row` is the row index inside the box.
 // ---------------------------------------------------------------------------------------------
-struct ChunkCtx {
-  float* scratch;      // this warp's [32][33] floats
-  int lane;
-  int rows_valid;      // rows of the chunk inside the matrix (0..32), warp uniform
-  int ncols;           // columns of the chunk inside the matrix (1..32), warp uniform
-};
-
-__device__ __forceinline__ void regs_to_scratch(const ChunkCtx& c, const float (&v)[32]) {
+__device__ __forceinline__ void st_row_f32(uint8_t* base, int row, const float (&v)[32]) {
+  uint8_t* r = base + row * 128;
+  const int x = row & 7;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) c.scratch[c.lane * 33 + j] = v[j];
-  __syncwarp();
+  for (int c = 0; c < 8; ++c)
+    *reinterpret_cast<float4*>(r + ((c ^ x) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
 }
-__device__ __forceinline__ void scratch_to_regs(const ChunkCtx& c, float (&v)[32]) {
-  __syncwarp();
+__device__ __forceinline__ void ld_row_f32(const uint8_t* base, int row, float (&v)[32]) {
+  const uint8_t* r = base + row * 128;
+  const int x = row & 7;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = c.scratch[c.lane * 33 + j];
-  __syncwarp();
-}
-
-// global (rows at base + r*ld) fp32 -> thread-row registers
-__device__ __forceinline__ void coop_load32(const ChunkCtx& c, const float* base, long ld, float (&v)[32]) {
-  const bool vec = (c.ncols == 32) && (ld % 4 == 0);
-  if (vec) {
-    const int cc = (c.lane & 7) * 4;
-#pragma unroll
-    for (int p = 0; p < 8; ++p) {
-      const int r = p * 4 + (c.lane >> 3);
-      float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < c.rows_valid) u = *reinterpret_cast<const float4*>(base + (long)r * ld + cc);
-      float* s = c.scratch + r * 33 + cc;
-      s[0] = u.x; s[1] = u.y; s[2] = u.z; s[3] = u.w;
-    }
-  } else {
-    for (int r = 0; r < c.rows_valid; ++r)
-      c.scratch[r * 33 + c.lane] = (c.lane < c.ncols) ? base[(long)r * ld + c.lane] : 0.f;
+  for (int c = 0; c < 8; ++c) {
+    const float4 u = *reinterpret_cast<const float4*>(r + ((c ^ x) << 4));
+    v[4 * c] = u.x; v[4 * c + 1] = u.y; v[4 * c + 2] = u.z; v[4 * c + 3] = u.w;
   }
-  scratch_to_regs(c, v);
 }
-
-__device__ __forceinline__ void coop_store32(const ChunkCtx& c, float* base, long ld, const float (&v)[32]) {
-  regs_to_scratch(c, v);
-  const bool vec = (c.ncols == 32) && (ld % 4 == 0);
-  if (vec) {
-    const int cc = (c.lane & 7) * 4;
-#pragma unroll
-    for (int p = 0; p < 8; ++p) {
-      const int r = p * 4 + (c.lane >> 3);
-      const float* s = c.scratch + r * 33 + cc;
-      if (r < c.rows_valid) *reinterpret_cast<float4*>(base + (long)r * ld + cc) = make_float4(s[0], s[1], s[2], s[3]);
-    }
-  } else {
-    for (int r = 0; r < c.rows_valid; ++r)
-      if (c.lane < c.ncols) base[(long)r * ld + c.lane] = c.scratch[r * 33 + c.lane];
-  }
-  __syncwarp();
-}
-
-__device__ __forceinline__ void coop_atomic32(const ChunkCtx& c, float* base, long ld, const float (&v)[32]) {
-  regs_to_scratch(c, v);
-  for (int r = 0; r < c.rows_valid; ++r)
-    if (c.lane < c.ncols) atomicAdd(base + (long)r * ld + c.lane, c.scratch[r * 33 + c.lane]);
-  __syncwarp();
-}
-
-// 16-bit rows; row r of the chunk lives at rowptr(r)
-template <typename T16, typename RowPtr>
-__device__ __forceinline__ void coop_store16(const ChunkCtx& c, RowPtr rowptr, bool aligned, const float (&v)[32]) {
-  regs_to_scratch(c, v);
-  if (aligned && c.ncols == 32) {
-    const int cc = (c.lane & 3) * 8;
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      const int r = p * 8 + (c.lane >> 2);
-      const float* s = c.scratch + r * 33 + cc;
-      if (r < c.rows_valid) {
-        uint4 u;
-        u.x = pack2<T16>(s[0], s[1]); u.y = pack2<T16>(s[2], s[3]);
-        u.z = pack2<T16>(s[4], s[5]); u.w = pack2<T16>(s[6], s[7]);
-        *reinterpret_cast<uint4*>(rowptr(r) + cc) = u;
-      }
-    }
-  } else {
-    for (int r = 0; r < c.rows_valid; ++r)
-      if (c.lane < c.ncols) rowptr(r)[c.lane] = from_f32<T16>(c.scratch[r * 33 + c.lane]);
-  }
-  __syncwarp();
-}
-
 template <typename T16>
-__device__ __forceinline__ void coop_load16(const ChunkCtx& c, const T16* base, long ld, float (&v)[32]) {
-  if ((ld % 8 == 0) && c.ncols == 32) {
-    const int cc = (c.lane & 3) * 8;
+__device__ __forceinline__ void st_row_16(uint8_t* base, int row, const float (&v)[32]) {
+  uint8_t* r = base + row * 64;
+  const int x = (row >> 1) & 3;
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      const int r = p * 8 + (c.lane >> 2);
-      uint4 u = make_uint4(0u, 0u, 0u, 0u);
-      if (r < c.rows_valid) u = *reinterpret_cast<const uint4*>(base + (long)r * ld + cc);
-      const float2 a = unpack2<T16>(u.x), b = unpack2<T16>(u.y), d = unpack2<T16>(u.z), e = unpack2<T16>(u.w);
-      float* s = c.scratch + r * 33 + cc;
-      s[0] = a.x; s[1] = a.y; s[2] = b.x; s[3] = b.y; s[4] = d.x; s[5] = d.y; s[6] = e.x; s[7] = e.y;
-    }
-  } else {
-    for (int r = 0; r < c.rows_valid; ++r)
-      c.scratch[r * 33 + c.lane] = (c.lane < c.ncols) ? to_f32<T16>(base[(long)r * ld + c.lane]) : 0.f;
+  for (int c = 0; c < 4; ++c) {
+    uint4 u;
+    u.x = pack2<T16>(v[8 * c], v[8 * c + 1]); u.y = pack2<T16>(v[8 * c + 2], v[8 * c + 3]);
+    u.z = pack2<T16>(v[8 * c + 4], v[8 * c + 5]); u.w = pack2<T16>(v[8 * c + 6], v[8 * c + 7]);
+    *reinterpret_cast<uint4*>(r + ((c ^ x) << 4)) = u;
   }
-  scratch_to_regs(c, v);
+}
+template <typename T16>
+__device__ __forceinline__ void ld_row_16(const uint8_t* base, int row, float (&v)[32]) {
+  const uint8_t* r = base + row * 64;
+  const int x = (row >> 1) & 3;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint4 u = *reinterpret_cast<const uint4*>(r + ((c ^ x) << 4));
+    const float2 a = unpack2<T16>(u.x), b = unpack2<T16>(u.y), d = unpack2<T16>(u.z), e = unpack2<T16>(u.w);
+    v[8 * c] = a.x; v[8 * c + 1] = a.y; v[8 * c + 2] = b.x; v[8 * c + 3] = b.y;
+    v[8 * c + 4] = d.x; v[8 * c + 5] = d.y; v[8 * c + 6] = e.x; v[8 * c + 7] = e.y;
+  }
 }
 
-// m_base: first global row of the chunk (warp uniform), n: first global column.  Thread `lane` holds row m_base+lane.
-template <typename T16>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const ChunkCtx& c, int m_base, int n, float (&acc)[32]) {
-  const bool a16 = (p.ldo % 8 == 0);
-  if (p.bias != nullptr) {
+// per-column fp32 vector (bias, scales): 32 consecutive entries starting at column n (warp-uniform address)
+__device__ __forceinline__ void load_cols(const float* vec, int n, int N, float (&o)[32]) {
+  if (n + 32 <= N) {
+    const float4* p4 = reinterpret_cast<const float4*>(vec + n);
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < c.ncols) acc[j] += __ldg(p.bias + n + j);
-  }
-  auto row16 = [&](void* ptr) {
-    T16* b = reinterpret_cast<T16*>(ptr) + (long)m_base * p.ldo + n;
-    const long ld = p.ldo;
-    return [b, ld](int r) { return b + (long)r * ld; };
-  };
-  switch (p.epilogue) {
-    case BF_EPI_STORE16: {
-      coop_store16<T16>(c, row16(p.out16), a16, acc);
-      break;
+    for (int q = 0; q < 8; ++q) {
+      const float4 u = __ldg(p4 + q);
+      o[4 * q] = u.x; o[4 * q + 1] = u.y; o[4 * q + 2] = u.z; o[4 * q + 3] = u.w;
     }
-    case BF_EPI_STORE32: {
-      coop_store32(c, p.out32 + (long)m_base * p.ld32 + n, p.ld32, acc);
-      break;
-    }
-    case BF_EPI_GELU: {
-      if (p.out16b != nullptr) coop_store16<T16>(c, row16(p.out16b), a16, acc);
+  } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = gelu_erf(acc[j]);
-      coop_store16<T16>(c, row16(p.out16), a16, acc);
-      break;
-    }
-    case BF_EPI_RESID: {
-      if (p.out16b != nullptr) coop_store16<T16>(c, row16(p.out16b), a16, acc);
-      const int m = m_base + c.lane;
-      const float rs = (p.row_scale != nullptr && c.lane < c.rows_valid) ? __ldg(p.row_scale + m / p.rows_per_group) : 1.f;
-      float xin[32];
-      coop_load32(c, p.in32 + (long)m_base * p.ld32 + n, p.ld32, xin);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (j < c.ncols) {
-          float v = acc[j];
-          if (p.col_scale != nullptr) v = fmaf(v, __ldg(p.col_scale + n + j), __ldg(p.col_shift + n + j));
-          acc[j] = fmaf(rs * __ldg(p.col_gamma + n + j), v, xin[j]);
-        }
-      }
-      coop_store32(c, p.out32 + (long)m_base * p.ld32 + n, p.ld32, acc);
-      if (p.out16 != nullptr) coop_store16<T16>(c, row16(p.out16), a16, acc);
-      break;
-    }
-    case BF_EPI_DGELU: {
-      float pre[32];
-      coop_load16<T16>(c, reinterpret_cast<const T16*>(p.aux16) + (long)m_base * p.ldo + n, p.ldo, pre);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] *= gelu_erf_grad(pre[j]);
-      coop_store16<T16>(c, row16(p.out16), a16, acc);
-      break;
-    }
-    case BF_EPI_ACC32: {
-      float g[32];
-      coop_load32(c, p.in32 + (long)m_base * p.ld32 + n, p.ld32, g);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] += g[j];
-      coop_store32(c, p.out32 + (long)m_base * p.ld32 + n, p.ld32, acc);
-      break;
-    }
-    case BF_EPI_ATOMIC32: {
-      coop_atomic32(c, p.out32 + (long)m_base * p.ld32 + n, p.ld32, acc);
-      break;
-    }
-    case BF_EPI_D2S: {
-      // m = (img, y, x), n = (ky, kx, co) -> out[((img*2h + 2y+ky)*2w + 2x+kx)*cout + co]
-      const int w = p.d2s_w, h = p.d2s_h, co = p.d2s_cout;
-      T16* out = reinterpret_cast<T16*>(p.out16);
-      if (co % 32 == 0) {
-        const int q = n / co, c0 = n - q * co;
-        auto rowptr = [=](int r) {
-          const int m = m_base + r;
-          const int x = m % w, y = (m / w) % h, img = m / (w * h);
-          const long pix = ((long)(img * 2 * h + 2 * y + (q >> 1)) * (2 * w) + 2 * x + (q & 1));
-          return out + pix * co + c0;
-        };
-        coop_store16<T16>(c, rowptr, true, acc);
-      } else {
-        const int m = m_base + c.lane;
-        if (c.lane < c.rows_valid) {
-          const int x = m % w, y = (m / w) % h, img = m / (w * h);
-          for (int j = 0; j < c.ncols; ++j) {
-            const int q = (n + j) / co, c0 = (n + j) - q * co;
-            const long pix = ((long)(img * 2 * h + 2 * y + (q >> 1)) * (2 * w) + 2 * x + (q & 1));
-            out[pix * co + c0] = from_f32<T16>(acc[j]);
-          }
-        }
-      }
-      break;
-    }
-    default: break;
+    for (int j = 0; j < 32; ++j) o[j] = (n + j < N) ? __ldg(vec + n + j) : 0.f;
   }
 }
 
@@ -285,17 +131,26 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const ChunkC
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_o16,
+                    const __grid_constant__ CUtensorMap map_o16b, const __grid_constant__ CUtensorMap map_o32,
                     const GemmParams p) {
-  using L = SmemLayout<BN>;
+  constexpr int kABytes = BM * BK * 2;
+  constexpr int kBBytes = BN * BK * 2;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  constexpr int kChunks = BN / 32;                 // 32-column chunks per tile
+  constexpr int kChunksPerWarp = kChunks / 2;      // two warps share one TMEM lane quadrant
+
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  float* scratch_all = reinterpret_cast<float*>(smem + L::kTileBytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kTileBytes + L::kScratchBytes);
-  uint64_t* empty_bar = full_bar + L::kStages;
-  uint64_t* tmem_full = empty_bar + L::kStages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.bar_off);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full = empty_bar + kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* in_full = tmem_empty + 2;
+  uint64_t* in_empty = in_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(in_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -303,17 +158,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
-    for (int s = 0; s < L::kStages; ++s) {
+    for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tmem_full + s, 1);
       mbar_init(tmem_empty + s, kEpiWarps);
+      mbar_init(in_full + s, 1);
+      mbar_init(in_empty + s, kEpiWarps);
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, L::kTmemCols);
+  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -323,7 +180,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const int num_tiles = tiles_mn * p.split_k;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer: operands =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -335,9 +192,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int m0 = m_blk * BM, n0 = n_blk * BN;
         for (int it = 0; it < p.k_iters; ++it) {
           mbar_wait(empty_bar + stage, phase ^ 1u);
-          uint8_t* sa = smem + stage * L::kStageBytes;
-          uint8_t* sb = sa + L::kABytes;
-          mbar_arrive_expect_tx(full_bar + stage, L::kStageBytes);
+          uint8_t* sa = smem + stage * kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_arrive_expect_tx(full_bar + stage, kStageBytes);
           const int kit = ks * p.k_iters + it;      // global k iteration
           if (p.s2d) {
             const int ky = kit / p.k_seg_iters;
@@ -351,7 +208,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const int k0 = kit * BK;
             if (A_MN) {
               tma_load_2d(sa, &map_a, full_bar + stage, m0, k0);
-              tma_load_2d(sa + L::kABytes / 2, &map_a, full_bar + stage, m0 + 64, k0);
+              tma_load_2d(sa + kABytes / 2, &map_a, full_bar + stage, m0 + 64, k0);
             } else {
               tma_load_2d(sa, &map_a, full_bar + stage, k0, m0);
             }
@@ -363,7 +220,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               tma_load_2d(sb, &map_b, full_bar + stage, k0, n0);
             }
           }
-          if (++stage == L::kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -381,8 +238,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int it = 0; it < p.k_iters; ++it) {
           mbar_wait(full_bar + stage, phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
-          const uint32_t sb = sa + L::kABytes;
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint32_t sb = sa + kABytes;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // K-major: advance 16 elements = 32 B inside the 128 B swizzle row.
@@ -394,56 +251,270 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             umma_f16(d_tmem, da, db, p.idesc, (it | k) != 0 ? 1u : 0u);
           }
           umma_commit(empty_bar + stage);
-          if (++stage == L::kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tmem_full + as);
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
-  } else {
+  } else if (warp == 2) {
+    // ===================== TMA producer: epilogue input tile =====================
+    if (lane == 0 && p.in_kind != 0) {
+      tma_prefetch_desc(&map_in);
+      int ib = 0;
+      uint32_t iphase = 0;
+      const int box_bytes = BM * (p.in_kind == 2 ? 128 : 64);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mn = tile % tiles_mn;
+        const int m_blk = mn / p.num_n_blocks;
+        const int n_blk = mn - m_blk * p.num_n_blocks;
+        mbar_wait(in_empty + ib, iphase ^ 1u);
+        uint8_t* dst = smem + p.in_off + ib * p.in_bytes;
+        mbar_arrive_expect_tx(in_full + ib, kChunks * box_bytes);
+#pragma unroll 1
+        for (int c = 0; c < kChunks; ++c)
+          tma_load_2d(dst + c * box_bytes, &map_in, in_full + ib, n_blk * BN + 32 * c, m_blk * BM);
+        if (++ib == p.in_bufs) { ib = 0; iphase ^= 1u; }
+      }
+    }
+  } else if (warp >= kFirstEpiWarp) {
     // ===================== epilogue warps =====================
-    const int ew = warp - 2;
+    const int ew = warp - kFirstEpiWarp;
     const int quad = warp & 3;              // TMEM lane quadrant this warp may access
-    const int half = ew >> 2;               // which half of the tile's columns
-    ChunkCtx cc;
-    cc.scratch = scratch_all + ew * (32 * 33);
-    cc.lane = lane;
-    int as = 0;
-    uint32_t aphase = 0;
+    const int half = ew >> 2;               // which half of the tile's 32-column chunks
+    const int row = quad * 32 + lane;       // row inside the tile
+    uint8_t* slab = smem + p.slab_off + ew * kSlabBytes;
+    if (lane == 0) {
+      if (p.has_out16) tma_prefetch_desc(&map_o16);
+      if (p.has_out16b) tma_prefetch_desc(&map_o16b);
+      if (p.epilogue != BF_EPI_STORE16 && p.epilogue != BF_EPI_GELU && p.epilogue != BF_EPI_DGELU &&
+          p.epilogue != BF_EPI_D2S)
+        tma_prefetch_desc(&map_o32);
+    }
+    int as = 0, ib = 0, sb = 0;             // accumulator stage, input buffer, slab double-buffer index
+    uint32_t aphase = 0, iphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int ks = tile / tiles_mn;
-      const int mn = tile - ks * tiles_mn;
+      const int mn = tile % tiles_mn;
       const int m_blk = mn / p.num_n_blocks;
       const int n_blk = mn - m_blk * p.num_n_blocks;
-      const int m_base = m_blk * BM + quad * 32;
-      const int n0 = n_blk * BN;
-      cc.rows_valid = min(32, max(0, p.M - m_base));
+      const int m0 = m_blk * BM, n0 = n_blk * BN;
+      const int m = m0 + row;
       mbar_wait(tmem_full + as, aphase);
       tc_fence_after();
+      uint8_t* in_tile = nullptr;
+      if (p.in_kind != 0) {
+        mbar_wait(in_full + ib, iphase);
+        in_tile = smem + p.in_off + ib * p.in_bytes;
+      }
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN);
+      float rs = 1.f;
+      if (p.epilogue == BF_EPI_RESID && p.row_scale != nullptr && m < p.M) rs = __ldg(p.row_scale + m / p.rows_per_group);
 #pragma unroll 1
-      for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+      for (int ci = 0; ci < kChunksPerWarp; ++ci) {
+        const int c = half * kChunksPerWarp + ci;
+        const int n = n0 + 32 * c;
         float acc[32];
-        tmem_ld_32x32(t_row + static_cast<uint32_t>(c), acc);
+        tmem_ld_32x32(t_row + static_cast<uint32_t>(32 * c), acc);
         tmem_ld_wait();
-        cc.ncols = min(32, p.N - (n0 + c));
-        if (cc.rows_valid > 0 && cc.ncols > 0) {
-          if (p.is_f16) epilogue_chunk<__half>(p, cc, m_base, n0 + c, acc);
-          else          epilogue_chunk<__nv_bfloat16>(p, cc, m_base, n0 + c, acc);
+        if (ci == kChunksPerWarp - 1) {
+          // accumulator fully read: hand the TMEM stage back to the MMA warp before finishing the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty + as);
+        }
+        if (n >= p.N || m0 + quad * 32 >= p.M) continue;     // chunk entirely outside the matrix (warp uniform)
+        if (p.bias != nullptr) {
+          float b[32];
+          load_cols(p.bias, n, p.N, b);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] += b[j];
+        }
+        const int mrow = m0 + quad * 32;                      // first global row of this warp's slab
+        switch (p.epilogue) {
+          case BF_EPI_STORE16: {
+            uint8_t* s = slab + sb * 2048;
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+            if (p.is_f16) st_row_16<__half>(s, lane, acc); else st_row_16<__nv_bfloat16>(s, lane, acc);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { tma_store_2d(&map_o16, s, n, mrow); tma_store_commit(); }
+            sb ^= 1;
+            break;
+          }
+          case BF_EPI_GELU: {
+            uint8_t* s = slab + sb * 2048;
+            uint8_t* s2 = slab + 4096 + sb * 2048;
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+            if (p.has_out16b) {
+              if (p.is_f16) st_row_16<__half>(s2, lane, acc); else st_row_16<__nv_bfloat16>(s2, lane, acc);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = gelu_fast(acc[j]);
+            if (p.is_f16) st_row_16<__half>(s, lane, acc); else st_row_16<__nv_bfloat16>(s, lane, acc);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&map_o16, s, n, mrow);
+              if (p.has_out16b) tma_store_2d(&map_o16b, s2, n, mrow);
+              tma_store_commit();
+            }
+            sb ^= 1;
+            break;
+          }
+          case BF_EPI_STORE32:
+          case BF_EPI_ATOMIC32: {
+            uint8_t* s = slab + sb * 4096;
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+            st_row_f32(s, lane, acc);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              if (p.epilogue == BF_EPI_ATOMIC32) tma_reduce_add_2d(&map_o32, s, n, mrow);
+              else tma_store_2d(&map_o32, s, n, mrow);
+              tma_store_commit();
+            }
+            sb ^= 1;
+            break;
+          }
+          case BF_EPI_DGELU: {
+            uint8_t* box = in_tile + c * (BM * 64);
+            float pre[32];
+            if (p.is_f16) ld_row_16<__half>(box, row, pre); else ld_row_16<__nv_bfloat16>(box, row, pre);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] *= gelu_grad_fast(pre[j]);
+            if (p.is_f16) st_row_16<__half>(box, row, acc); else st_row_16<__nv_bfloat16>(box, row, acc);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { tma_store_2d(&map_o16, box + quad * 32 * 64, n, mrow); tma_store_commit(); }
+            break;
+          }
+          case BF_EPI_ACC32: {
+            uint8_t* box = in_tile + c * (BM * 128);
+            float g[32];
+            ld_row_f32(box, row, g);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] += g[j];
+            st_row_f32(box, row, acc);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { tma_store_2d(&map_o32, box + quad * 32 * 128, n, mrow); tma_store_commit(); }
+            break;
+          }
+          case BF_EPI_RESID: {
+            uint8_t* box = in_tile + c * (BM * 128);
+            uint8_t* s = slab + sb * 2048;
+            uint8_t* s2 = slab + 4096 + sb * 2048;
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+            if (p.has_out16b) {
+              if (p.is_f16) st_row_16<__half>(s2, lane, acc); else st_row_16<__nv_bfloat16>(s2, lane, acc);
+            }
+            float t[32];
+            if (p.col_scale != nullptr) {
+              load_cols(p.col_scale, n, p.N, t);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[j] *= t[j];
+              load_cols(p.col_shift, n, p.N, t);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[j] += t[j];
+            }
+            load_cols(p.col_gamma, n, p.N, t);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] *= rs * t[j];
+            ld_row_f32(box, row, t);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] += t[j];
+            st_row_f32(box, row, acc);
+            if (p.has_out16) {
+              if (p.is_f16) st_row_16<__half>(s, lane, acc); else st_row_16<__nv_bfloat16>(s, lane, acc);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&map_o32, box + quad * 32 * 128, n, mrow);
+              if (p.has_out16) tma_store_2d(&map_o16, s, n, mrow);
+              if (p.has_out16b) tma_store_2d(&map_o16b, s2, n, mrow);
+              tma_store_commit();
+            }
+            if (p.stats_out != nullptr) {
+              // per-(image, channel) sums of the new residual stream for the next InstanceNorm: lane j owns
+              // column j of this warp's 32 x 32 block (conflict-free transposed read of the swizzled rows)
+              const uint8_t* sl = box + quad * 32 * 128;
+              float s1 = 0.f, s2q = 0.f;
+              const int rows_valid = min(32, p.M - mrow);
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r) {
+                const float v = *reinterpret_cast<const float*>(sl + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+                if (r < rows_valid) { s1 += v; s2q = fmaf(v, v, s2q); }
+              }
+              if (n + lane < p.N) {
+                float* dst = p.stats_out + ((long)(mrow / p.rows_per_group) * p.N + n + lane) * 2;
+                atomicAdd(dst, s1);
+                atomicAdd(dst + 1, s2q);
+              }
+            }
+            sb ^= 1;
+            break;
+          }
+          case BF_EPI_D2S: {
+            // m = (img, y, x), n = (ky, kx, co) -> out[((img*2h + 2y+ky)*2w + 2x+kx)*cout + co]   (direct stores)
+            if (m < p.M) {
+              const int w = p.d2s_w, h = p.d2s_h, co = p.d2s_cout;
+              const int x = m % w, y = (m / w) % h, img = m / (w * h);
+              if (co % 32 == 0) {
+                const int q = n / co, c0 = n - q * co;
+                const long pix = ((long)(img * 2 * h + 2 * y + (q >> 1)) * (2 * w) + 2 * x + (q & 1));
+                uint4 u[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (p.is_f16) {
+                    u[k].x = pack2<__half>(acc[8 * k], acc[8 * k + 1]); u[k].y = pack2<__half>(acc[8 * k + 2], acc[8 * k + 3]);
+                    u[k].z = pack2<__half>(acc[8 * k + 4], acc[8 * k + 5]); u[k].w = pack2<__half>(acc[8 * k + 6], acc[8 * k + 7]);
+                  } else {
+                    u[k].x = pack2<__nv_bfloat16>(acc[8 * k], acc[8 * k + 1]); u[k].y = pack2<__nv_bfloat16>(acc[8 * k + 2], acc[8 * k + 3]);
+                    u[k].z = pack2<__nv_bfloat16>(acc[8 * k + 4], acc[8 * k + 5]); u[k].w = pack2<__nv_bfloat16>(acc[8 * k + 6], acc[8 * k + 7]);
+                  }
+                }
+                uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out16) + pix * co + c0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) dst[k] = u[k];
+              } else {
+                uint16_t* out = reinterpret_cast<uint16_t*>(p.out16);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  if (n + j < p.N) {
+                    const int q = (n + j) / co, c0 = (n + j) - q * co;
+                    const long pix = ((long)(img * 2 * h + 2 * y + (q >> 1)) * (2 * w) + 2 * x + (q & 1));
+                    if (p.is_f16) { const __half hv = __float2half_rn(acc[j]); out[pix * co + c0] = *reinterpret_cast<const uint16_t*>(&hv); }
+                    else { const __nv_bfloat16 bv = __float2bfloat16_rn(acc[j]); out[pix * co + c0] = *reinterpret_cast<const uint16_t*>(&bv); }
+                  }
+                }
+              }
+            }
+            break;
+          }
+          default: break;
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty + as);
+      if (p.in_kind != 0) {
+        // the input tile buffer doubles as the output staging of this tile: release it once TMA has read it
+        if (lane == 0) { tma_store_wait_read<0>(); mbar_arrive(in_empty + ib); }
+        __syncwarp();
+        if (++ib == p.in_bufs) { ib = 0; iphase ^= 1u; }
+      }
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
+    if (lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, L::kTmemCols);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -467,9 +538,11 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// rank-d tensor map over 16-bit elements, 128B swizzle, zero fill out of bounds
-static int make_map(CUtensorMap* map, int dtype, const void* base, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box) {
+enum MapType { kMap16 = 0, kMapF32 = 1 };
+
+// rank-d tensor map, zero fill out of bounds.  dt: BF_BF16 / BF_F16 / BF_F32.
+static int make_map(CUtensorMap* map, int dt, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -480,9 +553,10 @@ static int make_map(CUtensorMap* map, int dtype, const void* base, int rank, con
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-  CUresult r = fn(map, dtype == BF_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
-                  static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  const CUtensorMapDataType cdt = dt == BF_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                               : (dt == BF_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  CUresult r = fn(map, cdt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u]",
@@ -494,19 +568,48 @@ static int make_map(CUtensorMap* map, int dtype, const void* base, int rank, con
   return BF_OK;
 }
 
+// (rows, cols) row-major matrix with leading dimension ld (elements): 32-column boxes of `box_rows` rows
+static int make_epi_map(CUtensorMap* map, int dt, const void* base, long rows, long cols, long ld, int box_rows) {
+  const int es = dt == BF_F32 ? 4 : 2;
+  BF_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * es) % 16 == 0,
+             "bf_gemm: epilogue tensors must be 16-byte aligned with 16-byte row pitch (ld=%ld)", ld);
+  uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows};
+  uint64_t str[1] = {(uint64_t)ld * es};
+  uint32_t box[2] = {32, (uint32_t)box_rows};
+  return make_map(map, dt, base, 2, dims, str, box, dt == BF_F32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
+struct Maps { CUtensorMap a, b, in, o16, o16b, o32; };
+
 template <int BN, bool A_MN, bool B_MN>
-static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
-  using L = SmemLayout<BN>;
+static int launch(const Maps& mp, GemmParams& p, cudaStream_t st) {
   auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
   });
   if (attr_err != cudaSuccess) return check_cuda(attr_err, "cudaFuncSetAttribute(gemm)");
+  // shared-memory plan: [operand ring][epilogue input tile(s)][per-warp output slabs][barriers]
+  constexpr int stage_bytes = BM * BK * 2 + BN * BK * 2;
+  const int bar_bytes = (2 * kMaxStages + 8) * 8 + 16;
+  const bool slabs = !(p.epilogue == BF_EPI_DGELU || p.epilogue == BF_EPI_ACC32 || p.epilogue == BF_EPI_D2S);
+  const int slab_bytes = slabs ? kEpiWarps * kSlabBytes : 0;
+  p.in_bytes = p.in_kind == 0 ? 0 : BM * BN * (p.in_kind == 2 ? 4 : 2);
+  const int avail = kSmemBudget - 1024 - bar_bytes - slab_bytes;
+  const int want_stages = p.k_iters < 4 ? (p.k_iters < 2 ? 2 : p.k_iters) : 4;
+  p.in_bufs = (p.in_kind != 0 && avail - 2 * p.in_bytes >= (want_stages < 3 ? want_stages : 3) * stage_bytes) ? 2 : 1;
+  int stages = (avail - p.in_bufs * p.in_bytes) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  BF_REQUIRE(stages >= 2, "bf_gemm: shared-memory plan leaves %d stages (BN=%d epilogue=%d)", stages, BN, p.epilogue);
+  p.stages = stages;
+  p.in_off = stages * stage_bytes;
+  p.slab_off = p.in_off + p.in_bufs * p.in_bytes;
+  p.bar_off = p.slab_off + slab_bytes;
+  const int total = p.bar_off + bar_bytes + 1024;
   const int tiles = p.num_m_blocks * p.num_n_blocks * p.split_k;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kThreads, L::kTotal, st>>>(ma, mb, p);
+  kern<<<grid, kThreads, total, st>>>(mp.a, mp.b, mp.in, mp.o16, mp.o16b, mp.o32, p);
   count_launch();
   return check_cuda(cudaGetLastError(), "gemm_tcgen05_kernel launch");
 }
@@ -515,8 +618,8 @@ static int pick_bn(const bf_gemm_args& a) {
   if (a.bn == 64 || a.bn == 128 || a.bn == 192 || a.bn == 256) return a.bn;   // caller override (tuning)
   const int N = a.N;
   if (N <= 64) return 64;
-  if (N <= 128) return 128;
-  if (a.epilogue == BF_EPI_ATOMIC32) return N % 128 == 0 ? 128 : (N % 192 == 0 ? 192 : 128);
+  if (N <= 128 || a.epilogue == BF_EPI_RESID) return 128;                     // fp32 in/out tile: smem bound
+  if (a.epilogue == BF_EPI_ACC32) return N % 192 == 0 ? 192 : 128;
   if (N % 256 == 0 && N >= 512) return 256;
   if (N % 192 == 0) return 192;
   if (N % 128 == 0) return 128;
@@ -556,9 +659,12 @@ extern "C" int bf_gemm(const bf_gemm_args* a, void* stream) {
   p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1;
   p.d2s_h = a->d2s_h; p.d2s_w = a->d2s_w; p.d2s_cout = a->d2s_cout;
   p.bias = a->bias; p.col_scale = a->col_scale; p.col_shift = a->col_shift; p.col_gamma = a->col_gamma;
-  p.row_scale = a->row_scale; p.in32 = a->in32; p.aux16 = a->aux16;
-  p.out16 = a->out16; p.out16b = a->out16b; p.out32 = a->out32;
-  p.ldo = a->ldo; p.ld32 = a->ld32;
+  p.row_scale = a->row_scale;
+  p.out16 = a->out16;
+  p.ldo = a->ldo;
+  p.stats_out = a->stats_out;
+  for (const float* v : {a->bias, a->col_scale, a->col_shift, a->col_gamma})
+    BF_REQUIRE((reinterpret_cast<uintptr_t>(v) & 15) == 0, "bf_gemm: per-column vectors must be 16-byte aligned");
 
   // epilogue operand checks
   switch (a->epilogue) {
@@ -567,6 +673,8 @@ extern "C" int bf_gemm(const bf_gemm_args* a, void* stream) {
     case BF_EPI_RESID:
       BF_REQUIRE(a->out32 && a->in32 && a->col_gamma, "bf_gemm: RESID needs in32/out32/col_gamma");
       BF_REQUIRE((a->col_scale == nullptr) == (a->col_shift == nullptr), "bf_gemm: col_scale/col_shift pair");
+      BF_REQUIRE(a->stats_out == nullptr || (a->rows_per_group % 32 == 0),
+                 "bf_gemm: stats_out needs rows_per_group to be a multiple of 32");
       break;
     case BF_EPI_DGELU: BF_REQUIRE(a->out16 && a->aux16, "bf_gemm: DGELU needs out16/aux16"); break;
     case BF_EPI_ACC32: BF_REQUIRE(a->out32 && a->in32, "bf_gemm: ACC32 needs in32/out32"); break;
@@ -574,9 +682,11 @@ extern "C" int bf_gemm(const bf_gemm_args* a, void* stream) {
       BF_REQUIRE(a->out16 && a->d2s_h > 0 && a->d2s_w > 0 && a->d2s_cout > 0, "bf_gemm: D2S geometry");
       BF_REQUIRE(a->N == 4 * a->d2s_cout, "bf_gemm: D2S needs N == 4*cout");
       BF_REQUIRE(a->M % (a->d2s_h * a->d2s_w) == 0, "bf_gemm: D2S M not a multiple of h*w");
+      BF_REQUIRE(a->d2s_cout % 8 == 0, "bf_gemm: D2S needs cout %% 8 == 0");
       break;
     default: BF_REQUIRE(false, "bf_gemm: unknown epilogue %d", a->epilogue);
   }
+  BF_REQUIRE(a->stats_out == nullptr || a->epilogue == BF_EPI_RESID, "bf_gemm: stats_out only with BF_EPI_RESID");
   if (a->out16 || a->out16b || a->aux16) BF_REQUIRE(a->ldo >= a->N || a->epilogue == BF_EPI_D2S, "bf_gemm: ldo < N");
   if (a->out32 || a->in32) BF_REQUIRE(a->ld32 >= a->N, "bf_gemm: ld32 < N");
 
@@ -586,8 +696,9 @@ extern "C" int bf_gemm(const bf_gemm_args* a, void* stream) {
   p.num_n_blocks = (a->N + bn - 1) / bn;
   p.idesc = make_idesc_f16(a->dtype == BF_F16 ? 0 : 1, a_mn ? 1 : 0, b_mn ? 1 : 0, BM, bn);
 
-  CUtensorMap ma, mb;
+  Maps mp;
   int st;
+  const CUtensorMapSwizzle SW128 = CU_TENSOR_MAP_SWIZZLE_128B;
   if (s2d) {
     const int C = a->s2d_cin, Hin = a->s2d_hin, Win = a->s2d_win, I = a->s2d_images;
     BF_REQUIRE(C > 0 && Hin > 0 && Win > 0 && I > 0 && Hin % 2 == 0 && Win % 2 == 0, "bf_gemm: S2D geometry");
@@ -607,13 +718,13 @@ extern "C" int bf_gemm(const bf_gemm_args* a, void* stream) {
     uint64_t dims[4] = {(uint64_t)seg, (uint64_t)Wo, 2, (uint64_t)I * Ho};
     uint64_t str[3] = {(uint64_t)seg * 2, (uint64_t)Win * C * 2, (uint64_t)2 * Win * C * 2};
     uint32_t box[4] = {BK, (uint32_t)box_w, 1, (uint32_t)(BM / box_w)};
-    if ((st = make_map(&ma, a->dtype, a->A, 4, dims, str, box))) return st;
+    if ((st = make_map(&mp.a, a->dtype, a->A, 4, dims, str, box, SW128))) return st;
     // B: weight (N, ky, 2C) -> (k = 2C, ky = 2, n = N)
     uint64_t bd[3] = {(uint64_t)seg, 2, (uint64_t)a->N};
     uint64_t bs[2] = {(uint64_t)seg * 2, (uint64_t)a->ldb * 2};
     uint32_t bb[3] = {BK, 1, (uint32_t)bn};
     BF_REQUIRE(a->ldb >= 4 * C && a->ldb % 8 == 0, "bf_gemm: S2D ldb");
-    if ((st = make_map(&mb, a->dtype, a->B, 3, bd, bs, bb))) return st;
+    if ((st = make_map(&mp.b, a->dtype, a->B, 3, bd, bs, bb, SW128))) return st;
   } else {
     BF_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0, "bf_gemm: leading dimensions must be multiples of 8 elements");
     const int k_total = (a->K + BK - 1) / BK;
@@ -625,35 +736,57 @@ extern "C" int bf_gemm(const bf_gemm_args* a, void* stream) {
       uint64_t dims[2] = {(uint64_t)a->M, (uint64_t)a->K};
       uint64_t str[1] = {(uint64_t)a->lda * 2};
       uint32_t box[2] = {64, BK};
-      if ((st = make_map(&ma, a->dtype, a->A, 2, dims, str, box))) return st;
+      if ((st = make_map(&mp.a, a->dtype, a->A, 2, dims, str, box, SW128))) return st;
     } else {
       BF_REQUIRE(a->lda >= a->K, "bf_gemm: lda < K");
       uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M};
       uint64_t str[1] = {(uint64_t)a->lda * 2};
       uint32_t box[2] = {BK, BM};
-      if ((st = make_map(&ma, a->dtype, a->A, 2, dims, str, box))) return st;
+      if ((st = make_map(&mp.a, a->dtype, a->A, 2, dims, str, box, SW128))) return st;
     }
     if (b_mn) {   // (K, N) row-major: inner dim N
       BF_REQUIRE(a->ldb >= a->N, "bf_gemm: ldb < N");
       uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->K};
       uint64_t str[1] = {(uint64_t)a->ldb * 2};
       uint32_t box[2] = {64, BK};
-      if ((st = make_map(&mb, a->dtype, a->B, 2, dims, str, box))) return st;
+      if ((st = make_map(&mp.b, a->dtype, a->B, 2, dims, str, box, SW128))) return st;
     } else {
       BF_REQUIRE(a->ldb >= a->K, "bf_gemm: ldb < K");
       uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
       uint64_t str[1] = {(uint64_t)a->ldb * 2};
       uint32_t box[2] = {BK, (uint32_t)bn};
-      if ((st = make_map(&mb, a->dtype, a->B, 2, dims, str, box))) return st;
+      if ((st = make_map(&mp.b, a->dtype, a->B, 2, dims, str, box, SW128))) return st;
     }
+  }
+
+  // epilogue tensor maps (unused ones alias the A map: never dereferenced)
+  mp.in = mp.a; mp.o16 = mp.a; mp.o16b = mp.a; mp.o32 = mp.a;
+  const int e = a->epilogue;
+  if (e == BF_EPI_DGELU) {
+    p.in_kind = 1;
+    if ((st = make_epi_map(&mp.in, a->dtype, a->aux16, a->M, a->N, a->ldo, BM))) return st;
+  } else if (e == BF_EPI_ACC32 || e == BF_EPI_RESID) {
+    p.in_kind = 2;
+    if ((st = make_epi_map(&mp.in, BF_F32, a->in32, a->M, a->N, a->ld32, BM))) return st;
+  }
+  if (e != BF_EPI_D2S && a->out16) {
+    p.has_out16 = 1;
+    if ((st = make_epi_map(&mp.o16, a->dtype, a->out16, a->M, a->N, a->ldo, 32))) return st;
+  }
+  if ((e == BF_EPI_GELU || e == BF_EPI_RESID) && a->out16b) {
+    p.has_out16b = 1;
+    if ((st = make_epi_map(&mp.o16b, a->dtype, a->out16b, a->M, a->N, a->ldo, 32))) return st;
+  }
+  if (a->out32 && (e == BF_EPI_STORE32 || e == BF_EPI_ATOMIC32 || e == BF_EPI_ACC32 || e == BF_EPI_RESID)) {
+    if ((st = make_epi_map(&mp.o32, BF_F32, a->out32, a->M, a->N, a->ld32, 32))) return st;
   }
 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 #define BF_DISPATCH(BN_)                                                          \
   if (bn == BN_) {                                                                \
-    if (a_mn) return launch<BN_, true, true>(ma, mb, p, s);                       \
-    if (b_mn) return launch<BN_, false, true>(ma, mb, p, s);                      \
-    return launch<BN_, false, false>(ma, mb, p, s);                               \
+    if (a_mn) return launch<BN_, true, true>(mp, p, s);                           \
+    if (b_mn) return launch<BN_, false, true>(mp, p, s);                          \
+    return launch<BN_, false, false>(mp, p, s);                                   \
   }
   BF_DISPATCH(64)
   BF_DISPATCH(128)

@@ -40,7 +40,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, epilogue: 
          lda: Optional[int] = None, ldb: Optional[int] = None,
          s2d: Optional[tuple] = None, d2s: Optional[tuple] = None, rows_per_group: int = 1,
          bias=None, col_scale=None, col_shift=None, col_gamma=None, row_scale=None,
-         in32=None, aux16=None, out16=None, out16b=None, out32=None,
+         in32=None, aux16=None, out16=None, out16b=None, out32=None, stats_out=None,
          ldo: Optional[int] = None, ld32: Optional[int] = None) -> None:
     """D[M,N] = sum_k A[m,k] B[n,k] with a fused epilogue; see bf_gemm in include/bubbleformer_b200.h."""
     if A.dtype not in _DT or B.dtype != A.dtype:
@@ -80,6 +80,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, epilogue: 
         ref = out32 if out32 is not None else in32
         ld32 = ref.stride(0) if (ref is not None and ref.dim() == 2) else N
     a.ldo, a.ld32 = ldo, ld32
+    if stats_out is not None:
+        a.stats_out = _f32(stats_out, 2 * N * ((M + rows_per_group - 1) // rows_per_group), "stats_out")
     L.check(L.lib.bf_gemm(C.byref(a), _stream()), "bf_gemm")
 
 

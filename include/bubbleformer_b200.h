@@ -70,7 +70,7 @@ enum bf_epilogue {
                          out16 = (16-bit) out32 (if non-null)                                          */
   BF_EPI_DGELU = 3,   /* out16 = acc * gelu_erf'(aux16)                                                */
   BF_EPI_ACC32 = 4,   /* out32 = in32 + acc                                                            */
-  BF_EPI_ATOMIC32 = 5,/* atomicAdd(out32, acc): split-K wgrad accumulating straight into the fp32 grad */
+  BF_EPI_ATOMIC32 = 5,/* out32 += acc (TMA reduce-add): split-K wgrad accumulating straight into the fp32 grad */
   BF_EPI_D2S = 6,     /* out16 scattered depth-to-space: m = (img, y, x), n = (ky, kx, co) ->
                          out16[((img*2h + 2y+ky)*2w + 2x+kx)*cout + co]  (ConvTranspose2d k2 s2)        */
   BF_EPI_STORE32 = 7  /* out32 = acc + bias                                                            */
@@ -104,6 +104,9 @@ typedef struct bf_gemm_args {
   void* out16b;           /* (M, N) ld = ldo  */
   float* out32;           /* (M, N) ld = ld32 */
   int64_t ldo, ld32;
+  float* stats_out;       /* BF_EPI_RESID only, may be NULL: stats_out[m / rows_per_group][n] += (sum, sum^2) of
+                             out32 -- the raw InstanceNorm statistics of the new residual stream, so the next
+                             norm needs no separate pass (rows_per_group = tokens per image, multiple of 32)   */
 } bf_gemm_args;
 
 BF_API int bf_gemm(const bf_gemm_args* args, void* stream);
