@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libbubbleformer_b200.so")
 BF_BF16, BF_F16 = 0, 1
 A_ROWMAJOR, A_S2D, A_KM = 0, 1, 2
 B_NK, B_KN = 0, 1
-EPI_STORE16, EPI_GELU, EPI_RESID, EPI_DGELU, EPI_ACC32, EPI_ATOMIC32, EPI_D2S, EPI_STORE32 = range(8)
+EPI_STORE16, EPI_GELU, EPI_RESID, EPI_DGELU, EPI_ACC32, EPI_ATOMIC32, EPI_D2S, EPI_STORE32, EPI_QKV_LN = range(9)
 
 
 class BubbleformerB200Error(RuntimeError):
@@ -25,7 +25,7 @@ class GemmArgs(C.Structure):
     _fields_ = [
         ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
         ("dtype", C.c_int32), ("a_mode", C.c_int32), ("b_mode", C.c_int32),
-        ("epilogue", C.c_int32), ("split_k", C.c_int32), ("bn", C.c_int32), ("reserved0", C.c_int32),
+        ("epilogue", C.c_int32), ("split_k", C.c_int32), ("bn", C.c_int32), ("ln_head_dim", C.c_int32),
         ("A", C.c_void_p), ("B", C.c_void_p),
         ("lda", C.c_int64), ("ldb", C.c_int64),
         ("s2d_images", C.c_int32), ("s2d_hin", C.c_int32), ("s2d_win", C.c_int32), ("s2d_cin", C.c_int32),
@@ -34,7 +34,7 @@ class GemmArgs(C.Structure):
         ("row_scale", C.c_void_p), ("in32", C.c_void_p), ("aux16", C.c_void_p),
         ("out16", C.c_void_p), ("out16b", C.c_void_p), ("out32", C.c_void_p),
         ("ldo", C.c_int64), ("ld32", C.c_int64),
-        ("stats_out", C.c_void_p),
+        ("stats_out", C.c_void_p), ("ln_rstd", C.c_void_p),
     ]
 
 
@@ -115,9 +115,10 @@ class AttnArgs(C.Structure):
         ("inner_stride", C.c_int64), ("tok_stride", C.c_int64),
         ("qn_w", C.c_void_p), ("qn_b", C.c_void_p), ("kn_w", C.c_void_p), ("kn_b", C.c_void_p),
         ("bias_emb", C.c_void_p), ("bucket", C.c_void_p), ("scale_factor", C.c_void_p),
-        ("out_scale", C.c_float), ("reserved0", C.c_int32),
+        ("out_scale", C.c_float), ("prenorm", C.c_int32),
         ("d_qn_w", C.c_void_p), ("d_qn_b", C.c_void_p), ("d_kn_w", C.c_void_p), ("d_kn_b", C.c_void_p),
         ("d_bias_emb", C.c_void_p), ("d_scale_factor", C.c_void_p),
+        ("rstd", C.c_void_p),
     ]
 
 

@@ -682,14 +682,18 @@ static int attn_common(const bf_attn_args* a, AttnParams& p, int& LP, bool bwd) 
   return BF_OK;
 }
 
+namespace bf { int launch_attn_fast(const bf_attn_args* a, bool bwd, cudaStream_t st); }
+
 extern "C" int bf_attention_fwd(const bf_attn_args* a, void* stream) {
   AttnParams p; int LP;
   if (int st = attn_common(a, p, LP, false)) return st;
+  if (a->prenorm) return launch_attn_fast(a, false, static_cast<cudaStream_t>(stream));
   return dispatch_attn<false>(a->head_dim, LP, p, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int bf_attention_bwd(const bf_attn_args* a, void* stream) {
   AttnParams p; int LP;
   if (int st = attn_common(a, p, LP, true)) return st;
+  if (a->prenorm) return launch_attn_fast(a, true, static_cast<cudaStream_t>(stream));
   return dispatch_attn<true>(a->head_dim, LP, p, static_cast<cudaStream_t>(stream));
 }

@@ -62,6 +62,7 @@ struct GemmParams {
   void* out16;        // D2S only (direct stores)
   int has_out16, has_out16b;
   float* stats_out;   // RESID: stats_out[(m / rows_per_group)][n][2] += (sum, sum^2) of out32 (may be null)
+  float* ln_rstd;     // QKV_LN: (M, heads, 2) rstd of the raw q / k rows
   long ldo;
 };
 
@@ -288,7 +289,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       if (p.has_out16) tma_prefetch_desc(&map_o16);
       if (p.has_out16b) tma_prefetch_desc(&map_o16b);
       if (p.epilogue != BF_EPI_STORE16 && p.epilogue != BF_EPI_GELU && p.epilogue != BF_EPI_DGELU &&
-          p.epilogue != BF_EPI_D2S)
+          p.epilogue != BF_EPI_D2S && p.epilogue != BF_EPI_QKV_LN)
         tma_prefetch_desc(&map_o32);
     }
     int as = 0, ib = 0, sb = 0;             // accumulator stage, input buffer, slab double-buffer index
@@ -309,6 +310,78 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN);
       float rs = 1.f;
       if (p.epilogue == BF_EPI_RESID && p.row_scale != nullptr && m < p.M) rs = __ldg(p.row_scale + m / p.rows_per_group);
+      if constexpr (BN == 192) {
+        if (p.epilogue == BF_EPI_QKV_LN) {
+          // One tile = one head: columns [q 0:64 | k 64:128 | v 128:192].  Warp `half` 0 normalises q, 1 normalises k
+          // (LayerNorm over the 64 columns of a row is thread local: tcgen05.ld hands each thread its row), and each
+          // takes half of v.  Stored: xhat = (x - mean) * rstd without the affine part, plus rstd for the backward.
+          const int mrow = m0 + quad * 32;
+          const bool live = mrow < p.M;                       // warp uniform
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+          const int cq = half * 2;
+          {
+            float x0[32], x1[32];
+            tmem_ld_32x32(t_row + static_cast<uint32_t>(32 * cq), x0);
+            tmem_ld_32x32(t_row + static_cast<uint32_t>(32 * cq + 32), x1);
+            tmem_ld_wait();
+            if (live) {
+              if (p.bias != nullptr) {
+                float b[32];
+                load_cols(p.bias, n0 + 32 * cq, p.N, b);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x0[j] += b[j];
+                load_cols(p.bias, n0 + 32 * cq + 32, p.N, b);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x1[j] += b[j];
+              }
+              float s = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) s += x0[j] + x1[j];
+              const float mean = s * (1.f / 64.f);
+              float q = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                x0[j] -= mean; x1[j] -= mean;
+                q = fmaf(x0[j], x0[j], q); q = fmaf(x1[j], x1[j], q);
+              }
+              const float rstd = rsqrtf(q * (1.f / 64.f) + 1e-5f);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { x0[j] *= rstd; x1[j] *= rstd; }
+              if (p.is_f16) { st_row_16<__half>(slab, lane, x0); st_row_16<__half>(slab + 2048, lane, x1); }
+              else { st_row_16<__nv_bfloat16>(slab, lane, x0); st_row_16<__nv_bfloat16>(slab + 2048, lane, x1); }
+              if (m < p.M) p.ln_rstd[((long)m * p.num_n_blocks + n_blk) * 2 + half] = rstd;
+            }
+          }
+          {
+            float v[32];
+            tmem_ld_32x32(t_row + static_cast<uint32_t>(128 + 32 * half), v);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + as);
+            if (live) {
+              if (p.bias != nullptr) {
+                float b[32];
+                load_cols(p.bias, n0 + 128 + 32 * half, p.N, b);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += b[j];
+              }
+              if (p.is_f16) st_row_16<__half>(slab + 4096, lane, v); else st_row_16<__nv_bfloat16>(slab + 4096, lane, v);
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&map_o16, slab, n0 + 32 * cq, mrow);
+                tma_store_2d(&map_o16, slab + 2048, n0 + 32 * cq + 32, mrow);
+                tma_store_2d(&map_o16, slab + 4096, n0 + 128 + 32 * half, mrow);
+                tma_store_commit();
+              }
+            }
+          }
+          if (++as == 2) { as = 0; aphase ^= 1u; }
+          continue;
+        }
+      }
 #pragma unroll 1
       for (int ci = 0; ci < kChunksPerWarp; ++ci) {
         const int c = half * kChunksPerWarp + ci;
@@ -615,6 +688,7 @@ static int launch(const Maps& mp, GemmParams& p, cudaStream_t st) {
 }
 
 static int pick_bn(const bf_gemm_args& a) {
+  if (a.epilogue == BF_EPI_QKV_LN) return 192;                                // one tile = one head (q | k | v)
   if (a.bn == 64 || a.bn == 128 || a.bn == 192 || a.bn == 256) return a.bn;   // caller override (tuning)
   const int N = a.N;
   if (N <= 64) return 64;
@@ -663,12 +737,20 @@ extern "C" int bf_gemm(const bf_gemm_args* a, void* stream) {
   p.out16 = a->out16;
   p.ldo = a->ldo;
   p.stats_out = a->stats_out;
+  p.ln_rstd = a->ln_rstd;
   for (const float* v : {a->bias, a->col_scale, a->col_shift, a->col_gamma})
     BF_REQUIRE((reinterpret_cast<uintptr_t>(v) & 15) == 0, "bf_gemm: per-column vectors must be 16-byte aligned");
 
   // epilogue operand checks
   switch (a->epilogue) {
     case BF_EPI_STORE16: case BF_EPI_GELU: BF_REQUIRE(a->out16, "bf_gemm: out16 required"); break;
+    case BF_EPI_QKV_LN:
+      BF_REQUIRE(a->out16 && a->ln_rstd, "bf_gemm: QKV_LN needs out16 and ln_rstd");
+      BF_REQUIRE(a->ln_head_dim == 64 && a->N % 192 == 0,
+                 "bf_gemm: QKV_LN is specialised for head_dim 64 (N a multiple of 192), got head_dim=%d N=%d",
+                 a->ln_head_dim, a->N);
+      BF_REQUIRE(a->bn == 0 || a->bn == 192, "bf_gemm: QKV_LN needs the 192-column tile");
+      break;
     case BF_EPI_STORE32: case BF_EPI_ATOMIC32: BF_REQUIRE(a->out32, "bf_gemm: out32 required"); break;
     case BF_EPI_RESID:
       BF_REQUIRE(a->out32 && a->in32 && a->col_gamma, "bf_gemm: RESID needs in32/out32/col_gamma");

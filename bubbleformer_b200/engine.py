@@ -111,7 +111,15 @@ def _attn_branch_fwd(X, g: Geom, p: Dict[str, torch.Tensor], w16, heads: int, ax
     Xn = _empty((N, E), BF16, X)
     ops.inorm_apply(X, Xn, I, P, st1, p["norm1.weight"], p["norm1.bias"])
     QKV = _empty((N, 3 * E), BF16, X)
-    ops.gemm(Xn, w16("input_head.weight"), N, 3 * E, E, epilogue=L.EPI_STORE16, bias=p["input_head.bias"], out16=QKV)
+    # head_dim 64 and short axes: LayerNorm(q), LayerNorm(k) are computed in the QKV GEMM epilogue (xhat + rstd) and
+    # the attention kernels work on the pre-normalised rows; otherwise the generic kernels normalise in place
+    prenorm = (E // heads == 64) and all(_axis(g, ax)["L_"] <= 32 for ax in axes)
+    rstd = _empty((N, heads, 2), F32, X) if prenorm else None
+    if prenorm:
+        ops.gemm(Xn, w16("input_head.weight"), N, 3 * E, E, epilogue=L.EPI_QKV_LN, bias=p["input_head.bias"], out16=QKV,
+                 ln_head_dim=64, ln_rstd=rstd)
+    else:
+        ops.gemm(Xn, w16("input_head.weight"), N, 3 * E, E, epilogue=L.EPI_STORE16, bias=p["input_head.bias"], out16=QKV)
     O = _empty((N, E), BF16, X)
     oscale = 1.0 / len(axes)
     for i, ax in enumerate(axes):
@@ -120,7 +128,7 @@ def _attn_branch_fwd(X, g: Geom, p: Dict[str, torch.Tensor], w16, heads: int, ax
         ops.attention(QKV, O, heads=heads, qn_w=p["qnorm.weight"], qn_b=p["qnorm.bias"], kn_w=p["knorm.weight"],
                       kn_b=p["knorm.bias"], bias_emb=p["rel_pos_bias.relative_attention_bias.weight"],
                       bucket=relpos_bucket_vector(geo["L_"], X.device), scale_factor=sf, out_scale=oscale,
-                      accumulate=i > 0, **geo)
+                      accumulate=i > 0, prenorm=prenorm, **geo)
     st2 = _zeros((I, E, 2), X)
     ops.inorm_stats(O, I, P, st2)
     On = _empty((N, E), BF16, X)
@@ -131,7 +139,7 @@ def _attn_branch_fwd(X, g: Geom, p: Dict[str, torch.Tensor], w16, heads: int, ax
     ops.gemm(On, w16("output_head.weight"), N, E, E, epilogue=L.EPI_RESID, bias=p["output_head.bias"],
              col_scale=col_scale, col_shift=col_shift, col_gamma=gamma, row_scale=mask_img, rows_per_group=P,
              in32=X, out32=Xout, out16=X16, out16b=Z)
-    saved = dict(X=X, st1=st1, Xn=Xn, QKV=QKV, O=O, st2=st2, On=On, Z=Z) if save else None
+    saved = dict(X=X, st1=st1, Xn=Xn, QKV=QKV, rstd=rstd, O=O, st2=st2, On=On, Z=Z) if save else None
     return Xout, X16, saved
 
 
@@ -172,7 +180,7 @@ def _attn_branch_bwd(dXout, g: Geom, p, w16, heads: int, axes, scale_keys, mask_
         ops.attention(QKV, dQKV, heads=heads, qn_w=p["qnorm.weight"], qn_b=p["qnorm.bias"], kn_w=p["knorm.weight"],
                       kn_b=p["knorm.bias"], bias_emb=p["rel_pos_bias.relative_attention_bias.weight"],
                       bucket=relpos_bucket_vector(geo["L_"], dXout.device), scale_factor=sf, out_scale=oscale,
-                      accumulate=i > 0, dout=dO, grads=gr, **geo)
+                      accumulate=i > 0, dout=dO, grads=gr, prenorm=sv["rstd"] is not None, rstd=sv["rstd"], **geo)
     ops.colsum16(dQKV, grads["input_head.bias"])
     # input_head
     dXn = _empty((N, E), BF16, dXout)

@@ -41,6 +41,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, epilogue: 
          s2d: Optional[tuple] = None, d2s: Optional[tuple] = None, rows_per_group: int = 1,
          bias=None, col_scale=None, col_shift=None, col_gamma=None, row_scale=None,
          in32=None, aux16=None, out16=None, out16b=None, out32=None, stats_out=None,
+         ln_head_dim: int = 0, ln_rstd=None,
          ldo: Optional[int] = None, ld32: Optional[int] = None) -> None:
     """D[M,N] = sum_k A[m,k] B[n,k] with a fused epilogue; see bf_gemm in include/bubbleformer_b200.h."""
     if A.dtype not in _DT or B.dtype != A.dtype:
@@ -82,6 +83,9 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, epilogue: 
     a.ldo, a.ld32 = ldo, ld32
     if stats_out is not None:
         a.stats_out = _f32(stats_out, 2 * N * ((M + rows_per_group - 1) // rows_per_group), "stats_out")
+    if ln_rstd is not None:
+        a.ln_head_dim = ln_head_dim
+        a.ln_rstd = _f32(ln_rstd, 2 * M * (N // (3 * max(ln_head_dim, 1))), "ln_rstd")
     L.check(L.lib.bf_gemm(C.byref(a), _stream()), "bf_gemm")
 
 
@@ -194,9 +198,11 @@ def colsum16(x, out) -> None:
 # attention
 # ---------------------------------------------------------------------------------------------
 def attention(qkv, out, *, heads, L_, n_seq, inner, outer_stride, inner_stride, tok_stride, qn_w, qn_b, kn_w, kn_b,
-              bias_emb, bucket, scale_factor=None, out_scale=1.0, accumulate=False, dout=None, grads=None) -> None:
+              bias_emb, bucket, scale_factor=None, out_scale=1.0, accumulate=False, dout=None, grads=None,
+              prenorm=False, rstd=None) -> None:
     """Forward (dout is None): out (tokens, E).  Backward: out is dqkv (tokens, 3E); grads = dict of fp32
-    accumulators d_qn_w, d_qn_b, d_kn_w, d_kn_b, d_bias_emb, d_scale_factor."""
+    accumulators d_qn_w, d_qn_b, d_kn_w, d_kn_b, d_bias_emb, d_scale_factor.
+    prenorm: qkv holds xhat_q | xhat_k | v from gemm(epilogue=EPI_QKV_LN); the backward needs `rstd`."""
     _mat(qkv, "qkv"); _mat(out, "out")
     if qkv.dtype != torch.bfloat16 or out.dtype != torch.bfloat16:
         raise L.BubbleformerB200Error("attention: bf16 tensors required")
@@ -214,6 +220,9 @@ def attention(qkv, out, *, heads, L_, n_seq, inner, outer_stride, inner_stride, 
     a.bucket = _ptr(bucket)
     a.scale_factor = _f32(scale_factor, heads, "scale_factor")
     a.out_scale = out_scale
+    a.prenorm = int(prenorm)
+    if rstd is not None:
+        a.rstd = _f32(rstd, 2 * heads * qkv.shape[0], "rstd")
     if dout is None:
         L.check(L.lib.bf_attention_fwd(C.byref(a), _stream()), "bf_attention_fwd")
         return

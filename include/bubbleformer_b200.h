@@ -73,7 +73,11 @@ enum bf_epilogue {
   BF_EPI_ATOMIC32 = 5,/* out32 += acc (TMA reduce-add): split-K wgrad accumulating straight into the fp32 grad */
   BF_EPI_D2S = 6,     /* out16 scattered depth-to-space: m = (img, y, x), n = (ky, kx, co) ->
                          out16[((img*2h + 2y+ky)*2w + 2x+kx)*cout + co]  (ConvTranspose2d k2 s2)        */
-  BF_EPI_STORE32 = 7  /* out32 = acc + bias                                                            */
+  BF_EPI_STORE32 = 7, /* out32 = acc + bias                                                            */
+  BF_EPI_QKV_LN = 8   /* QKV projection with the per-head LayerNorm of q and k (upstream layers/attention.py:82,
+                         214) fused in: columns are head*3d + [q | k | v], d = ln_head_dim = 64.  out16 receives
+                         xhat_q = (q - mean)*rstd, xhat_k (no affine part: bf_attention applies it) and v;
+                         ln_rstd[m][head][0..1] = rstd of the raw q / k rows (needed by the backward)          */
 };
 
 typedef struct bf_gemm_args {
@@ -84,7 +88,7 @@ typedef struct bf_gemm_args {
   int32_t epilogue;
   int32_t split_k; /* >= 1; > 1 only with BF_EPI_ATOMIC32 */
   int32_t bn;      /* 0 = choose the N tile automatically; 64/128/192/256 force it (tuning) */
-  int32_t reserved0;
+  int32_t ln_head_dim; /* BF_EPI_QKV_LN: head dimension (64) */
   const void* A;
   const void* B;
   int64_t lda, ldb;
@@ -107,6 +111,7 @@ typedef struct bf_gemm_args {
   float* stats_out;       /* BF_EPI_RESID only, may be NULL: stats_out[m / rows_per_group][n] += (sum, sum^2) of
                              out32 -- the raw InstanceNorm statistics of the new residual stream, so the next
                              norm needs no separate pass (rows_per_group = tokens per image, multiple of 32)   */
+  float* ln_rstd;         /* BF_EPI_QKV_LN only: (M, N / (3*ln_head_dim), 2) fp32                                */
 } bf_gemm_args;
 
 BF_API int bf_gemm(const bf_gemm_args* args, void* stream);
@@ -204,9 +209,13 @@ typedef struct bf_attn_args {
   const float* bias_emb;       /* [32][heads] */
   const int32_t* bucket;       /* [2L-1] */
   const float* scale_factor;   /* [heads] or NULL (attn_scale=False) */
-  float out_scale;  int32_t reserved0;
+  float out_scale;
+  int32_t prenorm;             /* 1: qkv holds xhat_q | xhat_k | v as written by bf_gemm(BF_EPI_QKV_LN): the kernel
+                                  applies the LayerNorm affine itself and the backward returns gradients w.r.t. the
+                                  RAW q / k using `rstd`.  Fast path: head_dim 64, L <= 32.                        */
   float* d_qn_w;  float* d_qn_b;  float* d_kn_w;  float* d_kn_b;
   float* d_bias_emb;  float* d_scale_factor;
+  const float* rstd;           /* prenorm backward: (tokens, heads, 2) rstd of the raw q / k rows                  */
 } bf_attn_args;
 BF_API int bf_attention_fwd(const bf_attn_args* args, void* stream);
 BF_API int bf_attention_bwd(const bf_attn_args* args, void* stream);

@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 
 VARIANTS = [
     "nk_small", "nk_ragged", "nk_bn64", "nk_bn128", "nk_bn192", "nk_bn256", "nk_big",
-    "nk_f16", "gelu", "resid", "dgelu", "acc32", "store32",
+    "nk_f16", "gelu", "resid", "resid_stats", "qkv_ln", "dgelu", "acc32", "store32",
     "kn_dgrad", "kn_dgrad_256", "wgrad", "wgrad_split", "wgrad_192",
     "s2d_w128", "s2d_w32", "s2d_c48", "d2s", "d2s_c48", "perf",
 ]
@@ -103,6 +103,36 @@ def run_variant(v):
             out = torch.zeros(M, N, device=dev)
             ops.gemm(A, B, M, N, K, epilogue=L.EPI_ACC32, in32=g, out32=out)
             ok &= report(v, out, g + A.float() @ B.float().t(), 1e-5)
+    elif v == "qkv_ln":
+        for (M, heads) in [(1000, 2), (4096, 6)]:
+            N, K, d = heads * 192, 384, 64
+            A, B = rnd(M, K), rnd(N, K, scale=K ** -0.5)
+            bias = torch.randn(N, device=dev)
+            ref = (A.float() @ B.float().t() + bias).reshape(M, heads, 3, d)
+            qk = ref[:, :, :2]
+            mu, var = qk.mean(-1, keepdim=True), qk.var(-1, unbiased=False, keepdim=True)
+            want = ref.clone()
+            want[:, :, :2] = (qk - mu) * torch.rsqrt(var + 1e-5)
+            out = torch.zeros(M, N, device=dev, dtype=dt)
+            rstd = torch.zeros(M, heads, 2, device=dev)
+            ops.gemm(A, B, M, N, K, epilogue=L.EPI_QKV_LN, bias=bias, out16=out, ln_head_dim=d, ln_rstd=rstd)
+            ok &= report(f"{v} xhat|v M={M}", out, want.reshape(M, N), 1e-2)
+            ok &= report(f"{v} rstd M={M}", rstd.reshape(M, -1), torch.rsqrt(var + 1e-5).reshape(M, -1), 1e-3)
+    elif v == "resid_stats":
+        M, N, K, rpg = 1024, 384, 384, 256
+        A, B = rnd(M, K), rnd(N, K, scale=K ** -0.5)
+        bias = torch.randn(N, device=dev)
+        xin = torch.randn(M, N, device=dev)
+        cg = torch.randn(N, device=dev)
+        rs = torch.rand(M // rpg, device=dev)
+        out32 = torch.zeros(M, N, device=dev)
+        st = torch.zeros(M // rpg, N, 2, device=dev)
+        ops.gemm(A, B, M, N, K, epilogue=L.EPI_RESID, bias=bias, col_gamma=cg, row_scale=rs, rows_per_group=rpg,
+                 in32=xin, out32=out32, stats_out=st)
+        want = xin + rs.repeat_interleave(rpg)[:, None] * cg * (A.float() @ B.float().t() + bias)
+        ok &= report(v + ".x32", out32, want, 1e-5)
+        wi = want.reshape(M // rpg, rpg, N)
+        ok &= report(v + ".stats", st, torch.stack([wi.sum(1), (wi * wi).sum(1)], dim=-1), 1e-4)
     elif v.startswith("kn_dgrad"):
         M, N, K = (4096, 384, 1536) if v == "kn_dgrad" else (2048, 1536, 384)
         A, Bkn = rnd(M, K), rnd(K, N, scale=K ** -0.5)          # B stored (K, N)

@@ -231,6 +231,39 @@ def run(group):
         ok &= report(f"{group} d_bias_emb", grads["d_bias_emb"], params[4].grad, 3e-2)
         if sf is not None:
             ok &= report(f"{group} d_scale_factor", grads["d_scale_factor"], sfp.grad, 3e-2)
+        if d == 64 and Ls <= 32:
+            # pre-normalised fast path: rows hold xhat_q | xhat_k | v (as the QKV GEMM epilogue writes them) + rstd
+            x4 = qkv.float().reshape(tokens, he, 3, d)
+            qk = x4[:, :, :2]
+            mu = qk.mean(-1, keepdim=True)
+            rstd = torch.rsqrt(qk.var(-1, unbiased=False, keepdim=True) + 1e-5)
+            xn = x4.clone()
+            xn[:, :, :2] = (qk - mu) * rstd
+            qkvn = xn.reshape(tokens, 3 * E).bfloat16()
+            rstd = rstd[..., 0].contiguous()
+            out = torch.zeros(tokens, E, device=dev, dtype=torch.bfloat16)
+            ops.attention(qkvn, out, prenorm=True, **common)
+            ok &= report(f"{group} prenorm fwd", out, ref, 1.5e-2)
+            out2 = out.clone()
+            ops.attention(qkvn, out2, accumulate=True, prenorm=True, **common)
+            ok &= report(f"{group} prenorm fwd accumulate", out2, 2 * ref, 1.5e-2)
+            dqkv = torch.zeros(tokens, 3 * E, device=dev, dtype=torch.bfloat16)
+            grads = dict(d_qn_w=torch.zeros(d, device=dev), d_qn_b=torch.zeros(d, device=dev), d_kn_w=torch.zeros(d, device=dev),
+                         d_kn_b=torch.zeros(d, device=dev), d_bias_emb=torch.zeros(32, he, device=dev),
+                         d_scale_factor=torch.zeros(he, device=dev) if sf is not None else None)
+            ops.attention(qkvn, dqkv, dout=dout, grads=grads, prenorm=True, rstd=rstd, **common)
+            got = dqkv.float().reshape(tokens, he, 3, d)
+            for i, nm in enumerate("qkv"):
+                ok &= report(f"{group} prenorm d{nm}", got[:, :, i], dq_ref[:, :, i], 3e-2)
+            ok &= report(f"{group} prenorm d_qn_w", grads["d_qn_w"], params[0].grad, 3e-2)
+            ok &= report(f"{group} prenorm d_qn_b", grads["d_qn_b"], params[1].grad, 3e-2)
+            ok &= report(f"{group} prenorm d_kn_w", grads["d_kn_w"], params[2].grad, 3e-2)
+            ok &= report(f"{group} prenorm d_bias_emb", grads["d_bias_emb"], params[4].grad, 3e-2)
+            if sf is not None:
+                ok &= report(f"{group} prenorm d_scale_factor", grads["d_scale_factor"], sfp.grad, 3e-2)
+            dq2 = dqkv.clone()
+            ops.attention(qkvn, dq2, dout=dout, grads=grads, prenorm=True, rstd=rstd, accumulate=True, **common)
+            ok &= report(f"{group} prenorm bwd accumulate", dq2, 2 * dqkv.float(), 1.5e-2)
     elif group == "patch":
         for (I, Fd, H, W, N, dt) in [(2, 4, 64, 64, 96, torch.float16), (3, 2, 32, 48, 24, torch.float16),
                                      (1, 1, 16, 16, 384, torch.bfloat16)]:

@@ -21,7 +21,8 @@ def _gelu_grad(x):
 
 def gemm(A, B, M, N, K, *, epilogue, a_mode=L.A_ROWMAJOR, b_mode=L.B_NK, split_k=1, bn=0, lda=None, ldb=None,
          s2d=None, d2s=None, rows_per_group=1, bias=None, col_scale=None, col_shift=None, col_gamma=None,
-         row_scale=None, in32=None, aux16=None, out16=None, out16b=None, out32=None, ldo=None, ld32=None):
+         row_scale=None, in32=None, aux16=None, out16=None, out16b=None, out32=None, stats_out=None,
+         ln_head_dim=0, ln_rstd=None, ldo=None, ld32=None):
     a = A.float()
     if a_mode == L.A_KM:
         a = a.reshape(K, M).t()
@@ -35,7 +36,16 @@ def gemm(A, B, M, N, K, *, epilogue, a_mode=L.A_ROWMAJOR, b_mode=L.B_NK, split_k
     acc = a @ b
     if bias is not None:
         acc = acc + bias
-    if epilogue == L.EPI_STORE16:
+    if epilogue == L.EPI_QKV_LN:
+        d = ln_head_dim
+        x = acc.reshape(M, N // (3 * d), 3, d).clone()
+        qk = x[:, :, :2]
+        mean = qk.mean(-1, keepdim=True)
+        rstd = torch.rsqrt(qk.var(-1, unbiased=False, keepdim=True) + EPS)
+        x[:, :, :2] = (qk - mean) * rstd
+        out16.reshape(M, N).copy_(x.reshape(M, N))
+        ln_rstd.reshape(M, N // (3 * d), 2).copy_(rstd[..., 0])
+    elif epilogue == L.EPI_STORE16:
         out16.reshape(M, N).copy_(acc)
     elif epilogue == L.EPI_STORE32:
         out32.reshape(M, N).copy_(acc)
@@ -56,6 +66,9 @@ def gemm(A, B, M, N, K, *, epilogue, a_mode=L.A_ROWMAJOR, b_mode=L.B_NK, split_k
         out32.reshape(M, N).copy_(xo)
         if out16 is not None:
             out16.reshape(M, N).copy_(xo)
+        if stats_out is not None:
+            xi = out32.reshape(-1, rows_per_group, N)
+            stats_out.reshape(-1, N, 2).add_(torch.stack([xi.sum(1), (xi * xi).sum(1)], dim=-1))
     elif epilogue == L.EPI_DGELU:
         out16.reshape(M, N).copy_(acc * _gelu_grad(aux16.reshape(M, N).float()))
     elif epilogue == L.EPI_ACC32:
@@ -164,14 +177,15 @@ def _seq_index(n_seq, L_, inner, outer_stride, inner_stride, tok_stride):
 
 
 def attention(qkv, out, *, heads, L_, n_seq, inner, outer_stride, inner_stride, tok_stride, qn_w, qn_b, kn_w, kn_b,
-              bias_emb, bucket, scale_factor=None, out_scale=1.0, accumulate=False, dout=None, grads=None):
+              bias_emb, bucket, scale_factor=None, out_scale=1.0, accumulate=False, dout=None, grads=None,
+              prenorm=False, rstd=None):
     with torch.enable_grad():       # called from inside autograd.Function.backward (grad mode off)
         return _attention(qkv, out, heads, L_, n_seq, inner, outer_stride, inner_stride, tok_stride, qn_w, qn_b, kn_w,
-                          kn_b, bias_emb, bucket, scale_factor, out_scale, accumulate, dout, grads)
+                          kn_b, bias_emb, bucket, scale_factor, out_scale, accumulate, dout, grads, prenorm, rstd)
 
 
 def _attention(qkv, out, heads, L_, n_seq, inner, outer_stride, inner_stride, tok_stride, qn_w, qn_b, kn_w, kn_b,
-               bias_emb, bucket, scale_factor, out_scale, accumulate, dout, grads):
+               bias_emb, bucket, scale_factor, out_scale, accumulate, dout, grads, prenorm=False, rstd=None):
     idx = _seq_index(n_seq, L_, inner, outer_stride, inner_stride, tok_stride)
     E3 = qkv.shape[1]
     E = E3 // 3
@@ -181,8 +195,12 @@ def _attention(qkv, out, heads, L_, n_seq, inner, outer_stride, inner_stride, to
     q32 = leaves[0]
     x = q32[idx].reshape(n_seq, L_, heads, 3, d).permute(0, 2, 3, 1, 4)
     q, k, v = x[:, :, 0], x[:, :, 1], x[:, :, 2]
-    q = F.layer_norm(q, (d,), leaves[1], leaves[2], EPS)
-    k = F.layer_norm(k, (d,), leaves[3], leaves[4], EPS)
+    if prenorm:                     # rows already hold xhat: only the affine part is left
+        q = q * leaves[1] + leaves[2]
+        k = k * leaves[3] + leaves[4]
+    else:
+        q = F.layer_norm(q, (d,), leaves[1], leaves[2], EPS)
+        k = F.layer_norm(k, (d,), leaves[3], leaves[4], EPS)
     i = torch.arange(L_)
     bias = leaves[5][bucket.long()[i[None, :] - i[:, None] + L_ - 1]].permute(2, 0, 1)
     p = torch.softmax(q @ k.transpose(-1, -2) * d ** -0.5 + bias, dim=-1)
@@ -200,6 +218,14 @@ def _attention(qkv, out, heads, L_, n_seq, inner, outer_stride, inner_stride, to
         return
     (o * dout.float()[idx]).sum().backward()
     dq = leaves[0].grad
+    if prenorm:                     # gradient w.r.t. xhat -> gradient w.r.t. the raw rows (LayerNorm backward)
+        T = qkv.shape[0]
+        gx = dq.reshape(T, heads, 3, d).clone()
+        xh = qkv.float().reshape(T, heads, 3, d)[:, :, :2]
+        gqk = gx[:, :, :2]
+        gx[:, :, :2] = rstd.reshape(T, heads, 2, 1) * (gqk - gqk.mean(-1, keepdim=True)
+                                                      - xh * (gqk * xh).mean(-1, keepdim=True))
+        dq = gx.reshape(T, 3 * heads * d)
     if accumulate:
         out.copy_(out.float() + dq)
     else:

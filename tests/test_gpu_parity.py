@@ -24,7 +24,7 @@ def _native_loaded():
 
 
 @pytest.mark.parametrize("variant", [
-    "nk_small", "nk_ragged", "nk_bn64", "nk_bn128", "nk_bn192", "nk_bn256", "nk_big", "nk_f16", "gelu", "resid",
+    "nk_small", "nk_ragged", "nk_bn64", "nk_bn128", "nk_bn192", "nk_bn256", "nk_big", "nk_f16", "gelu", "resid", "resid_stats", "qkv_ln",
     "dgelu", "acc32", "store32", "kn_dgrad", "kn_dgrad_256", "wgrad", "wgrad_split", "wgrad_192", "s2d_w128",
     "s2d_w32", "s2d_c48", "d2s", "d2s_c48"])
 def test_gemm(variant):
