@@ -75,7 +75,7 @@ class InormApplyArgs(C.Structure):
         ("film_gamma", C.c_void_p), ("film_beta", C.c_void_p),
         ("film_T", C.c_int32), ("reserved0", C.c_int32),
         ("resid_in", C.c_void_p), ("row_scale", C.c_void_p), ("col_gamma", C.c_void_p),
-        ("out", C.c_void_p),
+        ("out", C.c_void_p), ("stats_out", C.c_void_p),
     ]
 
 

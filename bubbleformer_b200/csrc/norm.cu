@@ -5,62 +5,47 @@
 // GELU (patching.py:47,103), FiLM (linear_layers.py:71-77), layer-scale * drop-path + residual
 // (attention.py:317).  Also the residual-branch backward helper and column sums for bias gradients.
 //
-// All kernels are HBM-bound streaming passes: 16-byte vector accesses, each thread owns a fixed set of
-// channels and strides over rows, so consecutive threads touch consecutive addresses; block partials are
-// combined in shared memory and flushed with one fp32 atomic per (image, channel).
+// All kernels are HBM-bound streaming passes built on one pattern: a thread owns 8 consecutive channels and
+// walks down the rows of its image slice; its loads are issued several rows ahead with cp.async (16 B each)
+// into a private ring of shared-memory slots, so tens of KB per SM are in flight without holding registers
+// and without any block-level synchronisation in the loop (a thread only ever reads back what it copied).
+// The grid is sized to exactly one resident wave (3 CTAs per SM); per-(image, channel) partial sums are
+// combined in shared memory and flushed with one fp32 atomic per block.
 // Statistics are kept as raw sums (sum x, sum x^2) per (image, channel) so producers can accumulate them.
 #include "common.cuh"
 
 namespace bf {
 
-constexpr int kNormThreads = 256;
+constexpr int kNT = 256;                 // threads per block
+constexpr int kRingBytes = 64 * 1024;    // cp.async ring per block
+constexpr int kBlocksPerSM = 3;
 
-template <typename T> struct Vec;          // 16-byte vector of T
-template <> struct Vec<float> { static constexpr int N = 4; };
-template <> struct Vec<__nv_bfloat16> { static constexpr int N = 8; };
-template <> struct Vec<__half> { static constexpr int N = 8; };
-
-template <typename T, int N>
-__device__ __forceinline__ void load_vec(const T* p, float (&v)[N], bool vec) {
-  if (vec) {
-    if constexpr (sizeof(T) == 4) {
-      float4 u = *reinterpret_cast<const float4*>(p);
-      v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w;
-    } else {
-      uint4 u = *reinterpret_cast<const uint4*>(p);
-      float2 a = unpack2<T>(u.x), b = unpack2<T>(u.y), c = unpack2<T>(u.z), d = unpack2<T>(u.w);
-      v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < N; ++j) v[j] = to_f32<T>(p[j]);
-  }
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
 }
-template <typename T, int N>
-__device__ __forceinline__ void store_vec(T* p, const float (&v)[N], bool vec) {
-  if (vec) {
-    if constexpr (sizeof(T) == 4) {
-      *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-    } else {
-      uint4 u;
-      u.x = pack2<T>(v[0], v[1]); u.y = pack2<T>(v[2], v[3]); u.z = pack2<T>(v[4], v[5]); u.w = pack2<T>(v[6], v[7]);
-      *reinterpret_cast<uint4*>(p) = u;
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < N; ++j) p[j] = from_f32<T>(v[j]);
-  }
-}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// 8 consecutive channels per thread regardless of the storage type (16 B for 16-bit, 2 x 16 B for fp32)
+// number of 16-byte slots that 8 channels of type T occupy
+template <typename T> struct Slots { static constexpr int N = sizeof(T) * 8 / 16; };
+
 template <typename T>
-__device__ __forceinline__ void load8(const T* p, float (&v)[8]) {
+__device__ __forceinline__ void unpack8(const uint4* slot, float (&v)[8]) {
   if constexpr (sizeof(T) == 4) {
-    const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+    const float4 a = *reinterpret_cast<const float4*>(slot), b = *reinterpret_cast<const float4*>(slot + kNT);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   } else {
-    load_vec<T, 8>(p, v, true);
+    const uint4 u = *slot;
+    const float2 a = unpack2<T>(u.x), b = unpack2<T>(u.y), c = unpack2<T>(u.z), d = unpack2<T>(u.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
   }
+}
+// slot layout: ring[(stage * NSLOT + slot) * kNT + tid]; a fp32 tensor uses two consecutive slot indices
+template <typename T>
+__device__ __forceinline__ void issue8(uint4* slot, const T* src) {
+  cp_async16(slot, src);
+  if constexpr (sizeof(T) == 4) cp_async16(slot + kNT, src + 4);
 }
 template <typename T>
 __device__ __forceinline__ void store8(T* p, const float (&v)[8]) {
@@ -68,111 +53,144 @@ __device__ __forceinline__ void store8(T* p, const float (&v)[8]) {
     reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
     reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
   } else {
-    store_vec<T, 8>(p, v, true);
+    uint4 u;
+    u.x = pack2<T>(v[0], v[1]); u.y = pack2<T>(v[2], v[3]); u.z = pack2<T>(v[4], v[5]); u.w = pack2<T>(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = u;
   }
 }
 
-// Thread geometry shared by all row-streaming kernels: a block covers `tx_n` vector columns and
-// `ty_n` rows at a time; grid = (column chunks, row splits, images).
-struct RowGeom {
-  int vc;       // vector columns in a row (C / N)
-  int tx_n;     // vector columns per block
-  int ty_n;     // rows in flight per block
-  int chunks;   // column chunks
-  int splits;   // row splits per image
+// Geometry shared by all kernels: block = tx_n vector columns x ty_n rows; grid = (splits, images, column chunks)
+struct Geom {
+  int I, P, C;
+  int vc, tx_n, ty_n, chunks, splits, rows_per_split, n_it;
 };
-static RowGeom make_geom(int C, int vecn, int P, int I) {
-  RowGeom g;
-  g.vc = C / vecn;
-  g.tx_n = g.vc < 128 ? g.vc : 128;
-  g.chunks = (g.vc + g.tx_n - 1) / g.tx_n;
-  g.ty_n = kNormThreads / g.tx_n;
-  const int want_blocks = 4 * num_sms();
-  int splits = (want_blocks + I * g.chunks - 1) / (I * g.chunks);
-  const int max_splits = (P + 8 * g.ty_n - 1) / (8 * g.ty_n);     // keep >= 8 rows per thread (unrolled loops)
+static Geom make_geom(int I, int P, int C) {
+  Geom g;
+  g.I = I; g.P = P; g.C = C;
+  g.vc = C / 8;
+  // column chunking that keeps the most threads busy (tx_n * floor(256 / tx_n)), fewest chunks on ties
+  int best_chunks = 1, best_active = -1;
+  for (int ch = (g.vc + kNT - 1) / kNT; ch <= (g.vc + 31) / 32 || ch == 1; ++ch) {
+    const int tx = (g.vc + ch - 1) / ch;
+    if (tx > kNT) continue;
+    const int active = tx * (kNT / tx);
+    if (active > best_active) { best_active = active; best_chunks = ch; }
+    if (ch > 64) break;
+  }
+  g.chunks = best_chunks;
+  g.tx_n = (g.vc + g.chunks - 1) / g.chunks;
+  g.ty_n = kNT / g.tx_n;
+  const int target = num_sms() * kBlocksPerSM;                  // one resident wave
+  int splits = target / (I * g.chunks);
+  const int max_splits = (P + g.ty_n - 1) / g.ty_n;             // at least one row per thread row
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   g.splits = splits;
+  g.rows_per_split = (P + splits - 1) / splits;
+  g.n_it = (g.rows_per_split + g.ty_n - 1) / g.ty_n;
   return g;
 }
 
-struct NormCommon {
-  int I, P, C;
-  long ldx;
-  RowGeom g;
+struct Ctx {            // per-thread view of the geometry
+  int tx, ty, vcol, img, r0, r1;
+  bool active;
 };
+__device__ __forceinline__ Ctx make_ctx(const Geom& g) {
+  Ctx c;
+  c.tx = threadIdx.x % g.tx_n;
+  c.ty = threadIdx.x / g.tx_n;
+  c.vcol = blockIdx.z * g.tx_n + c.tx;
+  c.img = blockIdx.y;
+  c.r0 = blockIdx.x * g.rows_per_split;
+  c.r1 = min(g.P, c.r0 + g.rows_per_split);
+  c.active = c.ty < g.ty_n && c.vcol < g.vc;
+  return c;
+}
 
-// ---------------------------------------------------------------------------------------------
-// statistics: stats[img][c] += (sum x, sum x^2)
-// ---------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(kNormThreads)
-inorm_stats_kernel(const T* __restrict__ x, NormCommon nc, float* __restrict__ stats) {
-  constexpr int N = Vec<T>::N;
-  extern __shared__ float red[];                       // [ty_n][tx_n][2N]
-  const RowGeom& g = nc.g;
-  const int tx = threadIdx.x % g.tx_n, ty = threadIdx.x / g.tx_n;
-  const int vcol = blockIdx.x * g.tx_n + tx;
-  const int img = blockIdx.z;
-  const bool active = ty < g.ty_n && vcol < g.vc;
-  const int rows_per_split = (nc.P + g.splits - 1) / g.splits;
-  const int r0 = blockIdx.y * rows_per_split;
-  const int r1 = min(nc.P, r0 + rows_per_split);
-  float s[N], q[N];
+// block reduction of per-thread column partials v[NV] over ty, result in ty == 0 threads.  `red` >= ty_n*tx_n*NV floats.
+template <int NV>
+__device__ __forceinline__ void reduce_over_ty(float (&v)[NV], float* red, const Geom& g, const Ctx& c) {
+  __syncthreads();                                  // the ring is dead: reuse it
+  if (c.active) {
+    float* my = red + ((long)c.ty * g.tx_n + c.tx) * NV;
 #pragma unroll
-  for (int j = 0; j < N; ++j) { s[j] = 0.f; q[j] = 0.f; }
-  if (active) {
-    const T* base = x + ((long)img * nc.P) * nc.ldx + (long)vcol * N;
-    constexpr int UN = 4;
-    for (int r = r0 + ty; r < r1; r += UN * g.ty_n) {
-      float v[UN][N];
-#pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const int rr = r + u * g.ty_n;
-        if (rr < r1) load_vec<T, N>(base + (long)rr * nc.ldx, v[u], true);
-        else {
-#pragma unroll
-          for (int j = 0; j < N; ++j) v[u][j] = 0.f;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < UN; ++u) {
-#pragma unroll
-        for (int j = 0; j < N; ++j) { s[j] += v[u][j]; q[j] = fmaf(v[u][j], v[u][j], q[j]); }
-      }
-    }
-    float* my = red + ((long)ty * g.tx_n + tx) * 2 * N;
-#pragma unroll
-    for (int j = 0; j < N; ++j) { my[j] = s[j]; my[N + j] = q[j]; }
+    for (int j = 0; j < NV; ++j) my[j] = v[j];
   }
   __syncthreads();
-  if (active && ty == 0) {
+  if (c.active && c.ty == 0) {
     for (int t = 1; t < g.ty_n; ++t) {
-      const float* o = red + ((long)t * g.tx_n + tx) * 2 * N;
+      const float* o = red + ((long)t * g.tx_n + c.tx) * NV;
 #pragma unroll
-      for (int j = 0; j < N; ++j) { s[j] += o[j]; q[j] += o[N + j]; }
-    }
-    float* dst = stats + ((long)img * nc.C + (long)vcol * N) * 2;
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-      atomicAdd(dst + 2 * j, s[j]);
-      atomicAdd(dst + 2 * j + 1, q[j]);
+      for (int j = 0; j < NV; ++j) v[j] += o[j];
     }
   }
 }
 
 __device__ __forceinline__ void mean_rstd(const float* stats, long idx, float inv_p, float& mean, float& rstd) {
-  const float s = stats[2 * idx], q = stats[2 * idx + 1];
-  mean = s * inv_p;
-  const float var = fmaxf(q * inv_p - mean * mean, 0.f);
+  const float2 sq = *reinterpret_cast<const float2*>(stats + 2 * idx);
+  mean = sq.x * inv_p;
+  const float var = fmaxf(sq.y * inv_p - mean * mean, 0.f);
   rstd = rsqrtf(var + 1e-5f);
 }
 
+// The streaming loop.  ISSUE(row, stage) copies the thread's operands of one row; BODY(row, stage) consumes them.
+#define BF_STREAM_LOOP(S_, ISSUE, BODY)                                                   \
+  {                                                                                       \
+    _Pragma("unroll") for (int it_ = 0; it_ < (S_); ++it_) {                              \
+      const int row_ = c.r0 + c.ty + it_ * g.ty_n;                                        \
+      if (c.active && it_ < g.n_it && row_ < c.r1) { ISSUE(row_, it_) }                   \
+      cp_async_commit();                                                                  \
+    }                                                                                     \
+    int stage_ = 0;                                                                       \
+    for (int it_ = 0; it_ < g.n_it; ++it_) {                                              \
+      cp_async_wait<(S_) - 1>();                                                          \
+      const int row_ = c.r0 + c.ty + it_ * g.ty_n;                                        \
+      if (c.active && row_ < c.r1) { BODY(row_, stage_) }                                 \
+      const int nrow_ = row_ + (S_) * g.ty_n;                                             \
+      if (c.active && it_ + (S_) < g.n_it && nrow_ < c.r1) { ISSUE(nrow_, stage_) }       \
+      cp_async_commit();                                                                  \
+      if (++stage_ == (S_)) stage_ = 0;                                                   \
+    }                                                                                     \
+    cp_async_wait<0>();                                                                   \
+  }
+
+template <int NSLOT> struct Stages { static constexpr int S = (kRingBytes / (NSLOT * kNT * 16)) > 8 ? 8 : (kRingBytes / (NSLOT * kNT * 16)); };
+
 // ---------------------------------------------------------------------------------------------
-// apply: y = IN(x) [gelu] [film]; out = y | resid_in + row_scale*col_gamma*y
+// statistics: stats[img][c] += (sum x, sum x^2)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kNT, kBlocksPerSM)
+inorm_stats_kernel(const T* __restrict__ x, long ldx, Geom g, float* __restrict__ stats) {
+  constexpr int NSLOT = Slots<T>::N, S = Stages<NSLOT>::S;
+  extern __shared__ __align__(16) uint4 ring[];
+  const Ctx c = make_ctx(g);
+  const T* xb = x + ((long)c.img * g.P) * ldx + (long)c.vcol * 8;
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#define ISSUE(row, st) issue8<T>(ring + ((st) * NSLOT) * kNT + threadIdx.x, xb + (long)(row) * ldx);
+#define BODY(row, st)                                                        \
+  float v[8];                                                                \
+  unpack8<T>(ring + ((st) * NSLOT) * kNT + threadIdx.x, v);                  \
+  _Pragma("unroll") for (int j = 0; j < 8; ++j) { acc[j] += v[j]; acc[8 + j] = fmaf(v[j], v[j], acc[8 + j]); }
+  BF_STREAM_LOOP(S, ISSUE, BODY)
+#undef ISSUE
+#undef BODY
+  reduce_over_ty<16>(acc, reinterpret_cast<float*>(ring), g, c);
+  if (c.active && c.ty == 0) {
+    float* dst = stats + ((long)c.img * g.C + (long)c.vcol * 8) * 2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { atomicAdd(dst + 2 * j, acc[j]); atomicAdd(dst + 2 * j + 1, acc[8 + j]); }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// apply: y = IN(x) [gelu] [film]; out = y | resid_in + row_scale*col_gamma*y ; optional statistics of `out`
 // ---------------------------------------------------------------------------------------------
 struct ApplyParams {
-  NormCommon nc;
+  Geom g;
+  long ldx, ldo;
   const float* stats;
   const float* weight;
   const float* bias;
@@ -183,86 +201,77 @@ struct ApplyParams {
   const float* resid_in;     // fp32 (I*P, C) ld = ldo, or null
   const float* row_scale;    // [I] or null
   const float* col_gamma;    // [C] (with resid_in)
-  long ldo;
+  float* stats_out;          // [I][C][2] or null: += (sum, sum^2) of the values written
 };
 
-template <typename TI, typename TO>
-__global__ void __launch_bounds__(kNormThreads)
+template <typename TI, typename TO, bool RESID>
+__global__ void __launch_bounds__(kNT, kBlocksPerSM)
 inorm_apply_kernel(const TI* __restrict__ x, TO* __restrict__ out, ApplyParams p) {
-  constexpr int N = Vec<TI>::N;       // work unit = the input vector width
-  const RowGeom& g = p.nc.g;
-  const int tx = threadIdx.x % g.tx_n, ty = threadIdx.x / g.tx_n;
-  const int vcol = blockIdx.x * g.tx_n + tx;
-  const int img = blockIdx.z;
-  if (!(ty < g.ty_n && vcol < g.vc)) return;
-  const int c0 = vcol * N;
-  const float inv_p = 1.f / (float)p.nc.P;
-  float a[N], b[N], fg[N], fb[N], cg[N];
+  constexpr int NX = Slots<TI>::N, NSLOT = NX + (RESID ? 2 : 0), S = Stages<NSLOT>::S;
+  extern __shared__ __align__(16) uint4 ring[];
+  const Geom& g = p.g;
+  const Ctx c = make_ctx(g);
+  const int c0 = c.vcol * 8;
+  const float inv_p = 1.f / (float)g.P;
+  float a[8], b[8], fg[8], fb[8], cg[8];
+  if (c.active) {
 #pragma unroll
-  for (int j = 0; j < N; ++j) {
-    float mean, rstd;
-    mean_rstd(p.stats, (long)img * p.nc.C + c0 + j, inv_p, mean, rstd);
-    const float w = p.weight[c0 + j];
-    a[j] = rstd * w;
-    b[j] = p.bias[c0 + j] - mean * rstd * w;
-    if (p.film_gamma != nullptr) {
-      const long fi = (long)(img / p.film_T) * p.nc.C + c0 + j;
-      fg[j] = p.film_gamma[fi];
-      fb[j] = p.film_beta[fi];
+    for (int j = 0; j < 8; ++j) {
+      float mean, rstd;
+      mean_rstd(p.stats, (long)c.img * g.C + c0 + j, inv_p, mean, rstd);
+      const float w = p.weight[c0 + j];
+      a[j] = rstd * w;
+      b[j] = p.bias[c0 + j] - mean * rstd * w;
+      fg[j] = 1.f; fb[j] = 0.f; cg[j] = 1.f;
+      if (p.film_gamma != nullptr) {
+        const long fi = (long)(c.img / p.film_T) * g.C + c0 + j;
+        fg[j] = p.film_gamma[fi];
+        fb[j] = p.film_beta[fi];
+      }
+      if (RESID) cg[j] = p.col_gamma[c0 + j] * (p.row_scale != nullptr ? p.row_scale[c.img] : 1.f);
     }
-    if (p.resid_in != nullptr)
-      cg[j] = p.col_gamma[c0 + j] * (p.row_scale != nullptr ? p.row_scale[img] : 1.f);
+    if (!p.gelu && p.film_gamma != nullptr) {   // fold FiLM into the affine map
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a[j] *= fg[j]; b[j] = fmaf(fg[j], b[j], fb[j]); }
+    }
+    if (RESID) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a[j] *= cg[j]; b[j] *= cg[j]; }
+    }
   }
-  const int rows_per_split = (p.nc.P + g.splits - 1) / g.splits;
-  const int r0 = blockIdx.y * rows_per_split;
-  const int r1 = min(p.nc.P, r0 + rows_per_split);
-  const TI* xb = x + ((long)img * p.nc.P) * p.nc.ldx + c0;
-  TO* ob = out + ((long)img * p.nc.P) * p.ldo + c0;
-  const float* rb = p.resid_in != nullptr ? p.resid_in + ((long)img * p.nc.P) * p.ldo + c0 : nullptr;
-  constexpr int UN = 2;
-  for (int r = r0 + ty; r < r1; r += UN * g.ty_n) {
-    float vv[UN][N];
-    float xr[UN][N];
+  const bool post_film = p.gelu && p.film_gamma != nullptr;
+  const TI* xb = x + ((long)c.img * g.P) * p.ldx + c0;
+  TO* ob = out + ((long)c.img * g.P) * p.ldo + c0;
+  const float* rb = RESID ? p.resid_in + ((long)c.img * g.P) * p.ldo + c0 : nullptr;
+  float acc[16];
 #pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const int rr = r + u * g.ty_n;
-      if (rr < r1) {
-        load_vec<TI, N>(xb + (long)rr * p.nc.ldx, vv[u], true);
-        if (rb != nullptr) {
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  const bool want_stats = p.stats_out != nullptr;
+#define ISSUE(row, st)                                                                   \
+  issue8<TI>(ring + ((st) * NSLOT) * kNT + threadIdx.x, xb + (long)(row) * p.ldx);       \
+  if (RESID) issue8<float>(ring + ((st) * NSLOT + NX) * kNT + threadIdx.x, rb + (long)(row) * p.ldo);
+#define BODY(row, st)                                                                    \
+  float v[8];                                                                            \
+  unpack8<TI>(ring + ((st) * NSLOT) * kNT + threadIdx.x, v);                             \
+  _Pragma("unroll") for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], a[j], b[j]);          \
+  if (p.gelu) { _Pragma("unroll") for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]); }  \
+  if (post_film) { _Pragma("unroll") for (int j = 0; j < 8; ++j) v[j] = fmaf(fg[j], v[j], fb[j]); } \
+  if (RESID) {                                                                           \
+    float xr[8];                                                                         \
+    unpack8<float>(ring + ((st) * NSLOT + NX) * kNT + threadIdx.x, xr);                  \
+    _Pragma("unroll") for (int j = 0; j < 8; ++j) v[j] += xr[j];                         \
+  }                                                                                      \
+  if (want_stats) { _Pragma("unroll") for (int j = 0; j < 8; ++j) { acc[j] += v[j]; acc[8 + j] = fmaf(v[j], v[j], acc[8 + j]); } } \
+  store8<TO>(ob + (long)(row) * p.ldo, v);
+  BF_STREAM_LOOP(S, ISSUE, BODY)
+#undef ISSUE
+#undef BODY
+  if (want_stats) {
+    reduce_over_ty<16>(acc, reinterpret_cast<float*>(ring), g, c);
+    if (c.active && c.ty == 0) {
+      float* dst = p.stats_out + ((long)c.img * g.C + c0) * 2;
 #pragma unroll
-          for (int h = 0; h < N / 4; ++h) {
-            float t4[4];
-            load_vec<float, 4>(rb + (long)rr * p.ldo + 4 * h, t4, true);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) xr[u][4 * h + j] = t4[j];
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const int rr = r + u * g.ty_n;
-      if (rr >= r1) continue;
-      float (&v)[N] = vv[u];
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        float y = fmaf(v[j], a[j], b[j]);
-        if (p.gelu) y = gelu_erf(y);
-        if (p.film_gamma != nullptr) y = fmaf(fg[j], y, fb[j]);
-        if (rb != nullptr) y = fmaf(cg[j], y, xr[u][j]);
-        v[j] = y;
-      }
-      if constexpr (sizeof(TO) == 4 && N == 8) {
-        float lo[4] = {v[0], v[1], v[2], v[3]}, hi[4] = {v[4], v[5], v[6], v[7]};
-        store_vec<float, 4>(reinterpret_cast<float*>(ob + (long)rr * p.ldo), lo, true);
-        store_vec<float, 4>(reinterpret_cast<float*>(ob + (long)rr * p.ldo) + 4, hi, true);
-      } else if constexpr (sizeof(TO) == 2 && N == 4) {
-        uint2 u2;
-        u2.x = pack2<TO>(v[0], v[1]); u2.y = pack2<TO>(v[2], v[3]);
-        *reinterpret_cast<uint2*>(ob + (long)rr * p.ldo) = u2;
-      } else {
-        store_vec<TO, N>(ob + (long)rr * p.ldo, v, true);
-      }
+      for (int j = 0; j < 8; ++j) { atomicAdd(dst + 2 * j, acc[j]); atomicAdd(dst + 2 * j + 1, acc[8 + j]); }
     }
   }
 }
@@ -271,12 +280,12 @@ inorm_apply_kernel(const TI* __restrict__ x, TO* __restrict__ out, ApplyParams p
 // backward, pass 1: red[img][c] += (sum g, sum g * xhat), g = gin [* gelu'(xhat*w+b)]
 // ---------------------------------------------------------------------------------------------
 struct BwdParams {
-  NormCommon nc;
+  Geom g;
+  long ldg, ldx, ldo;
   const float* stats;
   const float* weight;
   const float* bias;
   int gelu;
-  long ldg;
   float* red;                // [I][C][2]
   // pass 2 only
   const float* row_scale;    // [I] or null
@@ -284,142 +293,118 @@ struct BwdParams {
   const float* film_gamma;   // [I / film_T][C] or null
   int film_T;
   const float* add32;        // fp32 tensor added to the result (residual-stream gradient), ld = ldo
-  long ldo;
 };
 
-template <typename TG, typename TX>
-__global__ void __launch_bounds__(kNormThreads)
+template <typename TG, typename TX, bool GELU>
+__global__ void __launch_bounds__(kNT, kBlocksPerSM)
 inorm_bwd_reduce_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, BwdParams p) {
-  constexpr int N = 8;                 // 8 channels per thread for every dtype combination
-  constexpr int UN = 2;
-  extern __shared__ float red[];       // [ty_n][tx_n][2N]
-  const RowGeom& g = p.nc.g;
-  const int tx = threadIdx.x % g.tx_n, ty = threadIdx.x / g.tx_n;
-  const int vcol = blockIdx.x * g.tx_n + tx;
-  const int img = blockIdx.z;
-  const bool active = ty < g.ty_n && vcol < g.vc;
-  const int c0 = vcol * N;
-  const float inv_p = 1.f / (float)p.nc.P;
-  float s[N], q[N], mean[N], rstd[N], w[N], b[N];
+  constexpr int NG = Slots<TG>::N, NSLOT = NG + Slots<TX>::N, S = Stages<NSLOT>::S;
+  extern __shared__ __align__(16) uint4 ring[];
+  const Geom& g = p.g;
+  const Ctx c = make_ctx(g);
+  const int c0 = c.vcol * 8;
+  const float inv_p = 1.f / (float)g.P;
+  float mean[8], rstd[8], wa[8], wb[8];
+  if (c.active) {
 #pragma unroll
-  for (int j = 0; j < N; ++j) { s[j] = 0.f; q[j] = 0.f; }
-  if (active) {
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-      mean_rstd(p.stats, (long)img * p.nc.C + c0 + j, inv_p, mean[j], rstd[j]);
-      w[j] = p.weight[c0 + j];
-      b[j] = p.bias[c0 + j];
-    }
-    const int rows_per_split = (p.nc.P + g.splits - 1) / g.splits;
-    const int r0 = blockIdx.y * rows_per_split;
-    const int r1 = min(p.nc.P, r0 + rows_per_split);
-    const TG* gb = gin + ((long)img * p.nc.P) * p.ldg + c0;
-    const TX* xb = x + ((long)img * p.nc.P) * p.nc.ldx + c0;
-    for (int r = r0 + ty; r < r1; r += UN * g.ty_n) {
-      float gv[UN][N], xv[UN][N];
-#pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const int rr = r + u * g.ty_n;
-        if (rr < r1) {
-          load8<TG>(gb + (long)rr * p.ldg, gv[u]);
-          load8<TX>(xb + (long)rr * p.nc.ldx, xv[u]);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        if (r + u * g.ty_n >= r1) continue;
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-          const float xh = (xv[u][j] - mean[j]) * rstd[j];
-          float gg = gv[u][j];
-          if (p.gelu) gg *= gelu_erf_grad(fmaf(xh, w[j], b[j]));
-          s[j] += gg;
-          q[j] = fmaf(gg, xh, q[j]);
-        }
+    for (int j = 0; j < 8; ++j) {
+      mean_rstd(p.stats, (long)c.img * g.C + c0 + j, inv_p, mean[j], rstd[j]);
+      if (GELU) {   // y = x*wa + wb
+        const float w = p.weight[c0 + j];
+        wa[j] = rstd[j] * w;
+        wb[j] = p.bias[c0 + j] - mean[j] * rstd[j] * w;
       }
     }
-    float* my = red + ((long)ty * g.tx_n + tx) * 2 * N;
-#pragma unroll
-    for (int j = 0; j < N; ++j) { my[j] = s[j]; my[N + j] = q[j]; }
   }
-  __syncthreads();
-  if (active && ty == 0) {
-    for (int t = 1; t < g.ty_n; ++t) {
-      const float* o = red + ((long)t * g.tx_n + tx) * 2 * N;
+  const TG* gb = gin + ((long)c.img * g.P) * p.ldg + c0;
+  const TX* xb = x + ((long)c.img * g.P) * p.ldx + c0;
+  float acc[16];                                  // [0..8): sum g, [8..16): sum g*x
 #pragma unroll
-      for (int j = 0; j < N; ++j) { s[j] += o[j]; q[j] += o[N + j]; }
-    }
-    float* dst = p.red + ((long)img * p.nc.C + c0) * 2;
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#define ISSUE(row, st)                                                                  \
+  issue8<TG>(ring + ((st) * NSLOT) * kNT + threadIdx.x, gb + (long)(row) * p.ldg);      \
+  issue8<TX>(ring + ((st) * NSLOT + NG) * kNT + threadIdx.x, xb + (long)(row) * p.ldx);
+#define BODY(row, st)                                                                   \
+  float gv[8], xv[8];                                                                   \
+  unpack8<TG>(ring + ((st) * NSLOT) * kNT + threadIdx.x, gv);                           \
+  unpack8<TX>(ring + ((st) * NSLOT + NG) * kNT + threadIdx.x, xv);                      \
+  _Pragma("unroll") for (int j = 0; j < 8; ++j) {                                       \
+    float gg = gv[j];                                                                   \
+    if (GELU) gg *= gelu_erf_grad(fmaf(xv[j], wa[j], wb[j]));                           \
+    acc[j] += gg;                                                                       \
+    acc[8 + j] = fmaf(gg, xv[j], acc[8 + j]);                                           \
+  }
+  BF_STREAM_LOOP(S, ISSUE, BODY)
+#undef ISSUE
+#undef BODY
+  reduce_over_ty<16>(acc, reinterpret_cast<float*>(ring), g, c);
+  if (c.active && c.ty == 0) {
+    float* dst = p.red + ((long)c.img * g.C + c0) * 2;
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-      atomicAdd(dst + 2 * j, s[j]);
-      atomicAdd(dst + 2 * j + 1, q[j]);
+    for (int j = 0; j < 8; ++j) {
+      // sum g*xhat = rstd * (sum g*x - mean * sum g)
+      atomicAdd(dst + 2 * j, acc[j]);
+      atomicAdd(dst + 2 * j + 1, rstd[j] * (acc[8 + j] - mean[j] * acc[j]));
     }
   }
 }
 
-// backward, pass 2: dx = rstd*w*cs*(g - R1/P - xhat*R2/P) [+ add32]
-template <typename TG, typename TX, typename TO>
-__global__ void __launch_bounds__(kNormThreads)
+// backward, pass 2: dx = rstd*w*cs*(g - R1/P - xhat*R2/P) [+ add32]   ( = A*g + B*x + C0 per channel )
+template <typename TG, typename TX, typename TO, bool GELU, bool ADD>
+__global__ void __launch_bounds__(kNT, kBlocksPerSM)
 inorm_bwd_apply_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, TO* __restrict__ out, BwdParams p) {
-  constexpr int N = 8;
-  constexpr int UN = 2;
-  const RowGeom& g = p.nc.g;
-  const int tx = threadIdx.x % g.tx_n, ty = threadIdx.x / g.tx_n;
-  const int vcol = blockIdx.x * g.tx_n + tx;
-  const int img = blockIdx.z;
-  if (!(ty < g.ty_n && vcol < g.vc)) return;
-  const int c0 = vcol * N;
-  const float inv_p = 1.f / (float)p.nc.P;
-  float mean[N], rstd[N], w[N], b[N], k[N], m1[N], m2[N];
+  constexpr int NG = Slots<TG>::N, NX = Slots<TX>::N, NSLOT = NG + NX + (ADD ? 2 : 0), S = Stages<NSLOT>::S;
+  extern __shared__ __align__(16) uint4 ring[];
+  const Geom& g = p.g;
+  const Ctx c = make_ctx(g);
+  const int c0 = c.vcol * 8;
+  const float inv_p = 1.f / (float)g.P;
+  float ka[8], kb[8], kc[8], wa[8], wb[8];
+  if (c.active) {
 #pragma unroll
-  for (int j = 0; j < N; ++j) {
-    const long idx = (long)img * p.nc.C + c0 + j;
-    mean_rstd(p.stats, idx, inv_p, mean[j], rstd[j]);
-    w[j] = p.weight[c0 + j];
-    b[j] = p.bias[c0 + j];
-    float cs = 1.f;
-    if (p.row_scale != nullptr) cs *= p.row_scale[img];
-    if (p.col_scale != nullptr) cs *= p.col_scale[c0 + j];
-    if (p.film_gamma != nullptr) cs *= p.film_gamma[(long)(img / p.film_T) * p.nc.C + c0 + j];
-    k[j] = rstd[j] * w[j] * cs;
-    m1[j] = p.red[2 * idx] * inv_p;
-    m2[j] = p.red[2 * idx + 1] * inv_p;
-  }
-  const int rows_per_split = (p.nc.P + g.splits - 1) / g.splits;
-  const int r0 = blockIdx.y * rows_per_split;
-  const int r1 = min(p.nc.P, r0 + rows_per_split);
-  const TG* gb = gin + ((long)img * p.nc.P) * p.ldg + c0;
-  const TX* xb = x + ((long)img * p.nc.P) * p.nc.ldx + c0;
-  TO* ob = out + ((long)img * p.nc.P) * p.ldo + c0;
-  const float* ab = p.add32 != nullptr ? p.add32 + ((long)img * p.nc.P) * p.ldo + c0 : nullptr;
-  for (int r = r0 + ty; r < r1; r += UN * g.ty_n) {
-    float gv[UN][N], xv[UN][N], av[UN][N];
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const int rr = r + u * g.ty_n;
-      if (rr < r1) {
-        load8<TG>(gb + (long)rr * p.ldg, gv[u]);
-        load8<TX>(xb + (long)rr * p.nc.ldx, xv[u]);
-        if (ab != nullptr) load8<float>(ab + (long)rr * p.ldo, av[u]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const int rr = r + u * g.ty_n;
-      if (rr >= r1) continue;
-      float o[N];
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        const float xh = (xv[u][j] - mean[j]) * rstd[j];
-        float gg = gv[u][j];
-        if (p.gelu) gg *= gelu_erf_grad(fmaf(xh, w[j], b[j]));
-        o[j] = k[j] * (gg - m1[j] - xh * m2[j]);
-        if (ab != nullptr) o[j] += av[u][j];
-      }
-      store8<TO>(ob + (long)rr * p.ldo, o);
+    for (int j = 0; j < 8; ++j) {
+      const long idx = (long)c.img * g.C + c0 + j;
+      float mean, rstd;
+      mean_rstd(p.stats, idx, inv_p, mean, rstd);
+      const float w = p.weight[c0 + j];
+      float cs = 1.f;
+      if (p.row_scale != nullptr) cs *= p.row_scale[c.img];
+      if (p.col_scale != nullptr) cs *= p.col_scale[c0 + j];
+      if (p.film_gamma != nullptr) cs *= p.film_gamma[(long)(c.img / p.film_T) * g.C + c0 + j];
+      const float k = rstd * w * cs;
+      const float m1 = p.red[2 * idx] * inv_p, m2 = p.red[2 * idx + 1] * inv_p;
+      ka[j] = k;
+      kb[j] = -k * m2 * rstd;
+      kc[j] = -k * m1 + k * m2 * rstd * mean;
+      if (GELU) { wa[j] = rstd * w; wb[j] = p.bias[c0 + j] - mean * rstd * w; }
     }
   }
+  const TG* gb = gin + ((long)c.img * g.P) * p.ldg + c0;
+  const TX* xb = x + ((long)c.img * g.P) * p.ldx + c0;
+  TO* ob = out + ((long)c.img * g.P) * p.ldo + c0;
+  const float* ab = ADD ? p.add32 + ((long)c.img * g.P) * p.ldo + c0 : nullptr;
+#define ISSUE(row, st)                                                                  \
+  issue8<TG>(ring + ((st) * NSLOT) * kNT + threadIdx.x, gb + (long)(row) * p.ldg);      \
+  issue8<TX>(ring + ((st) * NSLOT + NG) * kNT + threadIdx.x, xb + (long)(row) * p.ldx); \
+  if (ADD) issue8<float>(ring + ((st) * NSLOT + NG + NX) * kNT + threadIdx.x, ab + (long)(row) * p.ldo);
+#define BODY(row, st)                                                                   \
+  float gv[8], xv[8], o[8];                                                             \
+  unpack8<TG>(ring + ((st) * NSLOT) * kNT + threadIdx.x, gv);                           \
+  unpack8<TX>(ring + ((st) * NSLOT + NG) * kNT + threadIdx.x, xv);                      \
+  _Pragma("unroll") for (int j = 0; j < 8; ++j) {                                       \
+    float gg = gv[j];                                                                   \
+    if (GELU) gg *= gelu_erf_grad(fmaf(xv[j], wa[j], wb[j]));                           \
+    o[j] = fmaf(ka[j], gg, fmaf(kb[j], xv[j], kc[j]));                                  \
+  }                                                                                     \
+  if (ADD) {                                                                            \
+    float av[8];                                                                        \
+    unpack8<float>(ring + ((st) * NSLOT + NG + NX) * kNT + threadIdx.x, av);            \
+    _Pragma("unroll") for (int j = 0; j < 8; ++j) o[j] += av[j];                        \
+  }                                                                                     \
+  store8<TO>(ob + (long)(row) * p.ldo, o);
+  BF_STREAM_LOOP(S, ISSUE, BODY)
+#undef ISSUE
+#undef BODY
 }
 
 // parameter gradients from the per-(image, channel) reductions: 32 channels x 8 image lanes per block
@@ -479,163 +464,124 @@ __global__ void __launch_bounds__(256) inorm_bwd_params_kernel(BwdParamArgs a) {
 //   dz16 = row_scale[img] * coef[c] * dx ;  S0[c] += sum rs*dx ;  S1[c] += sum rs*dx*z
 // ---------------------------------------------------------------------------------------------
 struct ResidBwdParams {
-  NormCommon nc;             // ldx = ld of dx32
+  Geom g;
+  long lddx, ldz;
   const float* dx;
   const void* z16;           // (I*P, C) 16-bit, ld = ldz, may be null (then S1 untouched)
-  long ldz;
   const float* row_scale;    // [I] or null
   const float* coef;         // [C]
   void* dz16;                // out, ld = ldz, may be null
   float* S0; float* S1;      // [C]
 };
-template <typename T16>
-__global__ void __launch_bounds__(kNormThreads)
+template <typename T16, bool HASZ>
+__global__ void __launch_bounds__(kNT, kBlocksPerSM)
 resid_bwd_kernel(ResidBwdParams p) {
-  constexpr int N = 8;
-  constexpr int UN = 2;
-  extern __shared__ float red[];
-  const RowGeom& g = p.nc.g;
-  const int tx = threadIdx.x % g.tx_n, ty = threadIdx.x / g.tx_n;
-  const int vcol = blockIdx.x * g.tx_n + tx;
-  const int img = blockIdx.z;
-  const bool active = ty < g.ty_n && vcol < g.vc;
-  const int c0 = vcol * N;
-  float s[N], q[N];
+  constexpr int NSLOT = 2 + (HASZ ? 1 : 0), S = Stages<NSLOT>::S;
+  extern __shared__ __align__(16) uint4 ring[];
+  const Geom& g = p.g;
+  const Ctx c = make_ctx(g);
+  const int c0 = c.vcol * 8;
+  const float rs = (p.row_scale != nullptr && c.active) ? p.row_scale[c.img] : 1.f;
+  float cf[8];
+  if (c.active) {
 #pragma unroll
-  for (int j = 0; j < N; ++j) { s[j] = 0.f; q[j] = 0.f; }
-  if (active) {
-    const float rs = p.row_scale != nullptr ? p.row_scale[img] : 1.f;
-    float cf[N];
-#pragma unroll
-    for (int j = 0; j < N; ++j) cf[j] = p.coef[c0 + j] * rs;
-    const int rows_per_split = (p.nc.P + g.splits - 1) / g.splits;
-    const int r0 = blockIdx.y * rows_per_split;
-    const int r1 = min(p.nc.P, r0 + rows_per_split);
-    const float* db = p.dx + ((long)img * p.nc.P) * p.nc.ldx + c0;
-    const T16* zb = p.z16 ? reinterpret_cast<const T16*>(p.z16) + ((long)img * p.nc.P) * p.ldz + c0 : nullptr;
-    T16* ob = p.dz16 ? reinterpret_cast<T16*>(p.dz16) + ((long)img * p.nc.P) * p.ldz + c0 : nullptr;
-    for (int r = r0 + ty; r < r1; r += UN * g.ty_n) {
-      float dv[UN][N], zv[UN][N];
-#pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const int rr = r + u * g.ty_n;
-        if (rr < r1) {
-          load8<float>(db + (long)rr * p.nc.ldx, dv[u]);
-          if (zb != nullptr) load8<T16>(zb + (long)rr * p.ldz, zv[u]);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const int rr = r + u * g.ty_n;
-        if (rr >= r1) continue;
-        float o[N];
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-          if (zb != nullptr) q[j] = fmaf(rs * dv[u][j], zv[u][j], q[j]);
-          s[j] = fmaf(rs, dv[u][j], s[j]);
-          o[j] = cf[j] * dv[u][j];
-        }
-        if (ob != nullptr) store8<T16>(ob + (long)rr * p.ldz, o);
-      }
-    }
-    float* my = red + ((long)ty * g.tx_n + tx) * 2 * N;
-#pragma unroll
-    for (int j = 0; j < N; ++j) { my[j] = s[j]; my[N + j] = q[j]; }
+    for (int j = 0; j < 8; ++j) cf[j] = p.coef[c0 + j] * rs;
   }
-  __syncthreads();
-  if (active && ty == 0) {
-    for (int t = 1; t < g.ty_n; ++t) {
-      const float* o = red + ((long)t * g.tx_n + tx) * 2 * N;
+  const float* db = p.dx + ((long)c.img * g.P) * p.lddx + c0;
+  const T16* zb = HASZ ? reinterpret_cast<const T16*>(p.z16) + ((long)c.img * g.P) * p.ldz + c0 : nullptr;
+  T16* ob = p.dz16 ? reinterpret_cast<T16*>(p.dz16) + ((long)c.img * g.P) * p.ldz + c0 : nullptr;
+  float acc[16];
 #pragma unroll
-      for (int j = 0; j < N; ++j) { s[j] += o[j]; q[j] += o[N + j]; }
-    }
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#define ISSUE(row, st)                                                                  \
+  issue8<float>(ring + ((st) * NSLOT) * kNT + threadIdx.x, db + (long)(row) * p.lddx);  \
+  if (HASZ) issue8<T16>(ring + ((st) * NSLOT + 2) * kNT + threadIdx.x, zb + (long)(row) * p.ldz);
+#define BODY(row, st)                                                                   \
+  float dv[8], o[8];                                                                    \
+  unpack8<float>(ring + ((st) * NSLOT) * kNT + threadIdx.x, dv);                        \
+  if (HASZ) {                                                                           \
+    float zv[8];                                                                        \
+    unpack8<T16>(ring + ((st) * NSLOT + 2) * kNT + threadIdx.x, zv);                    \
+    _Pragma("unroll") for (int j = 0; j < 8; ++j) acc[8 + j] = fmaf(dv[j], zv[j], acc[8 + j]); \
+  }                                                                                     \
+  _Pragma("unroll") for (int j = 0; j < 8; ++j) { acc[j] += dv[j]; o[j] = cf[j] * dv[j]; } \
+  if (ob != nullptr) store8<T16>(ob + (long)(row) * p.ldz, o);
+  BF_STREAM_LOOP(S, ISSUE, BODY)
+#undef ISSUE
+#undef BODY
+  reduce_over_ty<16>(acc, reinterpret_cast<float*>(ring), g, c);
+  if (c.active && c.ty == 0) {
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-      atomicAdd(p.S0 + c0 + j, s[j]);
-      if (p.z16 != nullptr) atomicAdd(p.S1 + c0 + j, q[j]);
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(p.S0 + c0 + j, rs * acc[j]);
+      if (HASZ) atomicAdd(p.S1 + c0 + j, rs * acc[8 + j]);
     }
   }
 }
 
 // column sums of a 16-bit matrix: out[c] += sum_rows x[r, c]   (bias gradients)
 template <typename T16>
-__global__ void __launch_bounds__(kNormThreads)
-colsum16_kernel(const T16* __restrict__ x, NormCommon nc, float* __restrict__ out) {
-  constexpr int N = 8;
-  extern __shared__ float red[];
-  const RowGeom& g = nc.g;
-  const int tx = threadIdx.x % g.tx_n, ty = threadIdx.x / g.tx_n;
-  const int vcol = blockIdx.x * g.tx_n + tx;
-  const bool active = ty < g.ty_n && vcol < g.vc;
-  float s[N];
+__global__ void __launch_bounds__(kNT, kBlocksPerSM)
+colsum16_kernel(const T16* __restrict__ x, long ldx, Geom g, float* __restrict__ out) {
+  constexpr int NSLOT = 1, S = Stages<NSLOT>::S;
+  extern __shared__ __align__(16) uint4 ring[];
+  const Ctx c = make_ctx(g);
+  const T16* xb = x + ((long)c.img * g.P) * ldx + (long)c.vcol * 8;
+  float acc[8];
 #pragma unroll
-  for (int j = 0; j < N; ++j) s[j] = 0.f;
-  if (active) {
-    const int rows_per_split = (nc.P + g.splits - 1) / g.splits;
-    const int r0 = blockIdx.y * rows_per_split;
-    const int r1 = min(nc.P, r0 + rows_per_split);
-    const T16* base = x + (long)vcol * N;
-    constexpr int UN = 4;
-    for (int r = r0 + ty; r < r1; r += UN * g.ty_n) {
-      float v[UN][N];
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#define ISSUE(row, st) issue8<T16>(ring + (st) * kNT + threadIdx.x, xb + (long)(row) * ldx);
+#define BODY(row, st)                                                \
+  float v[8];                                                        \
+  unpack8<T16>(ring + (st) * kNT + threadIdx.x, v);                  \
+  _Pragma("unroll") for (int j = 0; j < 8; ++j) acc[j] += v[j];
+  BF_STREAM_LOOP(S, ISSUE, BODY)
+#undef ISSUE
+#undef BODY
+  reduce_over_ty<8>(acc, reinterpret_cast<float*>(ring), g, c);
+  if (c.active && c.ty == 0) {
 #pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const int rr = r + u * g.ty_n;
-        if (rr < r1) load_vec<T16, N>(base + (long)rr * nc.ldx, v[u], true);
-        else {
-#pragma unroll
-          for (int j = 0; j < N; ++j) v[u][j] = 0.f;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < UN; ++u) {
-#pragma unroll
-        for (int j = 0; j < N; ++j) s[j] += v[u][j];
-      }
-    }
-    float* my = red + ((long)ty * g.tx_n + tx) * N;
-#pragma unroll
-    for (int j = 0; j < N; ++j) my[j] = s[j];
-  }
-  __syncthreads();
-  if (active && ty == 0) {
-    for (int t = 1; t < g.ty_n; ++t) {
-      const float* o = red + ((long)t * g.tx_n + tx) * N;
-#pragma unroll
-      for (int j = 0; j < N; ++j) s[j] += o[j];
-    }
-#pragma unroll
-    for (int j = 0; j < N; ++j) atomicAdd(out + (long)vcol * N + j, s[j]);
+    for (int j = 0; j < 8; ++j) atomicAdd(out + (long)c.vcol * 8 + j, acc[j]);
   }
 }
 
-static int check_common(const char* fn, int I, int P, int C, long ld, int vecn, const void* x) {
+static int check_common(const char* fn, int I, int P, int C, long ld, const void* x) {
   BF_REQUIRE(I > 0 && P > 0 && C > 0, "%s: empty problem I=%d P=%d C=%d", fn, I, P, C);
-  BF_REQUIRE(C % vecn == 0, "%s: C=%d must be a multiple of %d", fn, C, vecn);
-  BF_REQUIRE(ld >= C && ld % vecn == 0, "%s: ld=%ld", fn, ld);
+  BF_REQUIRE(C % 8 == 0, "%s: C=%d must be a multiple of 8", fn, C);
+  BF_REQUIRE(ld >= C && ld % 8 == 0, "%s: ld=%ld must be a multiple of 8 and >= C", fn, ld);
   BF_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "%s: pointer must be 16-byte aligned", fn);
+  BF_REQUIRE(I <= 65535, "%s: more than 65535 images", fn);
   return BF_OK;
 }
+
+template <typename K>
+static int set_smem(K kern) {
+  return check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes),
+                    "cudaFuncSetAttribute(norm)");
+}
+// launch with the 64 KiB ring; the attribute is set once per kernel instantiation
+#define BF_NORM_LAUNCH(kern, grid, stream, ...)                                   \
+  do {                                                                            \
+    static bool done_ = false;                                                    \
+    if (!done_) { if (int e_ = set_smem(kern)) return e_; done_ = true; }         \
+    kern<<<grid, kNT, kRingBytes, stream>>>(__VA_ARGS__);                         \
+  } while (0)
 
 }  // namespace bf
 
 using namespace bf;
 
-static inline int dtype_vec(int dt) { return dt == BF_F32 ? 4 : 8; }
-
 extern "C" int bf_inorm_stats(const void* x, int x_dtype, int I, int P, int C, int64_t ldx, float* stats,
                               void* stream) {
   BF_REQUIRE(x && stats, "bf_inorm_stats: null pointer");
   BF_REQUIRE(x_dtype == BF_BF16 || x_dtype == BF_F16 || x_dtype == BF_F32, "bf_inorm_stats: dtype %d", x_dtype);
-  const int vn = dtype_vec(x_dtype);
-  if (int st = check_common("bf_inorm_stats", I, P, C, ldx, vn, x)) return st;
-  NormCommon nc{I, P, C, ldx, make_geom(C, vn, P, I)};
-  dim3 grid(nc.g.chunks, nc.g.splits, I);
-  const size_t sm = (size_t)nc.g.ty_n * nc.g.tx_n * 2 * vn * sizeof(float);
+  if (int st = check_common("bf_inorm_stats", I, P, C, ldx, x)) return st;
+  const Geom g = make_geom(I, P, C);
+  dim3 grid(g.splits, I, g.chunks);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (x_dtype == BF_F32) inorm_stats_kernel<float><<<grid, kNormThreads, sm, s>>>((const float*)x, nc, stats);
-  else if (x_dtype == BF_BF16) inorm_stats_kernel<__nv_bfloat16><<<grid, kNormThreads, sm, s>>>((const __nv_bfloat16*)x, nc, stats);
-  else inorm_stats_kernel<__half><<<grid, kNormThreads, sm, s>>>((const __half*)x, nc, stats);
+  if (x_dtype == BF_F32) BF_NORM_LAUNCH(inorm_stats_kernel<float>, grid, s, (const float*)x, (long)ldx, g, stats);
+  else if (x_dtype == BF_BF16) BF_NORM_LAUNCH(inorm_stats_kernel<__nv_bfloat16>, grid, s, (const __nv_bfloat16*)x, (long)ldx, g, stats);
+  else BF_NORM_LAUNCH(inorm_stats_kernel<__half>, grid, s, (const __half*)x, (long)ldx, g, stats);
   count_launch();
   BF_LAUNCH_CHECK("inorm_stats_kernel");
   return BF_OK;
@@ -643,20 +589,28 @@ extern "C" int bf_inorm_stats(const void* x, int x_dtype, int I, int P, int C, i
 
 extern "C" int bf_inorm_apply(const bf_inorm_apply_args* a, void* stream) {
   BF_REQUIRE(a && a->x && a->out && a->stats && a->weight && a->bias, "bf_inorm_apply: null pointer");
-  const int vn = dtype_vec(a->x_dtype);
-  if (int st = check_common("bf_inorm_apply", a->I, a->P, a->C, a->ldx, vn, a->x)) return st;
-  BF_REQUIRE(a->ldo >= a->C && a->ldo % vn == 0, "bf_inorm_apply: ldo");
+  if (int st = check_common("bf_inorm_apply", a->I, a->P, a->C, a->ldx, a->x)) return st;
+  BF_REQUIRE(a->ldo >= a->C && a->ldo % 8 == 0, "bf_inorm_apply: ldo");
+  BF_REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "bf_inorm_apply: out must be 16-byte aligned");
   BF_REQUIRE((a->film_gamma == nullptr) == (a->film_beta == nullptr), "bf_inorm_apply: film pair");
   BF_REQUIRE(a->film_gamma == nullptr || (a->film_T > 0 && a->I % a->film_T == 0), "bf_inorm_apply: film_T");
   BF_REQUIRE(a->resid_in == nullptr || (a->out_dtype == BF_F32 && a->col_gamma), "bf_inorm_apply: residual needs f32 out");
+  BF_REQUIRE(!(a->resid_in != nullptr && a->gelu), "bf_inorm_apply: gelu and the residual epilogue are exclusive");
   ApplyParams p{};
-  p.nc = NormCommon{a->I, a->P, a->C, a->ldx, make_geom(a->C, vn, a->P, a->I)};
+  p.g = make_geom(a->I, a->P, a->C);
+  p.ldx = a->ldx; p.ldo = a->ldo;
   p.stats = a->stats; p.weight = a->weight; p.bias = a->bias; p.gelu = a->gelu;
   p.film_gamma = a->film_gamma; p.film_beta = a->film_beta; p.film_T = a->film_T > 0 ? a->film_T : 1;
-  p.resid_in = a->resid_in; p.row_scale = a->row_scale; p.col_gamma = a->col_gamma; p.ldo = a->ldo;
-  dim3 grid(p.nc.g.chunks, p.nc.g.splits, a->I);
+  p.resid_in = a->resid_in; p.row_scale = a->row_scale; p.col_gamma = a->col_gamma;
+  p.stats_out = a->stats_out;
+  dim3 grid(p.g.splits, a->I, p.g.chunks);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define BF_APPLY(TI, TO) inorm_apply_kernel<TI, TO><<<grid, kNormThreads, 0, s>>>((const TI*)a->x, (TO*)a->out, p)
+  const bool resid = a->resid_in != nullptr;
+#define BF_APPLY(TI, TO)                                                                                       \
+  do {                                                                                                         \
+    if (resid) BF_NORM_LAUNCH((inorm_apply_kernel<TI, TO, true>), grid, s, (const TI*)a->x, (TO*)a->out, p);   \
+    else BF_NORM_LAUNCH((inorm_apply_kernel<TI, TO, false>), grid, s, (const TI*)a->x, (TO*)a->out, p);        \
+  } while (0)
   const int xi = a->x_dtype, xo = a->out_dtype;
   if (xi == BF_F32 && xo == BF_BF16) BF_APPLY(float, __nv_bfloat16);
   else if (xi == BF_F32 && xo == BF_F16) BF_APPLY(float, __half);
@@ -674,20 +628,26 @@ extern "C" int bf_inorm_apply(const bf_inorm_apply_args* a, void* stream) {
 
 extern "C" int bf_inorm_bwd(const bf_inorm_bwd_args* a, void* stream) {
   BF_REQUIRE(a && a->gin && a->x && a->stats && a->weight && a->bias && a->red, "bf_inorm_bwd: null pointer");
-  if (int st = check_common("bf_inorm_bwd", a->I, a->P, a->C, a->ldx, 8, a->x)) return st;
+  if (int st = check_common("bf_inorm_bwd", a->I, a->P, a->C, a->ldx, a->x)) return st;
   BF_REQUIRE(a->ldg >= a->C && a->ldg % 8 == 0, "bf_inorm_bwd: ldg");
+  BF_REQUIRE((reinterpret_cast<uintptr_t>(a->gin) & 15) == 0, "bf_inorm_bwd: gin must be 16-byte aligned");
   BF_REQUIRE(a->phase == 1 || a->phase == 2, "bf_inorm_bwd: phase %d", a->phase);
   BwdParams p{};
-  p.nc = NormCommon{a->I, a->P, a->C, a->ldx, make_geom(a->C, 8, a->P, a->I)};
-  p.stats = a->stats; p.weight = a->weight; p.bias = a->bias; p.gelu = a->gelu; p.ldg = a->ldg; p.red = a->red;
+  p.g = make_geom(a->I, a->P, a->C);
+  p.ldg = a->ldg; p.ldx = a->ldx; p.ldo = a->ldo;
+  p.stats = a->stats; p.weight = a->weight; p.bias = a->bias; p.gelu = a->gelu; p.red = a->red;
   p.row_scale = a->row_scale; p.col_scale = a->col_scale; p.film_gamma = a->film_gamma;
-  p.film_T = a->film_T > 0 ? a->film_T : 1; p.add32 = a->add32; p.ldo = a->ldo;
-  dim3 grid(p.nc.g.chunks, p.nc.g.splits, a->I);
-  const size_t sm = (size_t)p.nc.g.ty_n * p.nc.g.tx_n * 16 * sizeof(float);
+  p.film_T = a->film_T > 0 ? a->film_T : 1; p.add32 = a->add32;
+  dim3 grid(p.g.splits, a->I, p.g.chunks);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int gd = a->g_dtype, xd = a->x_dtype, od = a->out_dtype;
+  const bool gelu = a->gelu != 0;
   if (a->phase == 1) {
-#define BF_RED(TG, TX) inorm_bwd_reduce_kernel<TG, TX><<<grid, kNormThreads, sm, s>>>((const TG*)a->gin, (const TX*)a->x, p)
+#define BF_RED(TG, TX)                                                                                               \
+  do {                                                                                                               \
+    if (gelu) BF_NORM_LAUNCH((inorm_bwd_reduce_kernel<TG, TX, true>), grid, s, (const TG*)a->gin, (const TX*)a->x, p);  \
+    else BF_NORM_LAUNCH((inorm_bwd_reduce_kernel<TG, TX, false>), grid, s, (const TG*)a->gin, (const TX*)a->x, p);      \
+  } while (0)
     if (gd == BF_F32 && xd == BF_F32) BF_RED(float, float);
     else if (gd == BF_F32 && xd == BF_BF16) BF_RED(float, __nv_bfloat16);
     else if (gd == BF_F32 && xd == BF_F16) BF_RED(float, __half);
@@ -703,16 +663,23 @@ extern "C" int bf_inorm_bwd(const bf_inorm_bwd_args* a, void* stream) {
   }
   BF_REQUIRE(a->out, "bf_inorm_bwd: out required in phase 2");
   BF_REQUIRE(a->ldo >= a->C && a->ldo % 8 == 0, "bf_inorm_bwd: ldo");
+  BF_REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "bf_inorm_bwd: out must be 16-byte aligned");
   BF_REQUIRE(a->add32 == nullptr || od == BF_F32, "bf_inorm_bwd: add32 needs f32 out");
-#define BF_APP(TG, TX, TO) inorm_bwd_apply_kernel<TG, TX, TO><<<grid, kNormThreads, 0, s>>>((const TG*)a->gin, (const TX*)a->x, (TO*)a->out, p)
-  if (gd == BF_F32 && xd == BF_F32 && od == BF_F32) BF_APP(float, float, float);
-  else if (gd == BF_F32 && xd == BF_BF16 && od == BF_BF16) BF_APP(float, __nv_bfloat16, __nv_bfloat16);
-  else if (gd == BF_F32 && xd == BF_F16 && od == BF_F16) BF_APP(float, __half, __half);
-  else if (gd == BF_BF16 && xd == BF_F32 && od == BF_F32) BF_APP(__nv_bfloat16, float, float);
-  else if (gd == BF_BF16 && xd == BF_BF16 && od == BF_BF16) BF_APP(__nv_bfloat16, __nv_bfloat16, __nv_bfloat16);
-  else if (gd == BF_F16 && xd == BF_F16 && od == BF_F16) BF_APP(__half, __half, __half);
-  else if (gd == BF_BF16 && xd == BF_F16 && od == BF_BF16) BF_APP(__nv_bfloat16, __half, __nv_bfloat16);
-  else if (gd == BF_F32 && xd == BF_F16 && od == BF_BF16) BF_APP(float, __half, __nv_bfloat16);
+  const bool add = a->add32 != nullptr;
+#define BF_APP(TG, TX, TO, ADD_)                                                                                     \
+  do {                                                                                                               \
+    if (gelu) BF_NORM_LAUNCH((inorm_bwd_apply_kernel<TG, TX, TO, true, ADD_>), grid, s, (const TG*)a->gin, (const TX*)a->x, (TO*)a->out, p);  \
+    else BF_NORM_LAUNCH((inorm_bwd_apply_kernel<TG, TX, TO, false, ADD_>), grid, s, (const TG*)a->gin, (const TX*)a->x, (TO*)a->out, p);      \
+  } while (0)
+  if (gd == BF_F32 && xd == BF_F32 && od == BF_F32) { if (add) BF_APP(float, float, float, true); else BF_APP(float, float, float, false); }
+  else if (gd == BF_BF16 && xd == BF_F32 && od == BF_F32) { if (add) BF_APP(__nv_bfloat16, float, float, true); else BF_APP(__nv_bfloat16, float, float, false); }
+  else if (add) BF_REQUIRE(false, "bf_inorm_bwd: add32 is supported for (f32|bf16, f32) -> f32 only (g=%d x=%d)", gd, xd);
+  else if (gd == BF_F32 && xd == BF_BF16 && od == BF_BF16) BF_APP(float, __nv_bfloat16, __nv_bfloat16, false);
+  else if (gd == BF_F32 && xd == BF_F16 && od == BF_F16) BF_APP(float, __half, __half, false);
+  else if (gd == BF_BF16 && xd == BF_BF16 && od == BF_BF16) BF_APP(__nv_bfloat16, __nv_bfloat16, __nv_bfloat16, false);
+  else if (gd == BF_F16 && xd == BF_F16 && od == BF_F16) BF_APP(__half, __half, __half, false);
+  else if (gd == BF_BF16 && xd == BF_F16 && od == BF_BF16) BF_APP(__nv_bfloat16, __half, __nv_bfloat16, false);
+  else if (gd == BF_F32 && xd == BF_F16 && od == BF_BF16) BF_APP(float, __half, __nv_bfloat16, false);
   else BF_REQUIRE(false, "bf_inorm_bwd: unsupported dtype triple g=%d x=%d out=%d", gd, xd, od);
 #undef BF_APP
   count_launch();
@@ -740,16 +707,21 @@ extern "C" int bf_resid_bwd(const float* dx, int64_t lddx, const void* z16, void
   BF_REQUIRE(dx && coef && S0, "bf_resid_bwd: null pointer");
   BF_REQUIRE(z16 == nullptr || S1 != nullptr, "bf_resid_bwd: S1 required with z16");
   BF_REQUIRE(dtype == BF_BF16 || dtype == BF_F16, "bf_resid_bwd: dtype");
-  if (int st = check_common("bf_resid_bwd", I, P, C, lddx, 8, dx)) return st;
+  if (int st = check_common("bf_resid_bwd", I, P, C, lddx, dx)) return st;
   BF_REQUIRE((z16 == nullptr && dz16 == nullptr) || (ldz >= C && ldz % 8 == 0), "bf_resid_bwd: ldz");
   ResidBwdParams p{};
-  p.nc = NormCommon{I, P, C, lddx, make_geom(C, 8, P, I)};
-  p.dx = dx; p.z16 = z16; p.ldz = ldz; p.row_scale = row_scale; p.coef = coef; p.dz16 = dz16; p.S0 = S0; p.S1 = S1;
-  dim3 grid(p.nc.g.chunks, p.nc.g.splits, I);
-  const size_t sm = (size_t)p.nc.g.ty_n * p.nc.g.tx_n * 16 * sizeof(float);
+  p.g = make_geom(I, P, C);
+  p.lddx = lddx; p.ldz = ldz;
+  p.dx = dx; p.z16 = z16; p.row_scale = row_scale; p.coef = coef; p.dz16 = dz16; p.S0 = S0; p.S1 = S1;
+  dim3 grid(p.g.splits, I, p.g.chunks);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (dtype == BF_BF16) resid_bwd_kernel<__nv_bfloat16><<<grid, kNormThreads, sm, s>>>(p);
-  else resid_bwd_kernel<__half><<<grid, kNormThreads, sm, s>>>(p);
+  if (dtype == BF_BF16) {
+    if (z16) BF_NORM_LAUNCH((resid_bwd_kernel<__nv_bfloat16, true>), grid, s, p);
+    else BF_NORM_LAUNCH((resid_bwd_kernel<__nv_bfloat16, false>), grid, s, p);
+  } else {
+    if (z16) BF_NORM_LAUNCH((resid_bwd_kernel<__half, true>), grid, s, p);
+    else BF_NORM_LAUNCH((resid_bwd_kernel<__half, false>), grid, s, p);
+  }
   count_launch();
   BF_LAUNCH_CHECK("resid_bwd_kernel");
   return BF_OK;
@@ -759,13 +731,12 @@ extern "C" int bf_colsum16(const void* x, int dtype, int64_t rows, int C, int64_
   BF_REQUIRE(x && out, "bf_colsum16: null pointer");
   BF_REQUIRE(dtype == BF_BF16 || dtype == BF_F16, "bf_colsum16: dtype");
   BF_REQUIRE(rows > 0 && rows < (1ll << 31), "bf_colsum16: rows");
-  if (int st = check_common("bf_colsum16", 1, (int)rows, C, ldx, 8, x)) return st;
-  NormCommon nc{1, (int)rows, C, ldx, make_geom(C, 8, (int)rows, 1)};
-  dim3 grid(nc.g.chunks, nc.g.splits, 1);
-  const size_t sm = (size_t)nc.g.ty_n * nc.g.tx_n * 8 * sizeof(float);
+  if (int st = check_common("bf_colsum16", 1, (int)rows, C, ldx, x)) return st;
+  const Geom g = make_geom(1, (int)rows, C);
+  dim3 grid(g.splits, 1, g.chunks);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (dtype == BF_BF16) colsum16_kernel<__nv_bfloat16><<<grid, kNormThreads, sm, s>>>((const __nv_bfloat16*)x, nc, out);
-  else colsum16_kernel<__half><<<grid, kNormThreads, sm, s>>>((const __half*)x, nc, out);
+  if (dtype == BF_BF16) BF_NORM_LAUNCH(colsum16_kernel<__nv_bfloat16>, grid, s, (const __nv_bfloat16*)x, (long)ldx, g, out);
+  else BF_NORM_LAUNCH(colsum16_kernel<__half>, grid, s, (const __half*)x, (long)ldx, g, out);
   count_launch();
   BF_LAUNCH_CHECK("colsum16_kernel");
   return BF_OK;

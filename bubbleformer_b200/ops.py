@@ -116,7 +116,7 @@ def inorm_stats(x: torch.Tensor, I: int, P: int, stats: torch.Tensor) -> None:
 
 
 def inorm_apply(x, out, I, P, stats, weight, bias, *, gelu=False, film_gamma=None, film_beta=None, film_T=0,
-                resid_in=None, row_scale=None, col_gamma=None) -> None:
+                resid_in=None, row_scale=None, col_gamma=None, stats_out=None) -> None:
     _mat(x, "x"); _mat(out, "out")
     C_ = x.shape[1]
     a = L.InormApplyArgs()
@@ -135,6 +135,7 @@ def inorm_apply(x, out, I, P, stats, weight, bias, *, gelu=False, film_gamma=Non
     a.row_scale = _f32(row_scale, I, "row_scale")
     a.col_gamma = _f32(col_gamma, C_, "col_gamma")
     a.out = _ptr(out)
+    a.stats_out = _f32(stats_out, I * C_ * 2, "stats_out")
     L.check(L.lib.bf_inorm_apply(C.byref(a), _stream()), "bf_inorm_apply")
 
 

@@ -140,6 +140,8 @@ typedef struct bf_inorm_apply_args {
   const float* row_scale;     /* [I] or NULL */
   const float* col_gamma;     /* [C] (with resid_in) */
   void* out;
+  float* stats_out;           /* [I][C][2] or NULL: += (sum, sum^2) of the values written to `out`, i.e. the raw
+                                 statistics the NEXT InstanceNorm needs (saves its separate pass)               */
 } bf_inorm_apply_args;
 BF_API int bf_inorm_apply(const bf_inorm_apply_args* args, void* stream);
 

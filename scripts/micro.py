@@ -50,17 +50,23 @@ def main():
               d_kn_b=torch.zeros(64, device=dev), d_bias_emb=torch.zeros(32, he, device=dev),
               d_scale_factor=torch.zeros(he, device=dev))
 
+    rstd = torch.rand(N, he, 2, device=dev) + 0.5
+
     def attn(axis, bwd):
         geo = engine._axis(g, axis)
         kw = dict(heads=he, qn_w=ln[0], qn_b=ln[1], kn_w=ln[2], kn_b=ln[3], bias_emb=emb,
                   bucket=engine.relpos_bucket_vector(geo["L_"], dev), scale_factor=sf, out_scale=0.5, **geo)
         if bwd:
-            ops.attention(QKV, out3, dout=Xb, grads=gr, **kw)
+            ops.attention(QKV, out3, dout=Xb, grads=gr, prenorm=True, rstd=rstd, **kw)
         else:
-            ops.attention(QKV, O, **kw)
+            ops.attention(QKV, O, prenorm=True, **kw)
 
     table = {
         "gemm_qkv": (lambda: ops.gemm(Xb, Win, N, 3 * E, E, epilogue=L.EPI_STORE16, bias=v3E, out16=out3), 2.0 * N * 3 * E * E, (N * E + N * 3 * E) * 2),
+        "gemm_qkv_ln": (lambda: ops.gemm(Xb, Win, N, 3 * E, E, epilogue=L.EPI_QKV_LN, bias=v3E, out16=out3, ln_head_dim=64, ln_rstd=rstd),
+                        2.0 * N * 3 * E * E, (N * E + N * 3 * E) * 2),
+        "gemm_acc32": (lambda: ops.gemm(H, W1, N, E, 4 * E, epilogue=L.EPI_ACC32, b_mode=L.B_KN, in32=X32, out32=o32), 2.0 * N * 4 * E * E, N * 4 * E * 2 + N * E * 8),
+        "gemm_dgrad_qkv": (lambda: ops.gemm(QKV, Win, N, E, 3 * E, epilogue=L.EPI_STORE16, b_mode=L.B_KN, out16=O), 2.0 * N * 3 * E * E, (N * E + N * 3 * E) * 2),
         "gemm_fc1": (lambda: ops.gemm(Xb, W1, N, 4 * E, E, epilogue=L.EPI_GELU, bias=v4E, out16=out4, out16b=out4b), 2.0 * N * 4 * E * E, (N * E + 2 * N * 4 * E) * 2),
         "gemm_fc2": (lambda: ops.gemm(H, W2, N, E, 4 * E, epilogue=L.EPI_STORE16, bias=vE, out16=O), 2.0 * N * 4 * E * E, (N * 4 * E + N * E) * 2),
         "gemm_resid": (lambda: ops.gemm(Xb, Wo, N, E, E, epilogue=L.EPI_RESID, bias=vE, col_gamma=vE, row_scale=rs, rows_per_group=P,

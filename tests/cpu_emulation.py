@@ -96,7 +96,7 @@ def _mean_rstd(stats, P):
 
 
 def inorm_apply(x, out, I, P, stats, weight, bias, *, gelu=False, film_gamma=None, film_beta=None, film_T=0,
-                resid_in=None, row_scale=None, col_gamma=None):
+                resid_in=None, row_scale=None, col_gamma=None, stats_out=None):
     C = x.shape[1]
     mean, rstd = _mean_rstd(stats, P)
     xi = x.float().reshape(I, P, C)
@@ -109,6 +109,9 @@ def inorm_apply(x, out, I, P, stats, weight, bias, *, gelu=False, film_gamma=Non
         rs = row_scale[:, None, None] if row_scale is not None else 1.0
         y = resid_in.reshape(I, P, C) + rs * col_gamma * y
     out.copy_(y.reshape(I * P, C))
+    if stats_out is not None:
+        yo = out.float().reshape(I, P, C)
+        stats_out.add_(torch.stack([yo.sum(1), (yo * yo).sum(1)], dim=-1))
 
 
 def inorm_bwd(phase, gin, x, I, P, stats, weight, bias, red, *, gelu=False, out=None, row_scale=None, col_scale=None,
