@@ -59,6 +59,7 @@ class GradSink:
         self.flat.zero_()
         self._pending.clear()
         self._lo = self._hi = None
+        self._done: List = []
 
     def views(self, named: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         """Gradient views for the parameters of one autograd Function."""
@@ -90,7 +91,12 @@ class GradSink:
     def _flush(self) -> None:
         if self._lo is None:
             return
-        seg = self.flat[self._lo:self._hi]
+        self._done.append((self._lo, self._hi))
+        self._reduce(self._lo, self._hi)
+        self._lo = self._hi = None
+
+    def _reduce(self, lo: int, hi: int) -> None:
+        seg = self.flat[lo:hi]
         if self.comm_stream is not None:
             self.comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm_stream):
@@ -98,12 +104,19 @@ class GradSink:
         else:                                   # gloo (CPU tests): no AVG
             dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.group)
             seg.div_(self.world)
-        self._lo = self._hi = None
 
     def finish(self) -> None:
-        """Flush the last bucket and make the compute stream wait for all reductions."""
+        """Flush the last bucket, reduce whatever no Function owns (parameters differentiated by plain torch
+        autograd, e.g. the FiLM MLP), and make the compute stream wait for all reductions."""
         if self.world == 1:
             return
         self._flush()
+        pos = 0
+        for lo, hi in sorted(self._done):
+            if lo > pos:
+                self._reduce(pos, lo)
+            pos = max(pos, hi)
+        if pos < self.flat.numel():
+            self._reduce(pos, self.flat.numel())
         if self.comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self.comm_stream)

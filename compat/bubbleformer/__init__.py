@@ -1,0 +1,9 @@
+"""Drop-in `bubbleformer` package backed by bubbleformer_b200 (put `<repo>/compat` on sys.path / PYTHONPATH).
+
+Upstream callers (`scripts/train.py:18`, `bubbleformer/modules.py:13`, `scripts/inference.py:4`) import
+`bubbleformer.models.get_model`, `bubbleformer.models.axial_vit.SpaceTimeBlock` and the layer classes of
+`bubbleformer.layers`; those names resolve here to the B200-native implementations.  Everything outside the
+FiLMAViT hot path (UNets, data, Lightning modules, utils) stays upstream's and is not shadowed: keep upstream's
+own package for those and import the models from this one.
+"""
+from bubbleformer_b200 import __version__  # noqa: F401
