@@ -262,8 +262,9 @@ def main():
     roof = None
     if rank == 0:
         ops.GEMM_TIMING = []
-        step(x, tgt, cond)
-        torch.cuda.synchronize()
+    step(x, tgt, cond)                      # every rank steps (the gradient all-reduce is collective)
+    torch.cuda.synchronize()
+    if rank == 0:
         recs, ops.GEMM_TIMING = ops.GEMM_TIMING, None
         gemm_ms = sum(a.elapsed_time(b) for a, b, _ in recs)
         gemm_flops = sum(f for _, _, f in recs)
