@@ -254,7 +254,7 @@ inorm_apply_kernel(const TI* __restrict__ x, TO* __restrict__ out, ApplyParams p
   float v[8];                                                                            \
   unpack8<TI>(ring + ((st) * NSLOT) * kNT + threadIdx.x, v);                             \
   _Pragma("unroll") for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], a[j], b[j]);          \
-  if (p.gelu) { _Pragma("unroll") for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]); }  \
+  if (p.gelu) { _Pragma("unroll") for (int j = 0; j < 8; ++j) v[j] = gelu_fast(v[j]); }  \
   if (post_film) { _Pragma("unroll") for (int j = 0; j < 8; ++j) v[j] = fmaf(fg[j], v[j], fb[j]); } \
   if (RESID) {                                                                           \
     float xr[8];                                                                         \
@@ -330,7 +330,7 @@ inorm_bwd_reduce_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, Bw
   unpack8<TX>(ring + ((st) * NSLOT + NG) * kNT + threadIdx.x, xv);                      \
   _Pragma("unroll") for (int j = 0; j < 8; ++j) {                                       \
     float gg = gv[j];                                                                   \
-    if (GELU) gg *= gelu_erf_grad(fmaf(xv[j], wa[j], wb[j]));                           \
+    if (GELU) gg *= gelu_grad_fast(fmaf(xv[j], wa[j], wb[j]));                           \
     acc[j] += gg;                                                                       \
     acc[8 + j] = fmaf(gg, xv[j], acc[8 + j]);                                           \
   }
@@ -393,7 +393,7 @@ inorm_bwd_apply_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, TO*
   unpack8<TX>(ring + ((st) * NSLOT + NG) * kNT + threadIdx.x, xv);                      \
   _Pragma("unroll") for (int j = 0; j < 8; ++j) {                                       \
     float gg = gv[j];                                                                   \
-    if (GELU) gg *= gelu_erf_grad(fmaf(xv[j], wa[j], wb[j]));                           \
+    if (GELU) gg *= gelu_grad_fast(fmaf(xv[j], wa[j], wb[j]));                           \
     o[j] = fmaf(ka[j], gg, fmaf(kb[j], xv[j], kc[j]));                                  \
   }                                                                                     \
   if (ADD) {                                                                            \

@@ -265,6 +265,9 @@ cast16_kernel(const float* __restrict__ in, T16* __restrict__ out, long n) {
 
 using namespace bf;
 
+namespace bf { int launch_patch_in_mma(const float* x, const float* Wkn, void* out, int dtype, float* stats, int I, int F,
+                                       int H, int W, int N, cudaStream_t s); }
+
 extern "C" int bf_patch_in(const float* x, const float* Wkn, void* out, int dtype, float* stats, int I, int F, int H,
                            int W, int N, void* stream) {
   BF_REQUIRE(x && Wkn && out, "bf_patch_in: null pointer");
@@ -272,6 +275,7 @@ extern "C" int bf_patch_in(const float* x, const float* Wkn, void* out, int dtyp
   BF_REQUIRE(I > 0 && F > 0 && F <= kMaxF && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "bf_patch_in: geometry");
   BF_REQUIRE(N % 8 == 0 && N >= 8 && N <= 2048, "bf_patch_in: N=%d must be a multiple of 8 in [8, 2048]", N);
   BF_REQUIRE((reinterpret_cast<uintptr_t>(x) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "bf_patch_in: alignment");
+  if (F <= 8 && I <= 65535) return launch_patch_in_mma(x, Wkn, out, dtype, stats, I, F, H, W, N, static_cast<cudaStream_t>(stream));
   const long pix_img = (long)(H / 2) * (W / 2);
   const int ppi = 256 / (N / 8);
   long ppb = (long)ppi * 64;                         // 64 pixels per thread amortise the register-resident weights

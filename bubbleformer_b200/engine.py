@@ -17,6 +17,7 @@ Reference behaviour restated here (upstream paths):
 from __future__ import annotations
 
 import math
+import weakref
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -91,6 +92,24 @@ def _zeros(shape, like, dtype=F32):
     return torch.zeros(shape, dtype=dtype, device=like.device)
 
 
+# Producer -> consumer handoff of InstanceNorm statistics: the kernel that writes a residual-stream tensor also
+# accumulates its per-(image, channel) sums, so the next norm1 skips its statistics pass.  Keyed by tensor identity.
+_HANDOFF = None
+
+
+def _publish_stats(X: torch.Tensor, st: torch.Tensor) -> None:
+    global _HANDOFF
+    _HANDOFF = (weakref.ref(X), st)
+
+
+def _take_stats(X: torch.Tensor) -> Optional[torch.Tensor]:
+    global _HANDOFF
+    h, _HANDOFF = _HANDOFF, None
+    if h is not None and h[0]() is X:
+        return h[1]
+    return None
+
+
 def _axis(g: Geom, axis: str) -> dict:
     P = g.P
     if axis == "t":
@@ -104,10 +123,12 @@ def _axis(g: Geom, axis: str) -> dict:
 # shared pieces: IN -> QKV -> attention(s) -> IN -> out-projection with residual epilogue
 # ---------------------------------------------------------------------------------------------
 def _attn_branch_fwd(X, g: Geom, p: Dict[str, torch.Tensor], w16, heads: int, axes: List[str], scale_keys,
-                     mask_img, col_scale, col_shift, gamma, want_x16: bool, save: bool):
+                     mask_img, col_scale, col_shift, gamma, want_x16: bool, save: bool, want_stats: bool = False):
     I, P, N, E = g.I, g.P, g.N, X.shape[1]
-    st1 = _zeros((I, E, 2), X)
-    ops.inorm_stats(X, I, P, st1)
+    st1 = _take_stats(X)
+    if st1 is None:
+        st1 = _zeros((I, E, 2), X)
+        ops.inorm_stats(X, I, P, st1)
     Xn = _empty((N, E), BF16, X)
     ops.inorm_apply(X, Xn, I, P, st1, p["norm1.weight"], p["norm1.bias"])
     QKV = _empty((N, 3 * E), BF16, X)
@@ -136,9 +157,12 @@ def _attn_branch_fwd(X, g: Geom, p: Dict[str, torch.Tensor], w16, heads: int, ax
     Xout = _empty((N, E), F32, X)
     Z = _empty((N, E), BF16, X) if save else None
     X16 = _empty((N, E), BF16, X) if want_x16 else None
+    st_out = _zeros((I, E, 2), X) if (want_stats and P % 32 == 0) else None
     ops.gemm(On, w16("output_head.weight"), N, E, E, epilogue=L.EPI_RESID, bias=p["output_head.bias"],
              col_scale=col_scale, col_shift=col_shift, col_gamma=gamma, row_scale=mask_img, rows_per_group=P,
-             in32=X, out32=Xout, out16=X16, out16b=Z)
+             in32=X, out32=Xout, out16=X16, out16b=Z, stats_out=st_out)
+    if st_out is not None:
+        _publish_stats(Xout, st_out)
     saved = dict(X=X, st1=st1, Xn=Xn, QKV=QKV, rstd=rstd, O=O, st2=st2, On=On, Z=Z) if save else None
     return Xout, X16, saved
 
@@ -202,7 +226,8 @@ def _attn_branch_bwd(dXout, g: Geom, p, w16, heads: int, axes, scale_keys, mask_
 # ---------------------------------------------------------------------------------------------
 def temporal_forward(X, g: Geom, p, w16, heads: int, attn_scale: bool, mask_img, save: bool):
     keys = ["attn_scale_factor"] if attn_scale else None
-    Xout, _, saved = _attn_branch_fwd(X, g, p, w16, heads, ["t"], keys, mask_img, None, None, p["gamma"], False, save)
+    Xout, _, saved = _attn_branch_fwd(X, g, p, w16, heads, ["t"], keys, mask_img, None, None, p["gamma"], False, save,
+                                      want_stats=True)
     return Xout, saved
 
 
@@ -245,8 +270,10 @@ def spatial_forward(X, g: Geom, p, w16, heads: int, attn_scale: bool, feat_scale
     st3 = _zeros((I, E, 2), X)
     ops.inorm_stats(Y2, I, P, st3)
     Xout = _empty((N, E), F32, X)
+    st_out = _zeros((I, E, 2), X)
     ops.inorm_apply(Y2, Xout, I, P, st3, p["mlp_norm.weight"], p["mlp_norm.bias"], resid_in=Xmid, row_scale=mask_mlp,
-                    col_gamma=p["gamma_mlp"])
+                    col_gamma=p["gamma_mlp"], stats_out=st_out)
+    _publish_stats(Xout, st_out)
     if save:
         sv.update(Xb=Xb, G=G, Hpre=Hpre, Y2=Y2, st3=st3)
     return Xout, sv
@@ -345,12 +372,14 @@ def embed_forward(x, g_in, p, n_layers: int, film_gb: Optional[torch.Tensor], T:
             ops.inorm_apply(Y, An, I, ho * wo, st, nw, nb, gelu=True)
         else:
             X = _empty((M, Cout), F32, x)
+            st_out = _zeros((I, Cout, 2), x)
             if film_gb is not None:
                 E = Cout
                 fg, fb = film_gb[:, :E].contiguous(), film_gb[:, E:].contiguous()
-                ops.inorm_apply(Y, X, I, ho * wo, st, nw, nb, film_gamma=fg, film_beta=fb, film_T=T)
+                ops.inorm_apply(Y, X, I, ho * wo, st, nw, nb, film_gamma=fg, film_beta=fb, film_T=T, stats_out=st_out)
             else:
-                ops.inorm_apply(Y, X, I, ho * wo, st, nw, nb)
+                ops.inorm_apply(Y, X, I, ho * wo, st, nw, nb, stats_out=st_out)
+            _publish_stats(X, st_out)
             An = None
         if save:
             sv["Y"].append(Y); sv["st"].append(st); sv["A"].append(A); sv["dims"].append((h_, w_, Cin, Cout))
