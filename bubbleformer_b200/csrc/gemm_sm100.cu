@@ -424,7 +424,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               if (p.is_f16) st_row_16<__half>(s2, lane, acc); else st_row_16<__nv_bfloat16>(s2, lane, acc);
             }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = gelu_fast(acc[j]);
+            for (int j = 0; j < 32; ++j) acc[j] = gelu_tanh(acc[j]);
             if (p.is_f16) st_row_16<__half>(s, lane, acc); else st_row_16<__nv_bfloat16>(s, lane, acc);
             fence_proxy_async();
             __syncwarp();
@@ -457,7 +457,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             float pre[32];
             if (p.is_f16) ld_row_16<__half>(box, row, pre); else ld_row_16<__nv_bfloat16>(box, row, pre);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] *= gelu_grad_fast(pre[j]);
+            for (int j = 0; j < 32; ++j) acc[j] *= gelu_tanh_grad(pre[j]);
             if (p.is_f16) st_row_16<__half>(box, row, acc); else st_row_16<__nv_bfloat16>(box, row, acc);
             fence_proxy_async();
             __syncwarp();
@@ -810,8 +810,8 @@ extern "C" int bf_gemm(const bf_gemm_args* a, void* stream) {
   } else {
     BF_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0, "bf_gemm: leading dimensions must be multiples of 8 elements");
     const int k_total = (a->K + BK - 1) / BK;
-    BF_REQUIRE(k_total % a->split_k == 0, "bf_gemm: ceil(K/64)=%d not divisible by split_k=%d", k_total, a->split_k);
-    p.k_iters = k_total / a->split_k;
+    BF_REQUIRE(a->split_k <= k_total, "bf_gemm: split_k=%d exceeds ceil(K/64)=%d", a->split_k, k_total);
+    p.k_iters = (k_total + a->split_k - 1) / a->split_k;   // a ragged last split reads zero-filled (out-of-bounds) K rows
     p.k_seg_iters = k_total;
     if (a_mn) {   // (K, M) row-major: inner dim M
       BF_REQUIRE(a->lda >= a->M, "bf_gemm: lda < M");

@@ -75,13 +75,23 @@ def relpos_bucket_vector(Ln: int, device) -> torch.Tensor:
 
 
 def pick_split(k_tokens: int, m: int, n: int) -> int:
-    """Split-K factor for a token-contraction (wgrad) GEMM: fill ~2 waves of SMs, divide ceil(K/64)."""
+    """Split-K factor for a token-contraction (wgrad) GEMM: the (m-tiles x n-tiles x splits) work items should fill
+    the 148 SMs in as few, as full, waves as possible.  Mirrors pick_bn() of gemm_sm100.cu for the n tile."""
     k_total = (k_tokens + 63) // 64
-    tiles = ((m + 127) // 128) * ((n + 127) // 128)
-    s = max(1, min(k_total, (2 * 148) // max(tiles, 1)))
-    while k_total % s:
-        s -= 1
-    return s
+    bn = 256 if (n % 256 == 0 and n >= 512) else (192 if n % 192 == 0 else 128)
+    if n <= 64:
+        bn = 64
+    elif n <= 128:
+        bn = 128
+    tiles = ((m + 127) // 128) * ((n + bn - 1) // bn)
+    best, best_cost = 1, None
+    for s in range(1, min(k_total, 64) + 1):
+        waves = -(-tiles * s // 148)
+        iters = -(-k_total // s)
+        cost = waves * (iters + 6)            # k iterations per work item + a fixed prologue/epilogue share
+        if best_cost is None or cost < best_cost:
+            best, best_cost = s, cost
+    return best
 
 
 def _empty(shape, dtype, like):

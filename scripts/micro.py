@@ -71,6 +71,14 @@ def main():
         "gemm_fc2": (lambda: ops.gemm(H, W2, N, E, 4 * E, epilogue=L.EPI_STORE16, bias=vE, out16=O), 2.0 * N * 4 * E * E, (N * 4 * E + N * E) * 2),
         "gemm_resid": (lambda: ops.gemm(Xb, Wo, N, E, E, epilogue=L.EPI_RESID, bias=vE, col_gamma=vE, row_scale=rs, rows_per_group=P,
                                         in32=X32, out32=o32, out16=O, out16b=O2), 2.0 * N * E * E, N * E * (2 + 4 + 4 + 2 + 2)),
+        "gemm_resid64": (lambda: ops.gemm(Xb, Wo, N, E, E, epilogue=L.EPI_RESID, bias=vE, col_gamma=vE, row_scale=rs, rows_per_group=P,
+                                          in32=X32, out32=o32, out16=O, out16b=O2, bn=64), 2.0 * N * E * E, N * E * (2 + 4 + 4 + 2 + 2)),
+        "gemm_resid_noz": (lambda: ops.gemm(Xb, Wo, N, E, E, epilogue=L.EPI_RESID, bias=vE, col_gamma=vE, row_scale=rs, rows_per_group=P,
+                                          in32=X32, out32=o32), 2.0 * N * E * E, N * E * (2 + 4 + 4)),
+        "gemm_wgrad_qkv": (lambda: ops.gemm(QKV, Xb, 3 * E, E, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
+                                            split_k=engine.pick_split(N, 3 * E, E), out32=torch.zeros(3 * E, E, device=dev)), 2.0 * N * 3 * E * E, (N * 4 * E) * 2),
+        "gemm_wgrad_out": (lambda: ops.gemm(Xb, Xb, E, E, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
+                                            split_k=engine.pick_split(N, E, E), out32=torch.zeros(E, E, device=dev)), 2.0 * N * E * E, (N * 2 * E) * 2),
         "gemm_dgelu": (lambda: ops.gemm(Xb, W2, N, 4 * E, E, epilogue=L.EPI_DGELU, b_mode=L.B_KN, aux16=H, out16=out4), 2.0 * N * 4 * E * E, (N * E + 2 * N * 4 * E) * 2),
         "gemm_wgrad": (lambda: ops.gemm(H, Xb, 4 * E, E, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN, split_k=8,
                                         out32=torch.zeros(4 * E, E, device=dev)), 2.0 * N * 4 * E * E, (N * 4 * E + N * E) * 2),

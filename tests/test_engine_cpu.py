@@ -65,8 +65,8 @@ def test_relpos_bucket_vector_matches_oracle():
                 assert int(vec[j - i + Ln - 1]) == int(tab[i, j])
 
 
-def test_pick_split_divides_k_blocks():
+def test_pick_split_in_range():
     for tokens in (40960, 5120, 163840, 1000, 64, 63):
         for (m, n) in ((384, 384), (1152, 384), (1536, 384), (96, 384)):
             s = engine.pick_split(tokens, m, n)
-            assert s >= 1 and ((tokens + 63) // 64) % s == 0
+            assert 1 <= s <= (tokens + 63) // 64
