@@ -201,6 +201,11 @@ def main():
     model.train() if train else model.eval()
     sink = GradSink(model) if train else None
 
+    gstep = None
+    if not train:
+        from bubbleformer_b200.rollout import GraphedStep
+        gstep = GraphedStep(model, x, cond)       # the whole B=1 step replayed from one CUDA graph
+
     def step(xd, td, cd):
         if train:
             sink.begin_step()
@@ -209,8 +214,7 @@ def main():
             loss.backward()
             sink.finish()
             return loss
-        with torch.no_grad():
-            return model(xd, cd)
+        return gstep(xd, cd)
 
     def barrier():
         if world > 1:
