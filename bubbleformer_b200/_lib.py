@@ -34,7 +34,7 @@ class GemmArgs(C.Structure):
         ("row_scale", C.c_void_p), ("in32", C.c_void_p), ("aux16", C.c_void_p),
         ("out16", C.c_void_p), ("out16b", C.c_void_p), ("out32", C.c_void_p),
         ("ldo", C.c_int64), ("ld32", C.c_int64),
-        ("stats_out", C.c_void_p), ("ln_rstd", C.c_void_p),
+        ("stats_out", C.c_void_p), ("ln_rstd", C.c_void_p), ("colsum_out", C.c_void_p),
     ]
 
 
@@ -118,7 +118,7 @@ class AttnArgs(C.Structure):
         ("out_scale", C.c_float), ("prenorm", C.c_int32),
         ("d_qn_w", C.c_void_p), ("d_qn_b", C.c_void_p), ("d_kn_w", C.c_void_p), ("d_kn_b", C.c_void_p),
         ("d_bias_emb", C.c_void_p), ("d_scale_factor", C.c_void_p),
-        ("rstd", C.c_void_p),
+        ("rstd", C.c_void_p), ("d_qkv_bias", C.c_void_p),
     ]
 
 

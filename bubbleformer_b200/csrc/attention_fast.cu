@@ -39,6 +39,7 @@ struct FastParams {
   const float* bias_emb; const int* bucket; const float* scale_factor;
   float out_scale; int accumulate;
   float* d_qn_w; float* d_qn_b; float* d_kn_w; float* d_kn_b; float* d_bias_emb; float* d_scale_factor;
+  float* d_qkv_bias;                 // [heads * 3 * 64] or null: += column sums of the dqkv written by this launch
 };
 
 // per-warp shared memory
@@ -412,6 +413,37 @@ __device__ __forceinline__ void ln_bwd16(float (&acc)[8][4], float pre, const ui
   }
 }
 
+// column sums of a 32-row tile held as two 16-row C-fragment sets -> shared accumulators (8 lanes per column collide)
+__device__ __forceinline__ void colsum_frag(float* s_dst, const float (&o0)[8][4], const float (&o1)[8][4], int lane) {
+  const int t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      float v = (o0[nt][e] + o0[nt][2 + e]) + (o1[nt][e] + o1[nt][2 + e]);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if ((lane >> 2) == 0) atomicAdd(s_dst + nt * 8 + 2 * t + e, v);
+    }
+  }
+}
+
+__device__ __forceinline__ void colsum_frag1(float* s_dst, const float (&o)[8][4], int lane) {
+  const int t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      float v = o[nt][e] + o[nt][2 + e];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if ((lane >> 2) == 0) atomicAdd(s_dst + nt * 8 + 2 * t + e, v);
+    }
+  }
+}
+
 __device__ __forceinline__ void stage16(uint8_t* stage, int pitch, int m0, const float (&o)[8][4], int lane) {
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
@@ -435,7 +467,8 @@ attn_fast_bwd_kernel(FastParams p) {
   float* s_dkw = s_dqb + FD;
   float* s_demb = s_dkw + FD;           // [32 * heads]
   float* s_dsf = s_demb + 32 * p.heads; // [heads]
-  const int n_acc = 3 * FD + 33 * p.heads;
+  float* s_dbias = s_dsf + p.heads;     // [heads * 3 * 64] column sums of dq | dk | dv (input_head bias gradient)
+  const int n_acc = 3 * FD + 33 * p.heads + (p.d_qkv_bias != nullptr ? 3 * FD * p.heads : 0);
   for (int i = threadIdx.x; i < n_acc; i += blockDim.x) s_acc[i] = 0.f;
   uint8_t* my = smem + kTabBytes + warp * BwdWarp::kBytes;
   uint8_t* sdo = my + BwdWarp::kDo;
@@ -585,6 +618,7 @@ attn_fast_bwd_kernel(FastParams p) {
         }
         stage16(sdo, kRG, mt * 16, o[mt], lane);
       }
+      if (p.d_qkv_bias != nullptr) colsum_frag(s_dbias + head * 3 * FD + 2 * FD, o[0], o[1], lane);
       __syncwarp();
       store_rows64(sdo, kRG, p.out + (long)head * 3 * FD + 2 * FD, p.ld_out, rowtok, p.accumulate, lane);
       __syncwarp();
@@ -621,6 +655,7 @@ attn_fast_bwd_kernel(FastParams p) {
         ln_bwd16<false>(o[mt], 1.f, my + FD * 2, rstd_s, 1, mt * 16, wk, dwk, dbk_unused, lane);
         stage16(sdo, kRG, mt * 16, o[mt], lane);
       }
+      if (p.d_qkv_bias != nullptr) colsum_frag(s_dbias + head * 3 * FD + FD, o[0], o[1], lane);
       __syncwarp();
       store_rows64(sdo, kRG, p.out + (long)head * 3 * FD + FD, p.ld_out, rowtok, p.accumulate, lane);
       __syncwarp();
@@ -649,6 +684,7 @@ attn_fast_bwd_kernel(FastParams p) {
       }
       ln_bwd16<true>(o, qscale, my, rstd_s, 0, mt * 16, wq, dwq, dbq, lane);
       stage16(sdo, kRG, mt * 16, o, lane);
+      if (p.d_qkv_bias != nullptr) colsum_frag1(s_dbias + head * 3 * FD, o, lane);
     }
     __syncwarp();
     store_rows64(sdo, kRG, p.out + (long)head * 3 * FD, p.ld_out, rowtok, p.accumulate, lane);
@@ -684,6 +720,8 @@ attn_fast_bwd_kernel(FastParams p) {
     for (int i = threadIdx.x; i < 32 * p.heads; i += blockDim.x) atomicAdd(p.d_bias_emb + i, s_demb[i]);
   if (p.d_scale_factor != nullptr)
     for (int i = threadIdx.x; i < p.heads; i += blockDim.x) atomicAdd(p.d_scale_factor + i, s_dsf[i]);
+  if (p.d_qkv_bias != nullptr)
+    for (int i = threadIdx.x; i < 3 * FD * p.heads; i += blockDim.x) atomicAdd(p.d_qkv_bias + i, s_dbias[i]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -708,10 +746,11 @@ int launch_attn_fast(const bf_attn_args* a, bool bwd, cudaStream_t st) {
   p.out_scale = a->out_scale; p.accumulate = a->accumulate;
   p.d_qn_w = a->d_qn_w; p.d_qn_b = a->d_qn_b; p.d_kn_w = a->d_kn_w; p.d_kn_b = a->d_kn_b;
   p.d_bias_emb = a->d_bias_emb; p.d_scale_factor = a->d_scale_factor;
+  p.d_qkv_bias = bwd ? a->d_qkv_bias : nullptr;
   const bool packed = !(p.G == 1 && a->L == FLP);
   const int kFastWarps = bwd ? kBwdWarps : kFwdWarps;
   const size_t smem = kTabBytes + (size_t)kFastWarps * (bwd ? BwdWarp::kBytes : FwdWarp::kBytes) +
-                      (bwd ? (size_t)(3 * FD + 33 * p.heads) * sizeof(float) : 0);
+                      (bwd ? (size_t)(3 * FD + 33 * p.heads + 3 * FD * p.heads) * sizeof(float) : 0);
   BF_REQUIRE(smem <= 227 * 1024, "bf_attention (prenorm): shared memory %zu too large", smem);
   void (*kern)(FastParams);
   if (bwd) kern = packed ? attn_fast_bwd_kernel<true> : attn_fast_bwd_kernel<false>;

@@ -63,6 +63,7 @@ struct GemmParams {
   int has_out16, has_out16b;
   float* stats_out;   // RESID: stats_out[(m / rows_per_group)][n][2] += (sum, sum^2) of out32 (may be null)
   float* ln_rstd;     // QKV_LN: (M, heads, 2) rstd of the raw q / k rows
+  float* colsum_out;  // DGELU: [N] += column sums of the stored output (accumulated per CTA in shared memory)
   long ldo;
 };
 
@@ -156,6 +157,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  float* s_colsum = reinterpret_cast<float*>(smem + p.slab_off);       // DGELU + colsum_out only ([num_n_blocks * BN])
+  if (p.colsum_out != nullptr)
+    for (int i = threadIdx.x; i < p.num_n_blocks * BN; i += kThreads) s_colsum[i] = 0.f;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
@@ -462,6 +466,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) { tma_store_2d(&map_o16, box + quad * 32 * 64, n, mrow); tma_store_commit(); }
+            if (p.colsum_out != nullptr) {
+              // lane j sums column j of this warp's 32 x 32 block as stored (conflict-free read of the swizzled rows)
+              const uint8_t* sl = box + quad * 32 * 64;
+              const int rows_valid = min(32, p.M - mrow);
+              float cs = 0.f;
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r) {
+                const uint16_t h = *reinterpret_cast<const uint16_t*>(sl + r * 64 + ((((lane >> 3) ^ ((r >> 1) & 3)) << 4) | ((lane & 7) << 1)));
+                float v;
+                if (p.is_f16) v = __half2float(*reinterpret_cast<const __half*>(&h));
+                else v = __uint_as_float(static_cast<uint32_t>(h) << 16);
+                if (r < rows_valid) cs += v;
+              }
+              atomicAdd(s_colsum + n + lane, cs);
+            }
             break;
           }
           case BF_EPI_ACC32: {
@@ -589,6 +608,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
+  if (p.colsum_out != nullptr)
+    for (int i = threadIdx.x; i < p.N; i += kThreads) {
+      const float v = s_colsum[i];
+      if (v != 0.f) atomicAdd(p.colsum_out + i, v);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -667,7 +691,8 @@ static int launch(const Maps& mp, GemmParams& p, cudaStream_t st) {
   constexpr int stage_bytes = BM * BK * 2 + BN * BK * 2;
   const int bar_bytes = (2 * kMaxStages + 8) * 8 + 16;
   const bool slabs = !(p.epilogue == BF_EPI_DGELU || p.epilogue == BF_EPI_ACC32 || p.epilogue == BF_EPI_D2S);
-  const int slab_bytes = slabs ? kEpiWarps * kSlabBytes : 0;
+  const int slab_bytes = slabs ? kEpiWarps * kSlabBytes
+                               : (p.colsum_out != nullptr ? ((p.num_n_blocks * BN * 4 + 1023) / 1024) * 1024 : 0);
   p.in_bytes = p.in_kind == 0 ? 0 : BM * BN * (p.in_kind == 2 ? 4 : 2);
   const int avail = kSmemBudget - 1024 - bar_bytes - slab_bytes;
   const int want_stages = p.k_iters < 4 ? (p.k_iters < 2 ? 2 : p.k_iters) : 4;
@@ -738,6 +763,8 @@ extern "C" int bf_gemm(const bf_gemm_args* a, void* stream) {
   p.ldo = a->ldo;
   p.stats_out = a->stats_out;
   p.ln_rstd = a->ln_rstd;
+  p.colsum_out = a->colsum_out;
+  BF_REQUIRE(a->colsum_out == nullptr || a->epilogue == BF_EPI_DGELU, "bf_gemm: colsum_out only with BF_EPI_DGELU");
   for (const float* v : {a->bias, a->col_scale, a->col_shift, a->col_gamma})
     BF_REQUIRE((reinterpret_cast<uintptr_t>(v) & 15) == 0, "bf_gemm: per-column vectors must be 16-byte aligned");
 

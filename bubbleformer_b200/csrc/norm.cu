@@ -471,7 +471,7 @@ struct ResidBwdParams {
   const float* row_scale;    // [I] or null
   const float* coef;         // [C]
   void* dz16;                // out, ld = ldz, may be null
-  float* S0; float* S1;      // [C]
+  float* S0; float* S1;      // [I][C] per-image sums
 };
 template <typename T16, bool HASZ>
 __global__ void __launch_bounds__(kNT, kBlocksPerSM)
@@ -513,8 +513,8 @@ resid_bwd_kernel(ResidBwdParams p) {
   if (c.active && c.ty == 0) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(p.S0 + c0 + j, rs * acc[j]);
-      if (HASZ) atomicAdd(p.S1 + c0 + j, rs * acc[8 + j]);
+      atomicAdd(p.S0 + (long)c.img * g.C + c0 + j, rs * acc[j]);
+      if (HASZ) atomicAdd(p.S1 + (long)c.img * g.C + c0 + j, rs * acc[8 + j]);
     }
   }
 }

@@ -187,9 +187,10 @@ def _attn_branch_bwd(dXout, g: Geom, p, w16, heads: int, axes, scale_keys, mask_
     I, P, N = g.I, g.P, g.N
     E = dXout.shape[1]
     X, st1, Xn, QKV, O, st2, On, Z = (sv[k] for k in ("X", "st1", "Xn", "QKV", "O", "st2", "On", "Z"))
-    S0, S1 = _zeros((E,), dXout), _zeros((E,), dXout)
+    S01 = _zeros((2, I, E), dXout)                    # per-image partial sums (few atomics per address)
     dZ = _empty((N, E), BF16, dXout)
-    ops.resid_bwd(dXout, Z, dZ, I, P, mask_img, coef, S0, S1)
+    ops.resid_bwd(dXout, Z, dZ, I, P, mask_img, coef, S01[0], S01[1])
+    S0, S1 = S01.sum(dim=1)
     # output_head: dgrad reads W (E_out, E_in) as the (K, N) operand, wgrad contracts over tokens
     dOn = _empty((N, E), BF16, dXout)
     ops.gemm(dZ, w16("output_head.weight"), N, E, E, epilogue=L.EPI_STORE16, b_mode=L.B_KN, out16=dOn)
@@ -305,10 +306,10 @@ def spatial_backward(dXout, g: Geom, p, w16, heads: int, attn_scale: bool, feat_
                          dcol_scale=grads["gamma_mlp"])
     # fc2 (its bias feeds an InstanceNorm, so its gradient is identically zero and stays zero)
     dH = _empty((N, 4 * E), BF16, dXout)
-    ops.gemm(dY2, w16("mlp.fc2.weight"), N, 4 * E, E, epilogue=L.EPI_DGELU, b_mode=L.B_KN, aux16=Hpre, out16=dH)
+    ops.gemm(dY2, w16("mlp.fc2.weight"), N, 4 * E, E, epilogue=L.EPI_DGELU, b_mode=L.B_KN, aux16=Hpre, out16=dH,
+             colsum_out=grads["mlp.fc1.bias"])
     ops.gemm(dY2, G, E, 4 * E, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
              split_k=pick_split(N, E, 4 * E), out32=grads["mlp.fc2.weight"])
-    ops.colsum16(dH, grads["mlp.fc1.bias"])
     # fc1: the input gradient joins the residual-stream gradient in the epilogue
     dXmid = _empty((N, E), F32, dXout)
     ops.gemm(dH, w16("mlp.fc1.weight"), N, E, 4 * E, epilogue=L.EPI_ACC32, b_mode=L.B_KN, in32=dXout, out32=dXmid)

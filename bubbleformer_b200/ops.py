@@ -41,7 +41,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, epilogue: 
          s2d: Optional[tuple] = None, d2s: Optional[tuple] = None, rows_per_group: int = 1,
          bias=None, col_scale=None, col_shift=None, col_gamma=None, row_scale=None,
          in32=None, aux16=None, out16=None, out16b=None, out32=None, stats_out=None,
-         ln_head_dim: int = 0, ln_rstd=None,
+         ln_head_dim: int = 0, ln_rstd=None, colsum_out=None,
          ldo: Optional[int] = None, ld32: Optional[int] = None) -> None:
     """D[M,N] = sum_k A[m,k] B[n,k] with a fused epilogue; see bf_gemm in include/bubbleformer_b200.h."""
     if A.dtype not in _DT or B.dtype != A.dtype:
@@ -83,6 +83,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, epilogue: 
     a.ldo, a.ld32 = ldo, ld32
     if stats_out is not None:
         a.stats_out = _f32(stats_out, 2 * N * ((M + rows_per_group - 1) // rows_per_group), "stats_out")
+    if colsum_out is not None:
+        a.colsum_out = _f32(colsum_out, N, "colsum_out")
     if ln_rstd is not None:
         a.ln_head_dim = ln_head_dim
         a.ln_rstd = _f32(ln_rstd, 2 * M * (N // (3 * max(ln_head_dim, 1))), "ln_rstd")
@@ -185,8 +187,8 @@ def resid_bwd(dx, z16, dz16, I, P, row_scale, coef, S0, S1) -> None:
     ref = z16 if z16 is not None else dz16
     dt = _DT[ref.dtype]
     L.check(L.lib.bf_resid_bwd(_ptr(dx), dx.stride(0), _ptr(z16), _ptr(dz16), ref.stride(0), dt, I, P, Cn,
-                               _f32(row_scale, I, "row_scale"), _f32(coef, Cn, "coef"), _f32(S0, Cn, "S0"),
-                               _f32(S1, Cn, "S1"), _stream()), "bf_resid_bwd")
+                               _f32(row_scale, I, "row_scale"), _f32(coef, Cn, "coef"), _f32(S0, I * Cn, "S0"),
+                               _f32(S1, I * Cn, "S1"), _stream()), "bf_resid_bwd")
 
 
 def colsum16(x, out) -> None:
@@ -233,6 +235,7 @@ def attention(qkv, out, *, heads, L_, n_seq, inner, outer_stride, inner_stride, 
     a.d_kn_w, a.d_kn_b = _f32(grads["d_kn_w"], d, "d_kn_w"), _f32(grads["d_kn_b"], d, "d_kn_b")
     a.d_bias_emb = _f32(grads.get("d_bias_emb"), 32 * heads, "d_bias_emb")
     a.d_scale_factor = _f32(grads.get("d_scale_factor"), heads, "d_scale_factor")
+    a.d_qkv_bias = _f32(grads.get("d_qkv_bias"), E3, "d_qkv_bias")
     L.check(L.lib.bf_attention_bwd(C.byref(a), _stream()), "bf_attention_bwd")
 
 

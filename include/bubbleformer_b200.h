@@ -112,6 +112,7 @@ typedef struct bf_gemm_args {
                              out32 -- the raw InstanceNorm statistics of the new residual stream, so the next
                              norm needs no separate pass (rows_per_group = tokens per image, multiple of 32)   */
   float* ln_rstd;         /* BF_EPI_QKV_LN only: (M, N / (3*ln_head_dim), 2) fp32                                */
+  float* colsum_out;      /* BF_EPI_DGELU only, may be NULL: [N] += column sums of out16 (gradient of the fc1 bias) */
 } bf_gemm_args;
 
 BF_API int bf_gemm(const bf_gemm_args* args, void* stream);
@@ -177,7 +178,9 @@ typedef struct bf_inorm_bwd_params_args {
 BF_API int bf_inorm_bwd_params(const bf_inorm_bwd_params_args* args, void* stream);
 
 /* Residual-branch backward (layers/attention.py:123,309 reversed): one pass over the fp32 gradient stream
- *   dz16[m,c] = row_scale[img]*coef[c]*dx[m,c];  S0[c] += sum_m rs*dx;  S1[c] += sum_m rs*dx*z16[m,c]   */
+ *   dz16[m,c] = row_scale[img]*coef[c]*dx[m,c];  S0[img][c] += sum_{m in img} rs*dx;  S1[img][c] += sum rs*dx*z16[m,c]
+ * S0 / S1 are PER IMAGE, (I, C) fp32 (the caller sums over images): per-channel totals would funnel every block's
+ * atomics into C addresses.                                                                               */
 BF_API int bf_resid_bwd(const float* dx, int64_t lddx, const void* z16, void* dz16, int64_t ldz, int dtype,
                         int I, int P, int C, const float* row_scale, const float* coef, float* S0, float* S1,
                         void* stream);
@@ -218,6 +221,8 @@ typedef struct bf_attn_args {
   float* d_qn_w;  float* d_qn_b;  float* d_kn_w;  float* d_kn_b;
   float* d_bias_emb;  float* d_scale_factor;
   const float* rstd;           /* prenorm backward: (tokens, heads, 2) rstd of the raw q / k rows                  */
+  float* d_qkv_bias;           /* prenorm backward, may be NULL: [3E] += column sums of the d qkv this launch writes
+                                  (gradient of the input_head bias; replaces a separate bf_colsum16 pass)           */
 } bf_attn_args;
 BF_API int bf_attention_fwd(const bf_attn_args* args, void* stream);
 BF_API int bf_attention_bwd(const bf_attn_args* args, void* stream);

@@ -94,7 +94,9 @@ def run_variant(v):
         elif v == "dgelu":
             pre = rnd(M, N)
             out = torch.zeros(M, N, device=dev, dtype=dt)
-            ops.gemm(A, B, M, N, K, epilogue=L.EPI_DGELU, aux16=pre, out16=out)
+            cs = torch.zeros(N, device=dev)
+            ops.gemm(A, B, M, N, K, epilogue=L.EPI_DGELU, aux16=pre, out16=out, colsum_out=cs)
+            ok &= report(v + ".colsum", cs[None], out.float().sum(0)[None], 2e-3)
             p32 = pre.float().requires_grad_(True)
             torch.nn.functional.gelu(p32).sum().backward()
             ok &= report(v, out, (A.float() @ B.float().t()) * p32.grad, 1e-2)

@@ -148,8 +148,9 @@ def run(group):
         z = torch.randn(I * P, Cn, device=dev).bfloat16()
         rs, coef = torch.rand(I, device=dev), torch.randn(Cn, device=dev)
         dz = torch.zeros_like(z)
-        S0, S1 = torch.zeros(Cn, device=dev), torch.zeros(Cn, device=dev)
+        S0, S1 = torch.zeros(I, Cn, device=dev), torch.zeros(I, Cn, device=dev)
         ops.resid_bwd(dx, z, dz, I, P, rs, coef, S0, S1)
+        S0, S1 = S0.sum(0), S1.sum(0)
         rsx = rs.repeat_interleave(P)[:, None]
         ok &= report("resid dz", dz, rsx * coef * dx, 6e-3)
         ok &= report("resid S0", S0, (rsx * dx).sum(0), 1e-4)

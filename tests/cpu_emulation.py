@@ -22,7 +22,7 @@ def _gelu_grad(x):
 def gemm(A, B, M, N, K, *, epilogue, a_mode=L.A_ROWMAJOR, b_mode=L.B_NK, split_k=1, bn=0, lda=None, ldb=None,
          s2d=None, d2s=None, rows_per_group=1, bias=None, col_scale=None, col_shift=None, col_gamma=None,
          row_scale=None, in32=None, aux16=None, out16=None, out16b=None, out32=None, stats_out=None,
-         ln_head_dim=0, ln_rstd=None, ldo=None, ld32=None):
+         ln_head_dim=0, ln_rstd=None, colsum_out=None, ldo=None, ld32=None):
     a = A.float()
     if a_mode == L.A_KM:
         a = a.reshape(K, M).t()
@@ -71,6 +71,8 @@ def gemm(A, B, M, N, K, *, epilogue, a_mode=L.A_ROWMAJOR, b_mode=L.B_NK, split_k
             stats_out.reshape(-1, N, 2).add_(torch.stack([xi.sum(1), (xi * xi).sum(1)], dim=-1))
     elif epilogue == L.EPI_DGELU:
         out16.reshape(M, N).copy_(acc * _gelu_grad(aux16.reshape(M, N).float()))
+        if colsum_out is not None:
+            colsum_out.add_(out16.reshape(M, N).float().sum(0))
     elif epilogue == L.EPI_ACC32:
         out32.reshape(M, N).copy_(in32.reshape(M, N) + acc)
     elif epilogue == L.EPI_ATOMIC32:
@@ -164,9 +166,9 @@ def resid_bwd(dx, z16, dz16, I, P, row_scale, coef, S0, S1):
     rs = row_scale.repeat_interleave(P)[:, None] if row_scale is not None else 1.0
     if dz16 is not None:
         dz16.copy_(rs * coef * dx)
-    S0.add_((rs * dx).sum(0))
+    S0.reshape(I, C).add_((rs * dx).reshape(I, P, C).sum(1))
     if z16 is not None:
-        S1.add_((rs * dx * z16.float()).sum(0))
+        S1.reshape(I, C).add_((rs * dx * z16.float()).reshape(I, P, C).sum(1))
 
 
 def colsum16(x, out):
@@ -237,6 +239,8 @@ def _attention(qkv, out, heads, L_, n_seq, inner, outer_stride, inner_stride, to
     grads["d_qn_b"].add_(leaves[2].grad)
     grads["d_kn_w"].add_(leaves[3].grad)
     grads["d_kn_b"].add_(leaves[4].grad)
+    if grads.get("d_qkv_bias") is not None:
+        grads["d_qkv_bias"].add_(dq.reshape(-1, E3).sum(0))
     if grads.get("d_bias_emb") is not None:
         grads["d_bias_emb"].add_(leaves[5].grad)
     if sf is not None and grads.get("d_scale_factor") is not None:
