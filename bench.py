@@ -90,10 +90,10 @@ class ClockSampler:
 
 
 def rel_l2_loss(pred, tgt):
-    """LpLoss(d=2, p=2, reduce_dims=[0,1,2], reductions=[mean,mean,sum]) -- upstream utils/losses.py:67-94."""
-    diff = (pred - tgt).flatten(-2).norm(dim=-1)
-    ynorm = tgt.flatten(-2).norm(dim=-1)
-    return (diff / ynorm).mean(0).mean(0).sum()
+    """LpLoss(d=2, p=2, reduce_dims=[0,1,2], reductions=[mean,mean,sum]) -- upstream utils/losses.py:67-94,
+    through the fused CUDA loss of this repo (bubbleformer_b200.losses)."""
+    from bubbleformer_b200.losses import rel_l2_loss as fused
+    return fused(pred, tgt)
 
 
 def cpu_port_step(sd, x, tgt, cond, train: bool):
@@ -243,24 +243,51 @@ def main():
     value = world * B / (ms_per_step * 1e-3)
 
     # ---- end to end through the public API with host buffers ----
+    # Every step copies its own inputs from pinned host memory (H2D inside the timed region) and one step result
+    # is read back to the host per step.  Like a data loader with one batch of prefetch, the copy of step i+1 is
+    # issued on a copy stream while step i computes, and the loss read lags one step so it never stalls the GPU.
     xh, th, ch = (t.cpu().pin_memory() for t in (x, tgt, cond))
     Ke = max(3, min(K, 10))
-    for _ in range(2):
-        step(xh.to(dev, non_blocking=True), th.to(dev, non_blocking=True), ch.to(dev, non_blocking=True))
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def fetch():
+        with torch.cuda.stream(copy_stream):
+            bufs = tuple(t.to(dev, non_blocking=True) for t in (xh, th, ch))
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return bufs, ev
+
+    def run_e2e(n):
+        nxt = fetch()
+        prev = None
+        host = 0.0
+        for _ in range(n):
+            (xd, td, cd), ev = nxt
+            nxt = fetch()                                    # prefetch the next step's inputs
+            torch.cuda.current_stream().wait_event(ev)
+            for t_ in (xd, td, cd):
+                t_.record_stream(torch.cuda.current_stream())
+            r = step(xd, td, cd)
+            r = r.detach() if train else r[0, 0, 0, 0, :1].clone()
+            if prev is not None:
+                host = float(prev)                           # D2H read of the previous step's result
+            prev = r
+        host = float(prev)
+        torch.cuda.synchronize()
+        return host
+
+    run_e2e(2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(Ke):
-        r = step(xh.to(dev, non_blocking=True), th.to(dev, non_blocking=True), ch.to(dev, non_blocking=True))
-        host = float(r) if train else r[0, 0, 0, 0, 0].item()      # D2H read of the step's result
-    torch.cuda.synchronize()
+    run_e2e(Ke)
     e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t)
     e2e_value = world * B * Ke / e2e_s
-    h2d = (xh.numel() + (th.numel() if train else 0) + ch.numel()) * 4
-    d2h = 4 if train else 4
+    h2d = (xh.numel() + th.numel() + ch.numel()) * 4 * (Ke + 1) // Ke      # one extra prefetch is issued per run
+    d2h = 4
 
     # ---- roofline of the dominant kernel: one instrumented step, CUDA events around every GEMM launch ----
     roof = None

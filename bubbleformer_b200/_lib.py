@@ -124,7 +124,7 @@ class AttnArgs(C.Structure):
 
 EXPORTS = ["bf_last_error", "bf_version", "bf_launch_count", "bf_gemm", "bf_inorm_stats", "bf_inorm_apply",
            "bf_inorm_bwd", "bf_inorm_bwd_params", "bf_resid_bwd", "bf_colsum16", "bf_attention_fwd",
-           "bf_attention_bwd", "bf_patch_in", "bf_patch_out", "bf_patch_wgrad", "bf_s2d_gather", "bf_cast16", "bf_convert16"]
+           "bf_attention_bwd", "bf_lploss_sums", "bf_lploss_bwd", "bf_patch_in", "bf_patch_out", "bf_patch_wgrad", "bf_s2d_gather", "bf_cast16", "bf_convert16"]
 
 _vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
 lib.bf_gemm.argtypes = [C.POINTER(GemmArgs), _vp]
@@ -142,3 +142,5 @@ lib.bf_patch_wgrad.argtypes = [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp]
 lib.bf_s2d_gather.argtypes = [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp]
 lib.bf_convert16.argtypes = [_vp, _i, _vp, _i, _i64, _vp]
 lib.bf_cast16.argtypes = [_vp, _vp, _i, _i64, _vp]
+lib.bf_lploss_sums.argtypes = [_vp, _vp, _vp, _i64, _i64, _vp]
+lib.bf_lploss_bwd.argtypes = [_vp, _vp, _vp, _vp, _i64, _i64, _vp]

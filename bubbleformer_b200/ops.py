@@ -288,6 +288,23 @@ def cast16(src, dst) -> None:
     L.check(L.lib.bf_cast16(_ptr(src), _ptr(dst), _DT[dst.dtype], src.numel(), _stream()), "bf_cast16")
 
 
+def lploss_sums(pred, tgt, sums) -> None:
+    """sums (slabs, 2) fp32 += (sum (pred-tgt)^2, sum tgt^2) per (b, t, c) field; pred/tgt (..., H, W) fp32 contiguous."""
+    assert pred.dtype == torch.float32 and tgt.dtype == torch.float32 and pred.is_contiguous() and tgt.is_contiguous()
+    assert pred.shape == tgt.shape
+    n = pred.shape[-1] * pred.shape[-2]
+    slabs = pred.numel() // n
+    L.check(L.lib.bf_lploss_sums(_ptr(pred), _ptr(tgt), _f32(sums, 2 * slabs, "sums"), slabs, n, _stream()), "bf_lploss_sums")
+
+
+def lploss_bwd(pred, tgt, coef, dpred) -> None:
+    n = pred.shape[-1] * pred.shape[-2]
+    slabs = pred.numel() // n
+    assert dpred.dtype == torch.float32 and dpred.is_contiguous() and dpred.shape == pred.shape
+    L.check(L.lib.bf_lploss_bwd(_ptr(pred), _ptr(tgt), _f32(coef, slabs, "coef"), _ptr(dpred), slabs, n, _stream()),
+            "bf_lploss_bwd")
+
+
 # ---------------------------------------------------------------------------------------------
 # optional per-launch timing (bench.py roofline, scripts/profile_step.py); zero overhead when off
 # ---------------------------------------------------------------------------------------------
@@ -330,5 +347,5 @@ def _attn_tag(a, k):
 gemm = _instrument("gemm", gemm, _gemm_tag)
 attention = _instrument("attention", attention, _attn_tag)
 for _n in ("inorm_stats", "inorm_apply", "inorm_bwd", "inorm_bwd_params", "resid_bwd", "colsum16", "patch_in",
-           "patch_out", "patch_wgrad", "s2d_gather", "cast16", "convert16"):
+           "patch_out", "patch_wgrad", "s2d_gather", "cast16", "convert16", "lploss_sums", "lploss_bwd"):
     globals()[_n] = _instrument(_n, globals()[_n], _shape_tag)

@@ -251,6 +251,16 @@ BF_API int bf_s2d_gather(const void* in, int in_dtype, void* out, int out_dtype,
 BF_API int bf_convert16(const void* in, int in_dtype, void* out, int out_dtype, int64_t n, void* stream);
 BF_API int bf_cast16(const float* in, void* out, int dtype, int64_t n, void* stream);
 
+/* ---- relative-L2 training loss (the step right after the path) ------------------------
+ * upstream utils/losses.py:67-94 with the configuration of modules.py:50 (d=2, p=2, mean b, mean t, sum c).
+ * A slab is one (b, t, c) field of n_per_slab = H*W contiguous fp32 values.
+ * bf_lploss_sums: sums[slab] += (sum (pred-tgt)^2, sum tgt^2)          (caller zeroes `sums`, finishes the scalar)
+ * bf_lploss_bwd : dpred[slab, :] = coef[slab] * (pred - tgt)                                            */
+BF_API int bf_lploss_sums(const float* pred, const float* tgt, float* sums, int64_t slabs, int64_t n_per_slab,
+                          void* stream);
+BF_API int bf_lploss_bwd(const float* pred, const float* tgt, const float* coef, float* dpred, int64_t slabs,
+                         int64_t n_per_slab, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -285,8 +285,17 @@ def convert16(src, dst):
     dst.copy_(src)
 
 
+def lploss_sums(pred, tgt, sums):
+    d = (pred - tgt).flatten(-2)
+    sums.reshape(-1, 2).add_(torch.stack([(d * d).sum(-1).reshape(-1), (tgt.flatten(-2) ** 2).sum(-1).reshape(-1)], dim=-1))
+
+
+def lploss_bwd(pred, tgt, coef, dpred):
+    dpred.copy_(coef.reshape(*pred.shape[:-2], 1, 1) * (pred - tgt))
+
+
 ALL = ["gemm", "inorm_stats", "inorm_apply", "inorm_bwd", "inorm_bwd_params", "resid_bwd", "colsum16", "attention",
-       "patch_in", "patch_out", "patch_wgrad", "s2d_gather", "cast16", "convert16"]
+       "patch_in", "patch_out", "patch_wgrad", "s2d_gather", "cast16", "convert16", "lploss_sums", "lploss_bwd"]
 
 
 def install(monkeypatch, wide: bool = True):

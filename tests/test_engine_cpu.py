@@ -70,3 +70,20 @@ def test_pick_split_in_range():
         for (m, n) in ((384, 384), (1152, 384), (1536, 384), (96, 384)):
             s = engine.pick_split(tokens, m, n)
             assert 1 <= s <= (tokens + 63) // 64
+
+
+def test_fused_rel_l2_loss_matches_oracle(monkeypatch):
+    """Host side of the fused loss (scalar assembly, gradient coefficients) against the oracle's LpLoss restatement."""
+    cpu_emulation.install(monkeypatch, wide=True)
+    from bubbleformer_b200 import losses
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
+    g = torch.Generator().manual_seed(0)
+    pred = torch.randn(2, 3, 4, 8, 8, generator=g, requires_grad=True)
+    tgt = torch.randn(2, 3, 4, 8, 8, generator=g)
+    loss = losses.rel_l2_loss(pred, tgt)
+    ref_in = pred.detach().clone().requires_grad_(True)
+    ref = O.rel_l2_loss(ref_in, tgt)
+    assert abs(float(loss) - float(ref)) < 1e-6 * abs(float(ref))
+    loss.backward()
+    ref.backward()
+    assert O.rel_l2(pred.grad, ref_in.grad) < 1e-6

@@ -99,3 +99,18 @@ def test_graphed_rollout_matches_eager():
     err = [float((a[i] - b[i]).norm() / b[i].norm()) for i in range(4)]
     print("graphed vs eager rel-L2 per step:", err, "eager vs eager:", noise)
     assert err[0] < 5e-3 and all(e < 10 * max(n, 1e-3) for e, n in zip(err, noise))
+
+
+def test_fused_rel_l2_loss_gpu():
+    import torch
+    from bubbleformer_b200.losses import rel_l2_loss
+    from oracle import filmavit_oracle as O
+    torch.manual_seed(0)
+    pred = torch.randn(2, 5, 4, 64, 96, device="cuda", requires_grad=True)
+    tgt = torch.randn(2, 5, 4, 64, 96, device="cuda")
+    loss = rel_l2_loss(pred, tgt)
+    ref_in = pred.detach().clone().requires_grad_(True)
+    ref = O.rel_l2_loss(ref_in, tgt)
+    assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
+    loss.backward(); ref.backward()
+    assert O.rel_l2(pred.grad.cpu(), ref_in.grad.cpu()) < 1e-5
