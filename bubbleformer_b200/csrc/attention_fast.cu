@@ -2,16 +2,18 @@
 //
 // The QKV projection (bf_gemm, BF_EPI_QKV_LN) already stored xhat_q, xhat_k (LayerNorm without its affine part)
 // and v, plus rstd of the raw rows.  What is left of upstream layers/attention.py:80-101 / :212-238 / :258-277
-// per (sequence, head) is tiny and HBM bound, so the kernels are built for low instruction count and many
-// resident warps:
-//   * one warp owns one (tile of <= 32 tokens, head); its q|k|v rows (384 B each, contiguous in the token-major
-//     QKV matrix whatever the axis) arrive by one 1-D bulk TMA copy per row (each lane issues its own row) on a
-//     per-warp mbarrier -- no staging through registers, no per-element copy instructions;
+// per (sequence, head) is tiny and HBM bound, so the kernels are built around the TMA unit and a low instruction
+// count:
+//   * one warp owns one (tile of <= 32 tokens, head).  The token-major QKV matrix is described to TMA as a 4-D
+//     tensor (column, position in sequence, sequence, outer index) whatever the axis (time / image row / image
+//     column), so the q, k and v tiles of an item arrive as THREE tensor copies (128B-swizzled 32 x 64 tiles)
+//     on a per-warp mbarrier, and results leave as ONE tensor store per tile (or a bf16 TMA reduce-add when a
+//     second axis accumulates into the same tensor) -- no per-row copies, no read-modify-write loops;
 //   * the LayerNorm affine (and d^-1/2) is applied to the ldmatrix fragments with packed bf16 FMAs;
 //   * attn = 1/L + (softmax - 1/L)*s  is folded into the probabilities (P' = s*P + (1-s)/L), so attn @ v is a
 //     single MMA and the mean-of-v term disappears; P stays in registers between the two MMAs;
-//   * backward keeps dP for the whole tile in registers, parks P' / dS in the (then dead) v columns of the
-//     tile, and accumulates LayerNorm weight gradients in registers across all items of the persistent loop.
+//   * backward keeps dP for the whole tile in registers, parks P' / dS in the (then dead) v tile, and accumulates
+//     LayerNorm weight gradients in registers across all items of the persistent loop.
 // Short sequences (temporal attention, L = 5) are packed G = 32 / L per tile with a block-diagonal mask.
 #include "common.cuh"
 
@@ -21,20 +23,16 @@ using bf16 = __nv_bfloat16;
 
 constexpr int FD = 64;                       // head dim
 constexpr int FLP = 32;                      // rows per tile
-constexpr int kRS = 3 * FD * 2 + 16;         // bytes per q|k|v row in shared memory (+16: conflict-free ldmatrix)
-constexpr int kRSe = kRS / 2;                // same in elements
-constexpr int kRG = FD * 2 + 16;             // bytes per dO row
-constexpr int kRGe = kRG / 2;
+constexpr int kTile = FLP * FD * 2;          // 4096 B: one 32 x 64 bf16 tile, rows of 128 B, TMA 128B swizzle
 constexpr int kFwdWarps = 16;                // one CTA per SM: per-warp tiles fill the shared memory
 constexpr int kBwdWarps = 12;
 
 struct FastParams {
-  const bf16* qkv; long ld_qkv;
-  bf16* out; long ld_out;
-  const bf16* dout; long ld_dout;
   const float* rstd;                 // (tokens, heads, 2)
   int heads, L, G;
-  long n_seq, inner, outer_stride, inner_stride, tok_stride;
+  int inner, tiles_per_outer;        // sequences per outer index, tiles (of G sequences) per outer index
+  long n_tiles;
+  long outer_stride, inner_stride, tok_stride;   // token index = outer*outer_stride + seq*inner_stride + pos*tok_stride
   const float* qn_w; const float* qn_b; const float* kn_w; const float* kn_b;
   const float* bias_emb; const int* bucket; const float* scale_factor;
   float out_scale; int accumulate;
@@ -42,31 +40,28 @@ struct FastParams {
   float* d_qkv_bias;                 // [heads * 3 * 64] or null: += column sums of the dqkv written by this launch
 };
 
-// per-warp shared memory
+// per-warp shared memory (tiles first: every tile must be 1 KiB aligned for the 128B swizzle)
 struct FwdWarp {
-  static constexpr int kTile = 0;                          // [32][kRS]
-  static constexpr int kBar = FLP * kRS;                   // mbarrier (8 B, 16 aligned)
-  static constexpr int kRowTok = kBar + 16;                // long[32]
-  static constexpr int kRowGp = kRowTok + FLP * 8;         // int[32]
-  static constexpr int kBrel = kRowGp + FLP * 4;           // float[64]
-  static constexpr int kBytes = ((kBrel + 64 * 4) + 127) / 128 * 128;
+  static constexpr int kQ = 0, kK = kTile, kV = 2 * kTile;
+  static constexpr int kBar = 3 * kTile;                   // mbarrier (8 B)
+  static constexpr int kRowGp = kBar + 16;                 // int[32]
+  static constexpr int kBytes = ((kRowGp + FLP * 4) + 1023) / 1024 * 1024;
 };
 struct BwdWarp {
-  static constexpr int kTile = 0;                          // [32][kRS]
-  static constexpr int kDo = FLP * kRS;                    // [32][kRG]
-  static constexpr int kBar = kDo + FLP * kRG;
-  static constexpr int kRowTok = kBar + 16;
-  static constexpr int kRowGp = kRowTok + FLP * 8;
-  static constexpr int kBrel = kRowGp + FLP * 4;           // float[64]
-  static constexpr int kRstd = kBrel + 64 * 4;             // float[32][2]
-  static constexpr int kBytes = ((kRstd + FLP * 8) + 127) / 128 * 128;
+  static constexpr int kQ = 0, kK = kTile, kV = 2 * kTile, kDo = 3 * kTile;
+  static constexpr int kBar = 4 * kTile;
+  static constexpr int kRowGp = kBar + 16;
+  static constexpr int kRstd = kRowGp + FLP * 4;           // float[32][2]
+  static constexpr int kBytes = ((kRstd + FLP * 8) + 1023) / 1024 * 1024;
 };
-// CTA-level tables: affine parts of the two LayerNorms as packed bf16 (pairs for the K-contiguous fragments,
-// splats for the transposed fragments) and fp32 weights for the backward
+// CTA-level tables (after the per-warp regions): affine parts of the two LayerNorms as packed bf16 (pairs for the
+// K-contiguous fragments, splats for the transposed fragments) and fp32 weights for the backward
 constexpr int kTabPairs = 0;        // uint32[4][32]: aq, bq, ak, bk  (pair i = columns 2i, 2i+1)
 constexpr int kTabSplat = 512;      // uint32[4][64]: aq, bq, ak, bk  (both halves = column i)
-constexpr int kTabW = 512 + 1024;   // float[2][64]: wq * d^-1/2 ... see kernels
-constexpr int kTabBytes = 512 + 1024 + 512;
+constexpr int kTabW = 512 + 1024;   // float[2][64]: wq, wk
+constexpr int kTabBrel = 512 + 1024 + 512;   // float[heads][64]: relative-position bias of every head, indexed by rel + L - 1
+constexpr int kTabFixed = 512 + 1024 + 512;
+__host__ __device__ constexpr int tab_bytes(int heads) { return kTabFixed + heads * 256; }
 
 __device__ __forceinline__ void ldsm4(uint32_t (&r)[4], const void* p) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -88,13 +83,6 @@ __device__ __forceinline__ uint32_t hfma2_bf16(uint32_t x, uint32_t a, uint32_t 
 }
 __device__ __forceinline__ uint32_t pack_bf2(float lo, float hi) { return pack2<bf16>(lo, hi); }
 
-// 1-D bulk TMA copy global -> shared with mbarrier completion (bytes: multiple of 16, both sides 16 B aligned)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
 __device__ __forceinline__ float qsum(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 1);
   v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -106,21 +94,26 @@ __device__ __forceinline__ float qmax(float v) {
   return v;
 }
 
-// A fragment (16 x 16 at rows m0, K columns k0) of a row-major [row][k] tile; `base` points at column 0 of row 0
-__device__ __forceinline__ void frag_a(uint32_t (&a)[4], const uint8_t* base, int row_bytes, int m0, int k0, int lane) {
-  ldsm4(a, base + (m0 + (lane & 15)) * row_bytes + (k0 + (lane >> 4) * 8) * 2);
+// byte offset of (row, element column) inside a 128B-swizzled 32 x 64 bf16 tile
+__device__ __forceinline__ int swz(int row, int col) {
+  const int cb = col * 2;
+  return row * 128 + ((((cb >> 4) ^ (row & 7)) << 4) | (cb & 15));
 }
-// A fragment of the TRANSPOSE of a [k][m] tile (A[m][k] = T[k][m])
-__device__ __forceinline__ void frag_a_t(uint32_t (&a)[4], const uint8_t* base, int row_bytes, int m0, int k0, int lane) {
-  ldsm4t(a, base + (k0 + (lane & 7) + (lane >> 4) * 8) * row_bytes + (m0 + ((lane >> 3) & 1) * 8) * 2);
+// A fragment (16 x 16 at rows m0, K columns k0) of a row-major [row][k] tile
+__device__ __forceinline__ void frag_a(uint32_t (&a)[4], const uint8_t* tile, int m0, int k0, int lane) {
+  ldsm4(a, tile + swz(m0 + (lane & 15), k0 + (lane >> 4) * 8));
+}
+// A fragment of the TRANSPOSE of a [k][m] tile (A[m][k] = T[k][m]); m0 may include a column offset
+__device__ __forceinline__ void frag_a_t(uint32_t (&a)[4], const uint8_t* tile, int m0, int k0, int lane) {
+  ldsm4t(a, tile + swz(k0 + (lane & 7) + (lane >> 4) * 8, m0 + ((lane >> 3) & 1) * 8));
 }
 // B fragments of two adjacent n tiles (n0, n0 + 8) at k0 from a [n][k] tile: b[0..1] tile 0, b[2..3] tile 1
-__device__ __forceinline__ void frag_b(uint32_t (&b)[4], const uint8_t* base, int row_bytes, int n0, int k0, int lane) {
-  ldsm4(b, base + (n0 + (lane & 7) + (lane >> 4) * 8) * row_bytes + (k0 + ((lane >> 3) & 1) * 8) * 2);
+__device__ __forceinline__ void frag_b(uint32_t (&b)[4], const uint8_t* tile, int n0, int k0, int lane) {
+  ldsm4(b, tile + swz(n0 + (lane & 7) + (lane >> 4) * 8, k0 + ((lane >> 3) & 1) * 8));
 }
 // ... from a [k][n] tile
-__device__ __forceinline__ void frag_b_t(uint32_t (&b)[4], const uint8_t* base, int row_bytes, int n0, int k0, int lane) {
-  ldsm4t(b, base + (k0 + (lane & 7) + ((lane >> 3) & 1) * 8) * row_bytes + (n0 + (lane >> 4) * 8) * 2);
+__device__ __forceinline__ void frag_b_t(uint32_t (&b)[4], const uint8_t* tile, int n0, int k0, int lane) {
+  ldsm4t(b, tile + swz(k0 + (lane & 7) + ((lane >> 3) & 1) * 8, n0 + (lane >> 4) * 8));
 }
 
 __device__ __forceinline__ void fill_tables(const FastParams& p, uint8_t* tab, int tid, int nthreads) {
@@ -142,52 +135,48 @@ __device__ __forceinline__ void fill_tables(const FastParams& p, uint8_t* tab, i
     wf[i] = p.qn_w[i];
     wf[64 + i] = p.kn_w[i];
   }
+  float* brel = reinterpret_cast<float*>(tab + kTabBrel);
+  for (int i = tid; i < p.heads * 64; i += nthreads) {
+    const int h = i >> 6, r = i & 63;
+    brel[i] = r < 2 * p.L - 1 ? p.bias_emb[p.bucket[r] * p.heads + h] : 0.f;
+  }
 }
 
-// Row tables + bias vector of one work item, then the bulk loads.  Returns after the data has landed.
+struct Item { int head, s_in0, s_out; };
+
+// Row tables + bias vector of one work item, then the tensor loads.  Returns after the data has landed.
 template <bool BWD>
-__device__ __forceinline__ void load_item(const FastParams& p, long tile, int head, uint8_t* my, uint64_t* bar,
-                                          uint32_t& phase, long* rowtok, int* rowgp, float* brel, float* rstd_s, int lane) {
+__device__ __forceinline__ Item load_item(const FastParams& p, const CUtensorMap* map_qkv, const CUtensorMap* map_do,
+                                          long wi, uint8_t* my, uint64_t* bar, uint32_t& phase, int* rowgp,
+                                          float* rstd_s, int lane) {
   const int L = p.L, G = p.G;
-  {
-    const int g = lane / L, i = lane - g * L;
-    const long sq = tile * G + g;
-    const bool ok = g < G && sq < p.n_seq;
-    long tok = -1;
-    if (ok) {
-      const unsigned long o = (unsigned long)sq / (unsigned long)p.inner;
-      const long in = sq - (long)o * p.inner;
-      tok = (long)o * p.outer_stride + in * p.inner_stride + (long)i * p.tok_stride;
-    }
-    rowtok[lane] = tok;
-    rowgp[lane] = ok ? ((g << 8) | i) : (255 << 8);
-    for (int r = lane; r < 2 * L - 1; r += 32) brel[r] = __ldg(p.bias_emb + __ldg(p.bucket + r) * p.heads + head);
-    const long seqs = min((long)G, p.n_seq - tile * G);
-    const uint32_t rows = (uint32_t)(seqs * L);
-    if (lane == 0) mbar_arrive_expect_tx(bar, rows * (uint32_t)((BWD ? 4 : 3) * FD * 2));
-    __syncwarp();
-    uint8_t* dst = my + lane * kRS;
-    if (tok >= 0) {
-      bulk_g2s(dst, p.qkv + tok * p.ld_qkv + (long)head * 3 * FD, 3 * FD * 2, bar);
-      if (BWD) {
-        bulk_g2s(my + BwdWarp::kDo + lane * kRG, p.dout + tok * p.ld_dout + (long)head * FD, FD * 2, bar);
-        const float2 rr = __ldg(reinterpret_cast<const float2*>(p.rstd + (tok * p.heads + head) * 2));
-        rstd_s[2 * lane] = rr.x; rstd_s[2 * lane + 1] = rr.y;
-      }
-    } else {
-      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-      for (int c = 0; c < 3 * FD * 2 / 16; ++c) *reinterpret_cast<uint4*>(dst + 16 * c) = z;
-      if (BWD) {
-#pragma unroll
-        for (int c = 0; c < FD * 2 / 16; ++c) *reinterpret_cast<uint4*>(my + BwdWarp::kDo + lane * kRG + 16 * c) = z;
-        rstd_s[2 * lane] = 0.f; rstd_s[2 * lane + 1] = 0.f;
-      }
-    }
+  Item it;
+  const long tile = wi / p.heads;
+  it.head = (int)(wi - tile * p.heads);
+  it.s_out = (int)(tile / p.tiles_per_outer);
+  it.s_in0 = (int)(tile - (long)it.s_out * p.tiles_per_outer) * G;
+  if (lane == 0) {
+    tma_store_wait_read<0>();          // the previous item's stores have finished reading the tiles
+    mbar_arrive_expect_tx(bar, (uint32_t)((BWD ? 4 : 3) * G * L * FD * 2));
+    const int col = it.head * 3 * FD;
+    tma_load_4d(my, map_qkv, bar, col, 0, it.s_in0, it.s_out);
+    tma_load_4d(my + kTile, map_qkv, bar, col + FD, 0, it.s_in0, it.s_out);
+    tma_load_4d(my + 2 * kTile, map_qkv, bar, col + 2 * FD, 0, it.s_in0, it.s_out);
+    if (BWD) tma_load_4d(my + 3 * kTile, map_do, bar, it.head * FD, 0, it.s_in0, it.s_out);
   }
+  const int g = lane / L, i = lane - g * L;
+  const bool ok = g < G && it.s_in0 + g < p.inner;
+  float2 rr = make_float2(0.f, 0.f);
+  if (BWD && ok) {     // issued now, consumed after the tiles have landed
+    const long tok = (long)it.s_out * p.outer_stride + (long)(it.s_in0 + g) * p.inner_stride + (long)i * p.tok_stride;
+    rr = __ldg(reinterpret_cast<const float2*>(p.rstd + (tok * p.heads + it.head) * 2));
+  }
+  rowgp[lane] = ok ? ((g << 8) | i) : (255 << 8);
   mbar_wait(bar, phase);
   phase ^= 1u;
+  if (BWD) { rstd_s[2 * lane] = rr.x; rstd_s[2 * lane + 1] = rr.y; }
   __syncwarp();
+  return it;
 }
 
 // scores of one 16-row tile (already = q'k'^T) -> + bias, mask -> softmax probabilities in place
@@ -235,7 +224,8 @@ __device__ __forceinline__ void softmax16(float (&acc)[4][4], const float* brel,
 }
 
 // S(16 x 32) = Q'[m0:m0+16] K'^T with the LayerNorm affine applied to the fragments
-__device__ __forceinline__ void scores16(float (&acc)[4][4], const uint8_t* tile, const uint32_t* pairs, int m0, int lane) {
+__device__ __forceinline__ void scores16(float (&acc)[4][4], const uint8_t* sQ, const uint8_t* sK, const uint32_t* pairs,
+                                         int m0, int lane) {
   const int t = lane & 3;
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
@@ -246,13 +236,13 @@ __device__ __forceinline__ void scores16(float (&acc)[4][4], const uint8_t* tile
     const uint32_t ak0 = pairs[64 + ks * 8 + t], ak1 = pairs[64 + ks * 8 + 4 + t];
     const uint32_t bk0 = pairs[96 + ks * 8 + t], bk1 = pairs[96 + ks * 8 + 4 + t];
     uint32_t a[4];
-    frag_a(a, tile, kRS, m0, ks * 16, lane);
+    frag_a(a, sQ, m0, ks * 16, lane);
     a[0] = hfma2_bf16(a[0], aq0, bq0); a[1] = hfma2_bf16(a[1], aq0, bq0);
     a[2] = hfma2_bf16(a[2], aq1, bq1); a[3] = hfma2_bf16(a[3], aq1, bq1);
 #pragma unroll
     for (int np = 0; np < 2; ++np) {
       uint32_t b[4];
-      frag_b(b, tile + FD * 2, kRS, np * 16, ks * 16, lane);
+      frag_b(b, sK, np * 16, ks * 16, lane);
       b[0] = hfma2_bf16(b[0], ak0, bk0); b[1] = hfma2_bf16(b[1], ak1, bk1);
       b[2] = hfma2_bf16(b[2], ak0, bk0); b[3] = hfma2_bf16(b[3], ak1, bk1);
       mma16816(acc[2 * np], a, b[0], b[1]);
@@ -261,29 +251,31 @@ __device__ __forceinline__ void scores16(float (&acc)[4][4], const uint8_t* tile
   }
 }
 
-// copy rows (64 bf16 each) staged at `stage` (row pitch `pitch` bytes) to dst[tok * ld + col0 ...]
-__device__ __forceinline__ void store_rows64(const uint8_t* stage, int pitch, bf16* dst, long ld, const long* rowtok,
-                                             int accumulate, int lane) {
+// 16 x 64 C fragments -> bf16 rows m0.. of a swizzled tile
+__device__ __forceinline__ void stage16(uint8_t* tile, int m0, const float (&o)[8][4], int lane) {
+  const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int idx = it * 32 + lane;
-    const int r = idx >> 3, ch = idx & 7;
-    const long tok = rowtok[r];
-    if (tok < 0) continue;
-    uint4 v = *reinterpret_cast<const uint4*>(stage + r * pitch + ch * 16);
-    bf16* gp = dst + tok * ld + ch * 8;
-    if (accumulate) {
-      const uint4 o = *reinterpret_cast<const uint4*>(gp);
-      uint32_t* vv = reinterpret_cast<uint32_t*>(&v);
-      const uint32_t* oo = reinterpret_cast<const uint32_t*>(&o);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 a = unpack2<bf16>(vv[k]), b = unpack2<bf16>(oo[k]);
-        vv[k] = pack2<bf16>(a.x + b.x, a.y + b.y);
-      }
-    }
-    *reinterpret_cast<uint4*>(gp) = v;
+  for (int nt = 0; nt < 8; ++nt) {
+    *reinterpret_cast<uint32_t*>(tile + swz(m0 + g, nt * 8 + 2 * t)) = pack_bf2(o[nt][0], o[nt][1]);
+    *reinterpret_cast<uint32_t*>(tile + swz(m0 + g + 8, nt * 8 + 2 * t)) = pack_bf2(o[nt][2], o[nt][3]);
   }
+}
+
+// tile (G*L rows x 64 columns) -> global through the 4-D map at column `col`; add = bf16 TMA reduction
+__device__ __forceinline__ void store_tile(const CUtensorMap* map, const uint8_t* tile, int col, const Item& it,
+                                           int accumulate, int lane) {
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    if (accumulate) tma_reduce_add_4d(map, tile, col, 0, it.s_in0, it.s_out);
+    else tma_store_4d(map, tile, col, 0, it.s_in0, it.s_out);
+    tma_store_commit();
+  }
+}
+
+__device__ __forceinline__ void zero_tiles(uint8_t* my, int bytes, int lane) {
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = lane * 16; i < bytes; i += 32 * 16) *reinterpret_cast<uint4*>(my + i) = z;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -291,36 +283,46 @@ __device__ __forceinline__ void store_rows64(const uint8_t* stage, int pitch, bf
 // ---------------------------------------------------------------------------------------------
 template <bool PACKED>
 __global__ void __launch_bounds__(kFwdWarps * 32, 1)
-attn_fast_fwd_kernel(FastParams p) {
-  constexpr int kFastWarps = kFwdWarps;
-  extern __shared__ __align__(128) uint8_t smem[];
+attn_fast_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_out,
+                     const FastParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  fill_tables(p, smem, threadIdx.x, blockDim.x);
-  uint8_t* my = smem + kTabBytes + warp * FwdWarp::kBytes;
+  uint8_t* tab = smem + kFwdWarps * FwdWarp::kBytes;
+  fill_tables(p, tab, threadIdx.x, blockDim.x);
+  uint8_t* my = smem + warp * FwdWarp::kBytes;
+  uint8_t* sQ = my + FwdWarp::kQ;
+  uint8_t* sK = my + FwdWarp::kK;
+  uint8_t* sV = my + FwdWarp::kV;
   uint64_t* bar = reinterpret_cast<uint64_t*>(my + FwdWarp::kBar);
-  long* rowtok = reinterpret_cast<long*>(my + FwdWarp::kRowTok);
   int* rowgp = reinterpret_cast<int*>(my + FwdWarp::kRowGp);
-  float* brel = reinterpret_cast<float*>(my + FwdWarp::kBrel);
-  if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  const float* brel_all = reinterpret_cast<const float*>(tab + kTabBrel);
+  zero_tiles(my, 3 * kTile, lane);          // rows beyond G*L are never written by TMA and must stay finite
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&map_qkv);
+    tma_prefetch_desc(&map_out);
+  }
+  fence_proxy_async();
   __syncthreads();
-  const uint32_t* pairs = reinterpret_cast<const uint32_t*>(smem + kTabPairs);
+  const uint32_t* pairs = reinterpret_cast<const uint32_t*>(tab + kTabPairs);
   uint32_t phase = 0;
-  const int L = p.L, G = p.G;
+  const int L = p.L;
   const float invL = 1.f / (float)L;
-  const long n_tiles = (p.n_seq + G - 1) / G;
-  const long n_work = n_tiles * p.heads;
+  const long n_work = p.n_tiles * p.heads;
   const int g8 = lane >> 2, t = lane & 3;
 
-  for (long wi = (long)blockIdx.x * kFastWarps + warp; wi < n_work; wi += (long)gridDim.x * kFastWarps) {
-    const long tile = wi / p.heads;
-    const int head = (int)(wi - tile * p.heads);
-    load_item<false>(p, tile, head, my, bar, phase, rowtok, rowgp, brel, nullptr, lane);
-    const float sf = p.scale_factor != nullptr ? __ldg(p.scale_factor + head) : 1.f;
+  for (long wi = (long)blockIdx.x * kFwdWarps + warp; wi < n_work; wi += (long)gridDim.x * kFwdWarps) {
+    const Item it = load_item<false>(p, &map_qkv, nullptr, wi, my, bar, phase, rowgp, nullptr, lane);
+    const float* brel = brel_all + it.head * 64;
+    const float sf = p.scale_factor != nullptr ? __ldg(p.scale_factor + it.head) : 1.f;
     const float lowc = (1.f - sf) * invL;
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
       float acc[4][4];
-      scores16(acc, my, pairs, mt * 16, lane);
+      scores16(acc, sQ, sK, pairs, mt * 16, lane);
       softmax16<PACKED>(acc, brel, rowgp, L, mt * 16, lane);
       // P' = s*P + (1-s)/L inside the query's own sequence, 0 elsewhere; straight into A fragments
       uint32_t pa[2][4];
@@ -348,35 +350,32 @@ attn_fast_fwd_kernel(FastParams p) {
 #pragma unroll
         for (int np = 0; np < 4; ++np) {
           uint32_t b[4];
-          frag_b_t(b, my + 2 * FD * 2, kRS, np * 16, kk * 16, lane);
+          frag_b_t(b, sV, np * 16, kk * 16, lane);
           mma16816(o[2 * np], pa[kk], b[0], b[1]);
           mma16816(o[2 * np + 1], pa[kk], b[2], b[3]);
         }
       }
-      // the q rows of this m tile are dead: stage the output there
-      __syncwarp();
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
-        *reinterpret_cast<uint32_t*>(my + (mt * 16 + g8) * kRS + (nt * 8 + 2 * t) * 2) =
-            pack_bf2(o[nt][0] * p.out_scale, o[nt][1] * p.out_scale);
-        *reinterpret_cast<uint32_t*>(my + (mt * 16 + g8 + 8) * kRS + (nt * 8 + 2 * t) * 2) =
-            pack_bf2(o[nt][2] * p.out_scale, o[nt][3] * p.out_scale);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[nt][e] *= p.out_scale;
       }
+      // the q rows of this m tile are dead: stage the output there
+      __syncwarp();
+      stage16(sQ, mt * 16, o, lane);
     }
-    __syncwarp();
-    store_rows64(my, kRS, p.out + (long)head * FD, p.ld_out, rowtok, p.accumulate, lane);
-    fence_proxy_async();          // generic writes to the tile precede the next item's async-proxy writes
-    __syncwarp();
+    store_tile(&map_out, sQ, it.head * FD, it, p.accumulate, lane);
   }
+  if (lane == 0) tma_store_wait_all();
 }
 
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
 // LayerNorm backward on a 16-row tile of gradients w.r.t. y = xhat*w + b held in C fragments.
-// xhat rows are read from `xh` (row pitch kRS); rstd per row from rstd_s[row*2 + which].
+// xhat rows are read from the tile `xh`; rstd per row from rstd_s[row*2 + which].
 // Writes d(raw) into acc, accumulates per-lane partial dw (and db when DB) over rows.
-template <bool DB>
+template <bool DB, bool SCALE>
 __device__ __forceinline__ void ln_bwd16(float (&acc)[8][4], float pre, const uint8_t* xh, const float* rstd_s, int which,
                                          int m0, const float* w, float (&dw)[8][2], float (&db)[8][2], int lane) {
   const int g = lane >> 2, t = lane & 3;
@@ -388,12 +387,12 @@ __device__ __forceinline__ void ln_bwd16(float (&acc)[8][4], float pre, const ui
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const float2 xv = unpack2<bf16>(*reinterpret_cast<const uint32_t*>(xh + r * kRS + (nt * 8 + 2 * t) * 2));
+      const float2 xv = unpack2<bf16>(*reinterpret_cast<const uint32_t*>(xh + swz(r, nt * 8 + 2 * t)));
       const float2 wv = *reinterpret_cast<const float2*>(w + nt * 8 + 2 * t);
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const float n = e ? xv.y : xv.x;
-        const float dy = acc[nt][half * 2 + e] * pre;
+        const float dy = SCALE ? acc[nt][half * 2 + e] * pre : acc[nt][half * 2 + e];
         nrm[nt][e] = n;
         dw[nt][e] = fmaf(dy, n, dw[nt][e]);
         if (DB) db[nt][e] += dy;
@@ -403,32 +402,17 @@ __device__ __forceinline__ void ln_bwd16(float (&acc)[8][4], float pre, const ui
         s2 = fmaf(dn, n, s2);
       }
     }
-    s1 = qsum(s1) * (1.f / FD);
-    s2 = qsum(s2) * (1.f / FD);
+    const float c0 = -rstd * qsum(s1) * (1.f / FD);
+    const float c1 = -rstd * qsum(s2) * (1.f / FD);
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) acc[nt][half * 2 + e] = rstd * (acc[nt][half * 2 + e] - s1 - nrm[nt][e] * s2);
+      for (int e = 0; e < 2; ++e) acc[nt][half * 2 + e] = fmaf(nrm[nt][e], c1, fmaf(acc[nt][half * 2 + e], rstd, c0));
     }
   }
 }
 
-// column sums of a 32-row tile held as two 16-row C-fragment sets -> shared accumulators (8 lanes per column collide)
-__device__ __forceinline__ void colsum_frag(float* s_dst, const float (&o0)[8][4], const float (&o1)[8][4], int lane) {
-  const int t = lane & 3;
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      float v = (o0[nt][e] + o0[nt][2 + e]) + (o1[nt][e] + o1[nt][2 + e]);
-      v += __shfl_xor_sync(0xffffffffu, v, 4);
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if ((lane >> 2) == 0) atomicAdd(s_dst + nt * 8 + 2 * t + e, v);
-    }
-  }
-}
-
+// column sums of a 16-row tile held in C fragments -> shared accumulators
 __device__ __forceinline__ void colsum_frag1(float* s_dst, const float (&o)[8][4], int lane) {
   const int t = lane & 3;
 #pragma unroll
@@ -444,24 +428,18 @@ __device__ __forceinline__ void colsum_frag1(float* s_dst, const float (&o)[8][4
   }
 }
 
-__device__ __forceinline__ void stage16(uint8_t* stage, int pitch, int m0, const float (&o)[8][4], int lane) {
-  const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    *reinterpret_cast<uint32_t*>(stage + (m0 + g) * pitch + (nt * 8 + 2 * t) * 2) = pack_bf2(o[nt][0], o[nt][1]);
-    *reinterpret_cast<uint32_t*>(stage + (m0 + g + 8) * pitch + (nt * 8 + 2 * t) * 2) = pack_bf2(o[nt][2], o[nt][3]);
-  }
-}
-
 template <bool PACKED>
 __global__ void __launch_bounds__(kBwdWarps * 32, 1)
-attn_fast_bwd_kernel(FastParams p) {
-  constexpr int kFastWarps = kBwdWarps;
-  extern __shared__ __align__(128) uint8_t smem[];
+attn_fast_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
+                     const __grid_constant__ CUtensorMap map_dqkv, const FastParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  fill_tables(p, smem, threadIdx.x, blockDim.x);
-  // CTA-level gradient accumulators after the per-warp regions
-  float* s_acc = reinterpret_cast<float*>(smem + kTabBytes + kFastWarps * BwdWarp::kBytes);
+  uint8_t* tab = smem + kBwdWarps * BwdWarp::kBytes;
+  fill_tables(p, tab, threadIdx.x, blockDim.x);
+  // CTA-level gradient accumulators after the tables
+  float* s_acc = reinterpret_cast<float*>(tab + tab_bytes(p.heads));
   float* s_dqw = s_acc;                 // [64]
   float* s_dqb = s_dqw + FD;
   float* s_dkw = s_dqb + FD;
@@ -470,36 +448,51 @@ attn_fast_bwd_kernel(FastParams p) {
   float* s_dbias = s_dsf + p.heads;     // [heads * 3 * 64] column sums of dq | dk | dv (input_head bias gradient)
   const int n_acc = 3 * FD + 33 * p.heads + (p.d_qkv_bias != nullptr ? 3 * FD * p.heads : 0);
   for (int i = threadIdx.x; i < n_acc; i += blockDim.x) s_acc[i] = 0.f;
-  uint8_t* my = smem + kTabBytes + warp * BwdWarp::kBytes;
+  uint8_t* my = smem + warp * BwdWarp::kBytes;
+  uint8_t* sQ = my + BwdWarp::kQ;
+  uint8_t* sK = my + BwdWarp::kK;
+  uint8_t* sV = my + BwdWarp::kV;       // after dP: P' in columns 0..31, dS in columns 32..63
   uint8_t* sdo = my + BwdWarp::kDo;
   uint64_t* bar = reinterpret_cast<uint64_t*>(my + BwdWarp::kBar);
-  long* rowtok = reinterpret_cast<long*>(my + BwdWarp::kRowTok);
   int* rowgp = reinterpret_cast<int*>(my + BwdWarp::kRowGp);
-  float* brel = reinterpret_cast<float*>(my + BwdWarp::kBrel);
+  const float* brel_all = reinterpret_cast<const float*>(tab + kTabBrel);
   float* rstd_s = reinterpret_cast<float*>(my + BwdWarp::kRstd);
-  if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  zero_tiles(my, 4 * kTile, lane);
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&map_qkv);
+    tma_prefetch_desc(&map_do);
+    tma_prefetch_desc(&map_dqkv);
+  }
+  fence_proxy_async();
   __syncthreads();
-  const uint32_t* pairs = reinterpret_cast<const uint32_t*>(smem + kTabPairs);
-  const uint32_t* splat = reinterpret_cast<const uint32_t*>(smem + kTabSplat);
-  const float* wq = reinterpret_cast<const float*>(smem + kTabW);
+  const uint32_t* pairs = reinterpret_cast<const uint32_t*>(tab + kTabPairs);
+  const uint32_t* splat = reinterpret_cast<const uint32_t*>(tab + kTabSplat);
+  const float* wq = reinterpret_cast<const float*>(tab + kTabW);
   const float* wk = wq + FD;
-  uint8_t* sP = my + 2 * FD * 2;        // P' parked in the first half of the v columns, dS in the second
-  uint8_t* sS = sP + FLP * 2;
   uint32_t phase = 0;
   const int L = p.L, G = p.G;
   const float invL = 1.f / (float)L;
-  const long n_tiles = (p.n_seq + G - 1) / G;
-  const long n_work = n_tiles * p.heads;
+  const long n_work = p.n_tiles * p.heads;
   const int g8 = lane >> 2, t = lane & 3;
   const float qscale = rsqrtf((float)FD);
   float dwq[8][2], dbq[8][2], dwk[8][2], dbk_unused[8][2];
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) { dwq[nt][0] = dwq[nt][1] = dbq[nt][0] = dbq[nt][1] = dwk[nt][0] = dwk[nt][1] = 0.f; }
+  // !PACKED (one 32-token sequence per tile): the launch guarantees gridDim*warps % heads == 0, so a warp always
+  // works on the same head and can keep the relative-position-bias and scale-factor gradients in registers:
+  // a lane's dS elements fall on 14 diagonals  rel = 8*q + (2t + e - g),  q = nt - 2*mt - half in [-3, 3].
+  float dacc[14];
+#pragma unroll
+  for (int k = 0; k < 14; ++k) dacc[k] = 0.f;
+  float dsf_acc = 0.f;
+  const int my_head = (int)(((long)blockIdx.x * kBwdWarps + warp) % p.heads);
 
-  for (long wi = (long)blockIdx.x * kFastWarps + warp; wi < n_work; wi += (long)gridDim.x * kFastWarps) {
-    const long tile = wi / p.heads;
-    const int head = (int)(wi - tile * p.heads);
-    load_item<true>(p, tile, head, my, bar, phase, rowtok, rowgp, brel, rstd_s, lane);
+  for (long wi = (long)blockIdx.x * kBwdWarps + warp; wi < n_work; wi += (long)gridDim.x * kBwdWarps) {
+    const Item it = load_item<true>(p, &map_qkv, &map_do, wi, my, bar, phase, rowgp, rstd_s, lane);
+    const int head = it.head;
+    const float* brel = brel_all + head * 64;
     const float sf = p.scale_factor != nullptr ? __ldg(p.scale_factor + head) : 1.f;
     const float lowc = (1.f - sf) * invL;
     // ---- dP'(raw) = dO V^T for the whole tile (v is dead afterwards) ----
@@ -512,24 +505,24 @@ attn_fast_bwd_kernel(FastParams p) {
 #pragma unroll
     for (int ks = 0; ks < FD / 16; ++ks) {
       uint32_t a0[4], a1[4];
-      frag_a(a0, sdo, kRG, 0, ks * 16, lane);
-      frag_a(a1, sdo, kRG, 16, ks * 16, lane);
+      frag_a(a0, sdo, 0, ks * 16, lane);
+      frag_a(a1, sdo, 16, ks * 16, lane);
 #pragma unroll
       for (int np = 0; np < 2; ++np) {
         uint32_t b[4];
-        frag_b(b, my + 2 * FD * 2, kRS, np * 16, ks * 16, lane);
+        frag_b(b, sV, np * 16, ks * 16, lane);
         mma16816(dp[0][2 * np], a0, b[0], b[1]);
         mma16816(dp[0][2 * np + 1], a0, b[2], b[3]);
         mma16816(dp[1][2 * np], a1, b[0], b[1]);
         mma16816(dp[1][2 * np + 1], a1, b[2], b[3]);
       }
     }
-    __syncwarp();                       // every lane is done reading v: its columns now receive P' and dS
+    __syncwarp();                       // every lane is done reading v: its tile now receives P' and dS
     float dsf = 0.f;
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
       float acc[4][4];
-      scores16(acc, my, pairs, mt * 16, lane);
+      scores16(acc, sQ, sK, pairs, mt * 16, lane);
       softmax16<PACKED>(acc, brel, rowgp, L, mt * 16, lane);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -562,28 +555,36 @@ attn_fast_bwd_kernel(FastParams p) {
             if (PACKED) valid = gi != 255 && (rowgp[nt * 8 + 2 * t + e] >> 8) == gi;
             pp[e] = valid ? fmaf(pv, sf, lowc) : 0.f;
           }
-          *reinterpret_cast<uint32_t*>(sP + i * kRS + (nt * 8 + 2 * t) * 2) = pack_bf2(pp[0], pp[1]);
-          *reinterpret_cast<uint32_t*>(sS + i * kRS + (nt * 8 + 2 * t) * 2) = pack_bf2(ds[0], ds[1]);
+          *reinterpret_cast<uint32_t*>(sV + swz(i, nt * 8 + 2 * t)) = pack_bf2(pp[0], pp[1]);
+          *reinterpret_cast<uint32_t*>(sV + swz(i, 32 + nt * 8 + 2 * t)) = pack_bf2(ds[0], ds[1]);
+          if (!PACKED) {
+            dacc[(nt - 2 * mt - half + 3) * 2] += ds[0];
+            dacc[(nt - 2 * mt - half + 3) * 2 + 1] += ds[1];
+          }
         }
       }
     }
     __syncwarp();
     // ---- bias-embedding and scale-factor gradients ----
-    if (p.d_bias_emb != nullptr) {
-      for (int r = lane; r < 2 * L - 1; r += 32) {
-        float s = 0.f;
-        for (int gq = 0; gq < G; ++gq) {
-          for (int i = 0; i < L; ++i) {
-            const int j = i + r - (L - 1);
-            if (j >= 0 && j < L) s += __bfloat162float(*reinterpret_cast<const bf16*>(sS + (gq * L + i) * kRS + (gq * L + j) * 2));
+    if (PACKED) {
+      if (p.d_bias_emb != nullptr) {
+        for (int r = lane; r < 2 * L - 1; r += 32) {
+          float s = 0.f;
+          for (int gq = 0; gq < G; ++gq) {
+            for (int i = 0; i < L; ++i) {
+              const int j = i + r - (L - 1);
+              if (j >= 0 && j < L) s += __bfloat162float(*reinterpret_cast<const bf16*>(sV + swz(gq * L + i, 32 + gq * L + j)));
+            }
           }
+          atomicAdd(s_demb + __ldg(p.bucket + r) * p.heads + head, s);
         }
-        atomicAdd(s_demb + __ldg(p.bucket + r) * p.heads + head, s);
       }
-    }
-    if (p.d_scale_factor != nullptr) {
-      dsf = warp_sum(dsf);
-      if (lane == 0) atomicAdd(s_dsf + head, dsf);
+      if (p.d_scale_factor != nullptr) {
+        dsf = warp_sum(dsf);
+        if (lane == 0) atomicAdd(s_dsf + head, dsf);
+      }
+    } else {
+      dsf_acc += dsf;
     }
     // ---- dV = P'^T dO' ----
     {
@@ -596,12 +597,12 @@ attn_fast_bwd_kernel(FastParams p) {
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) {
         uint32_t a0[4], a1[4];
-        frag_a_t(a0, sP, kRS, 0, kk * 16, lane);
-        frag_a_t(a1, sP, kRS, 16, kk * 16, lane);
+        frag_a_t(a0, sV, 0, kk * 16, lane);
+        frag_a_t(a1, sV, 16, kk * 16, lane);
 #pragma unroll
         for (int np = 0; np < 4; ++np) {
           uint32_t b[4];
-          frag_b_t(b, sdo, kRG, np * 16, kk * 16, lane);
+          frag_b_t(b, sdo, np * 16, kk * 16, lane);
           mma16816(o[0][2 * np], a0, b[0], b[1]);
           mma16816(o[0][2 * np + 1], a0, b[2], b[3]);
           mma16816(o[1][2 * np], a1, b[0], b[1]);
@@ -616,12 +617,10 @@ attn_fast_bwd_kernel(FastParams p) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) o[mt][nt][e] *= p.out_scale;
         }
-        stage16(sdo, kRG, mt * 16, o[mt], lane);
+        stage16(sdo, mt * 16, o[mt], lane);
+        if (p.d_qkv_bias != nullptr) colsum_frag1(s_dbias + head * 3 * FD + 2 * FD, o[mt], lane);
       }
-      if (p.d_qkv_bias != nullptr) colsum_frag(s_dbias + head * 3 * FD + 2 * FD, o[0], o[1], lane);
-      __syncwarp();
-      store_rows64(sdo, kRG, p.out + (long)head * 3 * FD + 2 * FD, p.ld_out, rowtok, p.accumulate, lane);
-      __syncwarp();
+      store_tile(&map_dqkv, sdo, head * 3 * FD + 2 * FD, it, p.accumulate, lane);
     }
     // ---- dK' = dS^T Q'  -> LayerNorm backward -> d(raw k) ----
     {
@@ -634,12 +633,12 @@ attn_fast_bwd_kernel(FastParams p) {
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) {
         uint32_t a0[4], a1[4];
-        frag_a_t(a0, sS, kRS, 0, kk * 16, lane);
-        frag_a_t(a1, sS, kRS, 16, kk * 16, lane);
+        frag_a_t(a0, sV, 32, kk * 16, lane);
+        frag_a_t(a1, sV, 32 + 16, kk * 16, lane);
 #pragma unroll
         for (int np = 0; np < 4; ++np) {
           uint32_t b[4];
-          frag_b_t(b, my, kRS, np * 16, kk * 16, lane);      // Q as [k = i][n = d]: both halves of a register share d
+          frag_b_t(b, sQ, np * 16, kk * 16, lane);          // Q as [k = i][n = d]: both halves of a register share d
           const uint32_t al = splat[np * 16 + g8], ah = splat[np * 16 + 8 + g8];
           const uint32_t bl = splat[64 + np * 16 + g8], bh = splat[64 + np * 16 + 8 + g8];
           b[0] = hfma2_bf16(b[0], al, bl); b[1] = hfma2_bf16(b[1], al, bl);
@@ -651,16 +650,17 @@ attn_fast_bwd_kernel(FastParams p) {
         }
       }
 #pragma unroll
+      for (int mt = 0; mt < 2; ++mt) ln_bwd16<false, false>(o[mt], 1.f, sK, rstd_s, 1, mt * 16, wk, dwk, dbk_unused, lane);
+      if (lane == 0) tma_store_wait_read<0>();     // the dV store has finished reading the staging tile
+      __syncwarp();
+#pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        ln_bwd16<false>(o[mt], 1.f, my + FD * 2, rstd_s, 1, mt * 16, wk, dwk, dbk_unused, lane);
-        stage16(sdo, kRG, mt * 16, o[mt], lane);
+        stage16(sdo, mt * 16, o[mt], lane);
+        if (p.d_qkv_bias != nullptr) colsum_frag1(s_dbias + head * 3 * FD + FD, o[mt], lane);
       }
-      if (p.d_qkv_bias != nullptr) colsum_frag(s_dbias + head * 3 * FD + FD, o[0], o[1], lane);
-      __syncwarp();
-      store_rows64(sdo, kRG, p.out + (long)head * 3 * FD + FD, p.ld_out, rowtok, p.accumulate, lane);
-      __syncwarp();
+      store_tile(&map_dqkv, sdo, head * 3 * FD + FD, it, p.accumulate, lane);
     }
-    // ---- dQ' = dS K'  -> LayerNorm backward -> d(raw q) ----
+    // ---- dQ' = dS K'  -> LayerNorm backward -> d(raw q), staged over the (dead) q rows it was derived from ----
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
       float o[8][4];
@@ -669,11 +669,11 @@ attn_fast_bwd_kernel(FastParams p) {
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) {
         uint32_t a[4];
-        frag_a(a, sS, kRS, mt * 16, kk * 16, lane);
+        frag_a(a, sV, mt * 16, 32 + kk * 16, lane);
 #pragma unroll
         for (int np = 0; np < 4; ++np) {
           uint32_t b[4];
-          frag_b_t(b, my + FD * 2, kRS, np * 16, kk * 16, lane);
+          frag_b_t(b, sK, np * 16, kk * 16, lane);
           const uint32_t al = splat[128 + np * 16 + g8], ah = splat[128 + np * 16 + 8 + g8];
           const uint32_t bl = splat[192 + np * 16 + g8], bh = splat[192 + np * 16 + 8 + g8];
           b[0] = hfma2_bf16(b[0], al, bl); b[1] = hfma2_bf16(b[1], al, bl);
@@ -682,14 +682,26 @@ attn_fast_bwd_kernel(FastParams p) {
           mma16816(o[2 * np + 1], a, b[2], b[3]);
         }
       }
-      ln_bwd16<true>(o, qscale, my, rstd_s, 0, mt * 16, wq, dwq, dbq, lane);
-      stage16(sdo, kRG, mt * 16, o, lane);
+      ln_bwd16<true, true>(o, qscale, sQ, rstd_s, 0, mt * 16, wq, dwq, dbq, lane);
+      __syncwarp();                     // all lanes have read the xhat rows of this m tile
+      stage16(sQ, mt * 16, o, lane);
       if (p.d_qkv_bias != nullptr) colsum_frag1(s_dbias + head * 3 * FD, o, lane);
     }
-    __syncwarp();
-    store_rows64(sdo, kRG, p.out + (long)head * 3 * FD, p.ld_out, rowtok, p.accumulate, lane);
-    fence_proxy_async();
-    __syncwarp();
+    store_tile(&map_dqkv, sQ, head * 3 * FD, it, p.accumulate, lane);
+  }
+  if (lane == 0) tma_store_wait_all();
+  if (!PACKED) {
+    if (p.d_bias_emb != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 14; ++k) {
+        const int rel = 8 * ((k >> 1) - 3) + 2 * t + (k & 1) - g8;
+        atomicAdd(s_demb + __ldg(p.bucket + rel + FLP - 1) * p.heads + my_head, dacc[k]);
+      }
+    }
+    if (p.d_scale_factor != nullptr) {
+      dsf_acc = warp_sum(dsf_acc);
+      if (lane == 0) atomicAdd(s_dsf + my_head, dsf_acc);
+    }
   }
   // ---- LayerNorm parameter gradients: lanes with equal t hold partial sums of the same columns ----
 #pragma unroll
@@ -727,19 +739,30 @@ attn_fast_bwd_kernel(FastParams p) {
 // ---------------------------------------------------------------------------------------------
 // host launch
 // ---------------------------------------------------------------------------------------------
+// 4-D view (column, position, sequence, outer) of a token-major (tokens, width) bf16 matrix; box = 64 x L x G x 1
+static int make_seq_map(CUtensorMap* map, const void* base, long ld, int width, const bf_attn_args* a, int G) {
+  const long n_outer = a->n_seq / a->inner;
+  uint64_t dims[4] = {(uint64_t)width, (uint64_t)a->L, (uint64_t)a->inner, (uint64_t)n_outer};
+  uint64_t str[3] = {(uint64_t)a->tok_stride * ld * 2, (uint64_t)a->inner_stride * ld * 2, (uint64_t)a->outer_stride * ld * 2};
+  uint32_t box[4] = {FD, (uint32_t)a->L, (uint32_t)G, 1};
+  return make_map(map, BF_BF16, base, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 int launch_attn_fast(const bf_attn_args* a, bool bwd, cudaStream_t st) {
   BF_REQUIRE(a->head_dim == FD && a->L >= 1 && a->L <= FLP,
              "bf_attention (prenorm): the pre-normalised path handles head_dim 64 and L <= 32 (got d=%d L=%d)",
              a->head_dim, a->L);
   BF_REQUIRE(!bwd || a->rstd != nullptr, "bf_attention_bwd (prenorm): rstd required");
+  BF_REQUIRE(a->n_seq % a->inner == 0, "bf_attention (prenorm): n_seq=%ld must be a multiple of inner=%ld",
+             (long)a->n_seq, (long)a->inner);
+  BF_REQUIRE(a->inner < (1l << 31) && a->n_seq / a->inner < (1l << 31), "bf_attention (prenorm): geometry too large");
   FastParams p{};
-  p.qkv = static_cast<const bf16*>(a->qkv); p.ld_qkv = a->ld_qkv;
-  p.out = static_cast<bf16*>(a->out); p.ld_out = a->ld_out;
-  p.dout = static_cast<const bf16*>(a->dout); p.ld_dout = a->ld_dout;
   p.rstd = a->rstd;
   p.heads = a->heads; p.L = a->L;
   p.G = FLP / a->L;
-  p.n_seq = a->n_seq; p.inner = a->inner;
+  p.inner = (int)a->inner;
+  p.tiles_per_outer = (int)((a->inner + p.G - 1) / p.G);
+  p.n_tiles = (a->n_seq / a->inner) * p.tiles_per_outer;
   p.outer_stride = a->outer_stride; p.inner_stride = a->inner_stride; p.tok_stride = a->tok_stride;
   p.qn_w = a->qn_w; p.qn_b = a->qn_b; p.kn_w = a->kn_w; p.kn_b = a->kn_b;
   p.bias_emb = a->bias_emb; p.bucket = a->bucket; p.scale_factor = a->scale_factor;
@@ -748,26 +771,45 @@ int launch_attn_fast(const bf_attn_args* a, bool bwd, cudaStream_t st) {
   p.d_bias_emb = a->d_bias_emb; p.d_scale_factor = a->d_scale_factor;
   p.d_qkv_bias = bwd ? a->d_qkv_bias : nullptr;
   const bool packed = !(p.G == 1 && a->L == FLP);
-  const int kFastWarps = bwd ? kBwdWarps : kFwdWarps;
-  const size_t smem = kTabBytes + (size_t)kFastWarps * (bwd ? BwdWarp::kBytes : FwdWarp::kBytes) +
+  const int E3 = 3 * FD * a->heads;
+  CUtensorMap m_qkv, m_b, m_c;
+  if (int e = make_seq_map(&m_qkv, a->qkv, a->ld_qkv, E3, a, p.G)) return e;
+  if (bwd) {
+    if (int e = make_seq_map(&m_b, a->dout, a->ld_dout, E3 / 3, a, p.G)) return e;
+    if (int e = make_seq_map(&m_c, a->out, a->ld_out, E3, a, p.G)) return e;
+  } else {
+    if (int e = make_seq_map(&m_b, a->out, a->ld_out, E3 / 3, a, p.G)) return e;
+  }
+  const int warps = bwd ? kBwdWarps : kFwdWarps;
+  const size_t smem = 1024 + (size_t)warps * (bwd ? BwdWarp::kBytes : FwdWarp::kBytes) + tab_bytes(p.heads) +
                       (bwd ? (size_t)(3 * FD + 33 * p.heads + 3 * FD * p.heads) * sizeof(float) : 0);
-  BF_REQUIRE(smem <= 227 * 1024, "bf_attention (prenorm): shared memory %zu too large", smem);
-  void (*kern)(FastParams);
-  if (bwd) kern = packed ? attn_fast_bwd_kernel<true> : attn_fast_bwd_kernel<false>;
-  else kern = packed ? attn_fast_fwd_kernel<true> : attn_fast_fwd_kernel<false>;
+  BF_REQUIRE(smem <= 227 * 1024, "bf_attention (prenorm): shared memory %zu too large (heads=%d)", smem, p.heads);
   static bool attr_done[4] = {false, false, false, false};
   const int ki = (bwd ? 2 : 0) + (packed ? 1 : 0);
   if (!attr_done[ki]) {
-    if (int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
-                           "cudaFuncSetAttribute(attention fast)"))
-      return e;
+    cudaError_t e;
+    if (bwd) e = packed ? cudaFuncSetAttribute(attn_fast_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                        : cudaFuncSetAttribute(attn_fast_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    else e = packed ? cudaFuncSetAttribute(attn_fast_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                    : cudaFuncSetAttribute(attn_fast_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (int st_ = check_cuda(e, "cudaFuncSetAttribute(attention fast)")) return st_;
     attr_done[ki] = true;
   }
-  const long n_work = ((p.n_seq + p.G - 1) / p.G) * p.heads;
-  long blocks = (n_work + kFastWarps - 1) / kFastWarps;
-  const long cap = (long)num_sms();
-  if (blocks > cap) blocks = cap;
-  kern<<<(unsigned)blocks, kFastWarps * 32, smem, st>>>(p);
+  const long n_work = p.n_tiles * p.heads;
+  long blocks = (n_work + warps - 1) / warps;
+  if (blocks > num_sms()) blocks = num_sms();
+  if (bwd && !packed) {
+    // a warp must keep one head for the whole launch (work item wi -> head wi % heads, stride gridDim * warps)
+    while (blocks > 1 && (blocks * warps) % p.heads != 0) --blocks;
+    BF_REQUIRE((blocks * warps) % p.heads == 0, "bf_attention_bwd (prenorm): heads=%d does not divide %d warps", p.heads, warps);
+  }
+  if (bwd) {
+    if (packed) attn_fast_bwd_kernel<true><<<(unsigned)blocks, warps * 32, smem, st>>>(m_qkv, m_b, m_c, p);
+    else attn_fast_bwd_kernel<false><<<(unsigned)blocks, warps * 32, smem, st>>>(m_qkv, m_b, m_c, p);
+  } else {
+    if (packed) attn_fast_fwd_kernel<true><<<(unsigned)blocks, warps * 32, smem, st>>>(m_qkv, m_b, p);
+    else attn_fast_fwd_kernel<false><<<(unsigned)blocks, warps * 32, smem, st>>>(m_qkv, m_b, p);
+  }
   count_launch();
   return check_cuda(cudaGetLastError(), bwd ? "attn_fast_bwd_kernel launch" : "attn_fast_fwd_kernel launch");
 }

@@ -638,8 +638,8 @@ static EncodeTiledFn get_encode_fn() {
 enum MapType { kMap16 = 0, kMapF32 = 1 };
 
 // rank-d tensor map, zero fill out of bounds.  dt: BF_BF16 / BF_F16 / BF_F32.
-static int make_map(CUtensorMap* map, int dt, const void* base, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box, CUtensorMapSwizzle swz) {
+int make_map(CUtensorMap* map, int dt, const void* base, int rank, const uint64_t* dims,
+             const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
