@@ -91,6 +91,8 @@ class InormBwdArgs(C.Structure):
         ("row_scale", C.c_void_p), ("col_scale", C.c_void_p), ("film_gamma", C.c_void_p),
         ("film_T", C.c_int32), ("reserved0", C.c_int32),
         ("add32", C.c_void_p), ("out", C.c_void_p),
+        ("dweight", C.c_void_p), ("dbias", C.c_void_p), ("dcol_scale", C.c_void_p),
+        ("dfilm_gamma", C.c_void_p), ("dfilm_beta", C.c_void_p),
     ]
 
 

@@ -293,6 +293,8 @@ struct BwdParams {
   const float* film_gamma;   // [I / film_T][C] or null
   int film_T;
   const float* add32;        // fp32 tensor added to the result (residual-stream gradient), ld = ldo
+  // pass 2, optional: parameter gradients from `red` (fp32 atomics by the first row split of every image)
+  float* dweight; float* dbias; float* dcol_scale; float* dfilm_gamma; float* dfilm_beta;
 };
 
 template <typename TG, typename TX, bool GELU>
@@ -330,7 +332,7 @@ inorm_bwd_reduce_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, Bw
   unpack8<TX>(ring + ((st) * NSLOT + NG) * kNT + threadIdx.x, xv);                      \
   _Pragma("unroll") for (int j = 0; j < 8; ++j) {                                       \
     float gg = gv[j];                                                                   \
-    if (GELU) gg *= gelu_grad_fast(fmaf(xv[j], wa[j], wb[j]));                           \
+    if (GELU) gg *= gelu_tanh_grad(fmaf(xv[j], wa[j], wb[j]));                           \
     acc[j] += gg;                                                                       \
     acc[8 + j] = fmaf(gg, xv[j], acc[8 + j]);                                           \
   }
@@ -377,6 +379,20 @@ inorm_bwd_apply_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, TO*
       kb[j] = -k * m2 * rstd;
       kc[j] = -k * m1 + k * m2 * rstd * mean;
       if (GELU) { wa[j] = rstd * w; wb[j] = p.bias[c0 + j] - mean * rstd * w; }
+      if (blockIdx.x == 0 && c.ty == 0 && p.dweight != nullptr) {
+        // dweight += cs*R2, dbias += cs*R1, dcol_scale += rs*(w*R2 + b*R1), dfilm_gamma[b] += w*R2 + b*R1, dfilm_beta[b] += R1
+        const float R1 = p.red[2 * idx], R2 = p.red[2 * idx + 1];
+        const float b = p.bias[c0 + j];
+        atomicAdd(p.dweight + c0 + j, cs * R2);
+        atomicAdd(p.dbias + c0 + j, cs * R1);
+        if (p.dcol_scale != nullptr)
+          atomicAdd(p.dcol_scale + c0 + j, (p.row_scale != nullptr ? p.row_scale[c.img] : 1.f) * fmaf(w, R2, b * R1));
+        if (p.dfilm_gamma != nullptr) {
+          const long fi = (long)(c.img / p.film_T) * g.C + c0 + j;
+          atomicAdd(p.dfilm_gamma + fi, fmaf(w, R2, b * R1));
+          atomicAdd(p.dfilm_beta + fi, R1);
+        }
+      }
     }
   }
   const TG* gb = gin + ((long)c.img * g.P) * p.ldg + c0;
@@ -393,7 +409,7 @@ inorm_bwd_apply_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, TO*
   unpack8<TX>(ring + ((st) * NSLOT + NG) * kNT + threadIdx.x, xv);                      \
   _Pragma("unroll") for (int j = 0; j < 8; ++j) {                                       \
     float gg = gv[j];                                                                   \
-    if (GELU) gg *= gelu_grad_fast(fmaf(xv[j], wa[j], wb[j]));                           \
+    if (GELU) gg *= gelu_tanh_grad(fmaf(xv[j], wa[j], wb[j]));                           \
     o[j] = fmaf(ka[j], gg, fmaf(kb[j], xv[j], kc[j]));                                  \
   }                                                                                     \
   if (ADD) {                                                                            \
@@ -638,6 +654,12 @@ extern "C" int bf_inorm_bwd(const bf_inorm_bwd_args* a, void* stream) {
   p.stats = a->stats; p.weight = a->weight; p.bias = a->bias; p.gelu = a->gelu; p.red = a->red;
   p.row_scale = a->row_scale; p.col_scale = a->col_scale; p.film_gamma = a->film_gamma;
   p.film_T = a->film_T > 0 ? a->film_T : 1; p.add32 = a->add32;
+  p.dweight = a->dweight; p.dbias = a->dbias; p.dcol_scale = a->dcol_scale;
+  p.dfilm_gamma = a->dfilm_gamma; p.dfilm_beta = a->dfilm_beta;
+  BF_REQUIRE((a->dweight == nullptr) == (a->dbias == nullptr), "bf_inorm_bwd: dweight / dbias pair");
+  BF_REQUIRE((a->dfilm_gamma == nullptr) == (a->dfilm_beta == nullptr), "bf_inorm_bwd: film gradient pair");
+  BF_REQUIRE(a->dweight != nullptr || (a->dcol_scale == nullptr && a->dfilm_gamma == nullptr),
+             "bf_inorm_bwd: dcol_scale / dfilm gradients need dweight / dbias as well");
   dim3 grid(p.g.splits, a->I, p.g.chunks);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int gd = a->g_dtype, xd = a->x_dtype, od = a->out_dtype;

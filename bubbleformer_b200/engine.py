@@ -200,9 +200,8 @@ def _attn_branch_bwd(dXout, g: Geom, p, w16, heads: int, axes, scale_keys, mask_
     red2 = _zeros((I, E, 2), dXout)
     ops.inorm_bwd(1, dOn, O, I, P, st2, p["norm2.weight"], p["norm2.bias"], red2)
     dO = _empty((N, E), BF16, dXout)
-    ops.inorm_bwd(2, dOn, O, I, P, st2, p["norm2.weight"], p["norm2.bias"], red2, out=dO)
-    ops.inorm_bwd_params(red2, I, P, E, p["norm2.weight"], p["norm2.bias"], dweight=grads["norm2.weight"],
-                         dbias=grads["norm2.bias"])
+    ops.inorm_bwd(2, dOn, O, I, P, st2, p["norm2.weight"], p["norm2.bias"], red2, out=dO,
+                  dweight=grads["norm2.weight"], dbias=grads["norm2.bias"])
     # attention(s)
     dQKV = _empty((N, 3 * E), BF16, dXout)
     oscale = 1.0 / len(axes)
@@ -226,9 +225,8 @@ def _attn_branch_bwd(dXout, g: Geom, p, w16, heads: int, axes, scale_keys, mask_
     red1 = _zeros((I, E, 2), dXout)
     ops.inorm_bwd(1, dXn, X, I, P, st1, p["norm1.weight"], p["norm1.bias"], red1)
     dX = _empty((N, E), F32, dXout)
-    ops.inorm_bwd(2, dXn, X, I, P, st1, p["norm1.weight"], p["norm1.bias"], red1, out=dX, add32=dXout)
-    ops.inorm_bwd_params(red1, I, P, E, p["norm1.weight"], p["norm1.bias"], dweight=grads["norm1.weight"],
-                         dbias=grads["norm1.bias"])
+    ops.inorm_bwd(2, dXn, X, I, P, st1, p["norm1.weight"], p["norm1.bias"], red1, out=dX, add32=dXout,
+                  dweight=grads["norm1.weight"], dbias=grads["norm1.bias"])
     return dX, S0, S1
 
 
@@ -300,10 +298,8 @@ def spatial_backward(dXout, g: Geom, p, w16, heads: int, attn_scale: bool, feat_
     ops.inorm_bwd(1, dXout, Y2, I, P, st3, p["mlp_norm.weight"], p["mlp_norm.bias"], red3)
     dY2 = _empty((N, E), BF16, dXout)
     ops.inorm_bwd(2, dXout, Y2, I, P, st3, p["mlp_norm.weight"], p["mlp_norm.bias"], red3, out=dY2,
-                  row_scale=mask_mlp, col_scale=p["gamma_mlp"])
-    ops.inorm_bwd_params(red3, I, P, E, p["mlp_norm.weight"], p["mlp_norm.bias"], row_scale=mask_mlp,
-                         col_scale=p["gamma_mlp"], dweight=grads["mlp_norm.weight"], dbias=grads["mlp_norm.bias"],
-                         dcol_scale=grads["gamma_mlp"])
+                  row_scale=mask_mlp, col_scale=p["gamma_mlp"], dweight=grads["mlp_norm.weight"],
+                  dbias=grads["mlp_norm.bias"], dcol_scale=grads["gamma_mlp"])
     # fc2 (its bias feeds an InstanceNorm, so its gradient is identically zero and stays zero)
     dH = _empty((N, 4 * E), BF16, dXout)
     ops.gemm(dY2, w16("mlp.fc2.weight"), N, 4 * E, E, epilogue=L.EPI_DGELU, b_mode=L.B_KN, aux16=Hpre, out16=dH,
@@ -419,15 +415,14 @@ def embed_backward(dX, p, n_layers: int, film_gb, T: int, sv, grads, need_dx: bo
         if last and film_gb is not None:
             fg = film_gb[:, :Cout].contiguous()
             kw = dict(film_gamma=fg, film_T=T)
-        ops.inorm_bwd(2, gin, Y, I, ho * wo, st, nw, nb, red, gelu=not last, out=dY, **kw)
         pk = dict(dweight=grads[f"in_proj.{3 * i + 1}.weight"], dbias=grads[f"in_proj.{3 * i + 1}.bias"])
         if last and film_gb is not None:
-            dfg, dfb = _empty((I // T, Cout), F32, dX), _empty((I // T, Cout), F32, dX)
-            ops.inorm_bwd_params(red, I, ho * wo, Cout, nw, nb, film_gamma=kw["film_gamma"], film_T=T,
-                                 dfilm_gamma=dfg, dfilm_beta=dfb, **pk)
-            dfilm = torch.cat([dfg, dfb], dim=1)
+            dfg_c, dfb_c = _zeros((I // T, Cout), dX), _zeros((I // T, Cout), dX)
+            ops.inorm_bwd(2, gin, Y, I, ho * wo, st, nw, nb, red, gelu=not last, out=dY, dfilm_gamma=dfg_c,
+                          dfilm_beta=dfb_c, **kw, **pk)
+            dfilm = torch.cat([dfg_c, dfb_c], dim=1)
         else:
-            ops.inorm_bwd_params(red, I, ho * wo, Cout, nw, nb, **pk)
+            ops.inorm_bwd(2, gin, Y, I, ho * wo, st, nw, nb, red, gelu=not last, out=dY, **kw, **pk)
         wt = p[f"in_proj.{3 * i}.weight"]
         if i == 0:
             ops.patch_wgrad(dY.view(I, ho, wo, Cout), x, grads[f"in_proj.0.weight"])
@@ -517,9 +512,8 @@ def debed_backward(dOut, g: Geom, p, n_layers: int, sv, grads):
         red = _zeros((I, Cout, 2), dOut)
         ops.inorm_bwd(1, gin, Z, I, 4 * h_ * w_, st, nw, nb, red, gelu=True)
         dZ = _empty((4 * M, Cout), BF16, dOut)
-        ops.inorm_bwd(2, gin, Z, I, 4 * h_ * w_, st, nw, nb, red, gelu=True, out=dZ)
-        ops.inorm_bwd_params(red, I, 4 * h_ * w_, Cout, nw, nb, dweight=grads[f"out_proj.{3 * i + 1}.weight"],
-                             dbias=grads[f"out_proj.{3 * i + 1}.bias"])
+        ops.inorm_bwd(2, gin, Z, I, 4 * h_ * w_, st, nw, nb, red, gelu=True, out=dZ,
+                      dweight=grads[f"out_proj.{3 * i + 1}.weight"], dbias=grads[f"out_proj.{3 * i + 1}.bias"])
         # gather dZ (I, 2h, 2w, Cout) into (M, (ky, kx, co)): A operand of the dgrad and B operand of the wgrad
         dZg = _empty((M, 4 * Cout), BF16, dOut)
         ops.s2d_gather(dZ.view(I, 2 * h_, 2 * w_, Cout), dZg)

@@ -142,7 +142,8 @@ def inorm_apply(x, out, I, P, stats, weight, bias, *, gelu=False, film_gamma=Non
 
 
 def inorm_bwd(phase, gin, x, I, P, stats, weight, bias, red, *, gelu=False, out=None, row_scale=None,
-              col_scale=None, film_gamma=None, film_T=0, add32=None) -> None:
+              col_scale=None, film_gamma=None, film_T=0, add32=None, dweight=None, dbias=None, dcol_scale=None,
+              dfilm_gamma=None, dfilm_beta=None) -> None:
     _mat(gin, "gin"); _mat(x, "x")
     C_ = x.shape[1]
     a = L.InormBwdArgs()
@@ -163,6 +164,9 @@ def inorm_bwd(phase, gin, x, I, P, stats, weight, bias, red, *, gelu=False, out=
     if add32 is not None:
         assert add32.dtype == torch.float32 and add32.stride(0) == out.stride(0)
         a.add32 = _ptr(add32)
+    a.dweight, a.dbias = _f32(dweight, C_, "dweight"), _f32(dbias, C_, "dbias")
+    a.dcol_scale = _f32(dcol_scale, C_, "dcol_scale")
+    a.dfilm_gamma, a.dfilm_beta = _f32(dfilm_gamma, 1, "dfilm_gamma"), _f32(dfilm_beta, 1, "dfilm_beta")
     L.check(L.lib.bf_inorm_bwd(C.byref(a), _stream()), "bf_inorm_bwd")
 
 

@@ -162,6 +162,9 @@ typedef struct bf_inorm_bwd_args {
   int32_t film_T;  int32_t reserved0;
   const float* add32;         /* fp32 (I*P, C) ld = ldo or NULL */
   void* out;
+  /* phase 2, optional (all NULL = skip): the parameter gradients of bf_inorm_bwd_params accumulated by the same
+   * launch with fp32 atomics.  dfilm_gamma / dfilm_beta are ADDED to here (the caller zeroes them).            */
+  float* dweight;  float* dbias;  float* dcol_scale;  float* dfilm_gamma;  float* dfilm_beta;
 } bf_inorm_bwd_args;
 BF_API int bf_inorm_bwd(const bf_inorm_bwd_args* args, void* stream);
 

@@ -71,6 +71,10 @@ def main():
         "gemm_fc2": (lambda: ops.gemm(H, W2, N, E, 4 * E, epilogue=L.EPI_STORE16, bias=vE, out16=O), 2.0 * N * 4 * E * E, (N * 4 * E + N * E) * 2),
         "gemm_resid": (lambda: ops.gemm(Xb, Wo, N, E, E, epilogue=L.EPI_RESID, bias=vE, col_gamma=vE, row_scale=rs, rows_per_group=P,
                                         in32=X32, out32=o32, out16=O, out16b=O2), 2.0 * N * E * E, N * E * (2 + 4 + 4 + 2 + 2)),
+        "gemm_resid_stats": (lambda: ops.gemm(Xb, Wo, N, E, E, epilogue=L.EPI_RESID, bias=vE, col_gamma=vE, row_scale=rs, rows_per_group=P,
+                                        in32=X32, out32=o32, out16b=O2, stats_out=st), 2.0 * N * E * E, N * E * (2 + 4 + 4 + 2)),
+        "gemm_resid_nostats": (lambda: ops.gemm(Xb, Wo, N, E, E, epilogue=L.EPI_RESID, bias=vE, col_gamma=vE, row_scale=rs, rows_per_group=P,
+                                        in32=X32, out32=o32, out16b=O2), 2.0 * N * E * E, N * E * (2 + 4 + 4 + 2)),
         "gemm_resid64": (lambda: ops.gemm(Xb, Wo, N, E, E, epilogue=L.EPI_RESID, bias=vE, col_gamma=vE, row_scale=rs, rows_per_group=P,
                                           in32=X32, out32=o32, out16=O, out16b=O2, bn=64), 2.0 * N * E * E, N * E * (2 + 4 + 4 + 2 + 2)),
         "gemm_resid_noz": (lambda: ops.gemm(Xb, Wo, N, E, E, epilogue=L.EPI_RESID, bias=vE, col_gamma=vE, row_scale=rs, rows_per_group=P,

@@ -117,7 +117,8 @@ def inorm_apply(x, out, I, P, stats, weight, bias, *, gelu=False, film_gamma=Non
 
 
 def inorm_bwd(phase, gin, x, I, P, stats, weight, bias, red, *, gelu=False, out=None, row_scale=None, col_scale=None,
-              film_gamma=None, film_T=0, add32=None):
+              film_gamma=None, film_T=0, add32=None, dweight=None, dbias=None, dcol_scale=None, dfilm_gamma=None,
+              dfilm_beta=None):
     C = x.shape[1]
     mean, rstd = _mean_rstd(stats, P)
     xh = (x.float().reshape(I, P, C) - mean[:, None]) * rstd[:, None]
@@ -140,6 +141,14 @@ def inorm_bwd(phase, gin, x, I, P, stats, weight, bias, red, *, gelu=False, out=
     if add32 is not None:
         o = o + add32
     out.copy_(o)
+    if dweight is not None:
+        fg = torch.zeros_like(dfilm_gamma) if dfilm_gamma is not None else None
+        fb = torch.zeros_like(dfilm_beta) if dfilm_beta is not None else None
+        inorm_bwd_params(red, I, P, C, weight, bias, row_scale=row_scale, col_scale=col_scale, film_gamma=film_gamma,
+                         film_T=film_T, dweight=dweight, dbias=dbias, dcol_scale=dcol_scale, dfilm_gamma=fg, dfilm_beta=fb)
+        if fg is not None:
+            dfilm_gamma.add_(fg)
+            dfilm_beta.add_(fb)
 
 
 def inorm_bwd_params(red, I, P, Cn, weight, bias, *, row_scale=None, col_scale=None, film_gamma=None, film_T=0,
