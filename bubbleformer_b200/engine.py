@@ -98,7 +98,44 @@ def _empty(shape, dtype, like):
     return torch.empty(shape, dtype=dtype, device=like.device)
 
 
+class _ZeroArena:
+    """Small zero-initialised fp32 buffers (statistics, reductions) carved from one zero-filled chunk, so a step
+    issues a handful of fill kernels instead of one per buffer.  A region is handed out once and never reused;
+    `reset()` (called at the start of every model forward) drops the chunk, which also keeps CUDA-graph captures
+    self-contained (the fill of the chunk is recorded inside the capture)."""
+    CHUNK = 1 << 20          # floats
+
+    def __init__(self):
+        self.buf = None
+        self.off = 0
+
+    def reset(self):
+        self.buf = None
+        self.off = 0
+
+    def take(self, n: int, device) -> torch.Tensor:
+        n8 = (n + 7) // 8 * 8
+        if self.buf is None or self.buf.device != device or self.off + n8 > self.buf.numel():
+            self.buf = torch.zeros(max(self.CHUNK, n8), dtype=F32, device=device)
+            self.off = 0
+        v = self.buf[self.off:self.off + n]
+        self.off += n8
+        return v
+
+
+_ARENA = _ZeroArena()
+
+
+def reset_arena() -> None:
+    _ARENA.reset()
+
+
 def _zeros(shape, like, dtype=F32):
+    n = 1
+    for d in shape:
+        n *= d
+    if dtype == F32 and n <= (1 << 18):
+        return _ARENA.take(n, like.device).view(shape)
     return torch.zeros(shape, dtype=dtype, device=like.device)
 
 
@@ -271,6 +308,8 @@ def spatial_forward(X, g: Geom, p, w16, heads: int, attn_scale: bool, feat_scale
     keys = ["attn_scale_factor_x", "attn_scale_factor_y"] if attn_scale else None
     c, c1, c0 = _feat_consts(p, feat_scale)
     Xmid, Xb, sv = _attn_branch_fwd(X, g, p, w16, heads, ["x", "y"], keys, mask_att, c1, c0, p["gamma_att"], True, save)
+    if save:
+        sv["feat"] = (c, c1, c0)
     G = _empty((N, 4 * E), BF16, X)
     Hpre = _empty((N, 4 * E), BF16, X) if save else None
     ops.gemm(Xb, w16("mlp.fc1.weight"), N, 4 * E, E, epilogue=L.EPI_GELU, bias=p["mlp.fc1.bias"], out16=G, out16b=Hpre)
@@ -313,7 +352,7 @@ def spatial_backward(dXout, g: Geom, p, w16, heads: int, attn_scale: bool, feat_
              split_k=pick_split(N, 4 * E, E), out32=grads["mlp.fc1.weight"])
     # ---- attention branch ----
     keys = ["attn_scale_factor_x", "attn_scale_factor_y"] if attn_scale else None
-    c, c1, c0 = _feat_consts(p, feat_scale)
+    c, c1, c0 = sv["feat"] if "feat" in sv else _feat_consts(p, feat_scale)
     ga = p["gamma_att"]
     coef = (ga * c1).contiguous() if feat_scale else ga
     dX, S0, S1 = _attn_branch_bwd(dXmid, g, p, w16, heads, ["x", "y"], keys, mask_att, coef, sv, grads)

@@ -68,7 +68,12 @@ class AttentionBlock(nn.Module):
         """token-major (B*T*P, E) fp32 -> same.  mask_b: optional (B,) drop-path factors (else drawn)."""
         if mask_b is None:
             mask_b = _drop_mask(geom.B, self.drop_prob, self.training, X.device)
-        mask_img = mask_b.to(torch.float32).repeat_interleave(geom.T).contiguous() if mask_b is not None else None
+        if mask_b is None:
+            mask_img = None
+        elif mask_b.numel() == geom.I and geom.T > 1:          # already expanded to one factor per (b, t) image
+            mask_img = mask_b.to(torch.float32).contiguous()
+        else:
+            mask_img = mask_b.to(torch.float32).repeat_interleave(geom.T).contiguous()
         pd = dict(self.named_parameters())
         spec = _TemporalSpec(list(pd.keys()), geom, self.num_heads, self.attn_scale, mask_img, w16)
         return run(spec, X, None, pd)

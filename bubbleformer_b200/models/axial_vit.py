@@ -69,6 +69,24 @@ class _AViTBase(nn.Module):
         self._bank: Optional[WeightBank] = None
         self.drop_masks_override = None      # tests: list of (mask_b, mask_att, mask_mlp) per block
 
+    def _draw_drop_masks(self, B: int, T: int, device):
+        """All stochastic-depth masks of one forward in one draw (timm DropPath semantics per block: bernoulli(keep) /
+        keep over dim 0 -- per sample for the temporal block, per image for the two spatial residuals)."""
+        if not self.training or not any(float(d) > 0.0 for d in self.dp):
+            return None
+        nb, I = len(self.blocks), B * T
+        keep = torch.tensor([1.0 - float(d) for d in self.dp], dtype=torch.float32, device=device)[:, None]
+        u = torch.rand(nb, B + 2 * I, device=device)
+        m = (u < keep).to(torch.float32) / keep.clamp_min(1e-12)
+        mb = m[:, :B].repeat_interleave(T, dim=1).contiguous()        # (nb, I): per-sample mask expanded to images
+        out = []
+        for i in range(nb):
+            if float(self.dp[i]) == 0.0:
+                out.append((None, None, None))
+            else:
+                out.append((mb[i], m[i, B:B + I], m[i, B + I:]))
+        return out
+
     def _run(self, x: torch.Tensor, film_gb: Optional[torch.Tensor]) -> torch.Tensor:
         if x.dim() != 5:
             raise ValueError(f"expected (B, T, C, H, W), got {tuple(x.shape)}")
@@ -83,10 +101,12 @@ class _AViTBase(nn.Module):
             self._bank = WeightBank(self)
         self._bank.refresh()
         geom = engine.Geom(B, T, H // p, W // p)
+        engine.reset_arena()
         xi = x.to(torch.float32).contiguous().view(B * T, C, H, W)
         X = self.embed.tokens(xi, film_gb, T)
+        drawn = self._draw_drop_masks(B, T, x.device) if self.drop_masks_override is None else None
         for i, blk in enumerate(self.blocks):
-            masks = self.drop_masks_override[i] if self.drop_masks_override is not None else None
+            masks = self.drop_masks_override[i] if self.drop_masks_override is not None else (drawn[i] if drawn else None)
             X = blk.tokens(X, geom, self._bank.w16, masks)
         out = self.debed.images(X, geom)
         return out.view(B, T, -1, H, W)
