@@ -278,6 +278,7 @@ __device__ __forceinline__ void store_rows(const bf16* S, int ld, bf16* dst, lon
 template <int D, int LP, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 attn_fwd_kernel(AttnParams p) {
+  pdl_prologue_done();
   using SM = AttnSmem<D, LP>;
   constexpr int DS = SM::DS, LS = SM::LS, NT = LP / 8;
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -424,6 +425,7 @@ __device__ __forceinline__ void stage_rows(const bf16* src, long ld_src, const l
 template <int D, int LP, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 attn_bwd_kernel(AttnParams p) {
+  pdl_prologue_done();
   using SM = AttnSmem<D, LP>;
   constexpr int DS = SM::DS, LS = SM::LS, NT = LP / 8;
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -627,7 +629,7 @@ static int launch_attn(const AttnParams& p, cudaStream_t st) {
   long blocks = (n_work + WARPS - 1) / WARPS;
   const long cap = (long)num_sms() * (per_sm > 8 ? 8 : per_sm);
   if (blocks > cap) blocks = cap;
-  kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(p);
+  launch_k(kern, dim3((unsigned)blocks), dim3(WARPS * 32), (size_t)(smem), st, p);
   count_launch();
   return check_cuda(cudaGetLastError(), BWD ? "attn_bwd_kernel launch" : "attn_fwd_kernel launch");
 }

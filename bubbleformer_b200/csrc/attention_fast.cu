@@ -285,6 +285,7 @@ template <bool PACKED>
 __global__ void __launch_bounds__(kFwdWarps * 32, 1)
 attn_fast_fwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_out,
                      const FastParams p) {
+  pdl_prologue_done();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -432,6 +433,7 @@ template <bool PACKED>
 __global__ void __launch_bounds__(kBwdWarps * 32, 1)
 attn_fast_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
                      const __grid_constant__ CUtensorMap map_dqkv, const FastParams p) {
+  pdl_prologue_done();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -804,11 +806,11 @@ int launch_attn_fast(const bf_attn_args* a, bool bwd, cudaStream_t st) {
     BF_REQUIRE((blocks * warps) % p.heads == 0, "bf_attention_bwd (prenorm): heads=%d does not divide %d warps", p.heads, warps);
   }
   if (bwd) {
-    if (packed) attn_fast_bwd_kernel<true><<<(unsigned)blocks, warps * 32, smem, st>>>(m_qkv, m_b, m_c, p);
-    else attn_fast_bwd_kernel<false><<<(unsigned)blocks, warps * 32, smem, st>>>(m_qkv, m_b, m_c, p);
+    if (packed) launch_k(attn_fast_bwd_kernel<true>, dim3((unsigned)blocks), dim3(warps * 32), (size_t)(smem), st, m_qkv, m_b, m_c, p);
+    else launch_k(attn_fast_bwd_kernel<false>, dim3((unsigned)blocks), dim3(warps * 32), (size_t)(smem), st, m_qkv, m_b, m_c, p);
   } else {
-    if (packed) attn_fast_fwd_kernel<true><<<(unsigned)blocks, warps * 32, smem, st>>>(m_qkv, m_b, p);
-    else attn_fast_fwd_kernel<false><<<(unsigned)blocks, warps * 32, smem, st>>>(m_qkv, m_b, p);
+    if (packed) launch_k(attn_fast_fwd_kernel<true>, dim3((unsigned)blocks), dim3(warps * 32), (size_t)(smem), st, m_qkv, m_b, p);
+    else launch_k(attn_fast_fwd_kernel<false>, dim3((unsigned)blocks), dim3(warps * 32), (size_t)(smem), st, m_qkv, m_b, p);
   }
   count_launch();
   return check_cuda(cudaGetLastError(), bwd ? "attn_fast_bwd_kernel launch" : "attn_fast_fwd_kernel launch");

@@ -45,6 +45,36 @@ int  make_map(CUtensorMap* map, int dt, const void* base, int rank, const uint64
   } while (0)
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  Every kernel of this library is launched with the programmatic
+// stream-serialization attribute and starts with pdl_prologue_done(): its CTAs may become resident while the
+// previous kernel of the stream drains (launch latency, barrier / TMEM / shared-memory set-up overlap that tail),
+// but they touch global memory only after griddepcontrol.wait, i.e. after the previous grid has completed and
+// flushed.  The dependents of this grid are released right away: they wait the same way.  BF_PDL=0 disables it.
+// ---------------------------------------------------------------------------------------------
+bool pdl_enabled();
+
+__device__ __forceinline__ void pdl_prologue_done() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

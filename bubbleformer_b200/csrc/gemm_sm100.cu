@@ -180,6 +180,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_prologue_done();
 
   const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
   const int num_tiles = tiles_mn * p.split_k;
@@ -707,9 +708,10 @@ static int launch(const Maps& mp, GemmParams& p, cudaStream_t st) {
   const int total = p.bar_off + bar_bytes + 1024;
   const int tiles = p.num_m_blocks * p.num_n_blocks * p.split_k;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kThreads, total, st>>>(mp.a, mp.b, mp.in, mp.o16, mp.o16b, mp.o32, p);
+  const cudaError_t le = launch_k(kern, dim3(grid), dim3(kThreads), (size_t)total, st, mp.a, mp.b, mp.in, mp.o16, mp.o16b,
+                                 mp.o32, p);
   count_launch();
-  return check_cuda(cudaGetLastError(), "gemm_tcgen05_kernel launch");
+  return check_cuda(le != cudaSuccess ? le : cudaGetLastError(), "gemm_tcgen05_kernel launch");
 }
 
 static int pick_bn(const bf_gemm_args& a) {

@@ -12,6 +12,7 @@ namespace bf {
 __global__ void __launch_bounds__(256)
 lploss_sums_kernel(const float4* __restrict__ pred, const float4* __restrict__ tgt, float* __restrict__ sums,
                    long vec_per_slab, int blocks_per_slab) {
+  pdl_prologue_done();
   const int slab = blockIdx.x / blocks_per_slab, part = blockIdx.x - slab * blocks_per_slab;
   const float4* p = pred + (long)slab * vec_per_slab;
   const float4* t = tgt + (long)slab * vec_per_slab;
@@ -38,6 +39,7 @@ lploss_sums_kernel(const float4* __restrict__ pred, const float4* __restrict__ t
 __global__ void __launch_bounds__(256)
 lploss_bwd_kernel(const float4* __restrict__ pred, const float4* __restrict__ tgt, const float* __restrict__ coef,
                   float4* __restrict__ dpred, long vec_per_slab, int blocks_per_slab) {
+  pdl_prologue_done();
   const int slab = blockIdx.x / blocks_per_slab, part = blockIdx.x - slab * blocks_per_slab;
   const float c = __ldg(coef + slab);
   const long base = (long)slab * vec_per_slab;
@@ -69,7 +71,7 @@ extern "C" int bf_lploss_sums(const float* pred, const float* tgt, float* sums, 
   BF_REQUIRE(((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(tgt)) & 15) == 0, "bf_lploss_sums: alignment");
   int bps;
   if (int st = plan(slabs, n_per_slab, bps)) return st;
-  lploss_sums_kernel<<<(unsigned)(slabs * bps), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(lploss_sums_kernel, dim3((unsigned)(slabs * bps)), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const float4*>(pred), reinterpret_cast<const float4*>(tgt), sums, n_per_slab / 4, bps);
   count_launch();
   BF_LAUNCH_CHECK("lploss_sums_kernel");
@@ -83,7 +85,7 @@ extern "C" int bf_lploss_bwd(const float* pred, const float* tgt, const float* c
              "bf_lploss_bwd: alignment");
   int bps;
   if (int st = plan(slabs, n_per_slab, bps)) return st;
-  lploss_bwd_kernel<<<(unsigned)(slabs * bps), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(lploss_bwd_kernel, dim3((unsigned)(slabs * bps)), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const float4*>(pred), reinterpret_cast<const float4*>(tgt), coef, reinterpret_cast<float4*>(dpred),
       n_per_slab / 4, bps);
   count_launch();

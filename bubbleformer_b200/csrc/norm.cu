@@ -162,6 +162,7 @@ template <int NSLOT> struct Stages { static constexpr int S = (kRingBytes / (NSL
 template <typename T>
 __global__ void __launch_bounds__(kNT, kBlocksPerSM)
 inorm_stats_kernel(const T* __restrict__ x, long ldx, Geom g, float* __restrict__ stats) {
+  pdl_prologue_done();
   constexpr int NSLOT = Slots<T>::N, S = Stages<NSLOT>::S;
   extern __shared__ __align__(16) uint4 ring[];
   const Ctx c = make_ctx(g);
@@ -207,6 +208,7 @@ struct ApplyParams {
 template <typename TI, typename TO, bool RESID>
 __global__ void __launch_bounds__(kNT, kBlocksPerSM)
 inorm_apply_kernel(const TI* __restrict__ x, TO* __restrict__ out, ApplyParams p) {
+  pdl_prologue_done();
   constexpr int NX = Slots<TI>::N, NSLOT = NX + (RESID ? 2 : 0), S = Stages<NSLOT>::S;
   extern __shared__ __align__(16) uint4 ring[];
   const Geom& g = p.g;
@@ -300,6 +302,7 @@ struct BwdParams {
 template <typename TG, typename TX, bool GELU>
 __global__ void __launch_bounds__(kNT, kBlocksPerSM)
 inorm_bwd_reduce_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, BwdParams p) {
+  pdl_prologue_done();
   constexpr int NG = Slots<TG>::N, NSLOT = NG + Slots<TX>::N, S = Stages<NSLOT>::S;
   extern __shared__ __align__(16) uint4 ring[];
   const Geom& g = p.g;
@@ -355,6 +358,7 @@ inorm_bwd_reduce_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, Bw
 template <typename TG, typename TX, typename TO, bool GELU, bool ADD>
 __global__ void __launch_bounds__(kNT, kBlocksPerSM)
 inorm_bwd_apply_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, TO* __restrict__ out, BwdParams p) {
+  pdl_prologue_done();
   constexpr int NG = Slots<TG>::N, NX = Slots<TX>::N, NSLOT = NG + NX + (ADD ? 2 : 0), S = Stages<NSLOT>::S;
   extern __shared__ __align__(16) uint4 ring[];
   const Geom& g = p.g;
@@ -432,6 +436,7 @@ struct BwdParamArgs {
   float* dweight; float* dbias; float* dcol_scale; float* dfilm_gamma; float* dfilm_beta;
 };
 __global__ void __launch_bounds__(256) inorm_bwd_params_kernel(BwdParamArgs a) {
+  pdl_prologue_done();
   __shared__ float sh[3][8][33];
   const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
@@ -492,6 +497,7 @@ struct ResidBwdParams {
 template <typename T16, bool HASZ>
 __global__ void __launch_bounds__(kNT, kBlocksPerSM)
 resid_bwd_kernel(ResidBwdParams p) {
+  pdl_prologue_done();
   constexpr int NSLOT = 2 + (HASZ ? 1 : 0), S = Stages<NSLOT>::S;
   extern __shared__ __align__(16) uint4 ring[];
   const Geom& g = p.g;
@@ -539,6 +545,7 @@ resid_bwd_kernel(ResidBwdParams p) {
 template <typename T16>
 __global__ void __launch_bounds__(kNT, kBlocksPerSM)
 colsum16_kernel(const T16* __restrict__ x, long ldx, Geom g, float* __restrict__ out) {
+  pdl_prologue_done();
   constexpr int NSLOT = 1, S = Stages<NSLOT>::S;
   extern __shared__ __align__(16) uint4 ring[];
   const Ctx c = make_ctx(g);
@@ -580,7 +587,7 @@ static int set_smem(K kern) {
   do {                                                                            \
     static bool done_ = false;                                                    \
     if (!done_) { if (int e_ = set_smem(kern)) return e_; done_ = true; }         \
-    kern<<<grid, kNT, kRingBytes, stream>>>(__VA_ARGS__);                         \
+    launch_k(kern, dim3(grid), dim3(kNT), (size_t)(kRingBytes), stream, __VA_ARGS__);                         \
   } while (0)
 
 }  // namespace bf
@@ -717,7 +724,7 @@ extern "C" int bf_inorm_bwd_params(const bf_inorm_bwd_params_args* a, void* stre
   BwdParamArgs k{a->red, nullptr, a->I, a->P, a->C, a->row_scale, a->col_scale, a->film_gamma,
                  a->film_T > 0 ? a->film_T : 1, a->weight, a->bias, a->dweight, a->dbias, a->dcol_scale,
                  a->dfilm_gamma, a->dfilm_beta};
-  inorm_bwd_params_kernel<<<(a->C + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(k);
+  launch_k(inorm_bwd_params_kernel, dim3((a->C + 31) / 32), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream), k);
   count_launch();
   BF_LAUNCH_CHECK("inorm_bwd_params_kernel");
   return BF_OK;

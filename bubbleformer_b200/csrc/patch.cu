@@ -26,6 +26,7 @@ template <typename T16, int FMAX>
 __global__ void __launch_bounds__(256)
 patch_in_kernel(const float* __restrict__ x, const float* __restrict__ Wkn, T16* __restrict__ out, float* stats,
                 int I, int F, int H, int W, int N, int pix_per_block) {
+  pdl_prologue_done();
   extern __shared__ float sm[];
   float* sStat = sm;                 // [N][2]
   for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) sStat[i] = 0.f;
@@ -102,6 +103,7 @@ template <typename T16, int FMAX>
 __global__ void __launch_bounds__(256)
 patch_out_kernel(const T16* __restrict__ a, const float* __restrict__ Wck, float* __restrict__ out,
                  int I, int F, int h, int w, int C, int tile_px) {
+  pdl_prologue_done();
   extern __shared__ float sm[];
   const int K = 4 * F;
   float* sW = sm;                                               // [C][4*FMAX] (zero padded)
@@ -162,6 +164,7 @@ template <typename T16>
 __global__ void __launch_bounds__(1024)
 patch_wgrad_kernel(const T16* __restrict__ a, const float* __restrict__ x, float* __restrict__ dW,
                    int I, int F, int H, int W, int N, int lda, int pix_per_block) {
+  pdl_prologue_done();
   extern __shared__ float sm[];
   constexpr int TP = 32;                                 // pixels per staging tile
   const int K = 4 * F;
@@ -223,6 +226,7 @@ __device__ __forceinline__ uint4 bf16_to_half8(uint4 v) {
 // conv: 0 none, 1 fp16 -> bf16, 2 bf16 -> fp16
 __global__ void __launch_bounds__(256)
 s2d_gather_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, long M, int Ho, int Wo, int C8, int conv) {
+  pdl_prologue_done();
   // one 16-byte chunk per thread; a row of the output is 4*C8 chunks = two runs of 2*C8 chunks
   const long total = M * 4 * C8;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -241,6 +245,7 @@ s2d_gather_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, long M,
 
 __global__ void __launch_bounds__(256)
 convert16_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, long n8, int conv) {
+  pdl_prologue_done();
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
     uint4 v = in[i];
     out[i] = conv == 1 ? half8_to_bf16(v) : bf16_to_half8(v);
@@ -251,6 +256,7 @@ convert16_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, long n8,
 template <typename T16>
 __global__ void __launch_bounds__(256)
 cast16_kernel(const float* __restrict__ in, T16* __restrict__ out, long n) {
+  pdl_prologue_done();
   const long n8 = n / 8;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
     const float4 a = reinterpret_cast<const float4*>(in)[2 * i], b = reinterpret_cast<const float4*>(in)[2 * i + 1];
@@ -284,7 +290,7 @@ extern "C" int bf_patch_in(const float* x, const float* Wkn, void* out, int dtyp
   dim3 grid((unsigned)((pix_img + ppb - 1) / ppb), I);
   const size_t sm = (size_t)2 * N * sizeof(float);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define BF_PIN(T, FM) patch_in_kernel<T, FM><<<grid, 256, sm, s>>>(x, Wkn, (T*)out, stats, I, F, H, W, N, (int)ppb)
+#define BF_PIN(T, FM) launch_k(patch_in_kernel<T, FM>, dim3(grid), dim3(256), (size_t)(sm), s, x, Wkn, (T*)out, stats, I, F, H, W, N, (int)ppb)
   if (dtype == BF_BF16) { if (F <= 4) BF_PIN(__nv_bfloat16, 4); else BF_PIN(__nv_bfloat16, 8); }
   else                  { if (F <= 4) BF_PIN(__half, 4); else BF_PIN(__half, 8); }
 #undef BF_PIN
@@ -306,7 +312,7 @@ static int launch_patch_out(const void* a, const float* Wck, float* out, int I, 
     done = true;
   }
   dim3 grid((unsigned)((pix_img + tile_px - 1) / tile_px), I);
-  patch_out_kernel<T16, FM><<<grid, 256, sm, s>>>((const T16*)a, Wck, out, I, F, h, w, C, tile_px);
+  launch_k(patch_out_kernel<T16, FM>, dim3(grid), dim3(256), (size_t)(sm), s, (const T16*)a, Wck, out, I, F, h, w, C, tile_px);
   count_launch();
   BF_LAUNCH_CHECK("patch_out_kernel");
   return BF_OK;
@@ -344,9 +350,9 @@ extern "C" int bf_patch_wgrad(const void* a, int dtype, const float* x, float* d
     const size_t sm = (size_t)32 * 4 * F * sizeof(float) + (size_t)32 * nc * 2;
     float* dWc = dW + (long)n0 * 4 * F;
     if (dtype == BF_BF16)
-      patch_wgrad_kernel<__nv_bfloat16><<<grid, nc * F, sm, s>>>((const __nv_bfloat16*)a + n0, x, dWc, I, F, H, W, nc, N, (int)ppb);
+      launch_k(patch_wgrad_kernel<__nv_bfloat16>, dim3(grid), dim3(nc * F), (size_t)(sm), s, (const __nv_bfloat16*)a + n0, x, dWc, I, F, H, W, nc, N, (int)ppb);
     else
-      patch_wgrad_kernel<__half><<<grid, nc * F, sm, s>>>((const __half*)a + n0, x, dWc, I, F, H, W, nc, N, (int)ppb);
+      launch_k(patch_wgrad_kernel<__half>, dim3(grid), dim3(nc * F), (size_t)(sm), s, (const __half*)a + n0, x, dWc, I, F, H, W, nc, N, (int)ppb);
     count_launch();
     BF_LAUNCH_CHECK("patch_wgrad_kernel");
   }
@@ -364,7 +370,7 @@ extern "C" int bf_convert16(const void* in, int in_dtype, void* out, int out_dty
              "bf_convert16: dtype pair");
   long blocks = (n / 8 + 255) / 256;
   if (blocks > 8L * num_sms()) blocks = 8L * num_sms();
-  convert16_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(convert16_kernel, dim3((unsigned)blocks), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream), 
       (const uint4*)in, (uint4*)out, n / 8, conv_code(in_dtype, out_dtype));
   count_launch();
   BF_LAUNCH_CHECK("convert16_kernel");
@@ -382,7 +388,7 @@ extern "C" int bf_s2d_gather(const void* in, int in_dtype, void* out, int out_dt
   const long total = M * 4 * (C / 8);
   long blocks = (total + 255) / 256;
   if (blocks > 8L * num_sms()) blocks = 8L * num_sms();
-  s2d_gather_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(s2d_gather_kernel, dim3((unsigned)blocks), dim3(256), (size_t)(0), static_cast<cudaStream_t>(stream), 
       (const uint4*)in, (uint4*)out, M, Hin / 2, Win / 2, C / 8, conv_code(in_dtype, out_dtype));
   count_launch();
   BF_LAUNCH_CHECK("s2d_gather_kernel");
@@ -397,8 +403,8 @@ extern "C" int bf_cast16(const float* in, void* out, int dtype, int64_t n, void*
   if (blocks < 1) blocks = 1;
   if (blocks > 8L * num_sms()) blocks = 8L * num_sms();
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (dtype == BF_BF16) cast16_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>(in, (__nv_bfloat16*)out, n);
-  else cast16_kernel<__half><<<(unsigned)blocks, 256, 0, s>>>(in, (__half*)out, n);
+  if (dtype == BF_BF16) launch_k(cast16_kernel<__nv_bfloat16>, dim3((unsigned)blocks), dim3(256), (size_t)(0), s, in, (__nv_bfloat16*)out, n);
+  else launch_k(cast16_kernel<__half>, dim3((unsigned)blocks), dim3(256), (size_t)(0), s, in, (__half*)out, n);
   count_launch();
   BF_LAUNCH_CHECK("cast16_kernel");
   return BF_OK;

@@ -30,6 +30,7 @@ template <typename T16, bool STATS, int KS>
 __global__ void __launch_bounds__(kPinWarps * 32, 2)
 patch_in_mma_kernel(const float* __restrict__ x, const float* __restrict__ Wkn, T16* __restrict__ out, float* stats,
                     int F, int H, int W, int N, int tiles_per_block) {
+  pdl_prologue_done();
   extern __shared__ __align__(16) uint8_t smem[];
   const int K = 4 * F;
   const int WS = N + 8;                                   // padded weight row (words)
@@ -170,7 +171,7 @@ int launch_patch_in_mma(const float* x, const float* Wkn, void* out, int dtype, 
                                                    200 * 1024), "cudaFuncSetAttribute(patch_in)")) return e_;      \
       done_ = true;                                                                                                \
     }                                                                                                              \
-    patch_in_mma_kernel<T, ST, KS_><<<grid, kPinWarps * 32, sm, s>>>(x, Wkn, (T*)out, stats, F, H, W, N, tpb);          \
+    launch_k(patch_in_mma_kernel<T, ST, KS_>, dim3(grid), dim3(kPinWarps * 32), (size_t)(sm), s, x, Wkn, (T*)out, stats, F, H, W, N, tpb);          \
   } while (0)
 #define BF_PIN(T, ST) do { if (KS == 1) BF_PIN_(T, ST, 1); else if (KS == 2) BF_PIN_(T, ST, 2); else BF_PIN_(T, ST, 4); } while (0)
   if (dtype == BF_BF16) { if (stats) BF_PIN(__nv_bfloat16, true); else BF_PIN(__nv_bfloat16, false); }

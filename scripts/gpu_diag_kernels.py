@@ -251,9 +251,11 @@ def run(group):
             dqkv = torch.zeros(tokens, 3 * E, device=dev, dtype=torch.bfloat16)
             grads = dict(d_qn_w=torch.zeros(d, device=dev), d_qn_b=torch.zeros(d, device=dev), d_kn_w=torch.zeros(d, device=dev),
                          d_kn_b=torch.zeros(d, device=dev), d_bias_emb=torch.zeros(32, he, device=dev),
-                         d_scale_factor=torch.zeros(he, device=dev) if sf is not None else None)
+                         d_scale_factor=torch.zeros(he, device=dev) if sf is not None else None,
+                         d_qkv_bias=torch.zeros(3 * E, device=dev))
             ops.attention(qkvn, dqkv, dout=dout, grads=grads, prenorm=True, rstd=rstd, **common)
             got = dqkv.float().reshape(tokens, he, 3, d)
+            ok &= report(f"{group} prenorm d_qkv_bias (fused column sums)", grads["d_qkv_bias"], dqkv.float().sum(0), 1e-2)
             for i, nm in enumerate("qkv"):
                 ok &= report(f"{group} prenorm d{nm}", got[:, :, i], dq_ref[:, :, i], 3e-2)
             ok &= report(f"{group} prenorm d_qn_w", grads["d_qn_w"], params[0].grad, 3e-2)
