@@ -162,6 +162,7 @@ def main():
     ap.add_argument("--workload", default="train", choices=["train", "rollout"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured training step")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -206,7 +207,22 @@ def main():
         from bubbleformer_b200.rollout import GraphedStep
         gstep = GraphedStep(model, x, cond)       # the whole B=1 step replayed from one CUDA graph
 
+    gtrain = None
+    if train and not args.no_graph:
+        from bubbleformer_b200.parallel import GraphedTrainStep
+        gtrain = GraphedTrainStep(model, rel_l2_loss, sink, x, tgt, cond)    # fwd + loss + bwd (+ all-reduce) in one graph
+
+    def eager_step(xd, td, cd):
+        sink.begin_step()
+        y = model(xd, cd)
+        loss = rel_l2_loss(y, td)
+        loss.backward()
+        sink.finish()
+        return loss
+
     def step(xd, td, cd):
+        if gtrain is not None:
+            return gtrain(xd, td, cd)
         if train:
             sink.begin_step()
             y = model(xd, cd)
@@ -234,6 +250,9 @@ def main():
         e1.record()
         barrier()
     launches = _lib.launch_count() - n0
+    graphed = gtrain if train else gstep
+    if graphed is not None:                 # replays do not pass through the C ABI: count what the graph recorded
+        launches = graphed.launches_per_step * K
     ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms], device=dev)
@@ -293,7 +312,7 @@ def main():
     roof = None
     if rank == 0:
         ops.GEMM_TIMING = []
-    step(x, tgt, cond)                      # every rank steps (the gradient all-reduce is collective)
+    (eager_step if train else step)(x, tgt, cond)     # every rank steps (the gradient all-reduce is collective)
     torch.cuda.synchronize()
     if rank == 0:
         recs, ops.GEMM_TIMING = ops.GEMM_TIMING, None
@@ -324,7 +343,7 @@ def main():
             "config": {"workload": ("film_avit_small fwd+bwd (train mode, drop_path 0.2, rel-L2 loss), per-GPU batch %d, "
                                     "T=5, 4 fields, 512x512" % B) if train else
                                    "film_avit_small autoregressive rollout step (eval, no_grad), B=1, T=5, 4 fields, 512x512",
-                       "parallelism": f"dp{world}", "l2_policy": "per-step working set (>10 GB of activations) far exceeds the 126 MB L2",
+                       "parallelism": f"dp{world}", "cuda_graph": (gtrain is not None) if train else True, "l2_policy": "per-step working set (>10 GB of activations) far exceeds the 126 MB L2",
                        "precision": "bf16 block GEMMs / attention, fp16 patch embed+unembed forward, fp32 residual stream, statistics and gradients"},
             "e2e": {"value": e2e_value, "unit": "samples/s" if train else "steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": Ke},

@@ -271,6 +271,14 @@ cast16_kernel(const float* __restrict__ in, T16* __restrict__ out, long n) {
 
 using namespace bf;
 
+namespace bf {
+bool patch_wgrad_mma_ok(int F, int W, int N);
+bool patch_out_mma_ok(int F, int C);
+int launch_patch_wgrad_mma(const void* a, int dtype, const float* x, float* dW, int I, int F, int H, int W, int N,
+                           cudaStream_t s);
+int launch_patch_out_mma(const void* a, int dtype, const float* Wck, float* out, int I, int F, int h, int w, int C,
+                         cudaStream_t s);
+}
 namespace bf { int launch_patch_in_mma(const float* x, const float* Wkn, void* out, int dtype, float* stats, int I, int F,
                                        int H, int W, int N, cudaStream_t s); }
 
@@ -325,6 +333,7 @@ extern "C" int bf_patch_out(const void* a, int dtype, const float* Wck, float* o
   BF_REQUIRE(I > 0 && F > 0 && F <= kMaxF && h > 0 && w > 0 && C % 8 == 0 && C > 0, "bf_patch_out: geometry");
   BF_REQUIRE((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0, "bf_patch_out: alignment");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (patch_out_mma_ok(F, C) && I <= 65535) return launch_patch_out_mma(a, dtype, Wck, out, I, F, h, w, C, s);
   if (dtype == BF_BF16) return F <= 4 ? launch_patch_out<__nv_bfloat16, 4>(a, Wck, out, I, F, h, w, C, s)
                                       : launch_patch_out<__nv_bfloat16, 8>(a, Wck, out, I, F, h, w, C, s);
   return F <= 4 ? launch_patch_out<__half, 4>(a, Wck, out, I, F, h, w, C, s)
@@ -337,6 +346,9 @@ extern "C" int bf_patch_wgrad(const void* a, int dtype, const float* x, float* d
   BF_REQUIRE(dtype == BF_BF16 || dtype == BF_F16, "bf_patch_wgrad: dtype");
   BF_REQUIRE(I > 0 && F > 0 && F <= kMaxF && H % 2 == 0 && W % 2 == 0 && H > 0 && W > 0, "bf_patch_wgrad: geometry");
   BF_REQUIRE(N % 8 == 0, "bf_patch_wgrad: N=%d must be a multiple of 8", N);
+  if (patch_wgrad_mma_ok(F, W, N) && I <= 65535 && (reinterpret_cast<uintptr_t>(a) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(x) & 15) == 0)
+    return launch_patch_wgrad_mma(a, dtype, x, dW, I, F, H, W, N, static_cast<cudaStream_t>(stream));
   const long pix_img = (long)(H / 2) * (W / 2);
   long ppb = 1024;
   // enough blocks to fill the machine, few enough that the N*4F atomics per block stay cheap

@@ -75,7 +75,11 @@ class _AViTBase(nn.Module):
         if not self.training or not any(float(d) > 0.0 for d in self.dp):
             return None
         nb, I = len(self.blocks), B * T
-        keep = torch.tensor([1.0 - float(d) for d in self.dp], dtype=torch.float32, device=device)[:, None]
+        cache = getattr(self, "_keep_cache", None)
+        if cache is None or cache.device != device:       # one host->device copy per model, not per step
+            cache = torch.tensor([1.0 - float(d) for d in self.dp], dtype=torch.float32, device=device)[:, None]
+            self._keep_cache = cache
+        keep = cache
         u = torch.rand(nb, B + 2 * I, device=device)
         m = (u < keep).to(torch.float32) / keep.clamp_min(1e-12)
         mb = m[:, :B].repeat_interleave(T, dim=1).contiguous()        # (nb, I): per-sample mask expanded to images

@@ -30,9 +30,12 @@ class GraphedStep:
                 self.model(*args)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(x.device)
+        from . import _lib
         self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
         with torch.no_grad(), torch.cuda.graph(self.graph):
             self.y = self.model(*args)
+        self.launches_per_step = _lib.launch_count() - n0      # library kernels recorded in the graph
 
     def __call__(self, x: torch.Tensor, fluid_params: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Replays the step; the returned tensor is the graph's static output buffer (clone it to keep it)."""

@@ -269,7 +269,8 @@ def run(group):
             ok &= report(f"{group} prenorm bwd accumulate", dq2, 2 * dqkv.float(), 1.5e-2)
     elif group == "patch":
         for (I, Fd, H, W, N, dt) in [(2, 4, 64, 64, 96, torch.float16), (3, 2, 32, 48, 24, torch.float16),
-                                     (1, 1, 16, 16, 384, torch.bfloat16)]:
+                                     (1, 1, 16, 16, 384, torch.bfloat16), (2, 4, 32, 40, 96, torch.bfloat16),
+                                     (1, 3, 16, 24, 48, torch.float16), (3, 4, 128, 128, 96, torch.bfloat16)]:
             x = torch.randn(I, Fd, H, W, device=dev)
             Wc = torch.randn(N, Fd, 2, 2, device=dev) / (4 * Fd) ** 0.5
             out = torch.zeros(I, H // 2, W // 2, N, device=dev, dtype=dt)
@@ -290,7 +291,8 @@ def run(group):
             ops.patch_wgrad(a, x, dW)
             xs = x.reshape(I, Fd, H // 2, 2, W // 2, 2).permute(0, 2, 4, 1, 3, 5).reshape(-1, 4 * Fd)
             refw = a.float().reshape(-1, N).t() @ xs
-            ok &= report(f"patch_wgrad", dW.reshape(N, 4 * Fd), refw, 1e-4)
+            # fp16 activations are rounded to bf16 inside the tensor-core kernel (the gradient operand needs the range)
+            ok &= report(f"patch_wgrad", dW.reshape(N, 4 * Fd), refw, 1e-4 if dt == torch.bfloat16 else 3e-3)
     elif group == "misc":
         for (I, H, W, Cn) in [(2, 8, 12, 24), (3, 64, 64, 96)]:
             img = torch.randn(I, H, W, Cn, device=dev).half()

@@ -100,6 +100,20 @@ def main():
         "resid_bwd": (lambda: ops.resid_bwd(X32, Xb, O, I, P, rs, vE, torch.zeros(I, E, device=dev), torch.zeros(I, E, device=dev)), 0, N * E * 8),
         "colsum": (lambda: ops.colsum16(QKV, torch.zeros(3 * E, device=dev)), 0, N * 3 * E * 2),
     }
+    if any(n.startswith("patch") for n in names) or not names:
+        xf = torch.randn(I, 4, 512, 512, device=dev)
+        a16 = torch.randn(I, 256, 256, 96, device=dev).half()
+        ab16 = a16.bfloat16()
+        Wp = torch.randn(96, 16, device=dev) / 4
+        dWp = torch.zeros(96, 4, 2, 2, device=dev)
+        st96 = torch.zeros(I, 96, 2, device=dev)
+        pix = I * 256 * 256
+        table.update({
+            "patch_in": (lambda: ops.patch_in(xf, Wp.t().contiguous(), a16, st96), 0, pix * (64 + 192)),
+            "patch_out": (lambda: ops.patch_out(a16, Wp, xf), 0, pix * (64 + 192)),
+            "patch_wgrad": (lambda: ops.patch_wgrad(ab16, xf, dWp), 0, pix * (64 + 192)),
+            "patch_wgrad_f16": (lambda: ops.patch_wgrad(a16, xf, dWp), 0, pix * (64 + 192)),
+        })
     if not names:
         names = list(table)
     for n in names:

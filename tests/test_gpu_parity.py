@@ -114,3 +114,45 @@ def test_fused_rel_l2_loss_gpu():
     assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
     loss.backward(); ref.backward()
     assert O.rel_l2(pred.grad.cpu(), ref_in.grad.cpu()) < 1e-5
+
+
+def test_graphed_train_step_matches_eager():
+    """One captured fwd + loss + bwd step leaves the same loss and flat gradient as the eager step (drop_path 0)."""
+    import torch
+    from bubbleformer_b200 import get_model
+    from bubbleformer_b200.losses import rel_l2_loss
+    from bubbleformer_b200.parallel import GradSink, GraphedTrainStep
+    from oracle.param_init import fluid_params
+    torch.manual_seed(5)
+    m = get_model("filmavit", input_fields=4, output_fields=4, time_window=5, patch_size=16, embed_dim=128, num_heads=2,
+                  processor_blocks=2, num_fluid_params=9, drop_path=0.0).cuda().train()
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "gamma" in n:
+                p.copy_(0.05 * torch.randn_like(p))
+    x = torch.randn(2, 5, 4, 64, 64, device="cuda")
+    tgt = torch.randn_like(x)
+    cond = fluid_params(2).cuda()
+    sink = GradSink(m)
+    try:
+        sink.begin_step()
+        loss = rel_l2_loss(m(x, cond), tgt)
+        loss.backward()
+        sink.finish()
+        g_eager, l_eager = sink.flat.clone(), float(loss)
+        step = GraphedTrainStep(m, rel_l2_loss, sink, x, tgt, cond)
+        assert step.launches_per_step > 50
+        l_graph = float(step(x, tgt, cond))
+        g_graph = sink.flat.clone()
+        # new inputs go through the static buffers
+        x2 = torch.randn_like(x)
+        l2 = float(step(x2, tgt, cond))
+        sink.begin_step()
+        loss2 = rel_l2_loss(m(x2, cond), tgt)
+        loss2.backward()
+        sink.finish()
+        assert abs(l_graph - l_eager) < 2e-3 * abs(l_eager)
+        assert float((g_graph - g_eager).norm() / g_eager.norm()) < 2e-2      # bf16 roundings flipped by atomic order
+        assert abs(l2 - float(loss2)) < 2e-3 * abs(float(loss2))
+    finally:
+        sink.close()
