@@ -20,6 +20,7 @@
 // A can also be an implicit 2x2/stride-2 patch gather expressed purely as a 4-D TMA tensor map.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -54,6 +55,11 @@ struct GemmParams {
   int in_bufs;        // 1 or 2
   int in_bytes;       // bytes of one input tile buffer
   int in_off, slab_off, bar_off;
+  int b_resident;     // 1: the CTA's whole B block (k_iters boxes) stays in shared memory for all of its tiles
+  int a_off;          // start of the operand ring (after the resident B block)
+  int ln_heads;       // QKV_LN: heads = N / 192
+  int vec_off;        // per-column vectors staged in shared memory: [bias | col_scale | col_shift | col_gamma][vec_cols]
+  int vec_cols;       // columns staged per vector (a multiple of 32): BN when B-resident, else N rounded up
   const float* bias;
   const float* col_scale;
   const float* col_shift;
@@ -112,18 +118,14 @@ __device__ __forceinline__ void ld_row_16(const uint8_t* base, int row, float (&
   }
 }
 
-// per-column fp32 vector (bias, scales): 32 consecutive entries starting at column n (warp-uniform address)
-__device__ __forceinline__ void load_cols(const float* vec, int n, int N, float (&o)[32]) {
-  if (n + 32 <= N) {
-    const float4* p4 = reinterpret_cast<const float4*>(vec + n);
+// per-column fp32 vector (bias, scales) staged in shared memory at kernel start: 32 consecutive entries from a
+// 128-byte aligned, warp-uniform address (broadcast reads; no global-memory latency inside the tile loop)
+__device__ __forceinline__ void load_cols(const float* svec, float (&o)[32]) {
+  const float4* p4 = reinterpret_cast<const float4*>(svec);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 u = __ldg(p4 + q);
-      o[4 * q] = u.x; o[4 * q + 1] = u.y; o[4 * q + 2] = u.z; o[4 * q + 3] = u.w;
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) o[j] = (n + j < N) ? __ldg(vec + n + j) : 0.f;
+  for (int q = 0; q < 8; ++q) {
+    const float4 u = p4[q];
+    o[4 * q] = u.x; o[4 * q + 1] = u.y; o[4 * q + 2] = u.z; o[4 * q + 3] = u.w;
   }
 }
 
@@ -152,7 +154,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* in_full = tmem_empty + 2;
   uint64_t* in_empty = in_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(in_empty + 2);
+  uint64_t* b_full = in_empty + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -173,6 +176,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       mbar_init(in_full + s, 1);
       mbar_init(in_empty + s, kEpiWarps);
     }
+    mbar_init(b_full, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
@@ -181,6 +185,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   pdl_prologue_done();
+  // per-column vectors -> shared memory (zero padded); a B-resident CTA only ever needs its own BN columns
+  const int vec_base = p.b_resident ? ((int)blockIdx.x % p.num_n_blocks) * BN : 0;
+  float* s_vec = reinterpret_cast<float*>(smem + p.vec_off);
+  {
+    const float* const vsrc[4] = {p.bias, p.col_scale, p.col_shift, p.col_gamma};
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      if (vsrc[v] != nullptr) {
+        for (int i = threadIdx.x; i < p.vec_cols; i += kThreads)
+          s_vec[v * p.vec_cols + i] = (vec_base + i < p.N) ? __ldg(vsrc[v] + vec_base + i) : 0.f;
+      }
+    }
+  }
+  __syncthreads();
+  const float* s_bias = s_vec - vec_base;
+  const float* s_cscale = s_bias + p.vec_cols;
+  const float* s_cshift = s_cscale + p.vec_cols;
+  const float* s_cgamma = s_cshift + p.vec_cols;
 
   const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
   const int num_tiles = tiles_mn * p.split_k;
@@ -190,6 +212,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const bool res = p.b_resident != 0;
+      if (res && (int)blockIdx.x < num_tiles) {
+        // B-resident schedule: the grid is a multiple of num_n_blocks, so this CTA's n block never changes; its
+        // (BN x K) operand block is loaded once and every tile only streams its A rows through the ring
+        const int n0 = ((int)blockIdx.x % p.num_n_blocks) * BN;
+        mbar_arrive_expect_tx(b_full, p.k_iters * kBBytes);
+        for (int it = 0; it < p.k_iters; ++it) {
+          uint8_t* sb = smem + it * kBBytes;
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (64 * BK * 2), &map_b, b_full, n0 + 64 * j, it * BK);
+          } else {
+            tma_load_2d(sb, &map_b, b_full, it * BK, n0);
+          }
+        }
+      }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int ks = tile / tiles_mn;
         const int mn = tile - ks * tiles_mn;
@@ -198,9 +236,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int m0 = m_blk * BM, n0 = n_blk * BN;
         for (int it = 0; it < p.k_iters; ++it) {
           mbar_wait(empty_bar + stage, phase ^ 1u);
-          uint8_t* sa = smem + stage * kStageBytes;
+          uint8_t* sa = res ? smem + p.a_off + stage * kABytes : smem + stage * kStageBytes;
           uint8_t* sb = sa + kABytes;
-          mbar_arrive_expect_tx(full_bar + stage, kStageBytes);
+          mbar_arrive_expect_tx(full_bar + stage, res ? kABytes : kStageBytes);
           const int kit = ks * p.k_iters + it;      // global k iteration
           if (p.s2d) {
             const int ky = kit / p.k_seg_iters;
@@ -218,7 +256,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             } else {
               tma_load_2d(sa, &map_a, full_bar + stage, k0, m0);
             }
-            if (B_MN) {
+            if (res) {
+              // B is already resident
+            } else if (B_MN) {
 #pragma unroll
               for (int j = 0; j < BN / 64; ++j)
                 tma_load_2d(sb + j * (64 * BK * 2), &map_b, full_bar + stage, n0 + 64 * j, k0);
@@ -237,6 +277,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
+      const bool res = p.b_resident != 0;
+      if (res && (int)blockIdx.x < num_tiles) mbar_wait(b_full, 0);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(tmem_empty + as, aphase ^ 1u);
         tc_fence_after();
@@ -244,8 +286,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int it = 0; it < p.k_iters; ++it) {
           mbar_wait(full_bar + stage, phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-          const uint32_t sb = sa + kABytes;
+          const uint32_t sa = smem_u32(res ? smem + p.a_off + stage * kABytes : smem + stage * kStageBytes);
+          const uint32_t sb = res ? smem_u32(smem + it * kBBytes) : sa + kABytes;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // K-major: advance 16 elements = 32 B inside the 128 B swizzle row.
@@ -333,10 +375,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             if (live) {
               if (p.bias != nullptr) {
                 float b[32];
-                load_cols(p.bias, n0 + 32 * cq, p.N, b);
+                load_cols(s_bias + n0 + 32 * cq, b);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) x0[j] += b[j];
-                load_cols(p.bias, n0 + 32 * cq + 32, p.N, b);
+                load_cols(s_bias + n0 + 32 * cq + 32, b);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) x1[j] += b[j];
               }
@@ -355,7 +397,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               for (int j = 0; j < 32; ++j) { x0[j] *= rstd; x1[j] *= rstd; }
               if (p.is_f16) { st_row_16<__half>(slab, lane, x0); st_row_16<__half>(slab + 2048, lane, x1); }
               else { st_row_16<__nv_bfloat16>(slab, lane, x0); st_row_16<__nv_bfloat16>(slab + 2048, lane, x1); }
-              if (m < p.M) p.ln_rstd[((long)m * p.num_n_blocks + n_blk) * 2 + half] = rstd;
+              if (m < p.M) p.ln_rstd[((long)m * p.ln_heads + n_blk) * 2 + half] = rstd;
             }
           }
           {
@@ -368,7 +410,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             if (live) {
               if (p.bias != nullptr) {
                 float b[32];
-                load_cols(p.bias, n0 + 128 + 32 * half, p.N, b);
+                load_cols(s_bias + n0 + 128 + 32 * half, b);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] += b[j];
               }
@@ -382,6 +424,68 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 tma_store_commit();
               }
             }
+          }
+          if (++as == 2) { as = 0; aphase ^= 1u; }
+          continue;
+        }
+      }
+      if constexpr (BN == 128) {
+        if (p.epilogue == BF_EPI_QKV_LN) {
+          // Columns are ordered (head, q | k | v, 64): a tile is two 64-column groups, group gi = n0 / 64 + half belongs
+          // to head gi / 3 and is its q (0), k (1) or v (2) part.  The warp pair of a lane quadrant splits the groups;
+          // LayerNorm over the 64 columns of a row is thread local (tcgen05.ld hands each thread its row).  Stored:
+          // xhat = (x - mean) * rstd without the affine part (v unchanged), plus rstd of q / k for the backward.
+          const int mrow = m0 + quad * 32;
+          const int gi = (n0 >> 6) + half;
+          const int part = gi % 3;
+          const int ncol = n0 + 64 * half;
+          const bool live = mrow < p.M && ncol < p.N;           // warp uniform
+          uint8_t* s = slab + sb * 4096;
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          float x0[32], x1[32];
+          tmem_ld_32x32(t_row + static_cast<uint32_t>(64 * half), x0);
+          tmem_ld_32x32(t_row + static_cast<uint32_t>(64 * half + 32), x1);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty + as);
+          if (live) {
+            if (p.bias != nullptr) {
+              float b[32];
+              load_cols(s_bias + ncol, b);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x0[j] += b[j];
+              load_cols(s_bias + ncol + 32, b);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x1[j] += b[j];
+            }
+            if (part < 2) {
+              float sm_ = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sm_ += x0[j] + x1[j];
+              const float mean = sm_ * (1.f / 64.f);
+              float q = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                x0[j] -= mean; x1[j] -= mean;
+                q = fmaf(x0[j], x0[j], q); q = fmaf(x1[j], x1[j], q);
+              }
+              const float rstd = rsqrtf(q * (1.f / 64.f) + 1e-5f);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { x0[j] *= rstd; x1[j] *= rstd; }
+              if (m < p.M) p.ln_rstd[((long)m * p.ln_heads + gi / 3) * 2 + part] = rstd;
+            }
+            if (p.is_f16) { st_row_16<__half>(s, lane, x0); st_row_16<__half>(s + 2048, lane, x1); }
+            else { st_row_16<__nv_bfloat16>(s, lane, x0); st_row_16<__nv_bfloat16>(s + 2048, lane, x1); }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&map_o16, s, ncol, mrow);
+              tma_store_2d(&map_o16, s + 2048, ncol + 32, mrow);
+              tma_store_commit();
+            }
+            sb ^= 1;
           }
           if (++as == 2) { as = 0; aphase ^= 1u; }
           continue;
@@ -403,7 +507,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (n >= p.N || m0 + quad * 32 >= p.M) continue;     // chunk entirely outside the matrix (warp uniform)
         if (p.bias != nullptr) {
           float b[32];
-          load_cols(p.bias, n, p.N, b);
+          load_cols(s_bias + n, b);
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc[j] += b[j];
         }
@@ -507,14 +611,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
             float t[32];
             if (p.col_scale != nullptr) {
-              load_cols(p.col_scale, n, p.N, t);
+              load_cols(s_cscale + n, t);
 #pragma unroll
               for (int j = 0; j < 32; ++j) acc[j] *= t[j];
-              load_cols(p.col_shift, n, p.N, t);
+              load_cols(s_cshift + n, t);
 #pragma unroll
               for (int j = 0; j < 32; ++j) acc[j] += t[j];
             }
-            load_cols(p.col_gamma, n, p.N, t);
+            load_cols(s_cgamma + n, t);
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc[j] *= rs * t[j];
             ld_row_f32(box, row, t);
@@ -689,33 +793,74 @@ static int launch(const Maps& mp, GemmParams& p, cudaStream_t st) {
   });
   if (attr_err != cudaSuccess) return check_cuda(attr_err, "cudaFuncSetAttribute(gemm)");
   // shared-memory plan: [operand ring][epilogue input tile(s)][per-warp output slabs][barriers]
-  constexpr int stage_bytes = BM * BK * 2 + BN * BK * 2;
-  const int bar_bytes = (2 * kMaxStages + 8) * 8 + 16;
+  const int b_res_bytes = p.b_resident ? p.k_iters * BN * BK * 2 : 0;
+  const int stage_bytes = p.b_resident ? BM * BK * 2 : BM * BK * 2 + BN * BK * 2;
+  const int bar_bytes = (2 * kMaxStages + 9) * 8 + 16;
   const bool slabs = !(p.epilogue == BF_EPI_DGELU || p.epilogue == BF_EPI_ACC32 || p.epilogue == BF_EPI_D2S);
   const int slab_bytes = slabs ? kEpiWarps * kSlabBytes
                                : (p.colsum_out != nullptr ? ((p.num_n_blocks * BN * 4 + 1023) / 1024) * 1024 : 0);
   p.in_bytes = p.in_kind == 0 ? 0 : BM * BN * (p.in_kind == 2 ? 4 : 2);
-  const int avail = kSmemBudget - 1024 - bar_bytes - slab_bytes;
+  int nvec = 0;
+  if (p.bias) nvec = 1;
+  if (p.col_scale) nvec = 3;
+  if (p.col_gamma) nvec = 4;
+  p.vec_cols = p.b_resident ? BN : (p.N + 31) / 32 * 32;
+  const int vec_bytes = (nvec * p.vec_cols * 4 + 127) / 128 * 128;
+  const int avail = kSmemBudget - 1024 - bar_bytes - slab_bytes - b_res_bytes - vec_bytes;
   const int want_stages = p.k_iters < 4 ? (p.k_iters < 2 ? 2 : p.k_iters) : 4;
   p.in_bufs = (p.in_kind != 0 && avail - 2 * p.in_bytes >= (want_stages < 3 ? want_stages : 3) * stage_bytes) ? 2 : 1;
   int stages = (avail - p.in_bufs * p.in_bytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  {
+    static int cap = -1;                       // BF_GEMM_STAGES=n caps the operand ring (measurements)
+    if (cap < 0) { const char* e = getenv("BF_GEMM_STAGES"); cap = e ? atoi(e) : 0; }
+    if (cap >= 2 && stages > cap) stages = cap;
+  }
   BF_REQUIRE(stages >= 2, "bf_gemm: shared-memory plan leaves %d stages (BN=%d epilogue=%d)", stages, BN, p.epilogue);
   p.stages = stages;
-  p.in_off = stages * stage_bytes;
+  p.a_off = b_res_bytes;
+  p.in_off = b_res_bytes + stages * stage_bytes;
   p.slab_off = p.in_off + p.in_bufs * p.in_bytes;
-  p.bar_off = p.slab_off + slab_bytes;
+  p.vec_off = p.slab_off + slab_bytes;
+  p.bar_off = p.vec_off + vec_bytes;
   const int total = p.bar_off + bar_bytes + 1024;
   const int tiles = p.num_m_blocks * p.num_n_blocks * p.split_k;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  if (p.b_resident) grid = (num_sms() / p.num_n_blocks) * p.num_n_blocks;   // a CTA keeps one n block for all its tiles
   const cudaError_t le = launch_k(kern, dim3(grid), dim3(kThreads), (size_t)total, st, mp.a, mp.b, mp.in, mp.o16, mp.o16b,
                                  mp.o32, p);
   count_launch();
   return check_cuda(le != cudaSuccess ? le : cudaGetLastError(), "gemm_tcgen05_kernel launch");
 }
 
+// B-resident schedule (see the producer warp) for short contractions (K <= 384) with many row blocks: it cuts the L2
+// operand traffic of a 128 x 192 x 384 tile from 240 KB to 96 KB.  Measured on B200 (config-2 shapes) it does NOT pay:
+// QKV 57 vs 48 us, fc1 87 vs 74 us, dGELU 91 vs 94 us, out-projection 54 vs 52 us -- these GEMMs are bound by the
+// epilogue's hold on the TMEM stage, not by operand loads, and the schedule needs 128-column tiles.  Opt-in
+// (BF_GEMM_RESIDENT=1) for measurements.
+static bool resident_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("BF_GEMM_RESIDENT");
+    on = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return on != 0;
+}
+static int resident_bn(const bf_gemm_args& a) {
+  if (!resident_enabled() || a.bn != 0) return 0;
+  if (a.a_mode != BF_A_ROWMAJOR || a.split_k != 1 || a.K > 6 * BK) return 0;
+  const int e = a.epilogue;
+  if (!(e == BF_EPI_STORE16 || e == BF_EPI_GELU || e == BF_EPI_DGELU || e == BF_EPI_RESID || e == BF_EPI_QKV_LN)) return 0;
+  const int bn = e == BF_EPI_RESID ? 64 : 128;
+  if (a.N % bn != 0) return 0;
+  const int nnb = a.N / bn, mb = (a.M + BM - 1) / BM;
+  if (nnb > num_sms() || mb < 4 * (num_sms() / nnb)) return 0;               // at least 4 tiles per CTA
+  return bn;
+}
+
 static int pick_bn(const bf_gemm_args& a) {
-  if (a.epilogue == BF_EPI_QKV_LN) return 192;                                // one tile = one head (q | k | v)
+  if (const int rb = resident_bn(a)) return rb;
+  if (a.epilogue == BF_EPI_QKV_LN) return a.bn == 128 ? 128 : 192;            // one head per tile (or two 64-column groups)
   if (a.bn == 64 || a.bn == 128 || a.bn == 192 || a.bn == 256) return a.bn;   // caller override (tuning)
   const int N = a.N;
   if (N <= 64) return 64;
@@ -778,7 +923,7 @@ extern "C" int bf_gemm(const bf_gemm_args* a, void* stream) {
       BF_REQUIRE(a->ln_head_dim == 64 && a->N % 192 == 0,
                  "bf_gemm: QKV_LN is specialised for head_dim 64 (N a multiple of 192), got head_dim=%d N=%d",
                  a->ln_head_dim, a->N);
-      BF_REQUIRE(a->bn == 0 || a->bn == 192, "bf_gemm: QKV_LN needs the 192-column tile");
+      BF_REQUIRE(a->bn == 0 || a->bn == 128 || a->bn == 192, "bf_gemm: QKV_LN needs the 192- or 128-column tile");
       break;
     case BF_EPI_STORE32: case BF_EPI_ATOMIC32: BF_REQUIRE(a->out32, "bf_gemm: out32 required"); break;
     case BF_EPI_RESID:
@@ -802,6 +947,8 @@ extern "C" int bf_gemm(const bf_gemm_args* a, void* stream) {
   if (a->out32 || a->in32) BF_REQUIRE(a->ld32 >= a->N, "bf_gemm: ld32 < N");
 
   const int bn = pick_bn(*a);
+  p.b_resident = resident_bn(*a) == bn ? 1 : 0;
+  p.ln_heads = a->epilogue == BF_EPI_QKV_LN ? a->N / 192 : 0;
   BF_REQUIRE(!b_mn || bn % 64 == 0, "bf_gemm: internal bn");
   p.num_m_blocks = (a->M + BM - 1) / BM;
   p.num_n_blocks = (a->N + bn - 1) / bn;

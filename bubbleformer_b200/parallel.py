@@ -129,7 +129,9 @@ class GraphedTrainStep:
     waits on the host for ~4 ms of a 33 ms step; replaying the captured step removes that.  Inputs live in static
     buffers (`x`, `tgt`, `cond`: the tensors passed at construction are adopted as those buffers); gradients land in
     the GradSink's flat buffer, so an optimizer step can follow each replay.  Stochastic-depth masks are redrawn on
-    every replay (torch's graph-safe Philox offsets).
+    every replay (torch's graph-safe Philox offsets).  Construct it before any eager backward of the same model (or
+    after every reference to earlier losses is gone): AccumulateGrad nodes kept alive from an eager step on the
+    default stream would pull the capture onto that stream and invalidate it.
     """
 
     def __init__(self, model: torch.nn.Module, loss_fn, sink: GradSink, x: torch.Tensor, tgt: torch.Tensor,

@@ -14,6 +14,7 @@ sys.path.insert(0, ROOT)
 VARIANTS = [
     "nk_small", "nk_ragged", "nk_bn64", "nk_bn128", "nk_bn192", "nk_bn256", "nk_big",
     "nk_f16", "gelu", "resid", "resid_stats", "qkv_ln", "dgelu", "acc32", "store32",
+    "gelu_big", "resid_big", "resid_stats_big", "dgelu_big", "kn_dgrad_res",        # config-2 shapes: the B-resident schedule
     "kn_dgrad", "kn_dgrad_256", "wgrad", "wgrad_split", "wgrad_192",
     "s2d_w128", "s2d_w32", "s2d_c48", "d2s", "d2s_c48", "perf",
 ]
@@ -53,11 +54,16 @@ def run_variant(v):
         return (torch.randn(*s, device=dev) * scale).to(dt)
 
     ok = True
+    big = v in ("gelu_big", "resid_big", "resid_stats_big", "dgelu_big")
+    if big:
+        v = v[:-4]
     if v.startswith("nk_") or v in ("gelu", "resid", "dgelu", "acc32", "store32"):
         shapes = {"nk_small": (128, 128, 64), "nk_ragged": (300, 200, 104), "nk_bn64": (256, 64, 128),
                   "nk_bn128": (4096, 384, 384), "nk_bn192": (4096, 1152, 384), "nk_bn256": (4096, 1536, 384),
                   "nk_big": (40960, 1152, 384), "nk_f16": (1024, 96, 384)}
         M, N, K = shapes.get(v, (1000, 384, 256))
+        if big:
+            M, N, K = (40960, 384, 384) if v == "resid" else (40960, 1536, 384)
         bn = {"nk_bn64": 64, "nk_bn128": 128, "nk_bn192": 192, "nk_bn256": 256}.get(v, 0)
         A, B = rnd(M, K), rnd(N, K, scale=K ** -0.5)
         bias = torch.randn(N, device=dev)
@@ -79,7 +85,7 @@ def run_variant(v):
         elif v == "resid":
             xin = torch.randn(M, N, device=dev)
             cs, ch, cg = torch.randn(N, device=dev), torch.randn(N, device=dev), torch.randn(N, device=dev)
-            rpg = 100
+            rpg = 1024 if big else 100
             rs = torch.rand((M + rpg - 1) // rpg, device=dev)
             out32 = torch.zeros(M, N, device=dev)
             out16 = torch.zeros(M, N, device=dev, dtype=dt)
@@ -95,7 +101,11 @@ def run_variant(v):
             pre = rnd(M, N)
             out = torch.zeros(M, N, device=dev, dtype=dt)
             cs = torch.zeros(N, device=dev)
-            ops.gemm(A, B, M, N, K, epilogue=L.EPI_DGELU, aux16=pre, out16=out, colsum_out=cs)
+            if big:      # as the engine calls it: B stored (K, N)
+                ops.gemm(A, B.t().contiguous(), M, N, K, epilogue=L.EPI_DGELU, b_mode=L.B_KN, aux16=pre, out16=out,
+                         colsum_out=cs)
+            else:
+                ops.gemm(A, B, M, N, K, epilogue=L.EPI_DGELU, aux16=pre, out16=out, colsum_out=cs)
             ok &= report(v + ".colsum", cs[None], out.float().sum(0)[None], 2e-3)
             p32 = pre.float().requires_grad_(True)
             torch.nn.functional.gelu(p32).sum().backward()
@@ -106,7 +116,7 @@ def run_variant(v):
             ops.gemm(A, B, M, N, K, epilogue=L.EPI_ACC32, in32=g, out32=out)
             ok &= report(v, out, g + A.float() @ B.float().t(), 1e-5)
     elif v == "qkv_ln":
-        for (M, heads) in [(1000, 2), (4096, 6)]:
+        for (M, heads, bn) in [(1000, 2, 0), (4096, 6, 0), (900, 3, 0), (40960, 6, 0), (900, 3, 128), (4096, 6, 128)]:
             N, K, d = heads * 192, 384, 64
             A, B = rnd(M, K), rnd(N, K, scale=K ** -0.5)
             bias = torch.randn(N, device=dev)
@@ -117,11 +127,11 @@ def run_variant(v):
             want[:, :, :2] = (qk - mu) * torch.rsqrt(var + 1e-5)
             out = torch.zeros(M, N, device=dev, dtype=dt)
             rstd = torch.zeros(M, heads, 2, device=dev)
-            ops.gemm(A, B, M, N, K, epilogue=L.EPI_QKV_LN, bias=bias, out16=out, ln_head_dim=d, ln_rstd=rstd)
-            ok &= report(f"{v} xhat|v M={M}", out, want.reshape(M, N), 1e-2)
+            ops.gemm(A, B, M, N, K, epilogue=L.EPI_QKV_LN, bias=bias, out16=out, ln_head_dim=d, ln_rstd=rstd, bn=bn)
+            ok &= report(f"{v} xhat|v M={M} bn={bn}", out, want.reshape(M, N), 1e-2)
             ok &= report(f"{v} rstd M={M}", rstd.reshape(M, -1), torch.rsqrt(var + 1e-5).reshape(M, -1), 1e-3)
     elif v == "resid_stats":
-        M, N, K, rpg = 1024, 384, 384, 256
+        M, N, K, rpg = (40960, 384, 384, 1024) if big else (1024, 384, 384, 256)
         A, B = rnd(M, K), rnd(N, K, scale=K ** -0.5)
         bias = torch.randn(N, device=dev)
         xin = torch.randn(M, N, device=dev)
@@ -136,7 +146,7 @@ def run_variant(v):
         wi = want.reshape(M // rpg, rpg, N)
         ok &= report(v + ".stats", st, torch.stack([wi.sum(1), (wi * wi).sum(1)], dim=-1), 1e-4)
     elif v.startswith("kn_dgrad"):
-        M, N, K = (4096, 384, 1536) if v == "kn_dgrad" else (2048, 1536, 384)
+        M, N, K = {"kn_dgrad": (4096, 384, 1536), "kn_dgrad_res": (40960, 384, 384)}.get(v, (2048, 1536, 384))
         A, Bkn = rnd(M, K), rnd(K, N, scale=K ** -0.5)          # B stored (K, N)
         out = torch.zeros(M, N, device=dev, dtype=dt)
         ops.gemm(A, Bkn, M, N, K, epilogue=L.EPI_STORE16, b_mode=L.B_KN, out16=out)

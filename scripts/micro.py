@@ -77,6 +77,10 @@ def main():
                                         in32=X32, out32=o32, out16b=O2), 2.0 * N * E * E, N * E * (2 + 4 + 4 + 2)),
         "gemm_resid64": (lambda: ops.gemm(Xb, Wo, N, E, E, epilogue=L.EPI_RESID, bias=vE, col_gamma=vE, row_scale=rs, rows_per_group=P,
                                           in32=X32, out32=o32, out16=O, out16b=O2, bn=64), 2.0 * N * E * E, N * E * (2 + 4 + 4 + 2 + 2)),
+        "gemm_resid_stats64": (lambda: ops.gemm(Xb, Wo, N, E, E, epilogue=L.EPI_RESID, bias=vE, col_gamma=vE, row_scale=rs, rows_per_group=P,
+                                        in32=X32, out32=o32, out16b=O2, stats_out=st, bn=64), 2.0 * N * E * E, N * E * (2 + 4 + 4 + 2)),
+        "gemm_qkv_ln128": (lambda: ops.gemm(Xb, Win, N, 3 * E, E, epilogue=L.EPI_QKV_LN, bias=v3E, out16=out3, ln_head_dim=64, ln_rstd=rstd, bn=128),
+                           2.0 * N * 3 * E * E, (N * E + N * 3 * E) * 2),
         "gemm_resid_noz": (lambda: ops.gemm(Xb, Wo, N, E, E, epilogue=L.EPI_RESID, bias=vE, col_gamma=vE, row_scale=rs, rows_per_group=P,
                                           in32=X32, out32=o32), 2.0 * N * E * E, N * E * (2 + 4 + 4)),
         "gemm_wgrad_qkv": (lambda: ops.gemm(QKV, Xb, 3 * E, E, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
