@@ -352,7 +352,24 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear-down: the captured graph holds NCCL kernels; release it before the process group goes away, and never
+        # let a stuck communicator destructor keep the job alive after the result line is out.
+        import threading
+        if gtrain is not None:
+            gtrain.graph.reset()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        done = threading.Event()
+
+        def _destroy():
+            try:
+                dist.destroy_process_group()
+            finally:
+                done.set()
+        threading.Thread(target=_destroy, daemon=True).start()
+        if not done.wait(20.0):
+            os._exit(0)
 
 
 if __name__ == "__main__":

@@ -124,7 +124,18 @@ class AttnArgs(C.Structure):
     ]
 
 
-EXPORTS = ["bf_last_error", "bf_version", "bf_launch_count", "bf_gemm", "bf_inorm_stats", "bf_inorm_apply",
+class BranchGradArgs(C.Structure):
+    _fields_ = [
+        ("S01", C.c_void_p), ("I", C.c_int32), ("E", C.c_int32),
+        ("gamma", C.c_void_p),
+        ("c", C.c_void_p), ("c1", C.c_void_p), ("c0", C.c_void_p), ("low", C.c_void_p), ("high", C.c_void_p),
+        ("W", C.c_void_p), ("norm2_bias", C.c_void_p),
+        ("d_gamma", C.c_void_p), ("d_out_bias", C.c_void_p), ("d_low", C.c_void_p), ("d_high", C.c_void_p),
+        ("d_W", C.c_void_p), ("d_norm2_bias", C.c_void_p),
+    ]
+
+
+EXPORTS = ["bf_feat_consts", "bf_branch_param_grads", "bf_last_error", "bf_version", "bf_launch_count", "bf_gemm", "bf_inorm_stats", "bf_inorm_apply",
            "bf_inorm_bwd", "bf_inorm_bwd_params", "bf_resid_bwd", "bf_colsum16", "bf_attention_fwd",
            "bf_attention_bwd", "bf_lploss_sums", "bf_lploss_bwd", "bf_patch_in", "bf_patch_out", "bf_patch_wgrad", "bf_s2d_gather", "bf_cast16", "bf_convert16"]
 
@@ -135,6 +146,8 @@ lib.bf_inorm_apply.argtypes = [C.POINTER(InormApplyArgs), _vp]
 lib.bf_inorm_bwd.argtypes = [C.POINTER(InormBwdArgs), _vp]
 lib.bf_inorm_bwd_params.argtypes = [C.POINTER(InormBwdParamsArgs), _vp]
 lib.bf_resid_bwd.argtypes = [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]
+lib.bf_feat_consts.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]
+lib.bf_branch_param_grads.argtypes = [C.POINTER(BranchGradArgs), _vp]
 lib.bf_colsum16.argtypes = [_vp, _i, _i64, _i, _i64, _vp, _vp]
 lib.bf_attention_fwd.argtypes = [C.POINTER(AttnArgs), _vp]
 lib.bf_attention_bwd.argtypes = [C.POINTER(AttnArgs), _vp]

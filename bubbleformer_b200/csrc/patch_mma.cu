@@ -63,23 +63,33 @@ patch_in_mma_kernel(const float* __restrict__ x, const float* __restrict__ Wkn, 
     float ssum[kPinNT][2], ssq[kPinNT][2];
 #pragma unroll
     for (int nt = 0; nt < kPinNT; ++nt) { ssum[nt][0] = ssum[nt][1] = ssq[nt][0] = ssq[nt][1] = 0.f; }
+    // A fragments: a0 (row g, k = t), a1 (row g+8, k = t), a2 (row g, k = t+4), a3 (row g+8, k = t+4); k = f*4 + ky*2 + kx.
+    // The gather of the next tile is issued before the current tile is multiplied and stored (its latency hides there).
+    auto gather = [&](int tile, float (&r)[KS][4]) {
+      const int yo = tile / tiles_x, xo0 = (tile - yo * tiles_x) * 16;
+      const bool ok0 = xo0 + g < Wo, ok1 = xo0 + g + 8 < Wo;
+#pragma unroll
+      for (int s = 0; s < KS; ++s) {
+        const int f0 = 2 * s, f1 = 2 * s + 1;
+        const float* p0 = ximg + ((long)f0 * H + 2 * yo + ky) * W + 2 * (xo0 + g) + kx;
+        const float* p1 = ximg + ((long)f1 * H + 2 * yo + ky) * W + 2 * (xo0 + g) + kx;
+        r[s][0] = (f0 < F && ok0) ? __ldg(p0) : 0.f;
+        r[s][1] = (f0 < F && ok1) ? __ldg(p0 + 16) : 0.f;
+        r[s][2] = (f1 < F && ok0) ? __ldg(p1) : 0.f;
+        r[s][3] = (f1 < F && ok1) ? __ldg(p1 + 16) : 0.f;
+      }
+    };
+    float raw[KS][4];
+    if (tile0 + warp < tile1) gather(tile0 + warp, raw);
     for (int tile = tile0 + warp; tile < tile1; tile += kPinWarps) {
       const int yo = tile / tiles_x, xo0 = (tile - yo * tiles_x) * 16;
       const bool ok0 = xo0 + g < Wo, ok1 = xo0 + g + 8 < Wo;
-      // A fragments: a0 (row g, k = t), a1 (row g+8, k = t), a2 (row g, k = t+4), a3 (row g+8, k = t+4); k = f*4 + ky*2 + kx
       uint32_t a[KS][4];
 #pragma unroll
-      for (int s = 0; s < KS; ++s) {
-        {
-          const int f0 = 2 * s, f1 = 2 * s + 1;
-          const float* p0 = ximg + ((long)f0 * H + 2 * yo + ky) * W + 2 * (xo0 + g) + kx;
-          const float* p1 = ximg + ((long)f1 * H + 2 * yo + ky) * W + 2 * (xo0 + g) + kx;
-          a[s][0] = (f0 < F && ok0) ? to_tf32(__ldg(p0)) : 0u;
-          a[s][1] = (f0 < F && ok1) ? to_tf32(__ldg(p0 + 16)) : 0u;
-          a[s][2] = (f1 < F && ok0) ? to_tf32(__ldg(p1)) : 0u;
-          a[s][3] = (f1 < F && ok1) ? to_tf32(__ldg(p1 + 16)) : 0u;
-        }
-      }
+      for (int s = 0; s < KS; ++s)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[s][q] = to_tf32(raw[s][q]);
+      if (tile + kPinWarps < tile1) gather(tile + kPinWarps, raw);
       float c[kPinNT][4];
 #pragma unroll
       for (int nt = 0; nt < kPinNT; ++nt) { c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f; }

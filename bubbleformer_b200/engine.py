@@ -217,8 +217,8 @@ def _attn_branch_fwd(X, g: Geom, p: Dict[str, torch.Tensor], w16, heads: int, ax
 def _attn_branch_bwd(dXout, g: Geom, p, w16, heads: int, axes, scale_keys, mask_img, coef, sv, grads):
     """Backward of X_out = X + mask*gamma*(Z*c1 + c0) through out-proj, IN, attention(s), QKV, IN.
 
-    `coef` = gamma*c1 (the factor between dX_out and dZ).  Returns (dX, S0, S1) with
-    S0[c] = sum mask*dX_out, S1[c] = sum mask*dX_out*Z for the caller's gamma / feature-scale gradients.
+    `coef` = gamma*c1 (the factor between dX_out and dZ).  Returns (dX, S01) with the per-image sums
+    S01[0][img, c] = sum mask*dX_out, S01[1][img, c] = sum mask*dX_out*Z for the caller's gamma / feature-scale gradients.
     Accumulates the gradients of norm1/2, input_head, output_head.weight, qnorm/knorm, bias table, scales.
     """
     I, P, N = g.I, g.P, g.N
@@ -227,7 +227,6 @@ def _attn_branch_bwd(dXout, g: Geom, p, w16, heads: int, axes, scale_keys, mask_
     S01 = _zeros((2, I, E), dXout)                    # per-image partial sums (few atomics per address)
     dZ = _empty((N, E), BF16, dXout)
     ops.resid_bwd(dXout, Z, dZ, I, P, mask_img, coef, S01[0], S01[1])
-    S0, S1 = S01.sum(dim=1)
     # output_head: dgrad reads W (E_out, E_in) as the (K, N) operand, wgrad contracts over tokens
     dOn = _empty((N, E), BF16, dXout)
     ops.gemm(dZ, w16("output_head.weight"), N, E, E, epilogue=L.EPI_STORE16, b_mode=L.B_KN, out16=dOn)
@@ -270,7 +269,7 @@ def _attn_branch_bwd(dXout, g: Geom, p, w16, heads: int, axes, scale_keys, mask_
     dX = _empty((N, E), F32, dXout)
     ops.inorm_bwd(2, dXn, X, I, P, st1, p["norm1.weight"], p["norm1.bias"], red1, out=dX, add32=dXout,
                   dweight=grads["norm1.weight"], dbias=grads["norm1.bias"])
-    return dX, S0, S1
+    return dX, S01
 
 
 # ---------------------------------------------------------------------------------------------
@@ -285,9 +284,9 @@ def temporal_forward(X, g: Geom, p, w16, heads: int, attn_scale: bool, mask_img,
 
 def temporal_backward(dXout, g: Geom, p, w16, heads: int, attn_scale: bool, mask_img, sv, grads):
     keys = ["attn_scale_factor"] if attn_scale else None
-    dX, S0, S1 = _attn_branch_bwd(dXout, g, p, w16, heads, ["t"], keys, mask_img, p["gamma"], sv, grads)
-    grads["gamma"] += S1                        # d/dgamma of mask*gamma*Z
-    grads["output_head.bias"] += p["gamma"] * S0
+    dX, S01 = _attn_branch_bwd(dXout, g, p, w16, heads, ["t"], keys, mask_img, p["gamma"], sv, grads)
+    # d_gamma += S1 (d/dgamma of mask*gamma*Z), d_output_head.bias += gamma*S0
+    ops.branch_param_grads(S01, p["gamma"], grads["gamma"], grads["output_head.bias"])
     return dX
 
 
@@ -302,11 +301,8 @@ def _feat_consts(p, feat_scale: bool):
     """
     if not feat_scale:
         return None, None, None
-    Wm = p["output_head.weight"].reshape(p["output_head.weight"].shape[0], -1)
-    c = (Wm * p["norm2.bias"][None, :]).sum(dim=1) + p["output_head.bias"]
-    c1 = (1.0 + p["high_freq_scalar"]).contiguous()
-    c0 = (c * (p["low_freq_scalar"] - p["high_freq_scalar"])).contiguous()
-    return c, c1, c0
+    return ops.feat_consts(p["output_head.weight"], p["norm2.bias"], p["output_head.bias"], p["low_freq_scalar"],
+                           p["high_freq_scalar"])
 
 
 def spatial_forward(X, g: Geom, p, w16, heads: int, attn_scale: bool, feat_scale: bool, mask_att, mask_mlp, save: bool):
@@ -361,20 +357,15 @@ def spatial_backward(dXout, g: Geom, p, w16, heads: int, attn_scale: bool, feat_
     c, c1, c0 = sv["feat"] if "feat" in sv else _feat_consts(p, feat_scale)
     ga = p["gamma_att"]
     coef = (ga * c1).contiguous() if feat_scale else ga
-    dX, S0, S1 = _attn_branch_bwd(dXmid, g, p, w16, heads, ["x", "y"], keys, mask_att, coef, sv, grads)
+    dX, S01 = _attn_branch_bwd(dXmid, g, p, w16, heads, ["x", "y"], keys, mask_att, coef, sv, grads)
+    feat = None
     if feat_scale:
-        lo, hi = p["low_freq_scalar"], p["high_freq_scalar"]
-        grads["gamma_att"] += c1 * S1 + c0 * S0
-        grads["high_freq_scalar"] += ga * (S1 - c * S0)
-        grads["low_freq_scalar"] += ga * c * S0
-        dc = ga * (lo - hi) * S0                     # gradient reaching c = W b_norm2 + b_out
-        Wm = p["output_head.weight"].reshape(E, E)
-        grads["output_head.weight"].view(E, E).add_(dc[:, None] * p["norm2.bias"][None, :])
-        grads["norm2.bias"] += (Wm * dc[:, None]).sum(dim=0)
-        grads["output_head.bias"] += coef * S0 + dc
-    else:
-        grads["gamma_att"] += S1
-        grads["output_head.bias"] += ga * S0
+        # gamma_att, low / high_freq_scalar, output_head.bias and -- through c = W b_norm2 + b_out -- output_head.weight
+        # and norm2.bias (formulas in include/bubbleformer_b200.h, bf_branch_param_grads)
+        feat = dict(c=c, c1=c1, c0=c0, low=p["low_freq_scalar"], high=p["high_freq_scalar"], W=p["output_head.weight"],
+                    norm2_bias=p["norm2.bias"], d_low=grads["low_freq_scalar"], d_high=grads["high_freq_scalar"],
+                    d_W=grads["output_head.weight"], d_norm2_bias=grads["norm2.bias"])
+    ops.branch_param_grads(S01, ga, grads["gamma_att"], grads["output_head.bias"], feat)
     return dX
 
 

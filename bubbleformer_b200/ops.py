@@ -195,6 +195,30 @@ def resid_bwd(dx, z16, dz16, I, P, row_scale, coef, S0, S1) -> None:
                                _f32(S1, I * Cn, "S1"), _stream()), "bf_resid_bwd")
 
 
+def feat_consts(W, norm2_bias, out_bias, low, high):
+    """(c, c1, c0) of the axial block's feature scaling; W: output_head.weight viewed (E, E) fp32."""
+    E = W.shape[0]
+    out = torch.empty(3, E, dtype=torch.float32, device=W.device)
+    L.check(L.lib.bf_feat_consts(_f32(W, E * E, "W"), _f32(norm2_bias, E, "norm2_bias"), _f32(out_bias, E, "out_bias"),
+                                 _f32(low, E, "low"), _f32(high, E, "high"), E, _ptr(out[0]), _ptr(out[1]), _ptr(out[2]),
+                                 _stream()), "bf_feat_consts")
+    return out[0], out[1], out[2]
+
+
+def branch_param_grads(S01, gamma, d_gamma, d_out_bias, feat=None) -> None:
+    """Parameter gradients of one residual branch from the per-image sums S01 (2, I, E) of resid_bwd.
+    feat = dict(c, c1, c0, low, high, W, norm2_bias, d_low, d_high, d_W, d_norm2_bias) with feature scaling."""
+    _, I, E = S01.shape
+    a = L.BranchGradArgs()
+    a.S01, a.I, a.E = _f32(S01, 2 * I * E, "S01"), I, E
+    a.gamma, a.d_gamma, a.d_out_bias = _f32(gamma, E, "gamma"), _f32(d_gamma, E, "d_gamma"), _f32(d_out_bias, E, "d_out_bias")
+    if feat is not None:
+        for k in ("c", "c1", "c0", "low", "high", "norm2_bias", "d_low", "d_high", "d_norm2_bias"):
+            setattr(a, k, _f32(feat[k], E, k))
+        a.W, a.d_W = _f32(feat["W"], E * E, "W"), _f32(feat["d_W"], E * E, "d_W")
+    L.check(L.lib.bf_branch_param_grads(C.byref(a), _stream()), "bf_branch_param_grads")
+
+
 def colsum16(x, out) -> None:
     _mat(x, "x")
     L.check(L.lib.bf_colsum16(_ptr(x), _DT[x.dtype], x.shape[0], x.shape[1], x.stride(0),
@@ -350,6 +374,7 @@ def _attn_tag(a, k):
 
 gemm = _instrument("gemm", gemm, _gemm_tag)
 attention = _instrument("attention", attention, _attn_tag)
-for _n in ("inorm_stats", "inorm_apply", "inorm_bwd", "inorm_bwd_params", "resid_bwd", "colsum16", "patch_in",
+for _n in ("inorm_stats", "inorm_apply", "inorm_bwd", "inorm_bwd_params", "resid_bwd", "colsum16", "feat_consts",
+           "branch_param_grads", "patch_in",
            "patch_out", "patch_wgrad", "s2d_gather", "cast16", "convert16", "lploss_sums", "lploss_bwd"):
     globals()[_n] = _instrument(_n, globals()[_n], _shape_tag)

@@ -188,6 +188,27 @@ BF_API int bf_resid_bwd(const float* dx, int64_t lddx, const void* z16, void* dz
                         int I, int P, int C, const float* row_scale, const float* coef, float* S0, float* S1,
                         void* stream);
 
+/* Feature-scaling constants of the axial block (upstream layers/attention.py:302-307).  The per-image mean of
+ * z = IN(o) W^T + b is exactly c = W b_norm2 + b_out, so  z + mean(z)*low + (z - mean(z))*high == z*c1 + c0  with
+ * c1 = 1 + high, c0 = c*(low - high).  W: output_head.weight (E, E) fp32; all outputs [E].                     */
+BF_API int bf_feat_consts(const float* W, const float* norm2_bias, const float* out_bias, const float* low,
+                          const float* high, int E, float* c, float* c1, float* c0, void* stream);
+
+/* Parameter gradients of one residual branch  X_out = X + mask*gamma*(Z*c1 + c0)  from the per-image sums of
+ * bf_resid_bwd (S01 = (2, I, E): S0 = sum mask*dX_out, S1 = sum mask*dX_out*Z), accumulated in place:
+ *   without feature scaling (c == NULL):  d_gamma += S1;  d_out_bias += gamma*S0
+ *   with:  d_gamma += c1*S1 + c0*S0;  d_high += gamma*(S1 - c*S0);  d_low += gamma*c*S0;  dc = gamma*(low-high)*S0;
+ *          d_out_bias += gamma*c1*S0 + dc;  d_W[j,:] += dc[j]*norm2_bias;  d_norm2_bias += W^T dc
+ * (layers/attention.py:123 and :302-309 reversed).                                                            */
+typedef struct {
+  const float* S01;  int32_t I, E;
+  const float* gamma;
+  const float* c;  const float* c1;  const float* c0;  const float* low;  const float* high;
+  const float* W;  const float* norm2_bias;
+  float* d_gamma;  float* d_out_bias;  float* d_low;  float* d_high;  float* d_W;  float* d_norm2_bias;
+} bf_branch_grad_args;
+BF_API int bf_branch_param_grads(const bf_branch_grad_args* args, void* stream);
+
 /* out[c] += sum_rows x[r, c] for a 16-bit matrix (bias gradients of the 1x1 convs / linears) */
 BF_API int bf_colsum16(const void* x, int dtype, int64_t rows, int C, int64_t ldx, float* out, void* stream);
 

@@ -11,7 +11,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-GROUPS = ["stats", "apply", "inorm_bwd", "resid_colsum", "attn_x", "attn_y", "attn_t", "attn_d48", "attn_l64",
+GROUPS = ["params", "stats", "apply", "inorm_bwd", "resid_colsum", "attn_x", "attn_y", "attn_t", "attn_d48", "attn_l64",
           "attn_noscale", "patch", "misc"]
 
 
@@ -293,6 +293,29 @@ def run(group):
             refw = a.float().reshape(-1, N).t() @ xs
             # fp16 activations are rounded to bf16 inside the tensor-core kernel (the gradient operand needs the range)
             ok &= report(f"patch_wgrad", dW.reshape(N, 4 * Fd), refw, 1e-4 if dt == torch.bfloat16 else 3e-3)
+    elif group == "params":
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import cpu_emulation as emu
+        for (I, E, fs) in [(40, 384, True), (6, 128, True), (10, 96, False)]:
+            S01 = torch.randn(2, I, E, device=dev)
+            ga, lo, hi, nb, bo = (torch.randn(E, device=dev) for _ in range(5))
+            W = torch.randn(E, E, 1, 1, device=dev) / E ** 0.5
+            if fs:
+                c, c1, c0 = ops.feat_consts(W, nb, bo, lo, hi)
+                rc, rc1, rc0 = emu.feat_consts(W, nb, bo, lo, hi)
+                for nm, a_, b_ in (("c", c, rc), ("c1", c1, rc1), ("c0", c0, rc0)):
+                    ok &= report(f"feat_consts {nm} E={E}", a_, b_, 1e-5)
+            names = ["d_gamma", "d_out_bias", "d_low", "d_high", "d_W", "d_norm2_bias"]
+            got = {n: torch.randn(E * E if n == "d_W" else E, device=dev) for n in names}
+            ref = {n: v.clone() for n, v in got.items()}
+            for dst, fn in ((got, ops.branch_param_grads), (ref, emu.branch_param_grads)):
+                feat = None
+                if fs:
+                    feat = dict(c=rc, c1=rc1, c0=rc0, low=lo, high=hi, W=W, norm2_bias=nb, d_low=dst["d_low"],
+                                d_high=dst["d_high"], d_W=dst["d_W"], d_norm2_bias=dst["d_norm2_bias"])
+                fn(S01, ga, dst["d_gamma"], dst["d_out_bias"], feat)
+            for n in names:
+                ok &= report(f"branch_param_grads {n} I={I} E={E} fs={fs}", got[n], ref[n], 1e-5)
     elif group == "misc":
         for (I, H, W, Cn) in [(2, 8, 12, 24), (3, 64, 64, 96)]:
             img = torch.randn(I, H, W, Cn, device=dev).half()

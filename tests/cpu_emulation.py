@@ -180,6 +180,29 @@ def resid_bwd(dx, z16, dz16, I, P, row_scale, coef, S0, S1):
         S1.reshape(I, C).add_((rs * dx * z16.float()).reshape(I, P, C).sum(1))
 
 
+def feat_consts(W, norm2_bias, out_bias, low, high):
+    Wm = W.reshape(W.shape[0], -1)
+    c = (Wm * norm2_bias[None, :]).sum(dim=1) + out_bias
+    return c, 1.0 + high, c * (low - high)
+
+
+def branch_param_grads(S01, gamma, d_gamma, d_out_bias, feat=None):
+    S0, S1 = S01.sum(dim=1)
+    if feat is None:
+        d_gamma.add_(S1)
+        d_out_bias.add_(gamma * S0)
+        return
+    c, c1, c0, lo, hi = feat["c"], feat["c1"], feat["c0"], feat["low"], feat["high"]
+    E = S0.shape[0]
+    d_gamma.add_(c1 * S1 + c0 * S0)
+    feat["d_high"].add_(gamma * (S1 - c * S0))
+    feat["d_low"].add_(gamma * c * S0)
+    dc = gamma * (lo - hi) * S0
+    feat["d_W"].view(E, E).add_(dc[:, None] * feat["norm2_bias"][None, :])
+    feat["d_norm2_bias"].add_((feat["W"].reshape(E, E) * dc[:, None]).sum(dim=0))
+    d_out_bias.add_(gamma * c1 * S0 + dc)
+
+
 def colsum16(x, out):
     out.add_(x.float().sum(0))
 
@@ -303,7 +326,8 @@ def lploss_bwd(pred, tgt, coef, dpred):
     dpred.copy_(coef.reshape(*pred.shape[:-2], 1, 1) * (pred - tgt))
 
 
-ALL = ["gemm", "inorm_stats", "inorm_apply", "inorm_bwd", "inorm_bwd_params", "resid_bwd", "colsum16", "attention",
+ALL = ["gemm", "inorm_stats", "inorm_apply", "inorm_bwd", "inorm_bwd_params", "resid_bwd", "colsum16", "feat_consts",
+       "branch_param_grads", "attention",
        "patch_in", "patch_out", "patch_wgrad", "s2d_gather", "cast16", "convert16", "lploss_sums", "lploss_bwd"]
 
 

@@ -34,7 +34,7 @@ def test_gemm(variant):
     assert _native_loaded()
 
 
-@pytest.mark.parametrize("group", ["stats", "apply", "inorm_bwd", "resid_colsum", "attn_x", "attn_y", "attn_t",
+@pytest.mark.parametrize("group", ["params", "stats", "apply", "inorm_bwd", "resid_colsum", "attn_x", "attn_y", "attn_t",
                                    "attn_d48", "attn_l64", "attn_noscale", "patch", "misc"])
 def test_kernels(group):
     import gpu_diag_kernels
@@ -138,7 +138,7 @@ def test_graphed_train_step_matches_eager():
     try:
         # capture first: autograd AccumulateGrad nodes created by an earlier eager backward on the default stream would
         # pull the capture onto that stream and invalidate it (construct the step before training starts)
-        step = GraphedTrainStep(m, rel_l2_loss, sink, x, tgt, cond)
+        step = GraphedTrainStep(m, rel_l2_loss, sink, x.clone(), tgt.clone(), cond.clone())   # adopted as static buffers
         assert step.launches_per_step > 50
         l_graph = float(step(x, tgt, cond))
         g_graph = sink.flat.clone()
