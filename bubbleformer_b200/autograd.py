@@ -119,7 +119,14 @@ class WeightBank:
 
     def refresh(self) -> None:
         self.ensure()
+        # the fused optimiser step rewrites the mirror itself; any other in-place change of a parameter bumps the
+        # version counter the views share with the flat buffer
+        if getattr(self, "_mirror_version", None) == self.flat._version:
+            return
         ops.cast16(self.flat, self.flat16)
+
+    def mark_mirror_fresh(self) -> None:
+        self._mirror_version = self.flat._version
 
     def w16(self, p: torch.Tensor) -> torch.Tensor:
         o = (p.data_ptr() - self.flat.data_ptr()) // 4

@@ -209,6 +209,14 @@ typedef struct {
 } bf_branch_grad_args;
 BF_API int bf_branch_param_grads(const bf_branch_grad_args* args, void* stream);
 
+/* Optimiser step over flat fp32 buffers (parameters, gradients, moments; n a multiple of 4), optionally refreshing
+ * the bf16 operand mirror p16 in the same pass.  Upstream: bubbleformer/modules.py:132-142 (torch.optim.AdamW / Adam,
+ * lion_pytorch.Lion with config/optim_cfg/{adamw,adam,lion}.yaml).  `step` counts from 1 (Adam bias correction);
+ * v is unused (may be NULL) for BF_OPT_LION.                                                                    */
+enum { BF_OPT_LION = 0, BF_OPT_ADAMW = 1, BF_OPT_ADAM = 2 };
+BF_API int bf_optim_step(int kind, float* p, const float* g, float* m, float* v, void* p16, int64_t n, float lr,
+                         float beta1, float beta2, float eps, float weight_decay, int64_t step, void* stream);
+
 /* out[c] += sum_rows x[r, c] for a 16-bit matrix (bias gradients of the 1x1 convs / linears) */
 BF_API int bf_colsum16(const void* x, int dtype, int64_t rows, int C, int64_t ldx, float* out, void* stream);
 
