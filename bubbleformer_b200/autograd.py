@@ -119,14 +119,17 @@ class WeightBank:
 
     def refresh(self) -> None:
         self.ensure()
-        # the fused optimiser step rewrites the mirror itself; any other in-place change of a parameter bumps the
-        # version counter the views share with the flat buffer
-        if getattr(self, "_mirror_version", None) == self.flat._version:
+        # the fused optimiser step rewrites the mirror itself; any other in-place change of a parameter (copy_,
+        # torch.optim, load_state_dict) bumps that parameter's version counter
+        if getattr(self, "_mirror_version", None) == self._versions():
             return
         ops.cast16(self.flat, self.flat16)
 
+    def _versions(self) -> int:
+        return sum(p._version for p in self.params)
+
     def mark_mirror_fresh(self) -> None:
-        self._mirror_version = self.flat._version
+        self._mirror_version = self._versions()
 
     def w16(self, p: torch.Tensor) -> torch.Tensor:
         o = (p.data_ptr() - self.flat.data_ptr()) // 4

@@ -72,10 +72,14 @@ def test_flat_optimizer_matches_oracle(name):
         w = m.blocks[0].spatial.mlp.fc1.weight
         assert w.data_ptr() >= opt.bank.flat.data_ptr()
         assert float((opt.bank.flat16.float() - opt.bank.flat).abs().max()) <= 2 ** -8 * float(opt.bank.flat.abs().max())
-        v0 = opt.bank.flat._version
+        from bubbleformer_b200 import _lib
+        n0 = _lib.launch_count()
         opt.bank.refresh()                              # mirror is fresh: no cast launch
+        assert _lib.launch_count() == n0
         with torch.no_grad():
-            w.mul_(1.0)
-        assert opt.bank.flat._version != v0              # any other in-place change invalidates it
+            w.mul_(2.0)
+        opt.bank.refresh()                              # any other in-place change of a parameter invalidates it
+        assert _lib.launch_count() == n0 + 1
+        assert float((opt.bank.flat16.float() - opt.bank.flat).abs().max()) <= 2 ** -8 * float(opt.bank.flat.abs().max())
     finally:
         sink.close()
