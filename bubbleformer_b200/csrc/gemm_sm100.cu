@@ -29,11 +29,15 @@ namespace bf {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kEpiWarps = 8;
 constexpr int kFirstEpiWarp = 4;
-constexpr int kThreads = 32 * (kFirstEpiWarp + kEpiWarps);
 constexpr int kMaxStages = 8;
-constexpr int kSlabBytes = 8192;          // per epilogue warp: output staging (see epilogue)
+// Epilogue warps: the tile period of the short-K GEMMs is the time ONE warp needs for its share of a tile's epilogue
+// (a latency chain of tcgen05.ld, math, shared-memory staging and the TMA store), so wide tiles get one warp per
+// (TMEM lane quadrant, 64-column group): 12 warps for 192 columns, 16 for 256; 8 for tiles up to 128 columns.
+__host__ __device__ constexpr int epi_warps(int bn) { return bn <= 128 ? 8 : 4 * (bn / 64); }
+__host__ __device__ constexpr int gemm_threads(int bn) { return 32 * (kFirstEpiWarp + epi_warps(bn)); }
+// per-warp output staging: 8 KiB (double buffered) with 8 epilogue warps, 4 KiB (single) with more
+__host__ __device__ constexpr int slab_bytes_per_warp(int bn) { return bn <= 128 ? 8192 : 4096; }
 constexpr int kSmemBudget = 227 * 1024;
 
 struct GemmParams {
@@ -133,7 +137,7 @@ __device__ __forceinline__ void load_cols(const float* svec, float (&o)[32]) {
 // the kernel
 // ---------------------------------------------------------------------------------------------
 template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(gemm_threads(BN), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_o16,
                     const __grid_constant__ CUtensorMap map_o16b, const __grid_constant__ CUtensorMap map_o32,
@@ -143,7 +147,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   constexpr int kStageBytes = kABytes + kBBytes;
   constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
   constexpr int kChunks = BN / 32;                 // 32-column chunks per tile
-  constexpr int kChunksPerWarp = kChunks / 2;      // two warps share one TMEM lane quadrant
+  constexpr int kEpiWarps = epi_warps(BN);
+  constexpr int kThreads = gemm_threads(BN);
+  constexpr int kChunksPerWarp = kChunks / (kEpiWarps / 4);   // kEpiWarps / 4 warps share one TMEM lane quadrant
+  constexpr int kSlabBytes = slab_bytes_per_warp(BN);
+  constexpr bool kDouble = kSlabBytes >= 8192;     // room for two sets of staging buffers per warp
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -329,7 +337,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // ===================== epilogue warps =====================
     const int ew = warp - kFirstEpiWarp;
     const int quad = warp & 3;              // TMEM lane quadrant this warp may access
-    const int half = ew >> 2;               // which half of the tile's 32-column chunks
+    const int half = ew >> 2;               // which group of the tile's 32-column chunks (0 .. kEpiWarps/4 - 1)
     const int row = quad * 32 + lane;       // row inside the tile
     uint8_t* slab = smem + p.slab_off + ew * kSlabBytes;
     if (lane == 0) {
@@ -359,33 +367,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       if (p.epilogue == BF_EPI_RESID && p.row_scale != nullptr && m < p.M) rs = __ldg(p.row_scale + m / p.rows_per_group);
       if constexpr (BN == 192) {
         if (p.epilogue == BF_EPI_QKV_LN) {
-          // One tile = one head: columns [q 0:64 | k 64:128 | v 128:192].  Warp `half` 0 normalises q, 1 normalises k
-          // (LayerNorm over the 64 columns of a row is thread local: tcgen05.ld hands each thread its row), and each
-          // takes half of v.  Stored: xhat = (x - mean) * rstd without the affine part, plus rstd for the backward.
+          // One tile = one head: columns [q 0:64 | k 64:128 | v 128:192], one epilogue warp per (lane quadrant, part):
+          // `half` = 0 normalises q, 1 normalises k, 2 copies v.  LayerNorm over the 64 columns of a row is thread
+          // local (tcgen05.ld hands each thread its row).  Stored: xhat = (x - mean) * rstd without the affine part,
+          // plus rstd for the backward.
           const int mrow = m0 + quad * 32;
           const bool live = mrow < p.M;                       // warp uniform
-          if (lane == 0) tma_store_wait_read<0>();
+          const int ncol = n0 + 64 * half;
+          float x0[32], x1[32];
+          tmem_ld_32x32(t_row + static_cast<uint32_t>(64 * half), x0);
+          tmem_ld_32x32(t_row + static_cast<uint32_t>(64 * half + 32), x1);
+          tmem_ld_wait();
+          tc_fence_before();
           __syncwarp();
-          const int cq = half * 2;
-          {
-            float x0[32], x1[32];
-            tmem_ld_32x32(t_row + static_cast<uint32_t>(32 * cq), x0);
-            tmem_ld_32x32(t_row + static_cast<uint32_t>(32 * cq + 32), x1);
-            tmem_ld_wait();
-            if (live) {
-              if (p.bias != nullptr) {
-                float b[32];
-                load_cols(s_bias + n0 + 32 * cq, b);
+          if (lane == 0) mbar_arrive(tmem_empty + as);
+          if (live) {
+            if (p.bias != nullptr) {
+              float b[32];
+              load_cols(s_bias + ncol, b);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) x0[j] += b[j];
-                load_cols(s_bias + n0 + 32 * cq + 32, b);
+              for (int j = 0; j < 32; ++j) x0[j] += b[j];
+              load_cols(s_bias + ncol + 32, b);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) x1[j] += b[j];
-              }
-              float s = 0.f;
+              for (int j = 0; j < 32; ++j) x1[j] += b[j];
+            }
+            if (half < 2) {
+              float sm_ = 0.f;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) s += x0[j] + x1[j];
-              const float mean = s * (1.f / 64.f);
+              for (int j = 0; j < 32; ++j) sm_ += x0[j] + x1[j];
+              const float mean = sm_ * (1.f / 64.f);
               float q = 0.f;
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
@@ -395,34 +405,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               const float rstd = rsqrtf(q * (1.f / 64.f) + 1e-5f);
 #pragma unroll
               for (int j = 0; j < 32; ++j) { x0[j] *= rstd; x1[j] *= rstd; }
-              if (p.is_f16) { st_row_16<__half>(slab, lane, x0); st_row_16<__half>(slab + 2048, lane, x1); }
-              else { st_row_16<__nv_bfloat16>(slab, lane, x0); st_row_16<__nv_bfloat16>(slab + 2048, lane, x1); }
               if (m < p.M) p.ln_rstd[((long)m * p.ln_heads + n_blk) * 2 + half] = rstd;
             }
-          }
-          {
-            float v[32];
-            tmem_ld_32x32(t_row + static_cast<uint32_t>(128 + 32 * half), v);
-            tmem_ld_wait();
-            tc_fence_before();
+            if (lane == 0) tma_store_wait_read<0>();          // the previous tile's boxes have left the slab
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty + as);
-            if (live) {
-              if (p.bias != nullptr) {
-                float b[32];
-                load_cols(s_bias + n0 + 128 + 32 * half, b);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += b[j];
-              }
-              if (p.is_f16) st_row_16<__half>(slab + 4096, lane, v); else st_row_16<__nv_bfloat16>(slab + 4096, lane, v);
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) {
-                tma_store_2d(&map_o16, slab, n0 + 32 * cq, mrow);
-                tma_store_2d(&map_o16, slab + 2048, n0 + 32 * cq + 32, mrow);
-                tma_store_2d(&map_o16, slab + 4096, n0 + 128 + 32 * half, mrow);
-                tma_store_commit();
-              }
+            if (p.is_f16) { st_row_16<__half>(slab, lane, x0); st_row_16<__half>(slab + 2048, lane, x1); }
+            else { st_row_16<__nv_bfloat16>(slab, lane, x0); st_row_16<__nv_bfloat16>(slab + 2048, lane, x1); }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&map_o16, slab, ncol, mrow);
+              tma_store_2d(&map_o16, slab + 2048, ncol + 32, mrow);
+              tma_store_commit();
             }
           }
           if (++as == 2) { as = 0; aphase ^= 1u; }
@@ -525,9 +519,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             break;
           }
           case BF_EPI_GELU: {
-            uint8_t* s = slab + sb * 2048;
-            uint8_t* s2 = slab + 4096 + sb * 2048;
-            if (lane == 0) tma_store_wait_read<1>();
+            uint8_t* s = slab + (kDouble ? sb * 2048 : 0);
+            uint8_t* s2 = slab + (kDouble ? 4096 + sb * 2048 : 2048);
+            if (lane == 0) { if (kDouble) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
             __syncwarp();
             if (p.has_out16b) {
               if (p.is_f16) st_row_16<__half>(s2, lane, acc); else st_row_16<__nv_bfloat16>(s2, lane, acc);
@@ -547,8 +541,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           }
           case BF_EPI_STORE32:
           case BF_EPI_ATOMIC32: {
-            uint8_t* s = slab + sb * 4096;
-            if (lane == 0) tma_store_wait_read<1>();
+            uint8_t* s = slab + (kDouble ? sb * 4096 : 0);
+            if (lane == 0) { if (kDouble) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
             __syncwarp();
             st_row_f32(s, lane, acc);
             fence_proxy_async();
@@ -602,9 +596,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           }
           case BF_EPI_RESID: {
             uint8_t* box = in_tile + c * (BM * 128);
-            uint8_t* s = slab + sb * 2048;
-            uint8_t* s2 = slab + 4096 + sb * 2048;
-            if (lane == 0) tma_store_wait_read<1>();
+            uint8_t* s = slab + (kDouble ? sb * 2048 : 0);
+            uint8_t* s2 = slab + (kDouble ? 4096 + sb * 2048 : 2048);
+            if (lane == 0) { if (kDouble) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
             __syncwarp();
             if (p.has_out16b) {
               if (p.is_f16) st_row_16<__half>(s2, lane, acc); else st_row_16<__nv_bfloat16>(s2, lane, acc);
@@ -797,7 +791,7 @@ static int launch(const Maps& mp, GemmParams& p, cudaStream_t st) {
   const int stage_bytes = p.b_resident ? BM * BK * 2 : BM * BK * 2 + BN * BK * 2;
   const int bar_bytes = (2 * kMaxStages + 9) * 8 + 16;
   const bool slabs = !(p.epilogue == BF_EPI_DGELU || p.epilogue == BF_EPI_ACC32 || p.epilogue == BF_EPI_D2S);
-  const int slab_bytes = slabs ? kEpiWarps * kSlabBytes
+  const int slab_bytes = slabs ? epi_warps(BN) * slab_bytes_per_warp(BN)
                                : (p.colsum_out != nullptr ? ((p.num_n_blocks * BN * 4 + 1023) / 1024) * 1024 : 0);
   p.in_bytes = p.in_kind == 0 ? 0 : BM * BN * (p.in_kind == 2 ? 4 : 2);
   int nvec = 0;
@@ -827,7 +821,7 @@ static int launch(const Maps& mp, GemmParams& p, cudaStream_t st) {
   const int tiles = p.num_m_blocks * p.num_n_blocks * p.split_k;
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (p.b_resident) grid = (num_sms() / p.num_n_blocks) * p.num_n_blocks;   // a CTA keeps one n block for all its tiles
-  const cudaError_t le = launch_k(kern, dim3(grid), dim3(kThreads), (size_t)total, st, mp.a, mp.b, mp.in, mp.o16, mp.o16b,
+  const cudaError_t le = launch_k(kern, dim3(grid), dim3(gemm_threads(BN)), (size_t)total, st, mp.a, mp.b, mp.in, mp.o16, mp.o16b,
                                  mp.o32, p);
   count_launch();
   return check_cuda(le != cudaSuccess ? le : cudaGetLastError(), "gemm_tcgen05_kernel launch");
