@@ -72,3 +72,15 @@ def rollout(model: torch.nn.Module, x0: torch.Tensor, steps: int, fluid_params: 
 def shard_trajectories(n_traj: int, rank: int, world: int) -> Sequence[int]:
     """Round-robin assignment of independent trajectories to ranks (no data-path collective)."""
     return range(rank, n_traj, world)
+
+
+def evaluate_rollout(preds: torch.Tensor, targets: torch.Tensor, sdf_channel: int = 0) -> dict:
+    """Metrics of one trajectory on the device: preds / targets (frames, C, H, W) as `scripts/inference.py:254-255`
+    concatenates them.  Relative L2 per field (the criterion inference.py prints) and the eikonal residual of the
+    predicted and the true signed-distance field (utils/losses.py:5-15)."""
+    from . import metrics
+    return {
+        "rel_l2_per_field": metrics.rel_l2_per_field(preds, targets),
+        "eikonal_pred": metrics.eikonal_loss(preds[:, sdf_channel].unsqueeze(0)),
+        "eikonal_target": metrics.eikonal_loss(targets[:, sdf_channel].unsqueeze(0)),
+    }

@@ -209,6 +209,16 @@ typedef struct {
 } bf_branch_grad_args;
 BF_API int bf_branch_param_grads(const bf_branch_grad_args* args, void* stream);
 
+/* Rollout metrics (upstream utils/losses.py:5-15 eikonal_loss, utils/heatflux.py:3-38).
+ * bf_eikonal_sums : sums[s] += sum_pixels (|grad phi| - 1)^2 for `slabs` contiguous (H, W) fp32 fields, torch.gradient
+ *                   stencil (central inside, first-order one-sided at the edges), spacing dx (upstream: 1/32).
+ * bf_heatflux_rows: flux[t] = mean over the W cells of the wall row (y = 0) of frame t of
+ *                   [-5 <= x_centre <= 5 and dfun < 0] * (heater_temp - temp) * 0.054 / (dx * lc); frames are
+ *                   `frame_stride` floats apart; x_centre = x_min + (i + 0.5) * dx (upstream: x_min -8, lc 0.0007).  */
+BF_API int bf_eikonal_sums(const float* phi, float* sums, int64_t slabs, int H, int W, float dx, void* stream);
+BF_API int bf_heatflux_rows(const float* dfun, const float* temp, float* flux, int64_t frames, int64_t frame_stride,
+                            int W, float heater_temp, float x_min, float dx, float lc, void* stream);
+
 /* Optimiser step over flat fp32 buffers (parameters, gradients, moments; n a multiple of 4), optionally refreshing
  * the bf16 operand mirror p16 in the same pass.  Upstream: bubbleformer/modules.py:132-142 (torch.optim.AdamW / Adam,
  * lion_pytorch.Lion with config/optim_cfg/{adamw,adam,lion}.yaml).  `step` counts from 1 (Adam bias correction);
