@@ -135,7 +135,7 @@ class BranchGradArgs(C.Structure):
     ]
 
 
-EXPORTS = ["bf_eikonal_sums", "bf_heatflux_rows", "bf_optim_step", "bf_feat_consts", "bf_branch_param_grads", "bf_last_error", "bf_version", "bf_launch_count", "bf_gemm", "bf_inorm_stats", "bf_inorm_apply",
+EXPORTS = ["bf_window_gather", "bf_eikonal_sums", "bf_heatflux_rows", "bf_optim_step", "bf_feat_consts", "bf_branch_param_grads", "bf_last_error", "bf_version", "bf_launch_count", "bf_gemm", "bf_inorm_stats", "bf_inorm_apply",
            "bf_inorm_bwd", "bf_inorm_bwd_params", "bf_resid_bwd", "bf_colsum16", "bf_attention_fwd",
            "bf_attention_bwd", "bf_lploss_sums", "bf_lploss_bwd", "bf_patch_in", "bf_patch_out", "bf_patch_wgrad", "bf_s2d_gather", "bf_cast16", "bf_convert16"]
 
@@ -146,6 +146,7 @@ lib.bf_inorm_apply.argtypes = [C.POINTER(InormApplyArgs), _vp]
 lib.bf_inorm_bwd.argtypes = [C.POINTER(InormBwdArgs), _vp]
 lib.bf_inorm_bwd_params.argtypes = [C.POINTER(InormBwdParamsArgs), _vp]
 lib.bf_resid_bwd.argtypes = [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]
+lib.bf_window_gather.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i64, _i, _vp]
 lib.bf_eikonal_sums.argtypes = [_vp, _vp, _i64, _i, _i, C.c_float, _vp]
 lib.bf_heatflux_rows.argtypes = [_vp, _vp, _vp, _i64, _i64, _i, C.c_float, C.c_float, C.c_float, C.c_float, _vp]
 lib.bf_optim_step.argtypes = [_i, _vp, _vp, _vp, _vp, _vp, _i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,

@@ -1,0 +1,130 @@
+"""Input pipeline for the hot path: BubbleForecast semantics with the data resident in HBM.
+
+Upstream (bubbleformer/data/dataset.py) opens the HDF5 trajectories with h5py and, per sample, slices every field,
+normalises and stacks on the host (`__getitem__`, :120-186).  At the throughput of this implementation (~280 samples/s
+per GPU x 21 MB per sample) that path would starve the GPU, and a B200 has room for the whole dataset: the
+trajectories are read once (dependency-free HDF5 reader, `hdf5_min.py`), uploaded as one (frames, C, H, W) fp32 tensor,
+and `batch(indices)` cuts, normalises and lays out B windows with one kernel per window (`bf_window_gather`).
+
+Kept from upstream: the sample index -> (file, start frame) arithmetic (`__len__`, `__getitem__`), the field lists, the
+`norm` modes and how the constants are averaged over files (`normalize`, :69-118), the order of the nine fluid
+parameters (:170-183), and the returned layouts (T, C, H, W) per sample.
+"""
+from __future__ import annotations
+
+import json
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .hdf5_min import read_hdf5
+
+DEFAULT_FIELDS = ["dfun", "temperature", "velx", "vely"]
+
+
+def fluid_param_vector(fp: dict) -> List[float]:
+    """The nine conditioning numbers in upstream's order (dataset.py:170-183)."""
+    return [fp["inv_reynolds"], fp["cpgas"], fp["mugas"], fp["rhogas"], fp["thcogas"], fp["stefan"], fp["prandtl"],
+            fp["heater"]["nucWaitTime"], fp["heater"]["wallTemp"]]
+
+
+class DeviceForecastWindows:
+    def __init__(self, filenames: Sequence[str], input_fields: Optional[List[str]] = None,
+                 output_fields: Optional[List[str]] = None, norm: str = "none", time_window: int = 16,
+                 start_time: int = 50, return_fluid_params: bool = False, device="cuda",
+                 arrays: Optional[List[Dict[str, np.ndarray]]] = None):
+        """`arrays` (one dict field -> (frames, H, W) array per trajectory) replaces reading `filenames`."""
+        self.input_fields = list(input_fields) if input_fields is not None else list(DEFAULT_FIELDS)
+        self.output_fields = list(output_fields) if output_fields is not None else list(DEFAULT_FIELDS)
+        if norm not in ("none", "std", "minmax", "tanh"):
+            raise ValueError(f"Unknown normalization type: {norm}")          # upstream dataset.py:109
+        self.norm, self.time_window, self.start_time = norm, time_window, start_time
+        self.fields = sorted(set(self.input_fields + self.output_fields), key=(self.input_fields + self.output_fields).index)
+        data = arrays if arrays is not None else [read_hdf5(f) for f in filenames]
+        self.traj_lens = [int(d[self.input_fields[0]].shape[0]) for d in data]
+        self.num_trajs = [1] * len(data)
+        self.host = [{k: np.asarray(d[k], dtype=np.float32) for k in self.fields} for d in data]
+        shapes = {d[k].shape[1:] for d in self.host for k in self.fields}
+        if len(shapes) != 1:
+            raise ValueError("all fields of all trajectories must share one (H, W)")
+        self.H, self.W = shapes.pop()
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("bubbleformer_b200 runs on CUDA only (no CPU fallback)")
+        stacked = np.concatenate([np.stack([d[k] for k in self.fields], axis=1) for d in self.host], axis=0)
+        self.frames = torch.from_numpy(np.ascontiguousarray(stacked)).to(dev)          # (sum frames, C, H, W)
+        self.frame_base = np.concatenate([[0], np.cumsum(self.traj_lens)])[:-1]
+        self.fluid_params = None
+        if return_fluid_params:
+            vecs = []
+            for fname in filenames:
+                with open(fname.replace(".hdf5", ".json"), "r", encoding="utf-8") as f:
+                    vecs.append(fluid_param_vector(json.load(f)))
+            self.fluid_params = torch.tensor(vecs, dtype=torch.float32, device=dev)
+        self._in_ch = torch.tensor([self.fields.index(k) for k in self.input_fields], dtype=torch.int32, device=dev)
+        self._out_ch = torch.tensor([self.fields.index(k) for k in self.output_fields], dtype=torch.int32, device=dev)
+        self.diff_terms = {k: 0.0 for k in self.fields}
+        self.div_terms = {k: 1.0 for k in self.fields}
+        self._upload_terms()
+
+    # ---- upstream dataset.py:62-67 -------------------------------------------------------------
+    def __len__(self) -> int:
+        return sum(n * (t - self.start_time - 2 * self.time_window + 1) for n, t in zip(self.num_trajs, self.traj_lens))
+
+    # ---- upstream dataset.py:69-118 ------------------------------------------------------------
+    def normalize(self, diff_terms: Optional[Dict] = None, div_terms: Optional[Dict] = None) -> Tuple[Dict, Dict]:
+        if diff_terms is None and div_terms is None:
+            diff_terms, div_terms = {}, {}
+            for k in self.fields:
+                dl, vl = [], []
+                for d in self.host:
+                    x = d[k]
+                    if self.norm == "std":
+                        dl.append(x.mean()); vl.append(x.std())
+                    elif self.norm == "minmax":
+                        dl.append(x.min()); vl.append(x.max() - x.min())
+                    elif self.norm == "tanh":
+                        dl.append((x.max() + x.min()) / 2.0); vl.append((x.max() - x.min()) / 2.0)
+                    else:
+                        dl.append(0.0); vl.append(1.0)
+                diff_terms[k] = np.mean(dl).item()
+                div_terms[k] = np.mean(vl).item() + 1e-8
+        self.diff_terms, self.div_terms = diff_terms, div_terms
+        self._upload_terms()
+        return self.diff_terms, self.div_terms
+
+    def _upload_terms(self) -> None:
+        dev = self.frames.device
+        self._diff = torch.tensor([self.diff_terms[k] for k in self.fields], dtype=torch.float32, device=dev)
+        self._inv = torch.tensor([1.0 / self.div_terms[k] for k in self.fields], dtype=torch.float32, device=dev)
+
+    # ---- upstream dataset.py:120-131 -----------------------------------------------------------
+    def locate(self, idx: int) -> Tuple[int, int]:
+        """Sample index -> (trajectory, first input frame)."""
+        per = [n * (t - self.start_time - 2 * self.time_window + 1) for n, t in zip(self.num_trajs, self.traj_lens)]
+        cum = np.cumsum(per)
+        file_idx = int(np.searchsorted(cum, idx, side="right"))
+        start = idx + self.start_time - (int(cum[file_idx - 1]) if file_idx > 0 else 0)
+        return file_idx, int(start)
+
+    def batch(self, indices: Sequence[int]):
+        """(inp, tgt[, fluid_params]) for the given sample indices: inp (B, T, C_in, H, W), tgt (B, T, C_out, H, W),
+        i.e. the default collate of upstream's per-sample (T, C, H, W) tensors."""
+        loc = [self.locate(int(i)) for i in indices]
+        first = torch.tensor([int(self.frame_base[f]) + s for f, s in loc], dtype=torch.int64).to(self.frames.device,
+                                                                                                  non_blocking=True)
+        B, T, HW = len(loc), self.time_window, self.H * self.W
+        stream = torch.cuda.current_stream().cuda_stream
+        outs = []
+        for ch, t_off in ((self._in_ch, 0), (self._out_ch, T)):
+            out = torch.empty(B, T, ch.numel(), self.H, self.W, dtype=torch.float32, device=self.frames.device)
+            L.check(L.lib.bf_window_gather(self.frames.data_ptr(), first.data_ptr(), ch.data_ptr(), self._diff.data_ptr(),
+                                           self._inv.data_ptr(), out.data_ptr(), B, T, len(self.fields), ch.numel(), HW,
+                                           t_off, stream), "bf_window_gather")
+            outs.append(out)
+        if self.fluid_params is not None:
+            sel = torch.tensor([f for f, _ in loc], dtype=torch.int64, device=self.frames.device)
+            return outs[0], outs[1], self.fluid_params[sel]
+        return outs[0], outs[1]

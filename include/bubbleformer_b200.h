@@ -209,6 +209,14 @@ typedef struct {
 } bf_branch_grad_args;
 BF_API int bf_branch_param_grads(const bf_branch_grad_args* args, void* stream);
 
+/* Input pipeline (upstream data/dataset.py:120-186, BubbleForecast.__getitem__): the trajectories are resident in HBM
+ * as frames (F, C_src, H*W) fp32; one launch cuts B windows of T frames, selects and normalises the fields and writes
+ * out (B, T, C_out, H*W):  out[b,t,j,:] = (frames[first_frame[b] + t_off + t, channels[j], :] - diff[c]) * inv_div[c]
+ * (t_off = 0 for the input window, T for the target window).  first_frame / channels / diff / inv_div are device arrays. */
+BF_API int bf_window_gather(const float* frames, const int64_t* first_frame, const int32_t* channels, const float* diff,
+                            const float* inv_div, float* out, int B, int T, int C_src, int C_out, int64_t HW, int t_off,
+                            void* stream);
+
 /* Rollout metrics (upstream utils/losses.py:5-15 eikonal_loss, utils/heatflux.py:3-38).
  * bf_eikonal_sums : sums[s] += sum_pixels (|grad phi| - 1)^2 for `slabs` contiguous (H, W) fp32 fields, torch.gradient
  *                   stencil (central inside, first-order one-sided at the edges), spacing dx (upstream: 1/32).
