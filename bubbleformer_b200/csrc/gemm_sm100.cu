@@ -8,7 +8,8 @@
 //   warp 2      : TMA producer of the epilogue *input* tile (fp32 residual stream / saved pre-activation),
 //                 prefetched while the tile's MMAs run
 //   warp 3      : idle (keeps the epilogue warps aligned to the TMEM lane quadrants)
-//   warps 4..11 : epilogue: tcgen05.ld -> registers -> fused math -> swizzled smem -> TMA store
+//   warps 4..   : epilogue (8 warps for tiles up to 128 columns, 12 for 192, 16 for 256: one warp per TMEM lane
+//                 quadrant and 64-column group): tcgen05.ld -> registers -> fused math -> swizzled smem -> TMA store
 //                 (cp.async.bulk.tensor shared -> global, or cp.reduce.async.bulk.tensor .add for split-K)
 // TMEM holds two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.  No epilogue
 // warp ever touches global memory with ld/st: inputs arrive by TMA into smem, outputs leave by TMA from
