@@ -102,32 +102,8 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
-// Cheaper erf for the fused GEMM epilogues (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7 + approx-unit noise,
-// far below the 16-bit storage rounding of every consumer): 2 MUFU + ~12 FMA-pipe instructions, branch free.
-// Returns erf(x/sqrt(2)) and, through `pdf`, the standard normal density exp(-x^2/2)/sqrt(2 pi).
-__device__ __forceinline__ float erf_sqrt2_fast(float x, float& pdf) {
-  const float ax = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float e = __expf(-ax * ax);
-  pdf = 0.39894228040143268f * e;
-  return copysignf(fmaf(-poly * t, e, 1.0f), x);
-}
-__device__ __forceinline__ float gelu_fast(float x) {
-  float pdf;
-  const float er = erf_sqrt2_fast(x, pdf);
-  return 0.5f * x * (1.0f + er);
-}
-__device__ __forceinline__ float gelu_grad_fast(float x) {
-  float pdf;
-  const float er = erf_sqrt2_fast(x, pdf);
-  return fmaf(x, pdf, 0.5f * (1.0f + er));
-}
-
-// tanh-form GELU for the MLP GEMM epilogues, where the exact erf would make the epilogue (not the MMAs) the bound:
+// tanh-form GELU for the MLP GEMM epilogues and the stem / head norm passes, where the exact erf would make the ALU
+// work (not the MMAs / the HBM stream) the bound:
 // one MUFU.TANH + ~6 FMA-pipe instructions per element.  |gelu_tanh - gelu_erf| <= 4.8e-4 absolute, 2e-4 rel-L2 on
 // N(0,1) pre-activations -- an eighth of the bf16 rounding (1.7e-3) the stored activation carries anyway.
 __device__ __forceinline__ float tanh_approx(float x) {

@@ -516,6 +516,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) { tma_store_2d(&map_o16, s, n, mrow); tma_store_commit(); }
+            if (p.stats_out != nullptr) {
+              // per-(image, channel) sums of the stored (rounded) values for the InstanceNorm that follows: lane j
+              // owns column j of this warp's 32 x 32 block (conflict-free transposed read of the swizzled rows)
+              const int rows_valid = min(32, p.M - mrow);
+              float s1 = 0.f, s2q = 0.f;
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r) {
+                const uint16_t h = *reinterpret_cast<const uint16_t*>(s + r * 64 + ((((lane >> 3) ^ ((r >> 1) & 3)) << 4) | ((lane & 7) << 1)));
+                float v;
+                if (p.is_f16) v = __half2float(*reinterpret_cast<const __half*>(&h));
+                else v = __uint_as_float(static_cast<uint32_t>(h) << 16);
+                if (r < rows_valid) { s1 += v; s2q = fmaf(v, v, s2q); }
+              }
+              if (n + lane < p.N) {
+                float* dst = p.stats_out + ((long)(mrow / p.rows_per_group) * p.N + n + lane) * 2;
+                atomicAdd(dst, s1);
+                atomicAdd(dst + 1, s2q);
+              }
+            }
             sb ^= 1;
             break;
           }
@@ -937,7 +956,9 @@ extern "C" int bf_gemm(const bf_gemm_args* a, void* stream) {
       break;
     default: BF_REQUIRE(false, "bf_gemm: unknown epilogue %d", a->epilogue);
   }
-  BF_REQUIRE(a->stats_out == nullptr || a->epilogue == BF_EPI_RESID, "bf_gemm: stats_out only with BF_EPI_RESID");
+  BF_REQUIRE(a->stats_out == nullptr || a->epilogue == BF_EPI_RESID || a->epilogue == BF_EPI_STORE16,
+             "bf_gemm: stats_out only with BF_EPI_RESID / BF_EPI_STORE16");
+  BF_REQUIRE(a->stats_out == nullptr || (a->rows_per_group % 32 == 0), "bf_gemm: stats_out needs rows_per_group %% 32 == 0");
   if (a->out16 || a->out16b || a->aux16) BF_REQUIRE(a->ldo >= a->N || a->epilogue == BF_EPI_D2S, "bf_gemm: ldo < N");
   if (a->out32 || a->in32) BF_REQUIRE(a->ld32 >= a->N, "bf_gemm: ld32 < N");
 

@@ -256,7 +256,7 @@ inorm_apply_kernel(const TI* __restrict__ x, TO* __restrict__ out, ApplyParams p
   float v[8];                                                                            \
   unpack8<TI>(ring + ((st) * NSLOT) * kNT + threadIdx.x, v);                             \
   _Pragma("unroll") for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], a[j], b[j]);          \
-  if (p.gelu) { _Pragma("unroll") for (int j = 0; j < 8; ++j) v[j] = gelu_fast(v[j]); }  \
+  if (p.gelu) { _Pragma("unroll") for (int j = 0; j < 8; ++j) v[j] = gelu_tanh(v[j]); }  \
   if (post_film) { _Pragma("unroll") for (int j = 0; j < 8; ++j) v[j] = fmaf(fg[j], v[j], fb[j]); } \
   if (RESID) {                                                                           \
     float xr[8];                                                                         \

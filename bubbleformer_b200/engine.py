@@ -316,9 +316,13 @@ def spatial_forward(X, g: Geom, p, w16, heads: int, attn_scale: bool, feat_scale
     Hpre = _empty((N, 4 * E), BF16, X) if save else None
     ops.gemm(Xb, w16("mlp.fc1.weight"), N, 4 * E, E, epilogue=L.EPI_GELU, bias=p["mlp.fc1.bias"], out16=G, out16b=Hpre)
     Y2 = _empty((N, E), BF16, X)
-    ops.gemm(G, w16("mlp.fc2.weight"), N, E, 4 * E, epilogue=L.EPI_STORE16, bias=p["mlp.fc2.bias"], out16=Y2)
     st3 = _zeros((I, E, 2), X)
-    ops.inorm_stats(Y2, I, P, st3)
+    if P % 32 == 0:      # the fc2 epilogue accumulates the statistics of what it stores
+        ops.gemm(G, w16("mlp.fc2.weight"), N, E, 4 * E, epilogue=L.EPI_STORE16, bias=p["mlp.fc2.bias"], out16=Y2,
+                 rows_per_group=P, stats_out=st3)
+    else:
+        ops.gemm(G, w16("mlp.fc2.weight"), N, E, 4 * E, epilogue=L.EPI_STORE16, bias=p["mlp.fc2.bias"], out16=Y2)
+        ops.inorm_stats(Y2, I, P, st3)
     Xout = _empty((N, E), F32, X)
     st_out = _zeros((I, E, 2), X)
     ops.inorm_apply(Y2, Xout, I, P, st3, p["mlp_norm.weight"], p["mlp_norm.bias"], resid_in=Xmid, row_scale=mask_mlp,

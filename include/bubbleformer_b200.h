@@ -108,9 +108,10 @@ typedef struct bf_gemm_args {
   void* out16b;           /* (M, N) ld = ldo  */
   float* out32;           /* (M, N) ld = ld32 */
   int64_t ldo, ld32;
-  float* stats_out;       /* BF_EPI_RESID only, may be NULL: stats_out[m / rows_per_group][n] += (sum, sum^2) of
-                             out32 -- the raw InstanceNorm statistics of the new residual stream, so the next
-                             norm needs no separate pass (rows_per_group = tokens per image, multiple of 32)   */
+  float* stats_out;       /* BF_EPI_RESID / BF_EPI_STORE16, may be NULL: stats_out[m / rows_per_group][n] += (sum, sum^2)
+                             of out32 (RESID) or of the stored out16 (STORE16) -- the raw InstanceNorm statistics of
+                             the tensor, so the norm that follows needs no separate pass (rows_per_group = tokens per
+                             image, multiple of 32)                                                             */
   float* ln_rstd;         /* BF_EPI_QKV_LN only: (M, N / (3*ln_head_dim), 2) fp32                                */
   float* colsum_out;      /* BF_EPI_DGELU only, may be NULL: [N] += column sums of out16 (gradient of the fc1 bias) */
 } bf_gemm_args;

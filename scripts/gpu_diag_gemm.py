@@ -70,8 +70,13 @@ def run_variant(v):
         ref = A.float() @ B.float().t() + bias
         if v.startswith("nk_"):
             out = torch.zeros(M, N, device=dev, dtype=dt)
-            ops.gemm(A, B, M, N, K, epilogue=L.EPI_STORE16, bias=bias, out16=out, bn=bn)
+            rpg = 128 if M % 128 == 0 else 0
+            st = torch.zeros(M // rpg, N, 2, device=dev) if rpg else None
+            ops.gemm(A, B, M, N, K, epilogue=L.EPI_STORE16, bias=bias, out16=out, bn=bn, rows_per_group=max(rpg, 1), stats_out=st)
             ok &= report(v, out, ref, 1e-2)
+            if rpg:       # fused InstanceNorm statistics of the stored values
+                oi = out.float().reshape(M // rpg, rpg, N)
+                ok &= report(v + ".stats", st, torch.stack([oi.sum(1), (oi * oi).sum(1)], dim=-1), 1e-4)
         elif v == "store32":
             out = torch.zeros(M, N, device=dev)
             ops.gemm(A, B, M, N, K, epilogue=L.EPI_STORE32, bias=bias, out32=out)

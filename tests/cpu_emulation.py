@@ -47,6 +47,9 @@ def gemm(A, B, M, N, K, *, epilogue, a_mode=L.A_ROWMAJOR, b_mode=L.B_NK, split_k
         ln_rstd.reshape(M, N // (3 * d), 2).copy_(rstd[..., 0])
     elif epilogue == L.EPI_STORE16:
         out16.reshape(M, N).copy_(acc)
+        if stats_out is not None:
+            xi = out16.reshape(-1, rows_per_group, N).float()
+            stats_out.reshape(-1, N, 2).add_(torch.stack([xi.sum(1), (xi * xi).sum(1)], dim=-1))
     elif epilogue == L.EPI_STORE32:
         out32.reshape(M, N).copy_(acc)
     elif epilogue == L.EPI_GELU:
