@@ -257,6 +257,8 @@ def _attn_branch_bwd(dXout, g: Geom, p, w16, heads: int, axes, scale_keys, mask_
                       bucket=relpos_bucket_vector(geo["L_"], dXout.device), scale_factor=sf, out_scale=oscale,
                       accumulate=i > 0, dout=dO, grads=gr, prenorm=sv["rstd"] is not None, rstd=sv["rstd"], **geo)
     if not fused_bias:
+        # (Measured: taking these column sums from one extra 16-column MMA against a tile of ones inside the weight-
+        # gradient GEMM costs 8 us there and saves nothing in the step -- dQKV is still L2 resident for this pass.)
         ops.colsum16(dQKV, grads["input_head.bias"])
     # input_head
     dXn = _empty((N, E), BF16, dXout)
@@ -405,14 +407,17 @@ def embed_forward(x, g_in, p, n_layers: int, film_gb: Optional[torch.Tensor], T:
             ops.patch_in(x, Wkn, Y.view(I, ho, wo, Cout), st)
         else:
             W16 = _conv_w_fwd(wt, F16)
+            fuse = (ho * wo) % 32 == 0          # the GEMM epilogue accumulates the statistics of what it stores
+            skw = dict(rows_per_group=ho * wo, stats_out=st) if fuse else {}
             if _s2d_ok(wo):
                 ops.gemm(A, W16, M, Cout, 4 * Cin, epilogue=L.EPI_STORE16, a_mode=L.A_S2D, ldb=4 * Cin,
-                         s2d=(I, h_, w_, Cin), out16=Y)
+                         s2d=(I, h_, w_, Cin), out16=Y, **skw)
             else:
                 Ag = _empty((M, 4 * Cin), F16, x)
                 ops.s2d_gather(A.view(I, h_, w_, Cin), Ag)
-                ops.gemm(Ag, W16, M, Cout, 4 * Cin, epilogue=L.EPI_STORE16, out16=Y)
-            ops.inorm_stats(Y, I, ho * wo, st)
+                ops.gemm(Ag, W16, M, Cout, 4 * Cin, epilogue=L.EPI_STORE16, out16=Y, **skw)
+            if not fuse:
+                ops.inorm_stats(Y, I, ho * wo, st)
         nw, nb = p[f"in_proj.{3 * i + 1}.weight"], p[f"in_proj.{3 * i + 1}.bias"]
         if not last:
             An = _empty((M, Cout), F16, x)
