@@ -163,6 +163,9 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the captured training step")
+    ap.add_argument("--profile", action="store_true",
+                    help="ncu captures only (scripts/ncu_profiles.sh): one eager warm-up step, then --steps replays of the "
+                         "captured step and exit; prints no bench line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -210,7 +213,8 @@ def main():
     gtrain = None
     if train and not args.no_graph:
         from bubbleformer_b200.parallel import GraphedTrainStep
-        gtrain = GraphedTrainStep(model, rel_l2_loss, sink, x, tgt, cond)    # fwd + loss + bwd (+ all-reduce) in one graph
+        gtrain = GraphedTrainStep(model, rel_l2_loss, sink, x, tgt, cond,    # fwd + loss + bwd (+ all-reduce) in one graph
+                                  warmup=1 if args.profile else 3)
 
     def eager_step(xd, td, cd):
         sink.begin_step()
@@ -219,6 +223,13 @@ def main():
         loss.backward()
         sink.finish()
         return loss
+
+    if args.profile:
+        for _ in range(K):
+            step_fn = gtrain if gtrain is not None else eager_step
+            step_fn(x, tgt, cond)
+        torch.cuda.synchronize()
+        return
 
     def step(xd, td, cd):
         if gtrain is not None:

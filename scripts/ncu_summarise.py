@@ -32,7 +32,7 @@ ik, iv = hdr.index("Kernel Name"), hdr.index("Metric Value")
 names = [r[ik] for r in data]
 vals = [float(r[iv].replace(",", "")) for r in data]
 starts = [i for i, n in enumerate(names) if "cast16_kernel" in n and vals[i] > 20000]
-s, e = starts[0], starts[1]
+s, e = starts[-2], starts[-1]          # the last complete step in the capture (a graph replay)
 agg = collections.defaultdict(lambda: [0, 0.0])
 for n, v in zip(names[s:e], vals[s:e]):
     agg[short(n)][0] += 1
