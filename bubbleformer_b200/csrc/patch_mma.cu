@@ -125,9 +125,13 @@ patch_in_mma_kernel(const float* __restrict__ x, const float* __restrict__ Wkn, 
       const int cpr = nts;                   // 16-byte chunks per pixel in this pass
       const int rows = min(16, Wo - xo0);
       T16* dst = oimg + ((long)yo * Wo + xo0) * N + nc0;
+      // idx = lane + 32 k -> (row, chunk) without a division per store (cpr is a run-time value)
+      int r = lane / cpr, ch = lane - r * cpr;
+      const int dr = 32 / cpr, dc = 32 - dr * cpr;
       for (int idx = lane; idx < rows * cpr; idx += 32) {
-        const int r = idx / cpr, ch = idx - r * cpr;
         *reinterpret_cast<uint4*>(dst + (long)r * N + ch * 8) = *reinterpret_cast<const uint4*>(sStage + r * SS + ch * 8);
+        r += dr; ch += dc;
+        if (ch >= cpr) { ch -= cpr; ++r; }
       }
     }
     if (STATS) {

@@ -58,10 +58,14 @@ __device__ __forceinline__ void mma_16816<__half>(float (&c)[4], const uint32_t 
 template <typename T16>
 __device__ __forceinline__ void issue_act_tile(uint8_t* sa, const T16* row0, long lda, int nc, int valid_px, int lane) {
   const int cpp = nc >> 3;                      // 16-byte chunks per pixel
+  // idx = lane + 32 k -> (pixel, chunk) without a division per copy (cpp is a run-time value)
+  int px = lane / cpp, ch = lane - px * cpp;
+  const int dp = 32 / cpp, dc = 32 - dp * cpp;
   for (int idx = lane; idx < 16 * cpp; idx += 32) {
-    const int px = idx / cpp, ch = idx - px * cpp;
     const bool ok = px < valid_px;
     cp_async16_zfill(sa + (px * kPsSA + ch * 8) * 2, ok ? row0 + (long)px * lda + ch * 8 : row0, ok);
+    px += dp; ch += dc;
+    if (ch >= cpp) { ch -= cpp; ++px; }
   }
 }
 
