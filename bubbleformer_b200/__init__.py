@@ -1,7 +1,7 @@
 """bubbleformer_b200: B200-native (sm_100a) implementation of the Bubbleformer FiLMAViT hot path.
 
 Importing the package loads libbubbleformer_b200.so and raises if it has not been built
-(`python -m bubbleformer_b200.build`); there is no CPU or eager-PyTorch fallback.
+(`python bubbleformer_b200/build.py`); there is no CPU or eager-PyTorch fallback.
 """
 from . import _lib  # noqa: F401  (fails loudly when the CUDA extension is missing)
 from .models import MODELS, get_model, list_models, register_model  # noqa: F401

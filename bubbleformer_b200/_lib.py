@@ -1,7 +1,7 @@
 """ctypes binding of libbubbleformer_b200.so (the C ABI declared in include/bubbleformer_b200.h).
 
 There is no fallback: if the shared library is missing the import raises, and every wrapper refuses
-tensors that are not on a CUDA device.  Build with `python -m bubbleformer_b200.build`.
+tensors that are not on a CUDA device.  Build with `python bubbleformer_b200/build.py`.
 """
 from __future__ import annotations
 
@@ -42,7 +42,7 @@ def _load() -> C.CDLL:
     if not os.path.exists(LIB_PATH):
         raise BubbleformerB200Error(
             f"{LIB_PATH} not found: the CUDA extension is not built "
-            "(run `python -m bubbleformer_b200.build`); there is no CPU or PyTorch fallback")
+            "(run `python bubbleformer_b200/build.py`); there is no CPU or PyTorch fallback")
     lib = C.CDLL(LIB_PATH)
     lib.bf_last_error.restype = C.c_char_p
     lib.bf_version.restype = C.c_int

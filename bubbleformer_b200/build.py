@@ -1,6 +1,6 @@
 """Build recipe for libbubbleformer_b200.so (plain nvcc, sm_100a only, in-tree).
 
-`python -m bubbleformer_b200.build` compiles every csrc/*.cu with
+`python bubbleformer_b200/build.py` compiles every csrc/*.cu with
 `-gencode arch=compute_100a,code=sm_100a -lineinfo` and links one shared library next to this
 file.  nvcc cross-compiles without a GPU; the .so travels to the GPU box with the repo snapshot.
 Objects are rebuilt only when a source or header is newer.
