@@ -145,6 +145,11 @@ class GraphedTrainStep:
         with torch.cuda.stream(side):
             for _ in range(max(warmup, 1)):      # kernel attributes, allocator pools, NCCL channels: outside the capture
                 self._step()
+        bank = getattr(model, "_bank", None)
+        if bank is not None:
+            # the weight-mirror cast must be part of the graph even if an optimiser step has just refreshed the mirror:
+            # replays must pick up any later change of the parameters
+            bank._mirror_version = None
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(x.device)
         from . import _lib
