@@ -109,6 +109,11 @@ class DeviceForecastWindows:
         start = idx + self.start_time - (int(cum[file_idx - 1]) if file_idx > 0 else 0)
         return file_idx, int(start)
 
+    def __getitem__(self, idx: int):
+        """One sample like upstream's __getitem__: (inp (T, C_in, H, W), tgt (T, C_out, H, W)[, fluid_params (9,)])."""
+        out = self.batch([idx])
+        return tuple(t[0] for t in out)
+
     def batch(self, indices: Sequence[int]):
         """(inp, tgt[, fluid_params]) for the given sample indices: inp (B, T, C_in, H, W), tgt (B, T, C_out, H, W),
         i.e. the default collate of upstream's per-sample (T, C, H, W) tensors."""

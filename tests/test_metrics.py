@@ -44,3 +44,19 @@ def test_metrics_kernels_match_reference_fixture():
     m, mx = metrics.heatflux(d, t, 95.0)
     rm, rmx = O.heatflux(d.cpu().numpy(), t.cpu().numpy(), 95.0)
     assert abs(float(m) - rm) < 1e-5 * abs(rm) and abs(float(mx) - rmx) < 1e-5 * abs(rmx)
+
+
+def test_lploss_inference_config_matches_reference_fixture(monkeypatch):
+    """LpLoss(d=2, p=2, reduce_dims=[0,1], reductions=[mean, mean]) (scripts/inference.py:231): host side of the fused
+    loss on the CPU emulation of the two kernels, against the value the reference printed for the fixture."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cpu_emulation
+    cpu_emulation.install(monkeypatch, wide=True)
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
+    from bubbleformer_b200.losses import LpLoss
+    g = np.load(GOLD)
+    crit = LpLoss(d=2, p=2, reduce_dims=[0, 1], reductions=["mean", "mean"])
+    assert abs(float(crit(torch.tensor(g["pred"]), torch.tensor(g["tgt"]))) - float(g["rel_l2"])) < 1e-6
+    with pytest.raises(NotImplementedError):
+        LpLoss(d=1, p=2)(torch.zeros(2, 3, 4), torch.ones(2, 3, 4))
