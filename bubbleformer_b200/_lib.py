@@ -73,7 +73,7 @@ class InormApplyArgs(C.Structure):
         ("I", C.c_int32), ("P", C.c_int32), ("C", C.c_int32), ("gelu", C.c_int32),
         ("stats", C.c_void_p), ("weight", C.c_void_p), ("bias", C.c_void_p),
         ("film_gamma", C.c_void_p), ("film_beta", C.c_void_p),
-        ("film_T", C.c_int32), ("reserved0", C.c_int32),
+        ("film_T", C.c_int32), ("film_ld", C.c_int32),
         ("resid_in", C.c_void_p), ("row_scale", C.c_void_p), ("col_gamma", C.c_void_p),
         ("out", C.c_void_p), ("stats_out", C.c_void_p),
     ]
@@ -89,7 +89,7 @@ class InormBwdArgs(C.Structure):
         ("stats", C.c_void_p), ("weight", C.c_void_p), ("bias", C.c_void_p),
         ("red", C.c_void_p),
         ("row_scale", C.c_void_p), ("col_scale", C.c_void_p), ("film_gamma", C.c_void_p),
-        ("film_T", C.c_int32), ("reserved0", C.c_int32),
+        ("film_T", C.c_int32), ("film_ld", C.c_int32),
         ("add32", C.c_void_p), ("out", C.c_void_p),
         ("dweight", C.c_void_p), ("dbias", C.c_void_p), ("dcol_scale", C.c_void_p),
         ("dfilm_gamma", C.c_void_p), ("dfilm_beta", C.c_void_p),
@@ -135,7 +135,7 @@ class BranchGradArgs(C.Structure):
     ]
 
 
-EXPORTS = ["bf_window_gather", "bf_eikonal_sums", "bf_heatflux_rows", "bf_optim_step", "bf_feat_consts", "bf_branch_param_grads", "bf_last_error", "bf_version", "bf_launch_count", "bf_gemm", "bf_inorm_stats", "bf_inorm_apply",
+EXPORTS = ["bf_set_gelu_mode", "bf_get_gelu_mode", "bf_film_fwd", "bf_film_bwd", "bf_window_gather", "bf_eikonal_sums", "bf_heatflux_rows", "bf_optim_step", "bf_feat_consts", "bf_branch_param_grads", "bf_last_error", "bf_version", "bf_launch_count", "bf_gemm", "bf_inorm_stats", "bf_inorm_apply",
            "bf_inorm_bwd", "bf_inorm_bwd_params", "bf_resid_bwd", "bf_colsum16", "bf_attention_fwd",
            "bf_attention_bwd", "bf_lploss_sums", "bf_lploss_bwd", "bf_patch_in", "bf_patch_out", "bf_patch_wgrad", "bf_s2d_gather", "bf_cast16", "bf_convert16"]
 
@@ -153,6 +153,9 @@ lib.bf_optim_step.argtypes = [_i, _vp, _vp, _vp, _vp, _vp, _i64, C.c_float, C.c_
                               _i64, _vp]
 lib.bf_feat_consts.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]
 lib.bf_branch_param_grads.argtypes = [C.POINTER(BranchGradArgs), _vp]
+lib.bf_set_gelu_mode.argtypes = [_i]
+lib.bf_film_fwd.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]
+lib.bf_film_bwd.argtypes = [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]
 lib.bf_colsum16.argtypes = [_vp, _i, _i64, _i, _i64, _vp, _vp]
 lib.bf_attention_fwd.argtypes = [C.POINTER(AttnArgs), _vp]
 lib.bf_attention_bwd.argtypes = [C.POINTER(AttnArgs), _vp]

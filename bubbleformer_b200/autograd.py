@@ -87,10 +87,10 @@ class WeightBank:
     def _ok(self) -> bool:
         if self.flat is None or not self.params:
             return False
-        first, last = self.params[0], self.params[-1]
-        return (first.data_ptr() == self.flat.data_ptr() + 4 * self.offsets[id(first)]
-                and last.data_ptr() == self.flat.data_ptr() + 4 * self.offsets[id(last)]
-                and first.device == self.flat.device)
+        base = self.flat.data_ptr()
+        if self.params[0].device != self.flat.device:
+            return False
+        return all(p.data_ptr() == base + 4 * self.offsets[id(p)] for p in self.params)
 
     def ensure(self) -> None:
         if self._ok():
@@ -116,6 +116,12 @@ class WeightBank:
                 p.data = flat[o:o + p.numel()].view(p.shape)
         self.flat, self.offsets, self.params = flat, offs, params
         self.flat16 = torch.empty(tot, dtype=torch.bfloat16, device=dev)
+        self._mirror_version = None          # a rebuilt bank has an uninitialised mirror
+
+    def invalidate(self) -> None:
+        """Force the next forward to re-cast the bf16 mirror (call after changing parameters through `.data`, which
+        does not bump their version counters)."""
+        self._mirror_version = None
 
     def refresh(self) -> None:
         self.ensure()

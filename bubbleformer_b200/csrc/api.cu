@@ -45,8 +45,24 @@ bool pdl_enabled() {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+static std::atomic<int> g_gelu_exact{-1};
+bool gelu_exact() {
+  int v = g_gelu_exact.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("BF_GELU_ERF");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    g_gelu_exact.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
+
 }  // namespace bf
 
 extern "C" const char* bf_last_error(void) { return bf::g_err; }
 extern "C" int bf_version(void) { return 100; }
 extern "C" int64_t bf_launch_count(void) { return bf::g_launches.load(std::memory_order_relaxed); }
+extern "C" int bf_set_gelu_mode(int exact_erf) {
+  bf::g_gelu_exact.store(exact_erf ? 1 : 0, std::memory_order_relaxed);
+  return BF_OK;
+}
+extern "C" int bf_get_gelu_mode(void) { return bf::gelu_exact() ? 1 : 0; }

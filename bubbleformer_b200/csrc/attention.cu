@@ -6,7 +6,7 @@
 // rearrange -- forward and backward -- without materialising any permuted copy: sequences are
 // addressed in place in the token-major (tokens, 3E) QKV matrix through (base, stride).
 //
-// The problems are tiny (L <= 64, head_dim <= 128, thousands of independent (sequence, head) pairs) and
+// The problems are tiny (L <= 128, head_dim <= 128, thousands of independent (sequence, head) pairs) and
 // HBM-bound, so one warp owns one (sequence, head) pair: operands are staged in shared memory with
 // 16-byte coalesced loads and multiplied with warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate).
 // tcgen05 tiles are 64/128 rows tall and would need block-diagonal packing of unrelated sequences.
@@ -637,11 +637,11 @@ static int launch_attn(const AttnParams& p, cudaStream_t st) {
 template <bool BWD>
 static int dispatch_attn(int D, int LP, const AttnParams& p, cudaStream_t st) {
 #define BF_CASE(D_, LP_) if (D == D_ && LP == LP_) return launch_attn<D_, LP_, BWD>(p, st);
-  BF_CASE(32, 32) BF_CASE(32, 64)
-  BF_CASE(48, 32) BF_CASE(48, 64)
-  BF_CASE(64, 32) BF_CASE(64, 64)
-  BF_CASE(96, 32) BF_CASE(96, 64)
-  BF_CASE(128, 32) BF_CASE(128, 64)
+  BF_CASE(32, 32) BF_CASE(32, 64) BF_CASE(32, 128)
+  BF_CASE(48, 32) BF_CASE(48, 64) BF_CASE(48, 128)
+  BF_CASE(64, 32) BF_CASE(64, 64) BF_CASE(64, 128)
+  BF_CASE(96, 32) BF_CASE(96, 64) BF_CASE(96, 128)
+  BF_CASE(128, 32) BF_CASE(128, 64) BF_CASE(128, 128)
 #undef BF_CASE
   set_error("bf_attention: unsupported head_dim %d (supported: 32, 48, 64, 96, 128)", D);
   return BF_ERR_INVALID;
@@ -655,7 +655,9 @@ static int attn_common(const bf_attn_args* a, AttnParams& p, int& LP, bool bwd) 
   BF_REQUIRE(a != nullptr, "bf_attention: null args");
   BF_REQUIRE(a->qkv && a->out, "bf_attention: null tensor");
   BF_REQUIRE(a->heads > 0 && a->heads <= 64 && a->head_dim > 0, "bf_attention: heads=%d head_dim=%d", a->heads, a->head_dim);
-  BF_REQUIRE(a->L >= 1 && a->L <= 64, "bf_attention: sequence length %d not in [1, 64] (longer axes are not supported yet)", a->L);
+  BF_REQUIRE(a->L >= 1 && a->L <= 128,
+             "bf_attention: sequence length %d not in [1, 128] (one warp holds a whole sequence: axes longer than 128 "
+             "tokens = 2048 pixels at patch 16 are not supported)", a->L);
   BF_REQUIRE(a->n_seq > 0 && a->inner > 0, "bf_attention: n_seq=%ld inner=%ld", (long)a->n_seq, (long)a->inner);
   BF_REQUIRE(a->qn_w && a->qn_b && a->kn_w && a->kn_b && a->bias_emb && a->bucket, "bf_attention: null parameter");
   BF_REQUIRE(a->ld_qkv % 8 == 0 && a->ld_out % 8 == 0, "bf_attention: leading dimensions must be multiples of 8");
@@ -666,7 +668,7 @@ static int attn_common(const bf_attn_args* a, AttnParams& p, int& LP, bool bwd) 
     BF_REQUIRE(a->d_qn_w && a->d_qn_b && a->d_kn_w && a->d_kn_b, "bf_attention_bwd: LayerNorm gradient buffers");
   }
   // short sequences are packed G per tile (block-diagonal attention): L <= 16 -> 32-row tiles holding 32/L of them
-  LP = a->L <= 32 ? 32 : 64;
+  LP = a->L <= 32 ? 32 : (a->L <= 64 ? 64 : 128);
   p = AttnParams{};
   p.G = LP / a->L;
   if (p.G > 8) p.G = 8;

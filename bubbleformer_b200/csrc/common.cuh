@@ -26,6 +26,7 @@ void set_error(const char* fmt, ...);
 int  check_cuda(cudaError_t e, const char* what);
 int  num_sms();
 void count_launch(int n = 1);
+bool gelu_exact();          // bf_set_gelu_mode / BF_GELU_ERF=1: exact-erf GELU instead of the tanh form
 // rank-d TMA tensor map (zero fill out of bounds); dt: BF_BF16 / BF_F16 / BF_F32.  Defined in gemm_sm100.cu.
 int  make_map(CUtensorMap* map, int dt, const void* base, int rank, const uint64_t* dims,
               const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box, CUtensorMapSwizzle swz);
@@ -123,6 +124,10 @@ __device__ __forceinline__ float gelu_tanh_grad(float x) {
   const float hx = 0.5f * x;
   return fmaf(hx * du, fmaf(-th, th, 1.0f), fmaf(0.5f, th, 0.5f));
 }
+
+// run-time selected form (kernel parameter, warp uniform): mode 2 = exact erf, otherwise the tanh form
+__device__ __forceinline__ float gelu_fwd(float x, int exact) { return exact ? gelu_erf(x) : gelu_tanh(x); }
+__device__ __forceinline__ float gelu_bwd(float x, int exact) { return exact ? gelu_erf_grad(x) : gelu_tanh_grad(x); }
 
 // 16-bit storage type helpers: T16 is __nv_bfloat16 (blocks) or __half (stem/head)
 template <typename T> struct T16x2;

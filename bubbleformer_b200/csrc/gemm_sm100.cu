@@ -51,6 +51,7 @@ struct GemmParams {
   int s2d_wo;         // output width
   uint32_t idesc;
   int is_f16;
+  int gelu_exact;     // GELU / DGELU epilogues: 1 = exact erf (bf_set_gelu_mode), 0 = tanh form
   int epilogue;
   int rows_per_group;
   int d2s_h, d2s_w, d2s_cout;
@@ -547,7 +548,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               if (p.is_f16) st_row_16<__half>(s2, lane, acc); else st_row_16<__nv_bfloat16>(s2, lane, acc);
             }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = gelu_tanh(acc[j]);
+            for (int j = 0; j < 32; ++j) acc[j] = gelu_fwd(acc[j], p.gelu_exact);
             if (p.is_f16) st_row_16<__half>(s, lane, acc); else st_row_16<__nv_bfloat16>(s, lane, acc);
             fence_proxy_async();
             __syncwarp();
@@ -580,7 +581,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             float pre[32];
             if (p.is_f16) ld_row_16<__half>(box, row, pre); else ld_row_16<__nv_bfloat16>(box, row, pre);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] *= gelu_tanh_grad(pre[j]);
+            for (int j = 0; j < 32; ++j) acc[j] *= gelu_bwd(pre[j], p.gelu_exact);
             if (p.is_f16) st_row_16<__half>(box, row, acc); else st_row_16<__nv_bfloat16>(box, row, acc);
             fence_proxy_async();
             __syncwarp();
@@ -916,6 +917,7 @@ extern "C" int bf_gemm(const bf_gemm_args* a, void* stream) {
   p.split_k = a->split_k;
   p.epilogue = a->epilogue;
   p.is_f16 = a->dtype == BF_F16;
+  p.gelu_exact = gelu_exact() ? 1 : 0;
   p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1;
   p.d2s_h = a->d2s_h; p.d2s_w = a->d2s_w; p.d2s_cout = a->d2s_cout;
   p.bias = a->bias; p.col_scale = a->col_scale; p.col_shift = a->col_shift; p.col_gamma = a->col_gamma;

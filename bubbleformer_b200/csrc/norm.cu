@@ -196,9 +196,10 @@ struct ApplyParams {
   const float* weight;
   const float* bias;
   int gelu;
-  const float* film_gamma;   // [I / film_T][C]
+  const float* film_gamma;   // [I / film_T][film_ld]
   const float* film_beta;
   int film_T;
+  int film_ld;               // row pitch of film_gamma / film_beta (C, or 2C when both live in one (B, 2C) matrix)
   const float* resid_in;     // fp32 (I*P, C) ld = ldo, or null
   const float* row_scale;    // [I] or null
   const float* col_gamma;    // [C] (with resid_in)
@@ -226,7 +227,7 @@ inorm_apply_kernel(const TI* __restrict__ x, TO* __restrict__ out, ApplyParams p
       b[j] = p.bias[c0 + j] - mean * rstd * w;
       fg[j] = 1.f; fb[j] = 0.f; cg[j] = 1.f;
       if (p.film_gamma != nullptr) {
-        const long fi = (long)(c.img / p.film_T) * g.C + c0 + j;
+        const long fi = (long)(c.img / p.film_T) * p.film_ld + c0 + j;
         fg[j] = p.film_gamma[fi];
         fb[j] = p.film_beta[fi];
       }
@@ -256,7 +257,7 @@ inorm_apply_kernel(const TI* __restrict__ x, TO* __restrict__ out, ApplyParams p
   float v[8];                                                                            \
   unpack8<TI>(ring + ((st) * NSLOT) * kNT + threadIdx.x, v);                             \
   _Pragma("unroll") for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], a[j], b[j]);          \
-  if (p.gelu) { _Pragma("unroll") for (int j = 0; j < 8; ++j) v[j] = gelu_tanh(v[j]); }  \
+  if (p.gelu) { _Pragma("unroll") for (int j = 0; j < 8; ++j) v[j] = gelu_fwd(v[j], p.gelu == 2); }  \
   if (post_film) { _Pragma("unroll") for (int j = 0; j < 8; ++j) v[j] = fmaf(fg[j], v[j], fb[j]); } \
   if (RESID) {                                                                           \
     float xr[8];                                                                         \
@@ -292,8 +293,9 @@ struct BwdParams {
   // pass 2 only
   const float* row_scale;    // [I] or null
   const float* col_scale;    // [C] or null
-  const float* film_gamma;   // [I / film_T][C] or null
+  const float* film_gamma;   // [I / film_T][film_ld] or null
   int film_T;
+  int film_ld;               // row pitch of film_gamma / dfilm_gamma / dfilm_beta
   const float* add32;        // fp32 tensor added to the result (residual-stream gradient), ld = ldo
   // pass 2, optional: parameter gradients from `red` (fp32 atomics by the first row split of every image)
   float* dweight; float* dbias; float* dcol_scale; float* dfilm_gamma; float* dfilm_beta;
@@ -335,7 +337,7 @@ inorm_bwd_reduce_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, Bw
   unpack8<TX>(ring + ((st) * NSLOT + NG) * kNT + threadIdx.x, xv);                      \
   _Pragma("unroll") for (int j = 0; j < 8; ++j) {                                       \
     float gg = gv[j];                                                                   \
-    if (GELU) gg *= gelu_tanh_grad(fmaf(xv[j], wa[j], wb[j]));                           \
+    if (GELU) gg *= gelu_bwd(fmaf(xv[j], wa[j], wb[j]), p.gelu == 2);                    \
     acc[j] += gg;                                                                       \
     acc[8 + j] = fmaf(gg, xv[j], acc[8 + j]);                                           \
   }
@@ -376,7 +378,7 @@ inorm_bwd_apply_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, TO*
       float cs = 1.f;
       if (p.row_scale != nullptr) cs *= p.row_scale[c.img];
       if (p.col_scale != nullptr) cs *= p.col_scale[c0 + j];
-      if (p.film_gamma != nullptr) cs *= p.film_gamma[(long)(c.img / p.film_T) * g.C + c0 + j];
+      if (p.film_gamma != nullptr) cs *= p.film_gamma[(long)(c.img / p.film_T) * p.film_ld + c0 + j];
       const float k = rstd * w * cs;
       const float m1 = p.red[2 * idx] * inv_p, m2 = p.red[2 * idx + 1] * inv_p;
       ka[j] = k;
@@ -392,7 +394,7 @@ inorm_bwd_apply_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, TO*
         if (p.dcol_scale != nullptr)
           atomicAdd(p.dcol_scale + c0 + j, (p.row_scale != nullptr ? p.row_scale[c.img] : 1.f) * fmaf(w, R2, b * R1));
         if (p.dfilm_gamma != nullptr) {
-          const long fi = (long)(c.img / p.film_T) * g.C + c0 + j;
+          const long fi = (long)(c.img / p.film_T) * p.film_ld + c0 + j;
           atomicAdd(p.dfilm_gamma + fi, fmaf(w, R2, b * R1));
           atomicAdd(p.dfilm_beta + fi, R1);
         }
@@ -413,7 +415,7 @@ inorm_bwd_apply_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, TO*
   unpack8<TX>(ring + ((st) * NSLOT + NG) * kNT + threadIdx.x, xv);                      \
   _Pragma("unroll") for (int j = 0; j < 8; ++j) {                                       \
     float gg = gv[j];                                                                   \
-    if (GELU) gg *= gelu_tanh_grad(fmaf(xv[j], wa[j], wb[j]));                           \
+    if (GELU) gg *= gelu_bwd(fmaf(xv[j], wa[j], wb[j]), p.gelu == 2);                    \
     o[j] = fmaf(ka[j], gg, fmaf(kb[j], xv[j], kc[j]));                                  \
   }                                                                                     \
   if (ADD) {                                                                            \
@@ -622,8 +624,10 @@ extern "C" int bf_inorm_apply(const bf_inorm_apply_args* a, void* stream) {
   ApplyParams p{};
   p.g = make_geom(a->I, a->P, a->C);
   p.ldx = a->ldx; p.ldo = a->ldo;
-  p.stats = a->stats; p.weight = a->weight; p.bias = a->bias; p.gelu = a->gelu;
+  p.stats = a->stats; p.weight = a->weight; p.bias = a->bias; p.gelu = a->gelu ? (gelu_exact() ? 2 : 1) : 0;
   p.film_gamma = a->film_gamma; p.film_beta = a->film_beta; p.film_T = a->film_T > 0 ? a->film_T : 1;
+  p.film_ld = a->film_ld > 0 ? a->film_ld : a->C;
+  BF_REQUIRE(p.film_ld >= a->C, "bf_inorm_apply: film_ld < C");
   p.resid_in = a->resid_in; p.row_scale = a->row_scale; p.col_gamma = a->col_gamma;
   p.stats_out = a->stats_out;
   dim3 grid(p.g.splits, a->I, p.g.chunks);
@@ -658,9 +662,11 @@ extern "C" int bf_inorm_bwd(const bf_inorm_bwd_args* a, void* stream) {
   BwdParams p{};
   p.g = make_geom(a->I, a->P, a->C);
   p.ldg = a->ldg; p.ldx = a->ldx; p.ldo = a->ldo;
-  p.stats = a->stats; p.weight = a->weight; p.bias = a->bias; p.gelu = a->gelu; p.red = a->red;
+  p.stats = a->stats; p.weight = a->weight; p.bias = a->bias; p.gelu = a->gelu ? (gelu_exact() ? 2 : 1) : 0; p.red = a->red;
   p.row_scale = a->row_scale; p.col_scale = a->col_scale; p.film_gamma = a->film_gamma;
   p.film_T = a->film_T > 0 ? a->film_T : 1; p.add32 = a->add32;
+  p.film_ld = a->film_ld > 0 ? a->film_ld : a->C;
+  BF_REQUIRE(p.film_ld >= a->C, "bf_inorm_bwd: film_ld < C");
   p.dweight = a->dweight; p.dbias = a->dbias; p.dcol_scale = a->dcol_scale;
   p.dfilm_gamma = a->dfilm_gamma; p.dfilm_beta = a->dfilm_beta;
   BF_REQUIRE((a->dweight == nullptr) == (a->dbias == nullptr), "bf_inorm_bwd: dweight / dbias pair");

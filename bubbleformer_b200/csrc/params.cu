@@ -84,9 +84,119 @@ __global__ void __launch_bounds__(128) branch_param_grads_kernel(BranchGradArgs 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// FiLM conditioning vector (upstream layers/linear_layers.py:58-61,71-72):  gb[b] = Linear(LayerNorm_F(cond[b]))
+// F = number of fluid parameters (9 in every shipped config), 2E outputs.  One block per sample.
+// ---------------------------------------------------------------------------------------------
+constexpr int kFilmMaxF = 32;
+
+__device__ __forceinline__ void film_ln_row(const float* cond, int F, const float* lw, const float* lb, float* xhat,
+                                            float* c, float& rstd_out) {
+  float mean = 0.f;
+  for (int f = 0; f < F; ++f) mean += cond[f];
+  mean /= (float)F;
+  float var = 0.f;
+  for (int f = 0; f < F; ++f) { const float d = cond[f] - mean; var = fmaf(d, d, var); }
+  const float rstd = rsqrtf(var / (float)F + 1e-5f);
+  for (int f = 0; f < F; ++f) {
+    xhat[f] = (cond[f] - mean) * rstd;
+    c[f] = fmaf(xhat[f], lw[f], lb[f]);
+  }
+  rstd_out = rstd;
+}
+
+__global__ void __launch_bounds__(256)
+film_fwd_kernel(const float* __restrict__ cond, int F, const float* __restrict__ lw, const float* __restrict__ lb,
+                const float* __restrict__ W, const float* __restrict__ bias, int E2, float* __restrict__ gb) {
+  pdl_prologue_done();
+  __shared__ float s_c[kFilmMaxF], s_x[kFilmMaxF];
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    float rstd;
+    film_ln_row(cond + (long)b * F, F, lw, lb, s_x, s_c, rstd);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < E2; j += blockDim.x) {
+    float acc = bias[j];
+    for (int f = 0; f < F; ++f) acc = fmaf(W[(long)j * F + f], s_c[f], acc);
+    gb[(long)b * E2 + j] = acc;
+  }
+}
+
+// one block: d_W[j,f] += sum_b dgb[b,j] c[b,f];  d_bias[j] += sum_b dgb[b,j];  dc[b,f] = sum_j dgb[b,j] W[j,f];
+// LayerNorm backward over F for the affine parameters:  d_lw[f] += sum_b dc*xhat,  d_lb[f] += sum_b dc.
+__global__ void __launch_bounds__(256)
+film_bwd_kernel(const float* __restrict__ dgb, const float* __restrict__ cond, int B, int F,
+                const float* __restrict__ lw, const float* __restrict__ lb, const float* __restrict__ W, int E2,
+                float* __restrict__ d_lw, float* __restrict__ d_lb, float* __restrict__ d_W, float* __restrict__ d_bias) {
+  pdl_prologue_done();
+  extern __shared__ float sm[];            // c[B][F], xhat[B][F], dc[B][F]
+  float* s_c = sm;
+  float* s_x = s_c + B * F;
+  float* s_dc = s_x + B * F;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    float rstd;
+    film_ln_row(cond + (long)b * F, F, lw, lb, s_x + b * F, s_c + b * F, rstd);
+  }
+  for (int i = threadIdx.x; i < B * F; i += blockDim.x) s_dc[i] = 0.f;
+  __syncthreads();
+  for (int j = threadIdx.x; j < E2; j += blockDim.x) {
+    float dw[kFilmMaxF];
+#pragma unroll
+    for (int f = 0; f < kFilmMaxF; ++f) dw[f] = 0.f;
+    float db = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const float g = dgb[(long)b * E2 + j];
+      db += g;
+#pragma unroll
+      for (int f = 0; f < kFilmMaxF; ++f)
+        if (f < F) {
+          dw[f] = fmaf(g, s_c[b * F + f], dw[f]);
+          atomicAdd(s_dc + b * F + f, g * W[(long)j * F + f]);
+        }
+    }
+    d_bias[j] += db;
+#pragma unroll
+    for (int f = 0; f < kFilmMaxF; ++f)
+      if (f < F) d_W[(long)j * F + f] += dw[f];
+  }
+  __syncthreads();
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    float a = 0.f, c = 0.f;
+    for (int b = 0; b < B; ++b) { a = fmaf(s_dc[b * F + f], s_x[b * F + f], a); c += s_dc[b * F + f]; }
+    d_lw[f] += a;
+    d_lb[f] += c;
+  }
+}
+
 }  // namespace bf
 
 using namespace bf;
+
+extern "C" int bf_film_fwd(const float* cond, int B, int F, const float* ln_w, const float* ln_b, const float* W,
+                           const float* bias, int E2, float* gb, void* stream) {
+  BF_REQUIRE(cond && ln_w && ln_b && W && bias && gb, "bf_film_fwd: null pointer");
+  BF_REQUIRE(B > 0 && E2 > 0 && F > 0 && F <= kFilmMaxF, "bf_film_fwd: B=%d F=%d (<= %d) E2=%d", B, F, kFilmMaxF, E2);
+  launch_k(film_fwd_kernel, dim3(B), dim3(256), (size_t)0, static_cast<cudaStream_t>(stream), cond, F, ln_w, ln_b, W,
+           bias, E2, gb);
+  count_launch();
+  BF_LAUNCH_CHECK("film_fwd_kernel");
+  return BF_OK;
+}
+
+extern "C" int bf_film_bwd(const float* dgb, const float* cond, int B, int F, const float* ln_w, const float* ln_b,
+                           const float* W, int E2, float* d_ln_w, float* d_ln_b, float* d_W, float* d_bias,
+                           void* stream) {
+  BF_REQUIRE(dgb && cond && ln_w && ln_b && W && d_ln_w && d_ln_b && d_W && d_bias, "bf_film_bwd: null pointer");
+  BF_REQUIRE(B > 0 && E2 > 0 && F > 0 && F <= kFilmMaxF, "bf_film_bwd: B=%d F=%d (<= %d) E2=%d", B, F, kFilmMaxF, E2);
+  const size_t smem = (size_t)3 * B * F * sizeof(float);
+  BF_REQUIRE(smem <= 48 * 1024, "bf_film_bwd: batch %d too large for one block", B);
+  launch_k(film_bwd_kernel, dim3(1), dim3(256), smem, static_cast<cudaStream_t>(stream), dgb, cond, B, F, ln_w, ln_b, W,
+           E2, d_ln_w, d_ln_b, d_W, d_bias);
+  count_launch();
+  BF_LAUNCH_CHECK("film_bwd_kernel");
+  return BF_OK;
+}
 
 extern "C" int bf_feat_consts(const float* W, const float* norm2_bias, const float* out_bias, const float* low,
                               const float* high, int E, float* c, float* c1, float* c0, void* stream) {

@@ -426,9 +426,7 @@ def embed_forward(x, g_in, p, n_layers: int, film_gb: Optional[torch.Tensor], T:
             X = _empty((M, Cout), F32, x)
             st_out = _zeros((I, Cout, 2), x)
             if film_gb is not None:
-                E = Cout
-                fg, fb = film_gb[:, :E].contiguous(), film_gb[:, E:].contiguous()
-                ops.inorm_apply(Y, X, I, ho * wo, st, nw, nb, film_gamma=fg, film_beta=fb, film_T=T, stats_out=st_out)
+                ops.inorm_apply(Y, X, I, ho * wo, st, nw, nb, film_gb=film_gb, film_T=T, stats_out=st_out)
             else:
                 ops.inorm_apply(Y, X, I, ho * wo, st, nw, nb, stats_out=st_out)
             _publish_stats(X, st_out)
@@ -456,18 +454,13 @@ def embed_backward(dX, p, n_layers: int, film_gb, T: int, sv, grads, need_dx: bo
         red = _zeros((I, Cout, 2), dX)
         ops.inorm_bwd(1, gin, Y, I, ho * wo, st, nw, nb, red, gelu=not last)
         dY = _empty((M, Cout), BF16, dX)
-        kw = {}
-        if last and film_gb is not None:
-            fg = film_gb[:, :Cout].contiguous()
-            kw = dict(film_gamma=fg, film_T=T)
         pk = dict(dweight=grads[f"in_proj.{3 * i + 1}.weight"], dbias=grads[f"in_proj.{3 * i + 1}.bias"])
         if last and film_gb is not None:
-            dfg_c, dfb_c = _zeros((I // T, Cout), dX), _zeros((I // T, Cout), dX)
-            ops.inorm_bwd(2, gin, Y, I, ho * wo, st, nw, nb, red, gelu=not last, out=dY, dfilm_gamma=dfg_c,
-                          dfilm_beta=dfb_c, **kw, **pk)
-            dfilm = torch.cat([dfg_c, dfb_c], dim=1)
+            dfilm = _zeros((I // T, 2 * Cout), dX)          # [d gamma | d beta], the layout of bf_film_fwd's output
+            ops.inorm_bwd(2, gin, Y, I, ho * wo, st, nw, nb, red, gelu=not last, out=dY, film_gb=film_gb, film_T=T,
+                          dfilm_gb=dfilm, **pk)
         else:
-            ops.inorm_bwd(2, gin, Y, I, ho * wo, st, nw, nb, red, gelu=not last, out=dY, **kw, **pk)
+            ops.inorm_bwd(2, gin, Y, I, ho * wo, st, nw, nb, red, gelu=not last, out=dY, **pk)
         wt = p[f"in_proj.{3 * i}.weight"]
         if i == 0:
             ops.patch_wgrad(dY.view(I, ho, wo, Cout), x, grads[f"in_proj.0.weight"])

@@ -49,6 +49,29 @@ class SirenMLP(nn.Module):
         raise NotImplementedError("SirenMLP is outside the B200 hot path (no upstream model uses it)")
 
 
+class _FilmFn(torch.autograd.Function):
+    """LayerNorm(F) -> Linear(F, 2E) on the device kernels (stand-alone use; inside FiLMConditionedAViT the same two
+    kernels run within the patch-embed Function so the parameter gradients land in the flat gradient buffer)."""
+
+    @staticmethod
+    def forward(ctx, cond, ln_w, ln_b, W, b):
+        ctx.save_for_backward(cond, ln_w, ln_b, W)
+        return ops.film_fwd(cond, ln_w.detach(), ln_b.detach(), W.detach(), b.detach())
+
+    @staticmethod
+    def backward(ctx, dgb):
+        cond, ln_w, ln_b, W = ctx.saved_tensors
+        flat = torch.zeros(2 * ln_w.numel() + W.numel() + W.shape[0] + 24, dtype=torch.float32, device=dgb.device)
+        F_, E2 = ln_w.numel(), W.shape[0]
+        o = [0, (F_ + 7) // 8 * 8, 2 * ((F_ + 7) // 8 * 8)]
+        d_lw, d_lb = flat[o[0]:o[0] + F_], flat[o[1]:o[1] + F_]
+        d_W = flat[o[2]:o[2] + E2 * F_].view(E2, F_)
+        ob = o[2] + (E2 * F_ + 7) // 8 * 8
+        d_b = flat[ob:ob + E2]
+        ops.film_bwd(dgb.contiguous(), cond, ln_w.detach(), ln_b.detach(), W.detach(), d_lw, d_lb, d_W, d_b)
+        return None, d_lw, d_lb, d_W, d_b
+
+
 class FiLMMLP(nn.Module):
     """LayerNorm(param_dim) -> Linear(param_dim, 2E) -> gamma * x + beta (upstream linear_layers.py:49-77).
 
@@ -61,7 +84,9 @@ class FiLMMLP(nn.Module):
         self.film_net = nn.Sequential(nn.LayerNorm(param_dim), nn.Linear(param_dim, embed_dim * 2))
 
     def gamma_beta(self, cond: torch.Tensor) -> torch.Tensor:
-        return self.film_net(cond.to(torch.float32))
+        """(B, F) fluid parameters -> (B, 2E) = [gamma | beta] through bf_film_fwd / bf_film_bwd."""
+        ln, lin = self.film_net[0], self.film_net[1]
+        return _FilmFn.apply(cond.to(torch.float32).contiguous(), ln.weight, ln.bias, lin.weight, lin.bias)
 
     def forward(self, x: torch.Tensor, cond) -> torch.Tensor:
         gamma, beta = self.gamma_beta(cond).chunk(2, dim=1)

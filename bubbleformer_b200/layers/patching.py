@@ -10,7 +10,7 @@ import math
 import torch
 import torch.nn as nn
 
-from .. import engine
+from .. import engine, ops
 from ..autograd import run
 
 
@@ -18,15 +18,33 @@ def _prefixed(module: nn.Module):
     return {k: v for k, v in module.named_parameters()}
 
 
+_FILM_KEYS = ("film.film_net.0.weight", "film.film_net.0.bias", "film.film_net.1.weight", "film.film_net.1.bias")
+
+
 class _EmbedSpec:
-    def __init__(self, names, n_layers, T):
-        self.names, self.n_layers, self.T = names, n_layers, T
+    """aux is the (B, 2E) FiLM matrix [gamma | beta] (film=False: produced elsewhere, gets a gradient) or the raw (B, F)
+    fluid parameters (film=True: the FiLM MLP of upstream linear_layers.py:58-61 runs inside this Function, so its
+    parameter gradients are part of the embed's segment of the flat gradient buffer)."""
+
+    def __init__(self, names, n_layers, T, film=False):
+        self.names, self.n_layers, self.T, self.film = names, n_layers, T, film
 
     def forward(self, x, aux, pd, save):
-        return engine.embed_forward(x, None, pd, self.n_layers, aux, self.T, save)
+        gb = aux
+        if self.film:
+            gb = ops.film_fwd(aux, *(pd[k] for k in _FILM_KEYS))
+        X, sv = engine.embed_forward(x, None, pd, self.n_layers, gb, self.T, save)
+        if sv is not None and self.film:
+            sv["cond"] = aux
+        return X, sv
 
     def backward(self, dout, pd, saved, grads, need_dx):
-        return engine.embed_backward(dout, pd, self.n_layers, saved.get("film_gb"), self.T, saved, grads, need_dx)
+        dx, dfilm = engine.embed_backward(dout, pd, self.n_layers, saved.get("film_gb"), self.T, saved, grads, need_dx)
+        if self.film:
+            lw, lb, W, _ = (pd[k] for k in _FILM_KEYS)
+            ops.film_bwd(dfilm, saved["cond"], lw, lb, W, *(grads[k] for k in _FILM_KEYS))
+            dfilm = None
+        return dx, dfilm
 
 
 class HMLPEmbed(nn.Module):
@@ -52,11 +70,16 @@ class HMLPEmbed(nn.Module):
             conv_in = conv_out
         self.in_proj = nn.Sequential(*layers)
 
-    def tokens(self, x: torch.Tensor, film_gb, T: int) -> torch.Tensor:
-        """x: (I, C, H, W) fp32 contiguous -> token-major (I*h*w, E) fp32."""
+    def tokens(self, x: torch.Tensor, film_in, T: int, film: nn.Module = None) -> torch.Tensor:
+        """x: (I, C, H, W) fp32 contiguous -> token-major (I*h*w, E) fp32.
+
+        film_in: None, the (B, 2E) FiLM matrix [gamma | beta], or -- with `film` (a FiLMMLP) -- the raw (B, F) fluid
+        parameters; FiLM is applied by the last InstanceNorm pass."""
         pd = _prefixed(self)
-        spec = _EmbedSpec(list(pd.keys()), self.num_layers, T)
-        return run(spec, x, film_gb, pd)
+        if film is not None:
+            pd.update({"film." + k: v for k, v in film.named_parameters()})
+        spec = _EmbedSpec(list(pd.keys()), self.num_layers, T, film=film is not None)
+        return run(spec, x, film_in, pd)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """(B, C, H, W) -> (B, E, H/p, W/p) like upstream."""

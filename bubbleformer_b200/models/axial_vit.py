@@ -91,7 +91,7 @@ class _AViTBase(nn.Module):
                 out.append((mb[i], m[i, B:B + I], m[i, B + I:]))
         return out
 
-    def _run(self, x: torch.Tensor, film_gb: Optional[torch.Tensor]) -> torch.Tensor:
+    def _run(self, x: torch.Tensor, cond: Optional[torch.Tensor]) -> torch.Tensor:
         if x.dim() != 5:
             raise ValueError(f"expected (B, T, C, H, W), got {tuple(x.shape)}")
         if not x.is_cuda:
@@ -107,7 +107,7 @@ class _AViTBase(nn.Module):
         geom = engine.Geom(B, T, H // p, W // p)
         engine.reset_arena()
         xi = x.to(torch.float32).contiguous().view(B * T, C, H, W)
-        X = self.embed.tokens(xi, film_gb, T)
+        X = self.embed.tokens(xi, cond, T, film=self.film_embed if cond is not None else None)
         drawn = self._draw_drop_masks(B, T, x.device) if self.drop_masks_override is None else None
         for i, blk in enumerate(self.blocks):
             masks = self.drop_masks_override[i] if self.drop_masks_override is not None else (drawn[i] if drawn else None)
@@ -150,5 +150,4 @@ class FiLMConditionedAViT(_AViTBase):
         """x: (B, T, C, H, W); fluid_params: (B, num_fluid_params) -> (B, T, C_out, H, W)."""
         if fluid_params.shape[0] != x.shape[0]:
             raise ValueError("fluid_params must have one row per batch sample")
-        gb = self.film_embed.gamma_beta(fluid_params.to(x.device))
-        return self._run(x, gb)
+        return self._run(x, fluid_params.to(device=x.device, dtype=torch.float32).contiguous())

@@ -117,8 +117,16 @@ def inorm_stats(x: torch.Tensor, I: int, P: int, stats: torch.Tensor) -> None:
     L.check(L.lib.bf_inorm_stats(_ptr(x), _dt(x), I, P, C_, x.stride(0), _ptr(stats), _stream()), "bf_inorm_stats")
 
 
+def _film_ptrs(film_gb: torch.Tensor, C_: int):
+    """(gamma pointer, beta pointer, row pitch) of a (B, 2C) FiLM matrix [gamma | beta] (bf_film_fwd's output)."""
+    if film_gb.dtype != torch.float32 or not film_gb.is_contiguous() or film_gb.dim() != 2 or film_gb.shape[1] != 2 * C_:
+        raise L.BubbleformerB200Error(f"film_gb: expected contiguous float32 (B, {2 * C_})")
+    base = _ptr(film_gb)
+    return base, base + 4 * C_, 2 * C_
+
+
 def inorm_apply(x, out, I, P, stats, weight, bias, *, gelu=False, film_gamma=None, film_beta=None, film_T=0,
-                resid_in=None, row_scale=None, col_gamma=None, stats_out=None) -> None:
+                film_gb=None, resid_in=None, row_scale=None, col_gamma=None, stats_out=None) -> None:
     _mat(x, "x"); _mat(out, "out")
     C_ = x.shape[1]
     a = L.InormApplyArgs()
@@ -129,6 +137,8 @@ def inorm_apply(x, out, I, P, stats, weight, bias, *, gelu=False, film_gamma=Non
     a.weight, a.bias = _f32(weight, C_, "weight"), _f32(bias, C_, "bias")
     a.film_gamma = _f32(film_gamma, 1, "film_gamma")
     a.film_beta = _f32(film_beta, 1, "film_beta")
+    if film_gb is not None:
+        a.film_gamma, a.film_beta, a.film_ld = _film_ptrs(film_gb, C_)
     a.film_T = film_T
     if resid_in is not None:
         _mat(resid_in, "resid_in")
@@ -143,7 +153,7 @@ def inorm_apply(x, out, I, P, stats, weight, bias, *, gelu=False, film_gamma=Non
 
 def inorm_bwd(phase, gin, x, I, P, stats, weight, bias, red, *, gelu=False, out=None, row_scale=None,
               col_scale=None, film_gamma=None, film_T=0, add32=None, dweight=None, dbias=None, dcol_scale=None,
-              dfilm_gamma=None, dfilm_beta=None) -> None:
+              dfilm_gamma=None, dfilm_beta=None, film_gb=None, dfilm_gb=None) -> None:
     _mat(gin, "gin"); _mat(x, "x")
     C_ = x.shape[1]
     a = L.InormBwdArgs()
@@ -167,6 +177,10 @@ def inorm_bwd(phase, gin, x, I, P, stats, weight, bias, red, *, gelu=False, out=
     a.dweight, a.dbias = _f32(dweight, C_, "dweight"), _f32(dbias, C_, "dbias")
     a.dcol_scale = _f32(dcol_scale, C_, "dcol_scale")
     a.dfilm_gamma, a.dfilm_beta = _f32(dfilm_gamma, 1, "dfilm_gamma"), _f32(dfilm_beta, 1, "dfilm_beta")
+    if film_gb is not None:          # [gamma | beta] rows of pitch 2C (bf_film_fwd's layout), gradients likewise
+        a.film_gamma, _, a.film_ld = _film_ptrs(film_gb, C_)
+        if dfilm_gb is not None:
+            a.dfilm_gamma, a.dfilm_beta, _ = _film_ptrs(dfilm_gb, C_)
     L.check(L.lib.bf_inorm_bwd(C.byref(a), _stream()), "bf_inorm_bwd")
 
 
@@ -217,6 +231,26 @@ def branch_param_grads(S01, gamma, d_gamma, d_out_bias, feat=None) -> None:
             setattr(a, k, _f32(feat[k], E, k))
         a.W, a.d_W = _f32(feat["W"], E * E, "W"), _f32(feat["d_W"], E * E, "d_W")
     L.check(L.lib.bf_branch_param_grads(C.byref(a), _stream()), "bf_branch_param_grads")
+
+
+def film_fwd(cond, ln_w, ln_b, W, bias) -> torch.Tensor:
+    """gb (B, 2E) = Linear(LayerNorm(cond)); cond (B, F) fp32 (upstream linear_layers.py:58-61, 71-72)."""
+    B, F = cond.shape
+    E2 = W.shape[0]
+    gb = torch.empty(B, E2, dtype=torch.float32, device=cond.device)
+    L.check(L.lib.bf_film_fwd(_f32(cond, B * F, "cond"), B, F, _f32(ln_w, F, "ln_w"), _f32(ln_b, F, "ln_b"),
+                              _f32(W, E2 * F, "W"), _f32(bias, E2, "bias"), E2, _ptr(gb), _stream()), "bf_film_fwd")
+    return gb
+
+
+def film_bwd(dgb, cond, ln_w, ln_b, W, d_ln_w, d_ln_b, d_W, d_bias) -> None:
+    """Accumulates the FiLM MLP's parameter gradients from dgb (B, 2E)."""
+    B, F = cond.shape
+    E2 = W.shape[0]
+    L.check(L.lib.bf_film_bwd(_f32(dgb, B * E2, "dgb"), _f32(cond, B * F, "cond"), B, F, _f32(ln_w, F, "ln_w"),
+                              _f32(ln_b, F, "ln_b"), _f32(W, E2 * F, "W"), E2, _f32(d_ln_w, F, "d_ln_w"),
+                              _f32(d_ln_b, F, "d_ln_b"), _f32(d_W, E2 * F, "d_W"), _f32(d_bias, E2, "d_bias"),
+                              _stream()), "bf_film_bwd")
 
 
 def colsum16(x, out) -> None:
@@ -375,6 +409,6 @@ def _attn_tag(a, k):
 gemm = _instrument("gemm", gemm, _gemm_tag)
 attention = _instrument("attention", attention, _attn_tag)
 for _n in ("inorm_stats", "inorm_apply", "inorm_bwd", "inorm_bwd_params", "resid_bwd", "colsum16", "feat_consts",
-           "branch_param_grads", "patch_in",
+           "branch_param_grads", "film_fwd", "film_bwd", "patch_in",
            "patch_out", "patch_wgrad", "s2d_gather", "cast16", "convert16", "lploss_sums", "lploss_bwd"):
     globals()[_n] = _instrument(_n, globals()[_n], _shape_tag)

@@ -32,6 +32,9 @@ class GradSink:
             o = self.offsets[id(p)]
             p.grad = self.flat[o:o + p.numel()].view(p.shape)
         self.params = params
+        self._views = {id(p): p.grad for p in params}
+        if self.world > 1:
+            self._sync_parameters()
         self.bucket_elems = bucket_bytes // 4
         self.comm_stream = torch.cuda.Stream(device=dev) if (self.world > 1 and dev.type == "cuda") else None
         self._pending: List = []
@@ -41,12 +44,37 @@ class GradSink:
         from . import autograd
         autograd.ACTIVE_SINK = self
 
+    def _sync_parameters(self) -> None:
+        """Rank 0's parameters become everyone's (what DistributedDataParallel does at construction, upstream
+        scripts/train.py:163): averaging the gradients of replicas that started from different weights is not
+        data-parallel training.  One broadcast of the flat weight bank when the model has one, else of a packed copy."""
+        bank = getattr(self.model, "_bank", None)
+        if bank is not None and bank.flat is not None:
+            dist.broadcast(bank.flat, src=0, group=self.group)
+            bank.invalidate()
+            return
+        with torch.no_grad():
+            packed = torch.cat([p.detach().reshape(-1) for p in self.params])
+            dist.broadcast(packed, src=0, group=self.group)
+            o = 0
+            for p in self.params:
+                p.copy_(packed[o:o + p.numel()].view(p.shape))
+                o += p.numel()
+
     def owns(self, p: torch.Tensor) -> bool:
+        """Ownership is by parameter identity, never by what `p.grad` currently points at: `zero_grad(set_to_none=True)`
+        (torch's default) must not silently route gradients around the flat buffer."""
+        return id(p) in self.offsets
+
+    def _attach(self, p: torch.Tensor) -> bool:
+        """Make `p.grad` the parameter's view of the flat buffer again.  Returns True when it had been lost (set to
+        None or replaced), in which case the caller zeroes the segment: a fresh gradient starts from zero."""
+        v = self._views[id(p)]
         g = p.grad
-        if g is None:
+        if g is not None and g.data_ptr() == v.data_ptr():
             return False
-        o = g.data_ptr() - self.flat.data_ptr()
-        return 0 <= o < 4 * self.flat.numel()
+        p.grad = v
+        return True
 
     def close(self) -> None:
         from . import autograd
@@ -65,15 +93,15 @@ class GradSink:
         """Gradient views for the parameters of one autograd Function."""
         out = {}
         for n, p in named.items():
-            o = self._offset_of(p)
-            out[n] = self.flat[o:o + p.numel()].view(p.shape)
+            if id(p) not in self.offsets:
+                raise RuntimeError(f"GradSink: parameter {n} is not part of the model this sink was built for")
+            if self._attach(p):
+                self._views[id(p)].zero_()           # zero_grad(set_to_none=True) semantics: start from zero
+            out[n] = self._views[id(p)]
         return out
 
     def _offset_of(self, p: torch.Tensor) -> int:
-        g = p.grad
-        if g is None:
-            raise RuntimeError("GradSink: parameter lost its gradient view (use sink.begin_step(), not zero_grad())")
-        return (g.data_ptr() - self.flat.data_ptr()) // 4
+        return self.offsets[id(p)]
 
     def segment_done(self, named: Dict[str, torch.Tensor]) -> None:
         """Called when one Function's backward kernels have been enqueued: maybe launch a bucket all-reduce."""
@@ -83,9 +111,10 @@ class GradSink:
         hi = max(self._offset_of(p) + p.numel() for p in named.values())
         self._lo = lo if self._lo is None else min(self._lo, lo)
         self._hi = hi if self._hi is None else max(self._hi, hi)
-        # the Function owning offset 0 (the embed) runs last, and the FiLM MLP's gradients (plain torch autograd,
-        # laid out right after it) only arrive once it has returned: leave that bucket to finish()
-        if lo > 0 and self._hi - self._lo >= self.bucket_elems:
+        # Buckets fill in reverse parameter order (debed first, embed last).  Near the front of the buffer, i.e. at the
+        # end of backward, every segment is flushed at once so that only a small reduction is still in flight when
+        # backward ends (the exposed tail of the step).
+        if self._hi - self._lo >= self.bucket_elems or lo < self.bucket_elems:
             self._flush()
 
     def _flush(self) -> None:
@@ -108,6 +137,15 @@ class GradSink:
     def finish(self) -> None:
         """Flush the last bucket, reduce whatever no Function owns (parameters differentiated by plain torch
         autograd, e.g. the FiLM MLP), and make the compute stream wait for all reductions."""
+        # parameters differentiated by plain torch autograd (none in the shipped models): if their .grad was replaced by
+        # a fresh tensor (zero_grad(set_to_none=True) before backward), fold it back into the flat buffer
+        for p in self.params:
+            g, v = p.grad, self._views[id(p)]
+            if g is None:
+                p.grad = v
+            elif g.data_ptr() != v.data_ptr():
+                v.copy_(g)
+                p.grad = v
         if self.world == 1:
             return
         self._flush()

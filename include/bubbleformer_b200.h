@@ -45,6 +45,15 @@ BF_API int bf_version(void);
 /* number of kernel launches issued through this library by the calling process (bench.py's gpu_launches) */
 BF_API int64_t bf_launch_count(void);
 
+/* GELU.  Upstream uses nn.GELU() = exact erf (layers/linear_layers.py:16, layers/patching.py:47,103).  The default
+ * here is the tanh form  0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))  with one MUFU.TANH: |tanh form - erf form|
+ * <= 4.8e-4 absolute, 2e-4 rel-L2 on N(0,1) pre-activations, an eighth of the rounding of the 16-bit value it is stored
+ * as; the erf form costs 2-3x the epilogue ALU work of the MLP GEMMs.  bf_set_gelu_mode(1) (or BF_GELU_ERF=1 in the
+ * environment) switches EVERY GELU and GELU' of the library (bf_gemm BF_EPI_GELU / BF_EPI_DGELU, bf_inorm_apply,
+ * bf_inorm_bwd) to the exact erf form: the validation configuration.  Process-wide, read at launch time.           */
+BF_API int bf_set_gelu_mode(int exact_erf);
+BF_API int bf_get_gelu_mode(void);
+
 /* ---- tcgen05 GEMM ---------------------------------------------------------------------------
  * D[M,N] = sum_k A[m,k] * B[n,k], fp32 accumulation in TMEM, operands staged by TMA.
  * Replaces: nn.Conv2d 1x1 input_head/output_head (upstream layers/attention.py:47-48,78,121,170-171,210,299),
@@ -64,11 +73,11 @@ enum bf_b_mode {
 };
 enum bf_epilogue {
   BF_EPI_STORE16 = 0, /* out16 = acc + bias                                                            */
-  BF_EPI_GELU = 1,    /* pre = acc + bias; out16 = gelu_erf(pre); out16b = pre (if non-null)           */
+  BF_EPI_GELU = 1,    /* pre = acc + bias; out16 = gelu(pre) (see GELU above); out16b = pre (if non-null) */
   BF_EPI_RESID = 2,   /* z = acc + bias; out16b = z (if non-null); v = z*col_scale + col_shift;
                          out32 = in32 + row_scale[m / rows_per_group] * col_gamma * v;
                          out16 = (16-bit) out32 (if non-null)                                          */
-  BF_EPI_DGELU = 3,   /* out16 = acc * gelu_erf'(aux16)                                                */
+  BF_EPI_DGELU = 3,   /* out16 = acc * gelu'(aux16)                                                    */
   BF_EPI_ACC32 = 4,   /* out32 = in32 + acc                                                            */
   BF_EPI_ATOMIC32 = 5,/* out32 += acc (TMA reduce-add): split-K wgrad accumulating straight into the fp32 grad */
   BF_EPI_D2S = 6,     /* out16 scattered depth-to-space: m = (img, y, x), n = (ky, kx, co) ->
@@ -130,13 +139,14 @@ typedef struct bf_inorm_apply_args {
   const void* x;  int32_t x_dtype;  int32_t out_dtype;   /* BF_BF16 | BF_F16 | BF_F32 */
   int64_t ldx, ldo;
   int32_t I, P, C;
-  int32_t gelu;               /* 1: y = gelu_erf(y)   (layers/patching.py:47,103)                       */
+  int32_t gelu;               /* 1: y = gelu(y)  (layers/patching.py:47,103; see "GELU" below)            */
   const float* stats;         /* [I][C][2] */
   const float* weight;        /* [C] */
   const float* bias;          /* [C] */
-  const float* film_gamma;    /* [I/film_T][C] or NULL: y = film_gamma*y + film_beta (linear_layers.py:77) */
+  const float* film_gamma;    /* [I/film_T][film_ld] or NULL: y = film_gamma*y + film_beta (linear_layers.py:77) */
   const float* film_beta;
-  int32_t film_T;  int32_t reserved0;
+  int32_t film_T;  int32_t film_ld;   /* film_ld: row pitch of film_gamma / film_beta; 0 = C.  2C lets both point
+                                         into the (B, 2C) output of bf_film_fwd (gamma = gb, beta = gb + C).       */
   const float* resid_in;      /* fp32 (I*P, C) ld = ldo or NULL: out = resid_in + row_scale[img]*col_gamma[c]*y
                                  (layer scale * drop-path + residual, layers/attention.py:317)           */
   const float* row_scale;     /* [I] or NULL */
@@ -160,7 +170,7 @@ typedef struct bf_inorm_bwd_args {
   const float* stats;  const float* weight;  const float* bias;
   float* red;                 /* [I][C][2] */
   const float* row_scale;  const float* col_scale;  const float* film_gamma;
-  int32_t film_T;  int32_t reserved0;
+  int32_t film_T;  int32_t film_ld;   /* row pitch of film_gamma / dfilm_gamma / dfilm_beta; 0 = C */
   const float* add32;         /* fp32 (I*P, C) ld = ldo or NULL */
   void* out;
   /* phase 2, optional (all NULL = skip): the parameter gradients of bf_inorm_bwd_params accumulated by the same
@@ -209,6 +219,16 @@ typedef struct {
   float* d_gamma;  float* d_out_bias;  float* d_low;  float* d_high;  float* d_W;  float* d_norm2_bias;
 } bf_branch_grad_args;
 BF_API int bf_branch_param_grads(const bf_branch_grad_args* args, void* stream);
+
+/* FiLM conditioning vector (upstream layers/linear_layers.py:58-61, 71-72: film_net = LayerNorm(F) -> Linear(F, 2E)):
+ *   gb[b, :] = W * LayerNorm_F(cond[b, :]; ln_w, ln_b) + bias       cond (B, F) fp32, W (2E, F), gb (B, 2E)
+ * gamma = gb[:, :E], beta = gb[:, E:] are applied by bf_inorm_apply (film_gamma / film_beta).  F <= 32.
+ * bf_film_bwd ACCUMULATES the parameter gradients from dgb (B, 2E) (the caller zeroes them); cond gets no gradient
+ * (the fluid parameters are data, dataset.py:170-178).                                                          */
+BF_API int bf_film_fwd(const float* cond, int B, int F, const float* ln_w, const float* ln_b, const float* W,
+                       const float* bias, int E2, float* gb, void* stream);
+BF_API int bf_film_bwd(const float* dgb, const float* cond, int B, int F, const float* ln_w, const float* ln_b,
+                       const float* W, int E2, float* d_ln_w, float* d_ln_b, float* d_W, float* d_bias, void* stream);
 
 /* Input pipeline (upstream data/dataset.py:120-186, BubbleForecast.__getitem__): the trajectories are resident in HBM
  * as frames (F, C_src, H*W) fp32; one launch cuts B windows of T frames, selects and normalises the fields and writes

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 GROUPS = ["params", "stats", "apply", "inorm_bwd", "resid_colsum", "attn_x", "attn_y", "attn_t", "attn_d48", "attn_l64",
-          "attn_noscale", "patch", "misc"]
+          "attn_noscale", "attn_l128", "patch", "misc", "film", "gelu_modes"]
 
 
 def rel(got, ref):
@@ -163,7 +163,8 @@ def run(group):
     elif group.startswith("attn"):
         cfg = {"attn_x": dict(I=6, h=8, w=32, E=384, he=6, axis="x"), "attn_y": dict(I=6, h=32, w=8, E=384, he=6, axis="y"),
                "attn_t": dict(I=10, h=4, w=8, E=384, he=6, axis="t", T=5), "attn_d48": dict(I=4, h=4, w=20, E=192, he=4, axis="x"),
-               "attn_l64": dict(I=2, h=3, w=64, E=128, he=2, axis="x"), "attn_noscale": dict(I=3, h=12, w=6, E=128, he=2, axis="y", noscale=True)}[group]
+               "attn_l64": dict(I=2, h=3, w=64, E=128, he=2, axis="x"), "attn_noscale": dict(I=3, h=12, w=6, E=128, he=2, axis="y", noscale=True),
+               "attn_l128": dict(I=2, h=2, w=128, E=128, he=2, axis="x")}[group]
         I, h, w, E, he, axis = cfg["I"], cfg["h"], cfg["w"], cfg["E"], cfg["he"], cfg["axis"]
         d = E // he
         P = h * w
@@ -208,10 +209,10 @@ def run(group):
         common = dict(heads=he, L_=Ls, qn_w=ln[0], qn_b=ln[1], kn_w=ln[2], kn_b=ln[3], bias_emb=emb, bucket=bvec,
                       scale_factor=sf, out_scale=0.5, **geo)
         ops.attention(qkv, out, **common)
-        ok &= report(f"{group} fwd", out, ref, 1.5e-2)
+        ok &= report(f"{group} fwd", out, ref, 1e-2)
         out2 = out.clone()
         ops.attention(qkv, out2, accumulate=True, **common)
-        ok &= report(f"{group} fwd accumulate", out2, 2 * ref, 1.5e-2)
+        ok &= report(f"{group} fwd accumulate", out2, 2 * ref, 1e-2)
         dout = torch.randn(tokens, E, device=dev).bfloat16()
         (ref * dout.float()).sum().backward()          # includes the 0.5
         dqkv = torch.zeros(tokens, 3 * E, device=dev, dtype=torch.bfloat16)
@@ -222,16 +223,16 @@ def run(group):
         dq_ref = q32.grad.reshape(tokens, he, 3, d)
         got = dqkv.float().reshape(tokens, he, 3, d)
         for i, nm in enumerate("qkv"):
-            ok &= report(f"{group} d{nm}", got[:, :, i], dq_ref[:, :, i], 3e-2)
-        ok &= report(f"{group} d_qn_w", grads["d_qn_w"], params[0].grad, 3e-2)
-        ok &= report(f"{group} d_qn_b", grads["d_qn_b"], params[1].grad, 3e-2)
-        ok &= report(f"{group} d_kn_w", grads["d_kn_w"], params[2].grad, 3e-2)
+            ok &= report(f"{group} d{nm}", got[:, :, i], dq_ref[:, :, i], 1e-2)
+        ok &= report(f"{group} d_qn_w", grads["d_qn_w"], params[0].grad, 1e-2)
+        ok &= report(f"{group} d_qn_b", grads["d_qn_b"], params[1].grad, 1e-2)
+        ok &= report(f"{group} d_kn_w", grads["d_kn_w"], params[2].grad, 1e-2)
         kb = float((grads["d_kn_b"] - params[3].grad).abs().max() / params[2].grad.abs().max())
         print(f"[{group} d_kn_b] (true gradient is 0) |err|/|d_kn_w|max = {kb:.3e}")
-        ok &= kb < 3e-2
-        ok &= report(f"{group} d_bias_emb", grads["d_bias_emb"], params[4].grad, 3e-2)
+        ok &= kb < 1e-2
+        ok &= report(f"{group} d_bias_emb", grads["d_bias_emb"], params[4].grad, 1e-2)
         if sf is not None:
-            ok &= report(f"{group} d_scale_factor", grads["d_scale_factor"], sfp.grad, 3e-2)
+            ok &= report(f"{group} d_scale_factor", grads["d_scale_factor"], sfp.grad, 1e-2)
         if d == 64 and Ls <= 32:
             # pre-normalised fast path: rows hold xhat_q | xhat_k | v (as the QKV GEMM epilogue writes them) + rstd
             x4 = qkv.float().reshape(tokens, he, 3, d)
@@ -244,10 +245,10 @@ def run(group):
             rstd = rstd[..., 0].contiguous()
             out = torch.zeros(tokens, E, device=dev, dtype=torch.bfloat16)
             ops.attention(qkvn, out, prenorm=True, **common)
-            ok &= report(f"{group} prenorm fwd", out, ref, 1.5e-2)
+            ok &= report(f"{group} prenorm fwd", out, ref, 1e-2)
             out2 = out.clone()
             ops.attention(qkvn, out2, accumulate=True, prenorm=True, **common)
-            ok &= report(f"{group} prenorm fwd accumulate", out2, 2 * ref, 1.5e-2)
+            ok &= report(f"{group} prenorm fwd accumulate", out2, 2 * ref, 1e-2)
             dqkv = torch.zeros(tokens, 3 * E, device=dev, dtype=torch.bfloat16)
             grads = dict(d_qn_w=torch.zeros(d, device=dev), d_qn_b=torch.zeros(d, device=dev), d_kn_w=torch.zeros(d, device=dev),
                          d_kn_b=torch.zeros(d, device=dev), d_bias_emb=torch.zeros(32, he, device=dev),
@@ -257,16 +258,16 @@ def run(group):
             got = dqkv.float().reshape(tokens, he, 3, d)
             ok &= report(f"{group} prenorm d_qkv_bias (fused column sums)", grads["d_qkv_bias"], dqkv.float().sum(0), 1e-2)
             for i, nm in enumerate("qkv"):
-                ok &= report(f"{group} prenorm d{nm}", got[:, :, i], dq_ref[:, :, i], 3e-2)
-            ok &= report(f"{group} prenorm d_qn_w", grads["d_qn_w"], params[0].grad, 3e-2)
-            ok &= report(f"{group} prenorm d_qn_b", grads["d_qn_b"], params[1].grad, 3e-2)
-            ok &= report(f"{group} prenorm d_kn_w", grads["d_kn_w"], params[2].grad, 3e-2)
-            ok &= report(f"{group} prenorm d_bias_emb", grads["d_bias_emb"], params[4].grad, 3e-2)
+                ok &= report(f"{group} prenorm d{nm}", got[:, :, i], dq_ref[:, :, i], 1e-2)
+            ok &= report(f"{group} prenorm d_qn_w", grads["d_qn_w"], params[0].grad, 1e-2)
+            ok &= report(f"{group} prenorm d_qn_b", grads["d_qn_b"], params[1].grad, 1e-2)
+            ok &= report(f"{group} prenorm d_kn_w", grads["d_kn_w"], params[2].grad, 1e-2)
+            ok &= report(f"{group} prenorm d_bias_emb", grads["d_bias_emb"], params[4].grad, 1e-2)
             if sf is not None:
-                ok &= report(f"{group} prenorm d_scale_factor", grads["d_scale_factor"], sfp.grad, 3e-2)
+                ok &= report(f"{group} prenorm d_scale_factor", grads["d_scale_factor"], sfp.grad, 1e-2)
             dq2 = dqkv.clone()
             ops.attention(qkvn, dq2, dout=dout, grads=grads, prenorm=True, rstd=rstd, accumulate=True, **common)
-            ok &= report(f"{group} prenorm bwd accumulate", dq2, 2 * dqkv.float(), 1.5e-2)
+            ok &= report(f"{group} prenorm bwd accumulate", dq2, 2 * dqkv.float(), 1e-2)
     elif group == "patch":
         for (I, Fd, H, W, N, dt) in [(2, 4, 64, 64, 96, torch.float16), (3, 2, 32, 48, 24, torch.float16),
                                      (1, 1, 16, 16, 384, torch.bfloat16), (2, 4, 32, 40, 96, torch.bfloat16),
@@ -329,6 +330,62 @@ def run(group):
                 dst = torch.zeros(n, device=dev, dtype=dt)
                 ops.cast16(src, dst)
                 ok &= report(f"cast16 {n} {dt}", dst, src.to(dt), 1e-7)
+    elif group == "film":
+        # bf_film_fwd / bf_film_bwd vs torch (upstream linear_layers.py:58-61: LayerNorm(F) -> Linear(F, 2E))
+        for (B, Fp, E) in [(8, 9, 384), (3, 8, 768), (1, 9, 128), (64, 9, 96)]:
+            cond = torch.randn(B, Fp, device=dev) * torch.logspace(-2, 1, Fp, device=dev)
+            lw, lb = (1 + 0.1 * torch.randn(Fp, device=dev)).requires_grad_(True), (0.1 * torch.randn(Fp, device=dev)).requires_grad_(True)
+            W = (torch.randn(2 * E, Fp, device=dev) / 3).requires_grad_(True)
+            b = (0.1 * torch.randn(2 * E, device=dev)).requires_grad_(True)
+            ref = F.linear(F.layer_norm(cond, (Fp,), lw, lb), W, b)
+            gb = ops.film_fwd(cond, lw.detach(), lb.detach(), W.detach(), b.detach())
+            ok &= report(f"film_fwd B={B} F={Fp} E={E}", gb, ref, 1e-5)
+            dgb = torch.randn(B, 2 * E, device=dev)
+            ref.backward(dgb)
+            g = [torch.zeros_like(t) for t in (lw, lb, W, b)]
+            ops.film_bwd(dgb, cond, lw.detach(), lb.detach(), W.detach(), *g)
+            for nm, got, r in zip(("d_ln_w", "d_ln_b", "d_W", "d_bias"), g, (lw.grad, lb.grad, W.grad, b.grad)):
+                ok &= report(f"film_bwd {nm} B={B} F={Fp} E={E}", got, r, 1e-4)
+    elif group == "gelu_modes":
+        # default = tanh form, bf_set_gelu_mode(1) = exact erf (upstream nn.GELU()): GEMM epilogues and the norm passes
+        from bubbleformer_b200 import _lib as L
+        M, N, K = 256, 256, 128
+        A = torch.randn(M, K, device=dev).bfloat16()
+        Wt = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+        bias = torch.randn(N, device=dev)
+        pre = A.float() @ Wt.float().t() + bias
+        dy = torch.randn(M, N, device=dev).bfloat16()
+        for exact in (0, 1):
+            L.lib.bf_set_gelu_mode(exact)
+            try:
+                approx = "none" if exact else "tanh"
+                G = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+                Hp = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+                ops.gemm(A, Wt, M, N, K, epilogue=L.EPI_GELU, bias=bias, out16=G, out16b=Hp)
+                ok &= report(f"gemm GELU exact={exact}", G, F.gelu(pre, approximate=approx), 4e-3)
+                # the two forms differ by ~2e-4 rel-L2: check that the switch really changes the function evaluated
+                p32 = Hp.float().requires_grad_(True)
+                F.gelu(p32, approximate=approx).backward(torch.ones_like(p32))
+                dH = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+                eye = torch.eye(N, device=dev).bfloat16()
+                ops.gemm(dy, eye, M, N, N, epilogue=L.EPI_DGELU, aux16=Hp, out16=dH)
+                ok &= report(f"gemm DGELU exact={exact}", dH, dy.float() * p32.grad, 4e-3)
+                # fp32 in / fp32 out norm pass isolates the GELU form from 16-bit rounding
+                I, P, Cn = 2, 256, 64
+                x = torch.randn(I * P, Cn, device=dev)
+                w, b = 1 + 0.1 * torch.randn(Cn, device=dev), 0.1 * torch.randn(Cn, device=dev)
+                st = torch.zeros(I, Cn, 2, device=dev)
+                ops.inorm_stats(x, I, P, st)
+                out = torch.zeros(I * P, Cn, device=dev)
+                ops.inorm_apply(x, out, I, P, st, w, b, gelu=True)
+                y = inorm_ref(x, I, P, w, b)
+                e_same = rel(out, F.gelu(y, approximate=approx))
+                e_other = rel(out, F.gelu(y, approximate="tanh" if exact else "none"))
+                good = e_same < 2e-5 and e_other > 5e-5
+                print(f"[inorm gelu exact={exact}] vs its own form {e_same:.2e}, vs the other form {e_other:.2e} {'OK' if good else 'MISMATCH'}")
+                ok &= good
+            finally:
+                L.lib.bf_set_gelu_mode(0)
     else:
         raise SystemExit(f"unknown group {group}")
     torch.cuda.synchronize()

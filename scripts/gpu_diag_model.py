@@ -9,7 +9,51 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-CASES = ["film_eval_e128", "film_train_masks_e128", "avit_generic_e96", "rollout", "shapes", "big512"]
+CASES = ["film_eval_e128", "film_train_masks_e128", "avit_generic_e96", "rollout", "shapes", "big512",
+         "oracle_cfg2", "oracle_cfg5_512", "oracle_cfg5_1024", "oracle_cfg4_strip"]
+
+SMALL = dict(input_fields=4, output_fields=4, patch_size=16, embed_dim=384, num_heads=6, processor_blocks=12,
+             drop_path=0.2, attn_scale=True, feat_scale=True, num_fluid_params=9)      # film_avit_small.yaml
+BIG = dict(SMALL, embed_dim=768, num_heads=12)                                          # film_avit_big.yaml
+
+
+def _host_mem_gb():
+    """Memory this process may still use on the host (cgroup limit when there is one)."""
+    import psutil
+    avail = psutil.virtual_memory().available
+    for f in ("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory/memory.limit_in_bytes"):
+        try:
+            v = open(f).read().strip()
+            if v.isdigit():
+                used = 0
+                for u in ("/sys/fs/cgroup/memory.current", "/sys/fs/cgroup/memory/memory.usage_in_bytes"):
+                    try:
+                        used = int(open(u).read().strip())
+                        break
+                    except OSError:
+                        pass
+                avail = min(avail, int(v) - used)
+        except OSError:
+            pass
+    return avail / 2**30
+
+
+def oracle_case(name, cfg, B, T, H, W, seed, train=True):
+    """Whole-model fwd + loss + every gradient on the CUDA path vs the CPU oracle on the host, same weights / inputs /
+    stochastic-depth masks, at a BASELINE.json shape (the code path bench.py times)."""
+    import torch
+    from bubbleformer_b200 import get_model
+    from bubbleformer_b200.losses import rel_l2_loss
+    from oracle import parity
+    case = parity.make_case(cfg, B, T, H, W, seed, train=train)
+    ref = parity.oracle_run(case["sd"], case["x"], case["tgt"], case["cond"], cfg, case["masks"])
+    print(f"[{name}] oracle on {torch.get_num_threads()} host threads: {ref['seconds']:.1f} s "
+          f"(E={cfg['embed_dim']} blocks={cfg['processor_blocks']} B={B} T={T} {H}x{W})", flush=True)
+    model = get_model("filmavit", time_window=T, **cfg).to("cuda")
+    model.load_state_dict(case["sd"], strict=True)
+    got = parity.candidate_run(model, case["x"], case["tgt"], case["cond"], case["masks"], loss_fn=rel_l2_loss)
+    res = parity.compare(ref, got, verbose_prefix=name)
+    return parity.passes(res)
 
 
 def rel(a, b):
@@ -123,6 +167,36 @@ def run_case(name):
                 p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in m.parameters())
             print(f"[shapes] avit fi={fi} fo={fo} patch={patch} E={E} attn_scale={a_s} feat_scale={f_s}: {'OK' if good else 'BAD'}")
             ok &= good
+    elif name == "oracle_cfg2":
+        # BASELINE configs[1]: film_avit_small, T=5, 4 fields, 512x512 (h=w=32, P=1024), train mode with masks, B=2
+        ok &= oracle_case(name, SMALL, 2, 5, 512, 512, seed=21)
+    elif name == "oracle_cfg5_512":
+        ok &= oracle_case(name, BIG, 1, 5, 512, 512, seed=22)
+    elif name == "oracle_cfg5_1024":
+        # BASELINE configs[4]: film_avit_big at 1024x1024 (h=w=64, L=64).  The fp32 autograd graph of the host oracle needs
+        # ~6.5 GB per block at this size; the depth is reduced when the host cannot hold all 12 (every block runs the same
+        # kernels, the full depth is checked at 512x512 above).
+        mem = _host_mem_gb()
+        blocks = 12 if mem > 110 else max(2, min(12, int((mem - 12) / 7)))
+        print(f"[{name}] host memory available {mem:.0f} GiB -> {blocks} blocks", flush=True)
+        ok &= oracle_case(name, dict(BIG, processor_blocks=blocks), 1, 5, 1024, 1024, seed=23)
+    elif name == "oracle_cfg4_strip":
+        # BASELINE configs[3]: non-square flow-boiling strip 128x1024 (h=8, w=64): 3 teacher-forced rollout steps
+        # (eval, no_grad; the input of step k is the ORACLE's output of step k-1) + one fwd/bwd parity at the same shape
+        from bubbleformer_b200 import get_model
+        from oracle import parity
+        cfg = dict(SMALL, drop_path=0.0)
+        case = parity.make_case(cfg, 1, 5, 128, 1024, seed=24, train=False)
+        model = get_model("filmavit", time_window=5, **cfg).to(dev).eval()
+        model.load_state_dict(case["sd"], strict=True)
+        inp = case["x"]
+        for s in range(3):
+            ref = parity.oracle_run(case["sd"], inp, None, case["cond"], cfg, None, grads=False)
+            got = parity.candidate_run(model, inp, None, case["cond"], None, grads=False)
+            res = parity.compare(ref, got, verbose_prefix=f"{name} step {s + 1}")
+            ok &= parity.passes(res)
+            inp = ref["y"]
+        ok &= oracle_case(name + " fwd+bwd", SMALL, 1, 5, 128, 1024, seed=25)
     elif name == "big512":
         # config 2 shape: does it run, how long does it take, how much memory
         cfg = dict(input_fields=4, output_fields=4, patch_size=16, embed_dim=384, num_heads=6, processor_blocks=12,

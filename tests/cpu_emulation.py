@@ -101,8 +101,10 @@ def _mean_rstd(stats, P):
 
 
 def inorm_apply(x, out, I, P, stats, weight, bias, *, gelu=False, film_gamma=None, film_beta=None, film_T=0,
-                resid_in=None, row_scale=None, col_gamma=None, stats_out=None):
+                film_gb=None, resid_in=None, row_scale=None, col_gamma=None, stats_out=None):
     C = x.shape[1]
+    if film_gb is not None:          # (B, 2C) = [gamma | beta], the layout bf_film_fwd writes
+        film_gamma, film_beta = film_gb[:, :C], film_gb[:, C:]
     mean, rstd = _mean_rstd(stats, P)
     xi = x.float().reshape(I, P, C)
     y = (xi - mean[:, None]) * rstd[:, None] * weight + bias
@@ -121,8 +123,12 @@ def inorm_apply(x, out, I, P, stats, weight, bias, *, gelu=False, film_gamma=Non
 
 def inorm_bwd(phase, gin, x, I, P, stats, weight, bias, red, *, gelu=False, out=None, row_scale=None, col_scale=None,
               film_gamma=None, film_T=0, add32=None, dweight=None, dbias=None, dcol_scale=None, dfilm_gamma=None,
-              dfilm_beta=None):
+              dfilm_beta=None, film_gb=None, dfilm_gb=None):
     C = x.shape[1]
+    if film_gb is not None:
+        film_gamma = film_gb[:, :C]
+        if dfilm_gb is not None:
+            dfilm_gamma, dfilm_beta = dfilm_gb[:, :C], dfilm_gb[:, C:]
     mean, rstd = _mean_rstd(stats, P)
     xh = (x.float().reshape(I, P, C) - mean[:, None]) * rstd[:, None]
     g = gin.float().reshape(I, P, C)
@@ -204,6 +210,22 @@ def branch_param_grads(S01, gamma, d_gamma, d_out_bias, feat=None):
     feat["d_W"].view(E, E).add_(dc[:, None] * feat["norm2_bias"][None, :])
     feat["d_norm2_bias"].add_((feat["W"].reshape(E, E) * dc[:, None]).sum(dim=0))
     d_out_bias.add_(gamma * c1 * S0 + dc)
+
+
+def film_fwd(cond, ln_w, ln_b, W, bias):
+    """bf_film_fwd: gb = Linear(LayerNorm(cond)) (upstream linear_layers.py:58-61)."""
+    return F.linear(F.layer_norm(cond.float(), (cond.shape[1],), ln_w, ln_b, EPS), W, bias).detach()
+
+
+def film_bwd(dgb, cond, ln_w, ln_b, W, d_ln_w, d_ln_b, d_W, d_bias):
+    """bf_film_bwd: accumulates the FiLM MLP parameter gradients."""
+    xh = F.layer_norm(cond.float(), (cond.shape[1],), None, None, EPS)
+    c = xh * ln_w + ln_b
+    d_W.add_(dgb.t() @ c)
+    d_bias.add_(dgb.sum(0))
+    dc = dgb @ W
+    d_ln_w.add_((dc * xh).sum(0))
+    d_ln_b.add_(dc.sum(0))
 
 
 def colsum16(x, out):
@@ -329,7 +351,7 @@ def lploss_bwd(pred, tgt, coef, dpred):
     dpred.copy_(coef.reshape(*pred.shape[:-2], 1, 1) * (pred - tgt))
 
 
-ALL = ["gemm", "inorm_stats", "inorm_apply", "inorm_bwd", "inorm_bwd_params", "resid_bwd", "colsum16", "feat_consts",
+ALL = ["film_fwd", "film_bwd", "gemm", "inorm_stats", "inorm_apply", "inorm_bwd", "inorm_bwd_params", "resid_bwd", "colsum16", "feat_consts",
        "branch_param_grads", "attention",
        "patch_in", "patch_out", "patch_wgrad", "s2d_gather", "cast16", "convert16", "lploss_sums", "lploss_bwd"]
 

@@ -26,8 +26,9 @@ def _forward(model, case, x):
     p = model.patch_size
     geom = engine.Geom(B, T, H // p, W // p)
     xi = x.reshape(B * T, C, H, W)
-    gb = model.film_embed.gamma_beta(case["cond"]) if case["cond"] is not None else None
-    X = model.embed.tokens(xi, gb, T)
+    # the FiLM MLP runs inside the patch-embed Function (bf_film_fwd / bf_film_bwd), as in FiLMConditionedAViT.forward
+    film = model.film_embed if case["cond"] is not None else None
+    X = model.embed.tokens(xi, case["cond"], T, film=film)
     for i, blk in enumerate(model.blocks):
         masks = case["masks"][i] if case["masks"] is not None else None
         X = blk.tokens(X, geom, _wide_w16, masks)

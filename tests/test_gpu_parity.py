@@ -35,7 +35,8 @@ def test_gemm(variant):
 
 
 @pytest.mark.parametrize("group", ["params", "stats", "apply", "inorm_bwd", "resid_colsum", "attn_x", "attn_y", "attn_t",
-                                   "attn_d48", "attn_l64", "attn_noscale", "patch", "misc"])
+                                   "attn_d48", "attn_l64", "attn_noscale", "attn_l128", "patch", "misc", "film",
+                                   "gelu_modes"])
 def test_kernels(group):
     import gpu_diag_kernels
     assert gpu_diag_kernels.run(group)
@@ -43,6 +44,15 @@ def test_kernels(group):
 
 @pytest.mark.parametrize("case", ["film_eval_e128", "film_train_masks_e128", "avit_generic_e96"])
 def test_model_forward_backward_vs_reference_fixture(case):
+    import gpu_diag_model
+    assert gpu_diag_model.run_case(case)
+    assert _native_loaded()
+
+
+@pytest.mark.parametrize("case", ["oracle_cfg2", "oracle_cfg5_512", "oracle_cfg5_1024", "oracle_cfg4_strip"])
+def test_model_vs_host_oracle_at_baseline_shapes(case):
+    """Whole model (fwd per channel, loss, dx, every parameter gradient) against the CPU oracle run on the host at the
+    shapes BASELINE.json names: config 2 (small, 512x512), config 5 (big, 512x512 and 1024x1024), config 4 (128x1024)."""
     import gpu_diag_model
     assert gpu_diag_model.run_case(case)
     assert _native_loaded()
