@@ -34,8 +34,13 @@ class DeviceForecastWindows:
     def __init__(self, filenames: Sequence[str], input_fields: Optional[List[str]] = None,
                  output_fields: Optional[List[str]] = None, norm: str = "none", time_window: int = 16,
                  start_time: int = 50, return_fluid_params: bool = False, device="cuda",
-                 arrays: Optional[List[Dict[str, np.ndarray]]] = None):
-        """`arrays` (one dict field -> (frames, H, W) array per trajectory) replaces reading `filenames`."""
+                 arrays: Optional[List[Dict[str, np.ndarray]]] = None, downsample_factor: int = 1):
+        """`arrays` (one dict field -> (frames, H, W) array per trajectory) replaces reading `filenames`.
+
+        downsample_factor > 1 (upstream dataset.py:138-153: F.interpolate(mode="nearest") to (H // f, W // f) per sample):
+        nearest-neighbour resampling is a fixed pixel selection, so it is applied ONCE to the resident frames on the
+        device (same source indices as ATen's nearest kernel); the normalisation constants are still those of the
+        full-resolution fields, as upstream computes them."""
         self.input_fields = list(input_fields) if input_fields is not None else list(DEFAULT_FIELDS)
         self.output_fields = list(output_fields) if output_fields is not None else list(DEFAULT_FIELDS)
         if norm not in ("none", "std", "minmax", "tanh"):
@@ -55,6 +60,17 @@ class DeviceForecastWindows:
             raise RuntimeError("bubbleformer_b200 runs on CUDA only (no CPU fallback)")
         stacked = np.concatenate([np.stack([d[k] for k in self.fields], axis=1) for d in self.host], axis=0)
         self.frames = torch.from_numpy(np.ascontiguousarray(stacked)).to(dev)          # (sum frames, C, H, W)
+        del stacked
+        self.downsample_factor = int(downsample_factor)
+        if self.downsample_factor < 1:
+            raise ValueError("downsample_factor must be >= 1")
+        if self.downsample_factor > 1:
+            iy = self._nearest_index(self.H, self.downsample_factor).to(dev)
+            ix = self._nearest_index(self.W, self.downsample_factor).to(dev)
+            self.frames = self.frames.index_select(2, iy).index_select(3, ix).contiguous()
+            self.H, self.W = int(iy.numel()), int(ix.numel())
+        if (self.H * self.W) % 4:
+            raise ValueError("H*W of the (downsampled) fields must be a multiple of 4")
         self.frame_base = np.concatenate([[0], np.cumsum(self.traj_lens)])[:-1]
         self.fluid_params = None
         if return_fluid_params:
@@ -68,6 +84,15 @@ class DeviceForecastWindows:
         self.diff_terms = {k: 0.0 for k in self.fields}
         self.div_terms = {k: 1.0 for k in self.fields}
         self._upload_terms()
+
+    @staticmethod
+    def _nearest_index(n_in: int, factor: int) -> torch.Tensor:
+        """Source indices of F.interpolate(mode="nearest") to n_in // factor: min(floor(dst * scale), n_in - 1), the
+        scale n_in / n_out evaluated in float32 like ATen."""
+        n_out = n_in // factor
+        scale = np.float32(n_in) / np.float32(n_out)
+        idx = np.minimum(np.floor(np.arange(n_out, dtype=np.float32) * scale).astype(np.int64), n_in - 1)
+        return torch.from_numpy(idx)
 
     # ---- upstream dataset.py:62-67 -------------------------------------------------------------
     def __len__(self) -> int:

@@ -1,9 +1,10 @@
 """CPU restatement of upstream's BubbleForecast sample construction -- TEST INFRASTRUCTURE ONLY (imported by tests/).
 
-Follows bubbleformer/data/dataset.py: __len__ (:62-67), normalize (:69-118), __getitem__ (:120-186).  The upstream
-module imports h5py, which is not installed here, so it cannot be executed: PARITY UNPINNED for the indexing logic.
-The HDF5 reader it stands on is pinned: tests compare `hdf5_min.read_hdf5` with the byte offsets of
-samples/sample_1.hdf5 recorded in the survey and with the committed fixture tests/golden/rollout_sample1_small.npz.
+Follows bubbleformer/data/dataset.py: __len__ (:62-67), normalize (:69-118), __getitem__ (:120-186, including the
+nearest-neighbour downsampling of :138-153).  Pinned: oracle/make_data_golden.py executed the UNMODIFIED upstream class on
+upstream's two sample files (with a stand-in for the absent h5py that serves the datasets as numpy arrays) and committed
+samples, lengths and normalisation constants to tests/golden/dataset.npz; tests/test_data.py checks this restatement
+against them.  The HDF5 reader is pinned separately on the raw bytes of samples/sample_1.hdf5.
 """
 import numpy as np
 
@@ -33,12 +34,25 @@ def norm_terms(arrays, fields, norm):
     return diff, div
 
 
-def get_item(arrays, idx, input_fields, output_fields, time_window, start_time, diff, div):
+def nearest_index(n_in, factor):
+    """Source indices of F.interpolate(mode="nearest") to size n_in // factor (dataset.py:141-147): ATen's
+    nearest_neighbor_compute_source_index, src = min(floor(dst * scale), n_in - 1) with scale = n_in / n_out in float32."""
+    n_out = n_in // factor
+    scale = np.float32(n_in) / np.float32(n_out)
+    return np.minimum(np.floor(np.arange(n_out, dtype=np.float32) * scale).astype(np.int64), n_in - 1)
+
+
+def get_item(arrays, idx, input_fields, output_fields, time_window, start_time, diff, div, downsample_factor=1):
     per = [d[input_fields[0]].shape[0] - start_time - 2 * time_window + 1 for d in arrays]
     cum = np.cumsum(per)
     file_idx = np.searchsorted(cum, idx, side="right")
     start = idx + start_time - (cum[file_idx - 1] if file_idx > 0 else 0)
     a, b = slice(start, start + time_window), slice(start + time_window, start + 2 * time_window)
-    inp = np.stack([(np.asarray(arrays[file_idx][k][a], dtype=np.float32) - diff[k]) / div[k] for k in input_fields])
-    out = np.stack([(np.asarray(arrays[file_idx][k][b], dtype=np.float32) - diff[k]) / div[k] for k in output_fields])
+    def cut(k, sl):
+        x = np.asarray(arrays[file_idx][k][sl], dtype=np.float32)
+        if downsample_factor > 1:
+            x = x[:, nearest_index(x.shape[1], downsample_factor)][:, :, nearest_index(x.shape[2], downsample_factor)]
+        return (x - diff[k]) / div[k]
+    inp = np.stack([cut(k, a) for k in input_fields])
+    out = np.stack([cut(k, b) for k in output_fields])
     return inp.astype(np.float32).transpose(1, 0, 2, 3), out.astype(np.float32).transpose(1, 0, 2, 3)

@@ -141,3 +141,75 @@ def test_device_windows_match_oracle(norm, tmp_path):
         assert float((inp[b].cpu() - torch.from_numpy(ri)).abs().max()) < 1e-5 * max(1.0, float(np.abs(ri).max()))
         assert float((tgt[b].cpu() - torch.from_numpy(ro)).abs().max()) < 1e-5 * max(1.0, float(np.abs(ro).max()))
     assert float(cond[2, 0]) == pytest.approx(1.1) and float(cond[0, 8]) == pytest.approx(90.0)
+
+
+def _golden_dataset():
+    import json
+    z = np.load(os.path.join(ROOT, "tests", "golden", "dataset.npz"))
+    return z, json.loads(str(z["meta"]))
+
+
+def _sample_arrays():
+    """The two upstream sample trajectories: from the reference checkout when mounted, else rebuilt from the fixture of
+    case 0 is not possible (it holds windows only) -> skip."""
+    from bubbleformer_b200.hdf5_min import read_hdf5
+    files = [f"/root/reference/samples/sample_{i}.hdf5" for i in (1, 2)]
+    if not all(os.path.exists(f) for f in files):
+        pytest.skip("reference checkout not mounted (GPU box)")
+    return files, [read_hdf5(f) for f in files]
+
+
+def test_data_oracle_matches_reference_dataset_fixture():
+    """oracle/data_oracle.py against samples produced by the UNMODIFIED upstream BubbleForecast (oracle/make_data_golden.py):
+    length, normalisation constants, window index arithmetic across the file boundary, nearest downsampling."""
+    from oracle import data_oracle as O
+    z, meta = _golden_dataset()
+    files, arrays = _sample_arrays()
+    for ci, m in enumerate(meta):
+        fields = sorted(set(m["input_fields"] + m["output_fields"]))
+        assert O.dataset_len([50, 50], m["time_window"], m["start_time"]) == m["length"]
+        diff, div = O.norm_terms(arrays, fields, m["norm"])
+        for k in fields:
+            assert abs(diff[k] - m["diff"][k]) <= 1e-6 * max(1.0, abs(m["diff"][k])), (ci, k)
+            assert abs(div[k] - m["div"][k]) <= 1e-6 * max(1.0, abs(m["div"][k])), (ci, k)
+        for i in m["indices"]:
+            inp, tgt = O.get_item(arrays, i, m["input_fields"], m["output_fields"], m["time_window"], m["start_time"],
+                                  m["diff"], m["div"], m["downsample_factor"])
+            assert inp.shape == z[f"c{ci}_i{i}_inp"].shape
+            assert np.allclose(inp, z[f"c{ci}_i{i}_inp"], rtol=1e-6, atol=1e-6), (ci, i)
+            assert np.allclose(tgt, z[f"c{ci}_i{i}_tgt"], rtol=1e-6, atol=1e-6), (ci, i)
+
+
+@pytest.mark.gpu
+def test_device_windows_downsample_and_fields_match_pinned_oracle(tmp_path):
+    """The device pipeline (hdf5_min reader + resident frames + bf_window_gather, downsample_factor included) on the
+    configurations of tests/golden/dataset.npz against oracle/data_oracle.py -- which the CPU test above pins to the
+    samples the UNMODIFIED upstream BubbleForecast produced.  (The GPU box has no upstream sample files: the
+    trajectories are seeded arrays written through the test's HDF5 writer.)"""
+    import torch
+    from bubbleformer_b200.data import DeviceForecastWindows
+    from oracle import data_oracle as O
+    _, meta = _golden_dataset()
+    rng = np.random.default_rng(5)
+    arrays = [{k: (rng.standard_normal((50, 64, 64)) * (1 + j) + j).astype(np.float32)
+               for j, k in enumerate(("dfun", "temperature", "velx", "vely"))} for _ in range(2)]
+    files = []
+    for j, a in enumerate(arrays):
+        p = str(tmp_path / f"s{j}.hdf5")
+        _write_h5_v0(p, a)
+        files.append(p)
+    for m in meta:
+        ds = DeviceForecastWindows(files, input_fields=m["input_fields"], output_fields=m["output_fields"], norm=m["norm"],
+                                   time_window=m["time_window"], start_time=m["start_time"],
+                                   downsample_factor=m["downsample_factor"])
+        ds.normalize()
+        assert len(ds) == m["length"]
+        rd, rv = O.norm_terms(arrays, ds.fields, m["norm"])
+        inp, tgt = ds.batch(m["indices"])
+        f = m["downsample_factor"]
+        assert inp.shape == (len(m["indices"]), m["time_window"], len(m["input_fields"]), 64 // f, 64 // f)
+        for b, i in enumerate(m["indices"]):
+            ri, ro = O.get_item(arrays, i, m["input_fields"], m["output_fields"], m["time_window"], m["start_time"], rd, rv, f)
+            assert tuple(inp[b].shape) == ri.shape and tuple(tgt[b].shape) == ro.shape
+            assert float((inp[b].cpu() - torch.from_numpy(ri)).abs().max()) < 1e-5 * max(1.0, float(np.abs(ri).max()))
+            assert float((tgt[b].cpu() - torch.from_numpy(ro)).abs().max()) < 1e-5 * max(1.0, float(np.abs(ro).max()))
