@@ -121,6 +121,7 @@ class AttnArgs(C.Structure):
         ("d_qn_w", C.c_void_p), ("d_qn_b", C.c_void_p), ("d_kn_w", C.c_void_p), ("d_kn_b", C.c_void_p),
         ("d_bias_emb", C.c_void_p), ("d_scale_factor", C.c_void_p),
         ("rstd", C.c_void_p), ("d_qkv_bias", C.c_void_p),
+        ("dtype", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 

@@ -125,6 +125,9 @@ class WeightBank:
 
     def refresh(self) -> None:
         self.ensure()
+        from . import engine
+        if engine.EXACT:                     # fp32 validation configuration: the GEMMs read the fp32 masters
+            return
         # the fused optimiser step rewrites the mirror itself; any other in-place change of a parameter (copy_,
         # torch.optim, load_state_dict) bumps that parameter's version counter
         if getattr(self, "_mirror_version", None) == self._versions():
@@ -138,6 +141,9 @@ class WeightBank:
         self._mirror_version = self._versions()
 
     def w16(self, p: torch.Tensor) -> torch.Tensor:
+        from . import engine
+        if engine.EXACT:
+            return p.detach().view(p.shape[0], -1)
         o = (p.data_ptr() - self.flat.data_ptr()) // 4
         if not (0 <= o and o + p.numel() <= self.flat.numel()):
             raise RuntimeError("bubbleformer_b200: parameter is not part of this model's flat weight buffer")
@@ -146,6 +152,9 @@ class WeightBank:
 
 def adhoc_w16(p: torch.Tensor) -> torch.Tensor:
     """bf16 operand copy of one weight (stand-alone layer use; the full model uses WeightBank)."""
+    from . import engine
+    if engine.EXACT:
+        return p.detach().contiguous().view(p.shape[0], -1)
     out = torch.empty(p.shape[0], p.numel() // p.shape[0], dtype=torch.bfloat16, device=p.device)
     ops.cast16(p.detach().contiguous().reshape(-1), out.reshape(-1))
     return out

@@ -660,6 +660,8 @@ static int attn_common(const bf_attn_args* a, AttnParams& p, int& LP, bool bwd) 
              "tokens = 2048 pixels at patch 16 are not supported)", a->L);
   BF_REQUIRE(a->n_seq > 0 && a->inner > 0, "bf_attention: n_seq=%ld inner=%ld", (long)a->n_seq, (long)a->inner);
   BF_REQUIRE(a->qn_w && a->qn_b && a->kn_w && a->kn_b && a->bias_emb && a->bucket, "bf_attention: null parameter");
+  BF_REQUIRE(a->dtype == BF_BF16 || a->dtype == BF_F32, "bf_attention: dtype %d (bf16, or fp32 for the validation backend)", a->dtype);
+  BF_REQUIRE(a->dtype == BF_BF16 || !a->prenorm, "bf_attention: the pre-normalised fast path is bf16 only");
   BF_REQUIRE(a->ld_qkv % 8 == 0 && a->ld_out % 8 == 0, "bf_attention: leading dimensions must be multiples of 8");
   BF_REQUIRE((reinterpret_cast<uintptr_t>(a->qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
              "bf_attention: tensors must be 16-byte aligned");
@@ -686,11 +688,15 @@ static int attn_common(const bf_attn_args* a, AttnParams& p, int& LP, bool bwd) 
   return BF_OK;
 }
 
-namespace bf { int launch_attn_fast(const bf_attn_args* a, bool bwd, cudaStream_t st); }
+namespace bf {
+int launch_attn_fast(const bf_attn_args* a, bool bwd, cudaStream_t st);
+int launch_attn_f32(const bf_attn_args* a, bool bwd, cudaStream_t st);
+}
 
 extern "C" int bf_attention_fwd(const bf_attn_args* a, void* stream) {
   AttnParams p; int LP;
   if (int st = attn_common(a, p, LP, false)) return st;
+  if (a->dtype == BF_F32) return launch_attn_f32(a, false, static_cast<cudaStream_t>(stream));
   if (a->prenorm) return launch_attn_fast(a, false, static_cast<cudaStream_t>(stream));
   return dispatch_attn<false>(a->head_dim, LP, p, static_cast<cudaStream_t>(stream));
 }
@@ -698,6 +704,7 @@ extern "C" int bf_attention_fwd(const bf_attn_args* a, void* stream) {
 extern "C" int bf_attention_bwd(const bf_attn_args* a, void* stream) {
   AttnParams p; int LP;
   if (int st = attn_common(a, p, LP, true)) return st;
+  if (a->dtype == BF_F32) return launch_attn_f32(a, true, static_cast<cudaStream_t>(stream));
   if (a->prenorm) return launch_attn_fast(a, true, static_cast<cudaStream_t>(stream));
   return dispatch_attn<true>(a->head_dim, LP, p, static_cast<cudaStream_t>(stream));
 }

@@ -61,6 +61,7 @@ struct GemmParams {
   int in_bufs;        // 1 or 2
   int in_bytes;       // bytes of one input tile buffer
   int in_off, slab_off, bar_off;
+  int cg;             // CTAs per tile: 1, or 2 = CTA pairs (cta_group::2)
   int b_resident;     // 1: the CTA's whole B block (k_iters boxes) stays in shared memory for all of its tiles
   int a_off;          // start of the operand ring (after the resident B block)
   int ln_heads;       // QKV_LN: heads = N / 192
@@ -138,14 +139,23 @@ __device__ __forceinline__ void load_cols(const float* svec, float (&o)[32]) {
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN>
+// CG = 2: a CTA PAIR (2-CTA cluster, tcgen05 cta_group::2) owns a 256 x BN tile: each CTA stages its own 128 rows of A
+// and HALF of the B tile (BN / 2 rows), the leader CTA issues 256-row MMAs that read both shared memories, and each CTA
+// runs the epilogue of its own 128 accumulator rows.  Per CTA and k step that is 16 KB + BN/2 * 128 B of operands instead
+// of 16 KB + BN * 128 B: the L2 -> SM operand traffic of a 128 x 192 tile (77 FLOP per L2 byte, ~955 TFLOP/s at the
+// measured ~12.4 TB/s L2 ceiling -- where the single-CTA kernel saturates) drops by 30 % (33 % for BN = 256).
+template <int BN, bool A_MN, bool B_MN, int CG>
 __global__ void __launch_bounds__(gemm_threads(BN), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_o16,
                     const __grid_constant__ CUtensorMap map_o16b, const __grid_constant__ CUtensorMap map_o32,
                     const GemmParams p) {
+  static_assert(CG == 1 || CG == 2, "cta_group");
+  static_assert(CG == 1 || !A_MN, "the pair kernel takes K-major A");
+  static_assert(CG == 1 || !B_MN || (BN / CG) % 64 == 0, "MN-major B halves must be whole 64-column blocks");
   constexpr int kABytes = BM * BK * 2;
-  constexpr int kBBytes = BN * BK * 2;
+  constexpr int kBRows = BN / CG;                  // B rows staged by this CTA
+  constexpr int kBBytes = kBRows * BK * 2;
   constexpr int kStageBytes = kABytes + kBBytes;
   constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
   constexpr int kChunks = BN / 32;                 // 32-column chunks per tile
@@ -169,6 +179,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const int first_tile = (int)blockIdx.x / CG;     // the CTAs of a pair walk the same tile sequence
+  const int tile_stride = (int)gridDim.x / CG;
 
   float* s_colsum = reinterpret_cast<float*>(smem + p.slab_off);       // DGELU + colsum_out only ([num_n_blocks * BN])
   if (p.colsum_out != nullptr)
@@ -182,16 +195,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tmem_full + s, 1);
-      mbar_init(tmem_empty + s, kEpiWarps);
+      mbar_init(tmem_empty + s, CG * kEpiWarps);
       mbar_init(in_full + s, 1);
       mbar_init(in_empty + s, kEpiWarps);
     }
     mbar_init(b_full, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+  if (warp == 1) {
+    if constexpr (CG == 2) tmem_alloc_pair(tmem_ptr, kTmemCols); else tmem_alloc(tmem_ptr, kTmemCols);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();       // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   pdl_prologue_done();
@@ -223,7 +239,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       const bool res = p.b_resident != 0;
-      if (res && (int)blockIdx.x < num_tiles) {
+      if (CG == 1 && res && (int)blockIdx.x < num_tiles) {
         // B-resident schedule: the grid is a multiple of num_n_blocks, so this CTA's n block never changes; its
         // (BN x K) operand block is loaded once and every tile only streams its A rows through the ring
         const int n0 = ((int)blockIdx.x % p.num_n_blocks) * BN;
@@ -238,18 +254,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           }
         }
       }
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
         const int ks = tile / tiles_mn;
         const int mn = tile - ks * tiles_mn;
         const int m_blk = mn / p.num_n_blocks;
         const int n_blk = mn - m_blk * p.num_n_blocks;
-        const int m0 = m_blk * BM, n0 = n_blk * BN;
+        const int m0 = (m_blk * CG + cta_rank) * BM, n0 = n_blk * BN;
         for (int it = 0; it < p.k_iters; ++it) {
           mbar_wait(empty_bar + stage, phase ^ 1u);
           uint8_t* sa = res ? smem + p.a_off + stage * kABytes : smem + stage * kStageBytes;
           uint8_t* sb = sa + kABytes;
-          mbar_arrive_expect_tx(full_bar + stage, res ? kABytes : kStageBytes);
           const int kit = ks * p.k_iters + it;      // global k iteration
+          if constexpr (CG == 2) {
+            // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of the whole pair
+            const uint32_t lead_bar = mapa_shared(smem_u32(full_bar + stage), 0);
+            if (cta_rank == 0) mbar_arrive_expect_tx(full_bar + stage, 2 * kStageBytes);
+            const int k0 = kit * BK;
+            const int nb0 = n0 + cta_rank * kBRows;
+            tma_load_2d_pair(sa, &map_a, lead_bar, k0, m0);
+            if (B_MN) {
+#pragma unroll
+              for (int j = 0; j < kBRows / 64; ++j)
+                tma_load_2d_pair(sb + j * (64 * BK * 2), &map_b, lead_bar, nb0 + 64 * j, k0);
+            } else {
+              tma_load_2d_pair(sb, &map_b, lead_bar, k0, nb0);
+            }
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            continue;
+          }
+          mbar_arrive_expect_tx(full_bar + stage, res ? kABytes : kStageBytes);
           if (p.s2d) {
             const int ky = kit / p.k_seg_iters;
             const int kc = (kit - ky * p.k_seg_iters) * BK;
@@ -282,14 +315,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && cta_rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
       const bool res = p.b_resident != 0;
       if (res && (int)blockIdx.x < num_tiles) mbar_wait(b_full, 0);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
         mbar_wait(tmem_empty + as, aphase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * BN);
@@ -306,12 +339,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                                      : make_smem_desc(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? make_smem_desc(sb + k * 2048, 64 * BK * 2, 1024)
                                      : make_smem_desc(sb + k * 32, 16, 1024);
-            umma_f16(d_tmem, da, db, p.idesc, (it | k) != 0 ? 1u : 0u);
+            if constexpr (CG == 2) umma_f16_pair(d_tmem, da, db, p.idesc, (it | k) != 0 ? 1u : 0u);
+            else umma_f16(d_tmem, da, db, p.idesc, (it | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar + stage);
+          if constexpr (CG == 2) umma_commit_pair(empty_bar + stage, 3); else umma_commit(empty_bar + stage);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tmem_full + as);
+        if constexpr (CG == 2) umma_commit_pair(tmem_full + as, 3); else umma_commit(tmem_full + as);
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
@@ -322,10 +356,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       int ib = 0;
       uint32_t iphase = 0;
       const int box_bytes = BM * (p.in_kind == 2 ? 128 : 64);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
         const int mn = tile % tiles_mn;
-        const int m_blk = mn / p.num_n_blocks;
-        const int n_blk = mn - m_blk * p.num_n_blocks;
+        const int m_blk = (mn / p.num_n_blocks) * CG + cta_rank;
+        const int n_blk = mn % p.num_n_blocks;
         mbar_wait(in_empty + ib, iphase ^ 1u);
         uint8_t* dst = smem + p.in_off + ib * p.in_bytes;
         mbar_arrive_expect_tx(in_full + ib, kChunks * box_bytes);
@@ -351,10 +385,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     int as = 0, ib = 0, sb = 0;             // accumulator stage, input buffer, slab double-buffer index
     uint32_t aphase = 0, iphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    // hand an accumulator stage back to the (leader's) MMA warp
+    const uint32_t lead_tmem_empty = CG == 2 ? mapa_shared(smem_u32(tmem_empty), 0) : 0u;
+    auto release_tmem = [&](int stage_) {
+      if constexpr (CG == 2) mbar_arrive_cluster(lead_tmem_empty + 8u * (uint32_t)stage_);
+      else mbar_arrive(tmem_empty + stage_);
+    };
+    for (int tile = first_tile; tile < num_tiles; tile += tile_stride) {
       const int mn = tile % tiles_mn;
-      const int m_blk = mn / p.num_n_blocks;
-      const int n_blk = mn - m_blk * p.num_n_blocks;
+      const int m_blk = (mn / p.num_n_blocks) * CG + cta_rank;
+      const int n_blk = mn % p.num_n_blocks;
       const int m0 = m_blk * BM, n0 = n_blk * BN;
       const int m = m0 + row;
       mbar_wait(tmem_full + as, aphase);
@@ -382,7 +422,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty + as);
+          if (lane == 0) release_tmem(as);
           if (live) {
             if (p.bias != nullptr) {
               float b[32];
@@ -445,7 +485,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty + as);
+          if (lane == 0) release_tmem(as);
           if (live) {
             if (p.bias != nullptr) {
               float b[32];
@@ -498,7 +538,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           // accumulator fully read: hand the TMEM stage back to the MMA warp before finishing the stores
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty + as);
+          if (lane == 0) release_tmem(as);
         }
         if (n >= p.N || m0 + quad * 32 >= p.M) continue;     // chunk entirely outside the matrix (warp uniform)
         if (p.bias != nullptr) {
@@ -724,9 +764,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();       // the peer has finished reading this CTA's operands / signalling its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
   if (p.colsum_out != nullptr)
     for (int i = threadIdx.x; i < p.N; i += kThreads) {
@@ -798,9 +839,9 @@ static int make_epi_map(CUtensorMap* map, int dt, const void* base, long rows, l
 
 struct Maps { CUtensorMap a, b, in, o16, o16b, o32; };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int CG = 1>
 static int launch(const Maps& mp, GemmParams& p, cudaStream_t st) {
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, CG>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
@@ -809,7 +850,7 @@ static int launch(const Maps& mp, GemmParams& p, cudaStream_t st) {
   if (attr_err != cudaSuccess) return check_cuda(attr_err, "cudaFuncSetAttribute(gemm)");
   // shared-memory plan: [operand ring][epilogue input tile(s)][per-warp output slabs][barriers]
   const int b_res_bytes = p.b_resident ? p.k_iters * BN * BK * 2 : 0;
-  const int stage_bytes = p.b_resident ? BM * BK * 2 : BM * BK * 2 + BN * BK * 2;
+  const int stage_bytes = p.b_resident ? BM * BK * 2 : BM * BK * 2 + (BN / CG) * BK * 2;
   const int bar_bytes = (2 * kMaxStages + 9) * 8 + 16;
   const bool slabs = !(p.epilogue == BF_EPI_DGELU || p.epilogue == BF_EPI_ACC32 || p.epilogue == BF_EPI_D2S);
   const int slab_bytes = slabs ? epi_warps(BN) * slab_bytes_per_warp(BN)
@@ -840,10 +881,15 @@ static int launch(const Maps& mp, GemmParams& p, cudaStream_t st) {
   p.bar_off = p.vec_off + vec_bytes;
   const int total = p.bar_off + bar_bytes + 1024;
   const int tiles = p.num_m_blocks * p.num_n_blocks * p.split_k;
-  int grid = tiles < num_sms() ? tiles : num_sms();
+  int grid = tiles < num_sms() / CG ? tiles * CG : (num_sms() / CG) * CG;   // tiles are per CTA pair when CG = 2
   if (p.b_resident) grid = (num_sms() / p.num_n_blocks) * p.num_n_blocks;   // a CTA keeps one n block for all its tiles
-  const cudaError_t le = launch_k(kern, dim3(grid), dim3(gemm_threads(BN)), (size_t)total, st, mp.a, mp.b, mp.in, mp.o16, mp.o16b,
-                                 mp.o32, p);
+  cudaError_t le;
+  if constexpr (CG == 2)
+    le = launch_k_cluster(kern, dim3(grid), dim3(gemm_threads(BN)), (size_t)total, st, 2u, mp.a, mp.b, mp.in, mp.o16,
+                          mp.o16b, mp.o32, p);
+  else
+    le = launch_k(kern, dim3(grid), dim3(gemm_threads(BN)), (size_t)total, st, mp.a, mp.b, mp.in, mp.o16, mp.o16b,
+                  mp.o32, p);
   count_launch();
   return check_cuda(le != cudaSuccess ? le : cudaGetLastError(), "gemm_tcgen05_kernel launch");
 }
@@ -894,13 +940,35 @@ static int pick_bn(const bf_gemm_args& a) {
   return best;
 }
 
+// CTA pairs (cta_group::2) for the big row-major GEMMs: BF_GEMM_CG=1 forces the single-CTA kernel, BF_GEMM_CG=2 is the
+// default (pairs wherever the kernel supports the operand layout and the problem has enough row blocks).
+static int cg_mode() {
+  static int m = -1;
+  if (m < 0) { const char* e = getenv("BF_GEMM_CG"); m = (e != nullptr && e[0] == '1') ? 1 : 2; }
+  return m;
+}
+static int pick_cg(const bf_gemm_args& a, int bn, int resident) {
+  if (cg_mode() != 2 || resident) return 1;
+  if (a.a_mode != BF_A_ROWMAJOR) return 1;                       // S2D gather and the wgrad form stay single-CTA
+  if (bn != 128 && bn != 192 && bn != 256) return 1;
+  if (a.b_mode == BF_B_KN && (bn / 2) % 64 != 0) return 1;       // MN-major B halves must be whole 64-column blocks
+  if (a.M < 256 * 16) return 1;                                  // too few row blocks to be worth pairing
+  return 2;
+}
+
 }  // namespace bf
 
 using namespace bf;
 
+namespace bf { int launch_gemm_f32(const bf_gemm_args* a, cudaStream_t st); }
+
 extern "C" int bf_gemm(const bf_gemm_args* a, void* stream) {
   BF_REQUIRE(a != nullptr, "bf_gemm: null args");
   BF_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "bf_gemm: empty problem M=%d N=%d K=%d", a->M, a->N, a->K);
+  if (a->dtype == BF_F32) {                        // fp32 validation backend (exact.cu)
+    BF_REQUIRE(a->A && a->B, "bf_gemm: null operand");
+    return launch_gemm_f32(a, static_cast<cudaStream_t>(stream));
+  }
   BF_REQUIRE(a->dtype == BF_BF16 || a->dtype == BF_F16, "bf_gemm: dtype %d", a->dtype);
   BF_REQUIRE(a->A && a->B, "bf_gemm: null operand");
   BF_REQUIRE((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->B) & 15) == 0,
@@ -966,11 +1034,13 @@ extern "C" int bf_gemm(const bf_gemm_args* a, void* stream) {
 
   const int bn = pick_bn(*a);
   p.b_resident = resident_bn(*a) == bn ? 1 : 0;
+  p.cg = pick_cg(*a, bn, p.b_resident);
+  const int cg = p.cg;
   p.ln_heads = a->epilogue == BF_EPI_QKV_LN ? a->N / 192 : 0;
   BF_REQUIRE(!b_mn || bn % 64 == 0, "bf_gemm: internal bn");
-  p.num_m_blocks = (a->M + BM - 1) / BM;
+  p.num_m_blocks = (a->M + BM * cg - 1) / (BM * cg);       // row blocks of a tile: 128 rows per CTA of the pair
   p.num_n_blocks = (a->N + bn - 1) / bn;
-  p.idesc = make_idesc_f16(a->dtype == BF_F16 ? 0 : 1, a_mn ? 1 : 0, b_mn ? 1 : 0, BM, bn);
+  p.idesc = make_idesc_f16(a->dtype == BF_F16 ? 0 : 1, a_mn ? 1 : 0, b_mn ? 1 : 0, BM * cg, bn);
 
   Maps mp;
   int st;
@@ -1030,7 +1100,7 @@ extern "C" int bf_gemm(const bf_gemm_args* a, void* stream) {
       BF_REQUIRE(a->ldb >= a->K, "bf_gemm: ldb < K");
       uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
       uint64_t str[1] = {(uint64_t)a->ldb * 2};
-      uint32_t box[2] = {BK, (uint32_t)bn};
+      uint32_t box[2] = {BK, (uint32_t)(bn / cg)};
       if ((st = make_map(&mp.b, a->dtype, a->B, 2, dims, str, box, SW128))) return st;
     }
   }
@@ -1058,6 +1128,13 @@ extern "C" int bf_gemm(const bf_gemm_args* a, void* stream) {
   }
 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (cg == 2) {
+    if (bn == 128) return b_mn ? launch<128, false, true, 2>(mp, p, s) : launch<128, false, false, 2>(mp, p, s);
+    if (bn == 192 && !b_mn) return launch<192, false, false, 2>(mp, p, s);
+    if (bn == 256) return b_mn ? launch<256, false, true, 2>(mp, p, s) : launch<256, false, false, 2>(mp, p, s);
+    set_error("bf_gemm: no pair kernel for BN=%d b_mode=%d", bn, (int)b_mn);
+    return BF_ERR_INVALID;
+  }
 #define BF_DISPATCH(BN_)                                                          \
   if (bn == BN_) {                                                                \
     if (a_mn) return launch<BN_, true, true>(mp, p, s);                           \

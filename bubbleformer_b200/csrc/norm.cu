@@ -500,7 +500,7 @@ template <typename T16, bool HASZ>
 __global__ void __launch_bounds__(kNT, kBlocksPerSM)
 resid_bwd_kernel(ResidBwdParams p) {
   pdl_prologue_done();
-  constexpr int NSLOT = 2 + (HASZ ? 1 : 0), S = Stages<NSLOT>::S;
+  constexpr int NSLOT = 2 + (HASZ ? Slots<T16>::N : 0), S = Stages<NSLOT>::S;
   extern __shared__ __align__(16) uint4 ring[];
   const Geom& g = p.g;
   const Ctx c = make_ctx(g);
@@ -548,17 +548,17 @@ template <typename T16>
 __global__ void __launch_bounds__(kNT, kBlocksPerSM)
 colsum16_kernel(const T16* __restrict__ x, long ldx, Geom g, float* __restrict__ out) {
   pdl_prologue_done();
-  constexpr int NSLOT = 1, S = Stages<NSLOT>::S;
+  constexpr int NSLOT = Slots<T16>::N, S = Stages<NSLOT>::S;
   extern __shared__ __align__(16) uint4 ring[];
   const Ctx c = make_ctx(g);
   const T16* xb = x + ((long)c.img * g.P) * ldx + (long)c.vcol * 8;
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#define ISSUE(row, st) issue8<T16>(ring + (st) * kNT + threadIdx.x, xb + (long)(row) * ldx);
+#define ISSUE(row, st) issue8<T16>(ring + (st) * NSLOT * kNT + threadIdx.x, xb + (long)(row) * ldx);
 #define BODY(row, st)                                                \
   float v[8];                                                        \
-  unpack8<T16>(ring + (st) * kNT + threadIdx.x, v);                  \
+  unpack8<T16>(ring + (st) * NSLOT * kNT + threadIdx.x, v);          \
   _Pragma("unroll") for (int j = 0; j < 8; ++j) acc[j] += v[j];
   BF_STREAM_LOOP(S, ISSUE, BODY)
 #undef ISSUE
@@ -741,7 +741,7 @@ extern "C" int bf_resid_bwd(const float* dx, int64_t lddx, const void* z16, void
                             void* stream) {
   BF_REQUIRE(dx && coef && S0, "bf_resid_bwd: null pointer");
   BF_REQUIRE(z16 == nullptr || S1 != nullptr, "bf_resid_bwd: S1 required with z16");
-  BF_REQUIRE(dtype == BF_BF16 || dtype == BF_F16, "bf_resid_bwd: dtype");
+  BF_REQUIRE(dtype == BF_BF16 || dtype == BF_F16 || dtype == BF_F32, "bf_resid_bwd: dtype");
   if (int st = check_common("bf_resid_bwd", I, P, C, lddx, dx)) return st;
   BF_REQUIRE((z16 == nullptr && dz16 == nullptr) || (ldz >= C && ldz % 8 == 0), "bf_resid_bwd: ldz");
   ResidBwdParams p{};
@@ -753,6 +753,9 @@ extern "C" int bf_resid_bwd(const float* dx, int64_t lddx, const void* z16, void
   if (dtype == BF_BF16) {
     if (z16) BF_NORM_LAUNCH((resid_bwd_kernel<__nv_bfloat16, true>), grid, s, p);
     else BF_NORM_LAUNCH((resid_bwd_kernel<__nv_bfloat16, false>), grid, s, p);
+  } else if (dtype == BF_F32) {            // fp32 validation backend
+    if (z16) BF_NORM_LAUNCH((resid_bwd_kernel<float, true>), grid, s, p);
+    else BF_NORM_LAUNCH((resid_bwd_kernel<float, false>), grid, s, p);
   } else {
     if (z16) BF_NORM_LAUNCH((resid_bwd_kernel<__half, true>), grid, s, p);
     else BF_NORM_LAUNCH((resid_bwd_kernel<__half, false>), grid, s, p);
@@ -764,13 +767,14 @@ extern "C" int bf_resid_bwd(const float* dx, int64_t lddx, const void* z16, void
 
 extern "C" int bf_colsum16(const void* x, int dtype, int64_t rows, int C, int64_t ldx, float* out, void* stream) {
   BF_REQUIRE(x && out, "bf_colsum16: null pointer");
-  BF_REQUIRE(dtype == BF_BF16 || dtype == BF_F16, "bf_colsum16: dtype");
+  BF_REQUIRE(dtype == BF_BF16 || dtype == BF_F16 || dtype == BF_F32, "bf_colsum16: dtype");
   BF_REQUIRE(rows > 0 && rows < (1ll << 31), "bf_colsum16: rows");
   if (int st = check_common("bf_colsum16", 1, (int)rows, C, ldx, x)) return st;
   const Geom g = make_geom(1, (int)rows, C);
   dim3 grid(g.splits, 1, g.chunks);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == BF_BF16) BF_NORM_LAUNCH(colsum16_kernel<__nv_bfloat16>, grid, s, (const __nv_bfloat16*)x, (long)ldx, g, out);
+  else if (dtype == BF_F32) BF_NORM_LAUNCH(colsum16_kernel<float>, grid, s, (const float*)x, (long)ldx, g, out);
   else BF_NORM_LAUNCH(colsum16_kernel<__half>, grid, s, (const __half*)x, (long)ldx, g, out);
   count_launch();
   BF_LAUNCH_CHECK("colsum16_kernel");

@@ -279,12 +279,22 @@ int launch_patch_wgrad_mma(const void* a, int dtype, const float* x, float* dW, 
 int launch_patch_out_mma(const void* a, int dtype, const float* Wck, float* out, int I, int F, int h, int w, int C,
                          cudaStream_t s);
 }
+namespace bf {
+int launch_patch_in_f32(const float* x, const float* Wkn, float* out, float* stats, int I, int F, int H, int W, int N, cudaStream_t st);
+int launch_patch_out_f32(const float* a, const float* Wck, float* out, int I, int F, int h, int w, int C, cudaStream_t st);
+int launch_patch_wgrad_f32(const float* a, const float* x, float* dW, int I, int F, int H, int W, int N, cudaStream_t st);
+int launch_s2d_gather_f32(const float* in, float* out, int I, int Hin, int Win, int C, cudaStream_t st);
+}
 namespace bf { int launch_patch_in_mma(const float* x, const float* Wkn, void* out, int dtype, float* stats, int I, int F,
                                        int H, int W, int N, cudaStream_t s); }
 
 extern "C" int bf_patch_in(const float* x, const float* Wkn, void* out, int dtype, float* stats, int I, int F, int H,
                            int W, int N, void* stream) {
   BF_REQUIRE(x && Wkn && out, "bf_patch_in: null pointer");
+  if (dtype == BF_F32) {                      // fp32 validation backend
+    BF_REQUIRE(I > 0 && F > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && N > 0, "bf_patch_in (fp32): geometry");
+    return launch_patch_in_f32(x, Wkn, static_cast<float*>(out), stats, I, F, H, W, N, static_cast<cudaStream_t>(stream));
+  }
   BF_REQUIRE(dtype == BF_BF16 || dtype == BF_F16, "bf_patch_in: dtype");
   BF_REQUIRE(I > 0 && F > 0 && F <= kMaxF && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "bf_patch_in: geometry");
   BF_REQUIRE(N % 8 == 0 && N >= 8 && N <= 2048, "bf_patch_in: N=%d must be a multiple of 8 in [8, 2048]", N);
@@ -329,6 +339,10 @@ static int launch_patch_out(const void* a, const float* Wck, float* out, int I, 
 extern "C" int bf_patch_out(const void* a, int dtype, const float* Wck, float* out, int I, int F, int h, int w, int C,
                             void* stream) {
   BF_REQUIRE(a && Wck && out, "bf_patch_out: null pointer");
+  if (dtype == BF_F32) {
+    BF_REQUIRE(I > 0 && F > 0 && h > 0 && w > 0 && C > 0, "bf_patch_out (fp32): geometry");
+    return launch_patch_out_f32(static_cast<const float*>(a), Wck, out, I, F, h, w, C, static_cast<cudaStream_t>(stream));
+  }
   BF_REQUIRE(dtype == BF_BF16 || dtype == BF_F16, "bf_patch_out: dtype");
   BF_REQUIRE(I > 0 && F > 0 && F <= kMaxF && h > 0 && w > 0 && C % 8 == 0 && C > 0, "bf_patch_out: geometry");
   BF_REQUIRE((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0, "bf_patch_out: alignment");
@@ -343,6 +357,10 @@ extern "C" int bf_patch_out(const void* a, int dtype, const float* Wck, float* o
 extern "C" int bf_patch_wgrad(const void* a, int dtype, const float* x, float* dW, int I, int F, int H, int W, int N,
                               void* stream) {
   BF_REQUIRE(a && x && dW, "bf_patch_wgrad: null pointer");
+  if (dtype == BF_F32) {
+    BF_REQUIRE(I > 0 && F > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && N > 0 && 4 * F <= 65535, "bf_patch_wgrad (fp32): geometry");
+    return launch_patch_wgrad_f32(static_cast<const float*>(a), x, dW, I, F, H, W, N, static_cast<cudaStream_t>(stream));
+  }
   BF_REQUIRE(dtype == BF_BF16 || dtype == BF_F16, "bf_patch_wgrad: dtype");
   BF_REQUIRE(I > 0 && F > 0 && F <= kMaxF && H % 2 == 0 && W % 2 == 0 && H > 0 && W > 0, "bf_patch_wgrad: geometry");
   BF_REQUIRE(N % 8 == 0, "bf_patch_wgrad: N=%d must be a multiple of 8", N);
@@ -392,6 +410,11 @@ extern "C" int bf_convert16(const void* in, int in_dtype, void* out, int out_dty
 extern "C" int bf_s2d_gather(const void* in, int in_dtype, void* out, int out_dtype, int I, int Hin, int Win, int C,
                              void* stream) {
   BF_REQUIRE(in && out, "bf_s2d_gather: null pointer");
+  if (in_dtype == BF_F32 && out_dtype == BF_F32) {
+    BF_REQUIRE(I > 0 && Hin > 0 && Win > 0 && Hin % 2 == 0 && Win % 2 == 0 && C > 0, "bf_s2d_gather (fp32): geometry");
+    return launch_s2d_gather_f32(static_cast<const float*>(in), static_cast<float*>(out), I, Hin, Win, C,
+                                 static_cast<cudaStream_t>(stream));
+  }
   BF_REQUIRE((in_dtype == BF_F16 || in_dtype == BF_BF16) && (out_dtype == BF_F16 || out_dtype == BF_BF16),
              "bf_s2d_gather: dtypes");
   BF_REQUIRE(I > 0 && Hin > 0 && Win > 0 && Hin % 2 == 0 && Win % 2 == 0 && C > 0 && C % 8 == 0,

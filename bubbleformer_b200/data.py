@@ -47,7 +47,7 @@ class DeviceForecastWindows:
             raise ValueError(f"Unknown normalization type: {norm}")          # upstream dataset.py:109
         self.norm, self.time_window, self.start_time = norm, time_window, start_time
         self.fields = sorted(set(self.input_fields + self.output_fields), key=(self.input_fields + self.output_fields).index)
-        data = arrays if arrays is not None else [read_hdf5(f) for f in filenames]
+        data = arrays if arrays is not None else [read_hdf5(f, self.fields) for f in filenames]   # only the fields used
         self.traj_lens = [int(d[self.input_fields[0]].shape[0]) for d in data]
         self.num_trajs = [1] * len(data)
         self.host = [{k: np.asarray(d[k], dtype=np.float32) for k in self.fields} for d in data]
@@ -60,7 +60,7 @@ class DeviceForecastWindows:
             raise RuntimeError("bubbleformer_b200 runs on CUDA only (no CPU fallback)")
         stacked = np.concatenate([np.stack([d[k] for k in self.fields], axis=1) for d in self.host], axis=0)
         self.frames = torch.from_numpy(np.ascontiguousarray(stacked)).to(dev)          # (sum frames, C, H, W)
-        del stacked
+        del stacked, data                   # the raw file mapping is dropped; self.host keeps the fields for normalize()
         self.downsample_factor = int(downsample_factor)
         if self.downsample_factor < 1:
             raise ValueError("downsample_factor must be >= 1")

@@ -27,6 +27,19 @@ from . import _lib as L
 from . import ops
 
 F32, BF16, F16 = torch.float32, torch.bfloat16, torch.float16
+EXACT = False
+
+
+def set_exact_mode(on: bool) -> None:
+    """fp32 validation configuration (north star: parity within 1e-4 "for the fp32 path"; upstream runs fp32 / TF32,
+    scripts/train.py:72): every activation that the production path stores in 16 bits becomes fp32, the GEMMs /
+    attention / patch kernels run their plain-fp32 forms (csrc/exact.cu) and every GELU is the exact erf form.  The
+    orchestration in this file is unchanged.  Process-wide; a checking mode, not a performance mode."""
+    global BF16, F16, EXACT
+    EXACT = bool(on)
+    BF16 = torch.float32 if on else torch.bfloat16
+    F16 = torch.float32 if on else torch.float16
+    L.lib.bf_set_gelu_mode(1 if on else 0)
 
 
 @dataclass(frozen=True)
@@ -181,7 +194,7 @@ def _attn_branch_fwd(X, g: Geom, p: Dict[str, torch.Tensor], w16, heads: int, ax
     QKV = _empty((N, 3 * E), BF16, X)
     # head_dim 64 and short axes: LayerNorm(q), LayerNorm(k) are computed in the QKV GEMM epilogue (xhat + rstd) and
     # the attention kernels work on the pre-normalised rows; otherwise the generic kernels normalise in place
-    prenorm = (E // heads == 64) and all(_axis(g, ax)["L_"] <= 32 for ax in axes)
+    prenorm = (E // heads == 64) and all(_axis(g, ax)["L_"] <= 32 for ax in axes) and BF16 == torch.bfloat16
     rstd = _empty((N, heads, 2), F32, X) if prenorm else None
     if prenorm:
         ops.gemm(Xn, w16("input_head.weight"), N, 3 * E, E, epilogue=L.EPI_QKV_LN, bias=p["input_head.bias"], out16=QKV,

@@ -17,7 +17,7 @@ _SIG = b"\x89HDF\r\n\x1a\n"
 
 class _File:
     def __init__(self, buf: bytes):
-        if buf[:8] != _SIG:
+        if bytes(buf[:8]) != _SIG:
             raise ValueError("not an HDF5 file")
         if buf[8] != 0:
             raise NotImplementedError(f"HDF5 superblock version {buf[8]} (only version 0 is supported)")
@@ -35,7 +35,7 @@ class _File:
         self.root_heap = self.u(p + 32, 8) if cache_type == 1 else None
 
     def u(self, off: int, n: int) -> int:
-        return int.from_bytes(self.buf[off:off + n], "little")
+        return int.from_bytes(bytes(self.buf[off:off + n]), "little")
 
     # ---- object headers (version 1) ----------------------------------------------------------
     def messages(self, addr: int):
@@ -94,33 +94,36 @@ class _File:
         n = int(np.prod(shape)) if shape else 1
         if n * np.dtype(dtype).itemsize != nbytes:
             raise ValueError("dataset size does not match its dataspace")
-        return np.frombuffer(self.buf, dtype=dtype, count=n, offset=self.base + off).reshape(shape)
+        start = self.base + off
+        return np.asarray(self.buf[start:start + nbytes]).view(dtype).reshape(shape)
 
     # ---- root group ----------------------------------------------------------------------------
     def links(self) -> Dict[str, int]:
         if self.root_btree is None:
             raise NotImplementedError("root group without a cached symbol table")
         heap = self.root_heap
-        if self.buf[heap:heap + 4] != b"HEAP":
+        if bytes(self.buf[heap:heap + 4]) != b"HEAP":
             raise ValueError("bad local heap")
         heap_data = self.u(heap + 8 + 2 * 8, 8)
         out: Dict[str, int] = {}
 
         def name_at(o: int) -> str:
             s = self.base + heap_data + o
-            e = self.buf.index(b"\x00", s)
-            return self.buf[s:e].decode("utf-8")
+            e = s
+            while self.buf[e] != 0:
+                e += 1
+            return bytes(self.buf[s:e]).decode("utf-8")
 
         def walk(node: int) -> None:
             b = self.buf
-            if b[node:node + 4] == b"TREE":
+            if bytes(b[node:node + 4]) == b"TREE":
                 level, used = b[node + 5], self.u(node + 6, 2)
                 p = node + 8 + 2 * 8                       # skip sibling addresses
                 for i in range(used):
                     child = self.u(p + 8 + i * 16, 8)      # key (8) then child pointer (8)
                     walk(self.base + child)
                 return
-            if b[node:node + 4] != b"SNOD":
+            if bytes(b[node:node + 4]) != b"SNOD":
                 raise ValueError("bad group node")
             n = self.u(node + 6, 2)
             p = node + 8
@@ -132,11 +135,54 @@ class _File:
         return out
 
 
-def read_hdf5(path: str) -> Dict[str, np.ndarray]:
-    """All simple datasets of the root group: name -> array (views of one read-only buffer)."""
-    with open(path, "rb") as f:
-        hf = _File(f.read())
-    return {name: hf.dataset(addr) for name, addr in hf.links().items()}
+class LazyFile:
+    """Mapping name -> array over the root group that decodes an object only when it is asked for (like h5py reads by
+    name): sub-groups, compound / string tables or chunked datasets elsewhere in the file do not get in the way of
+    reading the plain fields.  The file is memory-mapped, so only the datasets actually read are paged in."""
+
+    def __init__(self, path: str):
+        self._mm = np.memmap(path, dtype=np.uint8, mode="r")
+        self._hf = _File(self._mm)
+        self._links = self._hf.links()
+
+    def keys(self):
+        return self._links.keys()
+
+    def __contains__(self, name: str) -> bool:
+        return name in self._links
+
+    def __iter__(self):
+        return iter(self._links)
+
+    def __len__(self) -> int:
+        return len(self._links)
+
+    def __getitem__(self, name: str) -> np.ndarray:
+        if name not in self._links:
+            raise KeyError(f"no object named {name!r} in the root group (have: {sorted(self._links)})")
+        return self._hf.dataset(self._links[name])
+
+    def items(self):
+        return ((k, self[k]) for k in self._links)
+
+
+def open_hdf5(path: str) -> LazyFile:
+    return LazyFile(path)
+
+
+def read_hdf5(path: str, fields=None) -> Dict[str, np.ndarray]:
+    """Datasets of the root group as name -> array (views of the memory-mapped file).  `fields`: only these names are
+    decoded; by default every object of the root group that is a simple contiguous dataset (others are skipped)."""
+    f = LazyFile(path)
+    if fields is not None:
+        return {k: f[k] for k in fields}
+    out = {}
+    for k in f.keys():
+        try:
+            out[k] = f[k]
+        except (NotImplementedError, ValueError):
+            continue                      # not a plain dataset (group, compound table, chunked ...): read by name if needed
+    return out
 
 
 def dataset_shapes(path: str) -> Dict[str, Tuple[int, ...]]:

@@ -11,8 +11,55 @@ from .. import ops
 from ..autograd import adhoc_w16
 
 
+class _GeluMLPFn(torch.autograd.Function):
+    """Stand-alone fc1 -> GELU -> fc2 with its backward, on the same GEMM epilogues the axial block uses (bias + GELU
+    storing the pre-activation, dGELU with the fc1-bias column sums, split-K weight gradients)."""
+
+    @staticmethod
+    def forward(ctx, x, W1, b1, W2, b2):
+        from ..engine import pick_split
+        N, E = x.shape
+        Hd = W1.shape[0]
+        xb = torch.empty(N, E, dtype=torch.bfloat16, device=x.device)
+        ops.cast16(x.detach().float().contiguous().reshape(-1), xb.reshape(-1))
+        w1, w2 = adhoc_w16(W1), adhoc_w16(W2)
+        G = torch.empty(N, Hd, dtype=torch.bfloat16, device=x.device)
+        need = any(ctx.needs_input_grad)
+        Hpre = torch.empty(N, Hd, dtype=torch.bfloat16, device=x.device) if need else None
+        ops.gemm(xb, w1, N, Hd, E, epilogue=L.EPI_GELU, bias=b1.detach(), out16=G, out16b=Hpre)
+        out = torch.empty(N, E, dtype=torch.float32, device=x.device)
+        ops.gemm(G, w2, N, E, Hd, epilogue=L.EPI_STORE32, bias=b2.detach(), out32=out)
+        if need:
+            ctx.save_for_backward(xb, G, Hpre, w1, w2)
+            ctx.pick_split = pick_split
+        return out
+
+    @staticmethod
+    def backward(ctx, dY):
+        xb, G, Hpre, w1, w2 = ctx.saved_tensors
+        N, E = xb.shape
+        Hd = w1.shape[0]
+        dev = dY.device
+        dY16 = torch.empty(N, E, dtype=torch.bfloat16, device=dev)
+        ops.cast16(dY.float().contiguous().reshape(-1), dY16.reshape(-1))
+        dW1 = torch.zeros(Hd, E, dtype=torch.float32, device=dev)
+        db1 = torch.zeros(Hd, dtype=torch.float32, device=dev)
+        dW2 = torch.zeros(E, Hd, dtype=torch.float32, device=dev)
+        db2 = torch.zeros(E, dtype=torch.float32, device=dev)
+        dH = torch.empty(N, Hd, dtype=torch.bfloat16, device=dev)
+        ops.gemm(dY16, w2, N, Hd, E, epilogue=L.EPI_DGELU, b_mode=L.B_KN, aux16=Hpre, out16=dH, colsum_out=db1)
+        ops.gemm(dY16, G, E, Hd, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
+                 split_k=ctx.pick_split(N, E, Hd), out32=dW2)
+        ops.colsum16(dY16, db2)
+        dX = torch.empty(N, E, dtype=torch.float32, device=dev)
+        ops.gemm(dH, w1, N, E, Hd, epilogue=L.EPI_STORE32, b_mode=L.B_KN, out32=dX)
+        ops.gemm(dH, xb, Hd, E, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
+                 split_k=ctx.pick_split(N, Hd, E), out32=dW1)
+        return dX, dW1, db1, dW2, db2
+
+
 class GeluMLP(nn.Module):
-    """fc1 -> exact-erf GELU -> fc2 (upstream linear_layers.py:5-25)."""
+    """fc1 -> GELU -> fc2 (upstream linear_layers.py:5-25; GELU form: see include/bubbleformer_b200.h, "GELU")."""
 
     def __init__(self, hidden_dim, exp_factor=4.0):
         super().__init__()
@@ -21,19 +68,14 @@ class GeluMLP(nn.Module):
         self.act = nn.GELU()
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """Stand-alone inference path (..., E) -> (..., E); training goes through AxialAttentionBlock."""
-        if torch.is_grad_enabled() and (x.requires_grad or self.fc1.weight.requires_grad):
-            raise NotImplementedError("stand-alone GeluMLP is forward-only; wrap the call in torch.no_grad() "
-                                      "(training runs the MLP inside AxialAttentionBlock)")
+        """Stand-alone path (..., E) -> (..., E), forward and backward (inside AxialAttentionBlock the same GEMMs run
+        as part of the block's own Function).  The token count must be a multiple of 8 (16-byte rows of the operand
+        that the weight-gradient GEMM reads transposed)."""
+        if not x.is_cuda:
+            raise RuntimeError("bubbleformer_b200 runs on CUDA tensors only (no CPU fallback)")
         E = x.shape[-1]
         xt = x.reshape(-1, E)
-        N = xt.shape[0]
-        xb = xt.to(torch.bfloat16).contiguous()
-        Hd = self.fc1.weight.shape[0]
-        G = torch.empty(N, Hd, dtype=torch.bfloat16, device=x.device)
-        ops.gemm(xb, adhoc_w16(self.fc1.weight), N, Hd, E, epilogue=L.EPI_GELU, bias=self.fc1.bias.detach(), out16=G)
-        out = torch.empty(N, E, dtype=torch.float32, device=x.device)
-        ops.gemm(G, adhoc_w16(self.fc2.weight), N, E, Hd, epilogue=L.EPI_STORE32, bias=self.fc2.bias.detach(), out32=out)
+        out = _GeluMLPFn.apply(xt, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias)
         return out.reshape(x.shape)
 
 

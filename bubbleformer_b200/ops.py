@@ -12,7 +12,8 @@ import torch
 
 from . import _lib as L
 
-_DT = {torch.bfloat16: L.BF_BF16, torch.float16: L.BF_F16}
+# 16-bit storage types of the production kernels; float32 selects the fp32 validation backend (csrc/exact.cu)
+_DT = {torch.bfloat16: L.BF_BF16, torch.float16: L.BF_F16, torch.float32: L.BF_F32}
 
 
 def _stream() -> C.c_void_p:
@@ -45,7 +46,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, epilogue: 
          ldo: Optional[int] = None, ld32: Optional[int] = None) -> None:
     """D[M,N] = sum_k A[m,k] B[n,k] with a fused epilogue; see bf_gemm in include/bubbleformer_b200.h."""
     if A.dtype not in _DT or B.dtype != A.dtype:
-        raise L.BubbleformerB200Error(f"gemm: operands must both be bf16 or fp16, got {A.dtype}/{B.dtype}")
+        raise L.BubbleformerB200Error(f"gemm: operands must both be bf16, fp16 (or fp32: validation backend), got {A.dtype}/{B.dtype}")
     a = L.GemmArgs()
     a.M, a.N, a.K = M, N, K
     a.dtype = _DT[A.dtype]
@@ -269,8 +270,8 @@ def attention(qkv, out, *, heads, L_, n_seq, inner, outer_stride, inner_stride, 
     accumulators d_qn_w, d_qn_b, d_kn_w, d_kn_b, d_bias_emb, d_scale_factor.
     prenorm: qkv holds xhat_q | xhat_k | v from gemm(epilogue=EPI_QKV_LN); the backward needs `rstd`."""
     _mat(qkv, "qkv"); _mat(out, "out")
-    if qkv.dtype != torch.bfloat16 or out.dtype != torch.bfloat16:
-        raise L.BubbleformerB200Error("attention: bf16 tensors required")
+    if qkv.dtype not in (torch.bfloat16, torch.float32) or out.dtype != qkv.dtype:
+        raise L.BubbleformerB200Error("attention: bf16 tensors required (fp32: validation backend)")
     E3 = qkv.shape[1]
     d = E3 // (3 * heads)
     a = L.AttnArgs()
@@ -286,6 +287,7 @@ def attention(qkv, out, *, heads, L_, n_seq, inner, outer_stride, inner_stride, 
     a.scale_factor = _f32(scale_factor, heads, "scale_factor")
     a.out_scale = out_scale
     a.prenorm = int(prenorm)
+    a.dtype = _DT[qkv.dtype]
     if rstd is not None:
         a.rstd = _f32(rstd, 2 * heads * qkv.shape[0], "rstd")
     if dout is None:
@@ -341,12 +343,18 @@ def s2d_gather(img, out) -> None:
 
 def convert16(src, dst) -> None:
     assert src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel()
+    if src.dtype == dst.dtype:                       # fp32 validation configuration: nothing to convert
+        dst.copy_(src)
+        return
     L.check(L.lib.bf_convert16(_ptr(src), _DT[src.dtype], _ptr(dst), _DT[dst.dtype], src.numel(), _stream()),
             "bf_convert16")
 
 
 def cast16(src, dst) -> None:
     assert src.dtype == torch.float32 and src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel()
+    if dst.dtype == torch.float32:                   # fp32 validation configuration
+        dst.copy_(src)
+        return
     L.check(L.lib.bf_cast16(_ptr(src), _ptr(dst), _DT[dst.dtype], src.numel(), _stream()), "bf_cast16")
 
 

@@ -3,8 +3,11 @@
 
   AdamW / Adam: torch.optim (upstream bubbleformer/modules.py:134-138); pinned in tests against torch.optim itself.
   Lion: lion_pytorch.Lion (modules.py:139, env/requirements.txt, unpinned, NOT installed here) -- its published
-        `update_fn`: p *= 1 - lr*wd; p -= lr*sign(b1*m + (1-b1)*g); m = b2*m + (1-b2)*g.   PARITY UNPINNED for Lion
-        (no copy of the package to run against).
+        `update_fn`: p *= 1 - lr*wd; p -= lr*sign(b1*m + (1-b1)*g); m = b2*m + (1-b2)*g.  Unpinned against the
+        lion_pytorch PACKAGE (no copy to run); pinned instead against an independent torch.optim.Optimizer written from
+        the published algorithm (Chen et al. 2023, "Symbolic Discovery of Optimization Algorithms", Algorithm 1:
+        c = sign(b1 m + (1-b1) g); theta <- theta - lr (c + wd theta); m <- b2 m + (1-b2) g), 100 steps with weight
+        decay, in tests/test_optim.py::test_oracle_lion_matches_independent_torch_optimizer.
   Schedule: utils/lr_schedulers.py:4-31 (CosineWarmupLR), pinned in tests against torch's SequentialLR.
 """
 import torch

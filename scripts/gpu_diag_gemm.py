@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 VARIANTS = [
-    "nk_small", "nk_ragged", "nk_bn64", "nk_bn128", "nk_bn192", "nk_bn256", "nk_big",
+    "nk_small", "nk_ragged", "nk_bn64", "nk_bn128", "nk_bn192", "nk_bn256", "nk_big", "nk_pair_ragged", "nk_pair_odd",
     "nk_f16", "gelu", "resid", "resid_stats", "qkv_ln", "dgelu", "acc32", "store32",
     "gelu_big", "resid_big", "resid_stats_big", "dgelu_big", "kn_dgrad_res",        # config-2 shapes: the B-resident schedule
     "kn_dgrad", "kn_dgrad_256", "wgrad", "wgrad_split", "wgrad_192",
@@ -60,7 +60,9 @@ def run_variant(v):
     if v.startswith("nk_") or v in ("gelu", "resid", "dgelu", "acc32", "store32"):
         shapes = {"nk_small": (128, 128, 64), "nk_ragged": (300, 200, 104), "nk_bn64": (256, 64, 128),
                   "nk_bn128": (4096, 384, 384), "nk_bn192": (4096, 1152, 384), "nk_bn256": (4096, 1536, 384),
-                  "nk_big": (40960, 1152, 384), "nk_f16": (1024, 96, 384)}
+                  "nk_big": (40960, 1152, 384), "nk_f16": (1024, 96, 384),
+                  # CTA-pair kernel (M >= 4096): second CTA partly / wholly outside the matrix
+                  "nk_pair_ragged": (4200, 384, 200), "nk_pair_odd": (4224, 1152, 384)}
         M, N, K = shapes.get(v, (1000, 384, 256))
         if big:
             M, N, K = (40960, 384, 384) if v == "resid" else (40960, 1536, 384)

@@ -24,7 +24,7 @@ def _native_loaded():
 
 
 @pytest.mark.parametrize("variant", [
-    "nk_small", "nk_ragged", "nk_bn64", "nk_bn128", "nk_bn192", "nk_bn256", "nk_big", "nk_f16", "gelu", "resid", "resid_stats", "qkv_ln",
+    "nk_small", "nk_ragged", "nk_bn64", "nk_bn128", "nk_bn192", "nk_bn256", "nk_big", "nk_pair_ragged", "nk_pair_odd", "nk_f16", "gelu", "resid", "resid_stats", "qkv_ln",
     "dgelu", "acc32", "store32", "kn_dgrad", "kn_dgrad_256", "wgrad", "wgrad_split", "wgrad_192", "s2d_w128",
     "s2d_w32", "s2d_c48", "d2s", "d2s_c48",
     "gelu_big", "resid_big", "resid_stats_big", "dgelu_big", "kn_dgrad_res"])     # config-2 shapes: B-resident schedule
@@ -55,6 +55,17 @@ def test_model_vs_host_oracle_at_baseline_shapes(case):
     shapes BASELINE.json names: config 2 (small, 512x512), config 5 (big, 512x512 and 1024x1024), config 4 (128x1024)."""
     import gpu_diag_model
     assert gpu_diag_model.run_case(case)
+    assert _native_loaded()
+
+
+@pytest.mark.parametrize("case", ["film_eval_e128", "film_train_masks_e128", "avit_generic_e96", "rollout"])
+def test_exact_fp32_mode_within_1e4_of_reference_fixture(case):
+    """North star: "1e-4 for the fp32 path".  The same orchestration with fp32 storage, plain-fp32 GEMM / attention /
+    patch kernels and the exact-erf GELU (bubbleformer_b200.set_exact_mode) against the fp64 outputs of the live
+    reference: forward per channel, dx and all parameter gradients (global-norm-relative) within 1e-4; teacher-forced
+    10-step rollout within 1e-4 per channel."""
+    import gpu_diag_model
+    assert gpu_diag_model.run_case(case, exact=True)
     assert _native_loaded()
 
 
@@ -169,3 +180,27 @@ def test_graphed_train_step_matches_eager():
         assert abs(l2_graph - l2_eager) < 2e-3 * abs(l2_eager)
     finally:
         sink.close()
+
+
+def test_gelu_mlp_standalone_forward_backward():
+    """bubbleformer.layers.GeluMLP used on its own (upstream linear_layers.py:5-25): forward and every gradient against
+    torch fp32 with the exact-erf GELU; bf16 tolerance (1e-2, north star)."""
+    import torch
+    import torch.nn.functional as F
+    from bubbleformer_b200.layers import GeluMLP
+    torch.manual_seed(11)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    mlp = GeluMLP(128).cuda()
+    x = torch.randn(3, 40, 128, device="cuda", requires_grad=True)
+    y = mlp(x)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    got = [x.grad] + [p.grad for p in mlp.parameters()]
+    xr = x.detach().clone().requires_grad_(True)
+    ps = [p.detach().clone().requires_grad_(True) for p in mlp.parameters()]
+    yr = F.linear(F.gelu(F.linear(xr, ps[0], ps[1])), ps[2], ps[3])
+    yr.backward(dy)
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+    assert rel(y, yr) < 1e-2
+    for g, r in zip(got, [xr.grad] + [p.grad for p in ps]):
+        assert g is not None and rel(g, r) < 1e-2, rel(g, r)

@@ -25,6 +25,50 @@ def test_oracle_adam_family_matches_torch_optim():
         assert float((p - ref.detach()).abs().max()) < 1e-12
 
 
+class _PaperLion(torch.optim.Optimizer):
+    """Independent Lion written from the paper's Algorithm 1 (Chen et al. 2023), in-place torch ops, decoupled weight decay
+    inside the update:  theta <- theta - lr * (sign(b1 m + (1 - b1) g) + wd * theta);  m <- b2 m + (1 - b2) g."""
+
+    def __init__(self, params, lr, betas, weight_decay):
+        super().__init__(params, dict(lr=lr, betas=betas, weight_decay=weight_decay))
+
+    @torch.no_grad()
+    def step(self):
+        for grp in self.param_groups:
+            b1, b2 = grp["betas"]
+            for p in grp["params"]:
+                st = self.state[p]
+                if "m" not in st:
+                    st["m"] = torch.zeros_like(p)
+                c = torch.sign(torch.lerp(p.grad, st["m"], b1))            # b1*m + (1-b1)*g
+                p.add_(c + grp["weight_decay"] * p, alpha=-grp["lr"])
+                st["m"].lerp_(p.grad, 1 - b2)                               # b2*m + (1-b2)*g
+
+
+def test_oracle_lion_matches_independent_torch_optimizer():
+    """Lion is upstream's default optimiser (config/optim_cfg/lion.yaml:1-5: lr 0.5e-4, weight_decay 1e-1; lion_pytorch's
+    default betas (0.9, 0.99)).  100 steps, fp64: the oracle's restatement of lion_pytorch's update_fn (decay first, then
+    the signed step) against the paper's form (decay inside the step) -- same parameters and momenta up to rounding,
+    including the order of the momentum update (after the parameter step, from the OLD momentum)."""
+    from oracle import optim_oracle as O
+    torch.manual_seed(3)
+    lr, b1, b2, wd = 0.5e-4, 0.9, 0.99, 1e-1
+    p = torch.randn(4096, dtype=torch.float64)
+    ref = torch.nn.Parameter(p.clone())
+    opt = _PaperLion([ref], lr, (b1, b2), wd)
+    m = torch.zeros_like(p)
+    for _ in range(100):
+        g = torch.randn_like(p)
+        # keep b1*m + (1-b1)*g away from 0 so that sign() cannot differ by rounding between the two forms
+        interp = b1 * m + (1 - b1) * g
+        g = torch.where(interp.abs() < 1e-9, g + 1e-6, g)
+        ref.grad = g.clone()
+        opt.step()
+        p, m = O.lion_step(p, g, m, lr, b1, b2, wd)
+    assert float((p - ref.detach()).abs().max()) < 1e-12
+    assert float((m - opt.state[ref]["m"]).abs().max()) < 1e-12
+
+
 def test_cosine_warmup_matches_sequential_lr():
     from torch.optim.lr_scheduler import CosineAnnealingLR, LambdaLR, SequentialLR
     from bubbleformer_b200.optim import cosine_warmup_lr
