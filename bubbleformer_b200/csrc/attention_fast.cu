@@ -15,6 +15,8 @@
 //   * backward keeps dP for the whole tile in registers, parks P' / dS in the (then dead) v tile, and accumulates
 //     LayerNorm weight gradients in registers across all items of the persistent loop.
 // Short sequences (temporal attention, L = 5) are packed G = 32 / L per tile with a block-diagonal mask.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace bf {
@@ -739,6 +741,444 @@ attn_fast_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
 }
 
 // ---------------------------------------------------------------------------------------------
+// backward, two warps per work item
+// ---------------------------------------------------------------------------------------------
+// The one-warp backward above is bound by its own length: ~8 400 instructions per (tile, head) with 168 registers per
+// thread, so only 12 warps fit an SM (register file AND 17 KB of tiles per warp) and each of them is one long dependent
+// chain.  Here a PAIR of warps shares the 17 KB of one item: 24 warps per SM on the same shared memory, half the chain
+// per warp.
+//   phase 1 (split by query m-tile: warp h owns rows 16h..16h+15): dP = dO V^T, S = Q'K'^T, softmax, dS; P' and dS rows go
+//            into the (then dead) V tile
+//   phase 2 (split by output COLUMNS: warp h owns columns 32h..32h+31 of dV, dK, dQ): each warp only ever reads and
+//            overwrites its own column half of the dO / Q tiles, so staging needs no extra buffers; the LayerNorm
+//            backward's row sums over all 64 columns are exchanged through 512 B of shared memory.
+// Eight named barriers of 64 threads per item order the hand-offs.  Warp 0 lane 0 issues every TMA load and store.
+constexpr int kBwd2Pairs = 12;
+
+struct Bwd2Pair {
+  static constexpr int kPart = BwdWarp::kRstd + FLP * 8;          // float[2][32][2]: per-warp partial LayerNorm row sums
+  static constexpr int kBytes = ((kPart + 2 * FLP * 8) + 1023) / 1024 * 1024;
+};
+
+__device__ __forceinline__ void pair_sync(int pair) {
+  asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
+}
+
+// 16 x 32 C fragments (4 n tiles) -> bf16 columns col0.. of rows m0.. of a swizzled tile
+__device__ __forceinline__ void stage16h(uint8_t* tile, int m0, int col0, const float (&o)[4][4], int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    *reinterpret_cast<uint32_t*>(tile + swz(m0 + g, col0 + nt * 8 + 2 * t)) = pack_bf2(o[nt][0], o[nt][1]);
+    *reinterpret_cast<uint32_t*>(tile + swz(m0 + g + 8, col0 + nt * 8 + 2 * t)) = pack_bf2(o[nt][2], o[nt][3]);
+  }
+}
+
+// LayerNorm backward on this warp's 32 columns of a 16-row tile, first half: acc = dL/dy -> dn = dy * w (in place),
+// parameter-gradient partials, and this warp's share of the row sums (sum dn, sum dn * xhat) -> part[row][2]
+template <bool DB, bool SCALE>
+__device__ __forceinline__ void ln_bwd_h1(float (&acc)[4][4], float pre, const uint8_t* xh, int m0, int col0, const float* w,
+                                          float (&dw)[4][2], float (&db)[4][2], float* part, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int r = m0 + g + half * 8;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int c = col0 + nt * 8 + 2 * t;
+      const float2 xv = unpack2<bf16>(*reinterpret_cast<const uint32_t*>(xh + swz(r, c)));
+      const float2 wv = *reinterpret_cast<const float2*>(w + c);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float n = e ? xv.y : xv.x;
+        const float dy = SCALE ? acc[nt][half * 2 + e] * pre : acc[nt][half * 2 + e];
+        dw[nt][e] = fmaf(dy, n, dw[nt][e]);
+        if (DB) db[nt][e] += dy;
+        const float dn = dy * (e ? wv.y : wv.x);
+        acc[nt][half * 2 + e] = dn;
+        s1 += dn;
+        s2 = fmaf(dn, n, s2);
+      }
+    }
+    s1 = qsum(s1); s2 = qsum(s2);
+    if (t == 0) { part[2 * r] = s1; part[2 * r + 1] = s2; }
+  }
+}
+// second half, after the partner's partial sums are visible: d raw = rstd * (dn - mean(dn) - xhat * mean(dn * xhat))
+__device__ __forceinline__ void ln_bwd_h2(float (&acc)[4][4], const uint8_t* xh, const float* rstd_s, int which, int m0,
+                                          int col0, const float* part_a, const float* part_b, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int r = m0 + g + half * 8;
+    const float rstd = rstd_s[2 * r + which];
+    const float c0 = -rstd * (part_a[2 * r] + part_b[2 * r]) * (1.f / FD);
+    const float c1 = -rstd * (part_a[2 * r + 1] + part_b[2 * r + 1]) * (1.f / FD);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const float2 xv = unpack2<bf16>(*reinterpret_cast<const uint32_t*>(xh + swz(r, col0 + nt * 8 + 2 * t)));
+      acc[nt][half * 2] = fmaf(xv.x, c1, fmaf(acc[nt][half * 2], rstd, c0));
+      acc[nt][half * 2 + 1] = fmaf(xv.y, c1, fmaf(acc[nt][half * 2 + 1], rstd, c0));
+    }
+  }
+}
+
+template <bool PACKED>
+__global__ void __launch_bounds__(kBwd2Pairs * 64, 1)
+attn_fast_bwd2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do,
+                      const __grid_constant__ CUtensorMap map_dqkv, const FastParams p) {
+  pdl_prologue_done();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = warp >> 1, h = warp & 1;
+  uint8_t* tab = smem + kBwd2Pairs * Bwd2Pair::kBytes;
+  fill_tables(p, tab, threadIdx.x, blockDim.x);
+  float* s_acc = reinterpret_cast<float*>(tab + tab_bytes(p.heads));
+  float* s_dqw = s_acc;                 // [64]
+  float* s_dqb = s_dqw + FD;
+  float* s_dkw = s_dqb + FD;
+  float* s_demb = s_dkw + FD;           // [32 * heads]
+  float* s_dsf = s_demb + 32 * p.heads; // [heads]
+  const int n_acc = 3 * FD + 33 * p.heads;
+  for (int i = threadIdx.x; i < n_acc; i += blockDim.x) s_acc[i] = 0.f;
+  uint8_t* my = smem + pair * Bwd2Pair::kBytes;
+  uint8_t* sQ = my + BwdWarp::kQ;
+  uint8_t* sK = my + BwdWarp::kK;
+  uint8_t* sV = my + BwdWarp::kV;       // after dP: P' in columns 0..31, dS in columns 32..63
+  uint8_t* sdo = my + BwdWarp::kDo;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(my + BwdWarp::kBar);
+  int* rowgp = reinterpret_cast<int*>(my + BwdWarp::kRowGp);
+  float* rstd_s = reinterpret_cast<float*>(my + BwdWarp::kRstd);
+  float* part_me = reinterpret_cast<float*>(my + Bwd2Pair::kPart) + h * 2 * FLP;
+  float* part_ot = reinterpret_cast<float*>(my + Bwd2Pair::kPart) + (1 - h) * 2 * FLP;
+  const float* brel_all = reinterpret_cast<const float*>(tab + kTabBrel);
+  if (h == 0) zero_tiles(my, 4 * kTile, lane);
+  if (h == 0 && lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&map_qkv);
+    tma_prefetch_desc(&map_do);
+    tma_prefetch_desc(&map_dqkv);
+  }
+  fence_proxy_async();
+  __syncthreads();
+  const uint32_t* pairs = reinterpret_cast<const uint32_t*>(tab + kTabPairs);
+  const uint32_t* splat = reinterpret_cast<const uint32_t*>(tab + kTabSplat);
+  const float* wq = reinterpret_cast<const float*>(tab + kTabW);
+  const float* wk = wq + FD;
+  uint32_t phase = 0;
+  const int L = p.L, G = p.G;
+  const float invL = 1.f / (float)L;
+  const long n_work = p.n_tiles * p.heads;
+  const int g8 = lane >> 2, t = lane & 3;
+  const float qscale = rsqrtf((float)FD);
+  const int mt = h;                     // phase 1: this warp's query m-tile
+  const int col0 = 32 * h;              // phase 2: this warp's output columns
+  float dwq[4][2], dbq[4][2], dwk[4][2], dbk_unused[4][2];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) { dwq[nt][0] = dwq[nt][1] = dbq[nt][0] = dbq[nt][1] = dwk[nt][0] = dwk[nt][1] = 0.f; }
+  // !PACKED: the launch guarantees gridDim * pairs % heads == 0, so a pair keeps one head; a lane's dS elements of m-tile
+  // mt fall on the diagonals  rel = 8*q + (2t + e - g),  q = nt - 2*mt - half in [-3, 3]
+  float dacc[14];
+#pragma unroll
+  for (int k = 0; k < 14; ++k) dacc[k] = 0.f;
+  float dsf_acc = 0.f;
+  const int my_head = (int)(((long)blockIdx.x * kBwd2Pairs + pair) % p.heads);
+
+  for (long wi = (long)blockIdx.x * kBwd2Pairs + pair; wi < n_work; wi += (long)gridDim.x * kBwd2Pairs) {
+    // ---- item geometry (both warps), loads + row tables (warp 0) ----
+    Item it;
+    {
+      const long tile = wi / p.heads;
+      it.head = (int)(wi - tile * p.heads);
+      it.s_out = (int)(tile / p.tiles_per_outer);
+      it.s_in0 = (int)(tile - (long)it.s_out * p.tiles_per_outer) * G;
+    }
+    if (h == 0) {
+      if (lane == 0) {
+        tma_store_wait_read<0>();          // the previous item's three stores have finished reading the tiles
+        mbar_arrive_expect_tx(bar, (uint32_t)(4 * G * L * FD * 2));
+        const int col = it.head * 3 * FD;
+        tma_load_4d(my, &map_qkv, bar, col, 0, it.s_in0, it.s_out);
+        tma_load_4d(my + kTile, &map_qkv, bar, col + FD, 0, it.s_in0, it.s_out);
+        tma_load_4d(my + 2 * kTile, &map_qkv, bar, col + 2 * FD, 0, it.s_in0, it.s_out);
+        tma_load_4d(my + 3 * kTile, &map_do, bar, it.head * FD, 0, it.s_in0, it.s_out);
+      }
+      const int g = lane / L, i = lane - g * L;
+      const bool ok = g < G && it.s_in0 + g < p.inner;
+      float2 rr = make_float2(0.f, 0.f);
+      if (ok) {
+        const long tok = (long)it.s_out * p.outer_stride + (long)(it.s_in0 + g) * p.inner_stride + (long)i * p.tok_stride;
+        rr = __ldg(reinterpret_cast<const float2*>(p.rstd + (tok * p.heads + it.head) * 2));
+      }
+      rowgp[lane] = ok ? ((g << 8) | i) : (255 << 8);
+      rstd_s[2 * lane] = rr.x; rstd_s[2 * lane + 1] = rr.y;
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+    pair_sync(pair);                                         // B1: row tables visible to warp 1
+    const int head = it.head;
+    const float* brel = brel_all + head * 64;
+    const float sf = p.scale_factor != nullptr ? __ldg(p.scale_factor + head) : 1.f;
+    const float lowc = (1.f - sf) * invL;
+
+    // ---- phase 1: rows 16*mt .. 16*mt+15 ----
+    float dp[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) { dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < FD / 16; ++ks) {
+      uint32_t a0[4];
+      frag_a(a0, sdo, mt * 16, ks * 16, lane);
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t b[4];
+        frag_b(b, sV, np * 16, ks * 16, lane);
+        mma16816(dp[2 * np], a0, b[0], b[1]);
+        mma16816(dp[2 * np + 1], a0, b[2], b[3]);
+      }
+    }
+    float acc[4][4];
+    scores16(acc, sQ, sK, pairs, mt * 16, lane);
+    softmax16<PACKED>(acc, brel, rowgp, L, mt * 16, lane);
+    pair_sync(pair);                                         // B2: both warps are done reading v
+    float dsf = 0.f;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int i = mt * 16 + g8 + half * 8;
+      const int gi = rowgp[i] >> 8;
+      float dot = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          bool valid = true;
+          if (PACKED) valid = gi != 255 && (rowgp[nt * 8 + 2 * t + e] >> 8) == gi;
+          const float pv = valid ? acc[nt][half * 2 + e] : 0.f;
+          const float d = dp[nt][half * 2 + e] * p.out_scale;
+          acc[nt][half * 2 + e] = pv;
+          dp[nt][half * 2 + e] = d;
+          if (valid) dsf = fmaf(d, pv - invL, dsf);
+          dot = fmaf(pv, d, dot);
+        }
+      }
+      dot = qsum(dot);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        float ds[2], pp[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float pv = acc[nt][half * 2 + e];
+          ds[e] = sf * pv * (dp[nt][half * 2 + e] - dot);
+          bool valid = true;
+          if (PACKED) valid = gi != 255 && (rowgp[nt * 8 + 2 * t + e] >> 8) == gi;
+          pp[e] = valid ? fmaf(pv, sf, lowc) : 0.f;
+        }
+        *reinterpret_cast<uint32_t*>(sV + swz(i, nt * 8 + 2 * t)) = pack_bf2(pp[0], pp[1]);
+        *reinterpret_cast<uint32_t*>(sV + swz(i, 32 + nt * 8 + 2 * t)) = pack_bf2(ds[0], ds[1]);
+        if (!PACKED) {
+          dacc[(nt - 2 * mt - half + 3) * 2] += ds[0];
+          dacc[(nt - 2 * mt - half + 3) * 2 + 1] += ds[1];
+        }
+      }
+    }
+    pair_sync(pair);                                         // B3: all of P' and dS is in the v tile
+    if (PACKED) {
+      if (p.d_bias_emb != nullptr) {
+        const int r = lane + 32 * h;
+        if (r < 2 * L - 1) {
+          float s = 0.f;
+          for (int gq = 0; gq < G; ++gq) {
+            for (int i = 0; i < L; ++i) {
+              const int j = i + r - (L - 1);
+              if (j >= 0 && j < L) s += __bfloat162float(*reinterpret_cast<const bf16*>(sV + swz(gq * L + i, 32 + gq * L + j)));
+            }
+          }
+          atomicAdd(s_demb + __ldg(p.bucket + r) * p.heads + head, s);
+        }
+      }
+      if (p.d_scale_factor != nullptr) {
+        dsf = warp_sum(dsf);
+        if (lane == 0) atomicAdd(s_dsf + head, dsf);
+      }
+    } else {
+      dsf_acc += dsf;
+    }
+
+    // ---- phase 2: output columns col0 .. col0+31 ----
+    float o[2][4][4];
+    // dV = P'^T dO'
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) { o[m][nt][0] = o[m][nt][1] = o[m][nt][2] = o[m][nt][3] = 0.f; }
+    }
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      uint32_t a0[4], a1[4];
+      frag_a_t(a0, sV, 0, kk * 16, lane);
+      frag_a_t(a1, sV, 16, kk * 16, lane);
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t b[4];
+        frag_b_t(b, sdo, col0 + np * 16, kk * 16, lane);
+        mma16816(o[0][2 * np], a0, b[0], b[1]);
+        mma16816(o[0][2 * np + 1], a0, b[2], b[3]);
+        mma16816(o[1][2 * np], a1, b[0], b[1]);
+        mma16816(o[1][2 * np + 1], a1, b[2], b[3]);
+      }
+    }
+    __syncwarp();                       // this warp's columns of dO are dead: they become its staging columns
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[m][nt][e] *= p.out_scale;
+      }
+      stage16h(sdo, m * 16, col0, o[m], lane);
+    }
+    fence_proxy_async();
+    pair_sync(pair);                                         // B4: dV staged by both warps
+    if (h == 0 && lane == 0) {
+      if (p.accumulate) tma_reduce_add_4d(&map_dqkv, sdo, head * 3 * FD + 2 * FD, 0, it.s_in0, it.s_out);
+      else tma_store_4d(&map_dqkv, sdo, head * 3 * FD + 2 * FD, 0, it.s_in0, it.s_out);
+      tma_store_commit();
+    }
+    // dK' = dS^T Q'  -> LayerNorm backward -> d(raw k)
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) { o[m][nt][0] = o[m][nt][1] = o[m][nt][2] = o[m][nt][3] = 0.f; }
+    }
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      uint32_t a0[4], a1[4];
+      frag_a_t(a0, sV, 32, kk * 16, lane);
+      frag_a_t(a1, sV, 32 + 16, kk * 16, lane);
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t b[4];
+        const int n0 = col0 + np * 16;
+        frag_b_t(b, sQ, n0, kk * 16, lane);                  // Q as [k = i][n = d]: both halves of a register share d
+        const uint32_t al = splat[n0 + g8], ah = splat[n0 + 8 + g8];
+        const uint32_t bl = splat[64 + n0 + g8], bh = splat[64 + n0 + 8 + g8];
+        b[0] = hfma2_bf16(b[0], al, bl); b[1] = hfma2_bf16(b[1], al, bl);
+        b[2] = hfma2_bf16(b[2], ah, bh); b[3] = hfma2_bf16(b[3], ah, bh);
+        mma16816(o[0][2 * np], a0, b[0], b[1]);
+        mma16816(o[0][2 * np + 1], a0, b[2], b[3]);
+        mma16816(o[1][2 * np], a1, b[0], b[1]);
+        mma16816(o[1][2 * np + 1], a1, b[2], b[3]);
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 2; ++m) ln_bwd_h1<false, false>(o[m], 1.f, sK, m * 16, col0, wk, dwk, dbk_unused, part_me, lane);
+    if (h == 0 && lane == 0) tma_store_wait_read<0>();       // the dV store has finished reading the staging tile
+    pair_sync(pair);                                         // B5: partial row sums exchanged, staging tile free
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      ln_bwd_h2(o[m], sK, rstd_s, 1, m * 16, col0, part_me, part_ot, lane);
+      stage16h(sdo, m * 16, col0, o[m], lane);
+    }
+    fence_proxy_async();
+    pair_sync(pair);                                         // B6: dK staged (and the partial sums consumed)
+    if (h == 0 && lane == 0) {
+      if (p.accumulate) tma_reduce_add_4d(&map_dqkv, sdo, head * 3 * FD + FD, 0, it.s_in0, it.s_out);
+      else tma_store_4d(&map_dqkv, sdo, head * 3 * FD + FD, 0, it.s_in0, it.s_out);
+      tma_store_commit();
+    }
+    // dQ' = dS K'  -> LayerNorm backward -> d(raw q), staged over the q columns this warp owns
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) { o[m][nt][0] = o[m][nt][1] = o[m][nt][2] = o[m][nt][3] = 0.f; }
+    }
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      uint32_t a0[4], a1[4];
+      frag_a(a0, sV, 0, 32 + kk * 16, lane);
+      frag_a(a1, sV, 16, 32 + kk * 16, lane);
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t b[4];
+        const int n0 = col0 + np * 16;
+        frag_b_t(b, sK, n0, kk * 16, lane);
+        const uint32_t al = splat[128 + n0 + g8], ah = splat[128 + n0 + 8 + g8];
+        const uint32_t bl = splat[192 + n0 + g8], bh = splat[192 + n0 + 8 + g8];
+        b[0] = hfma2_bf16(b[0], al, bl); b[1] = hfma2_bf16(b[1], al, bl);
+        b[2] = hfma2_bf16(b[2], ah, bh); b[3] = hfma2_bf16(b[3], ah, bh);
+        mma16816(o[0][2 * np], a0, b[0], b[1]);
+        mma16816(o[0][2 * np + 1], a0, b[2], b[3]);
+        mma16816(o[1][2 * np], a1, b[0], b[1]);
+        mma16816(o[1][2 * np + 1], a1, b[2], b[3]);
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 2; ++m) ln_bwd_h1<true, true>(o[m], qscale, sQ, m * 16, col0, wq, dwq, dbq, part_me, lane);
+    pair_sync(pair);                                         // B7: partial row sums exchanged
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      ln_bwd_h2(o[m], sQ, rstd_s, 0, m * 16, col0, part_me, part_ot, lane);
+      __syncwarp();                     // all lanes have read the xhat values of these rows / columns
+      stage16h(sQ, m * 16, col0, o[m], lane);
+    }
+    fence_proxy_async();
+    pair_sync(pair);                                         // B8: dQ staged; row tables / partials free for the next item
+    if (h == 0 && lane == 0) {
+      if (p.accumulate) tma_reduce_add_4d(&map_dqkv, sQ, head * 3 * FD, 0, it.s_in0, it.s_out);
+      else tma_store_4d(&map_dqkv, sQ, head * 3 * FD, 0, it.s_in0, it.s_out);
+      tma_store_commit();
+    }
+  }
+  if (h == 0 && lane == 0) tma_store_wait_all();
+  if (!PACKED) {
+    if (p.d_bias_emb != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 14; ++k) {
+        const int rel = 8 * ((k >> 1) - 3) + 2 * t + (k & 1) - g8;
+        if (rel > -FLP && rel < FLP) atomicAdd(s_demb + __ldg(p.bucket + rel + FLP - 1) * p.heads + my_head, dacc[k]);
+      }
+    }
+    if (p.d_scale_factor != nullptr) {
+      dsf_acc = warp_sum(dsf_acc);
+      if (lane == 0) atomicAdd(s_dsf + my_head, dsf_acc);
+    }
+  }
+  // LayerNorm parameter gradients: lanes with equal t hold partial sums of the same columns
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      float a = dwq[nt][e], b = dbq[nt][e], c = dwk[nt][e];
+#pragma unroll
+      for (int o2 = 4; o2 < 32; o2 <<= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o2);
+        b += __shfl_xor_sync(0xffffffffu, b, o2);
+        c += __shfl_xor_sync(0xffffffffu, c, o2);
+      }
+      if (g8 == 0) {
+        atomicAdd(s_dqw + col0 + nt * 8 + 2 * t + e, a);
+        atomicAdd(s_dqb + col0 + nt * 8 + 2 * t + e, b);
+        atomicAdd(s_dkw + col0 + nt * 8 + 2 * t + e, c);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < FD; i += blockDim.x) {
+    atomicAdd(p.d_qn_w + i, s_dqw[i]);
+    atomicAdd(p.d_qn_b + i, s_dqb[i]);
+    atomicAdd(p.d_kn_w + i, s_dkw[i]);
+  }
+  if (p.d_bias_emb != nullptr)
+    for (int i = threadIdx.x; i < 32 * p.heads; i += blockDim.x) atomicAdd(p.d_bias_emb + i, s_demb[i]);
+  if (p.d_scale_factor != nullptr)
+    for (int i = threadIdx.x; i < p.heads; i += blockDim.x) atomicAdd(p.d_scale_factor + i, s_dsf[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
 // host launch
 // ---------------------------------------------------------------------------------------------
 // 4-D view (column, position, sequence, outer) of a token-major (tokens, width) bf16 matrix; box = 64 x L x G x 1
@@ -781,6 +1221,36 @@ int launch_attn_fast(const bf_attn_args* a, bool bwd, cudaStream_t st) {
     if (int e = make_seq_map(&m_c, a->out, a->ld_out, E3, a, p.G)) return e;
   } else {
     if (int e = make_seq_map(&m_b, a->out, a->ld_out, E3 / 3, a, p.G)) return e;
+  }
+  // backward: BF_ATTN_BWD2=1 selects the two-warps-per-item kernel (attn_fast_bwd2_kernel).  Measured on B200 (round 2,
+  // same-box A/B of the replayed step): 29.36 vs 29.24 ms per step, 105 vs 104 us per L = 32 launch -- doubling the
+  // resident warps and halving each warp's dependent chain buys nothing, i.e. the kernel is bound by its instruction
+  // count, not by latency; the one-warp kernel stays the default.
+  static int bwd2_on = -1;
+  if (bwd2_on < 0) { const char* e = getenv("BF_ATTN_BWD2"); bwd2_on = (e != nullptr && e[0] == '1') ? 1 : 0; }
+  if (bwd && bwd2_on && p.d_qkv_bias == nullptr) {
+    const size_t smem2 = 1024 + (size_t)kBwd2Pairs * Bwd2Pair::kBytes + tab_bytes(p.heads) +
+                         (size_t)(3 * FD + 33 * p.heads) * sizeof(float);
+    BF_REQUIRE(smem2 <= 227 * 1024, "bf_attention (prenorm): shared memory %zu too large (heads=%d)", smem2, p.heads);
+    static bool attr2[2] = {false, false};
+    if (!attr2[packed]) {
+      cudaError_t e = packed ? cudaFuncSetAttribute(attn_fast_bwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                             : cudaFuncSetAttribute(attn_fast_bwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (int st_ = check_cuda(e, "cudaFuncSetAttribute(attention fast bwd2)")) return st_;
+      attr2[packed] = true;
+    }
+    const long n_work2 = p.n_tiles * p.heads;
+    long blocks2 = (n_work2 + kBwd2Pairs - 1) / kBwd2Pairs;
+    if (blocks2 > num_sms()) blocks2 = num_sms();
+    if (!packed) {
+      while (blocks2 > 1 && (blocks2 * kBwd2Pairs) % p.heads != 0) --blocks2;
+      BF_REQUIRE((blocks2 * kBwd2Pairs) % p.heads == 0, "bf_attention_bwd (prenorm): heads=%d does not divide %d warp pairs",
+                 p.heads, kBwd2Pairs);
+    }
+    if (packed) launch_k(attn_fast_bwd2_kernel<true>, dim3((unsigned)blocks2), dim3(kBwd2Pairs * 64), smem2, st, m_qkv, m_b, m_c, p);
+    else launch_k(attn_fast_bwd2_kernel<false>, dim3((unsigned)blocks2), dim3(kBwd2Pairs * 64), smem2, st, m_qkv, m_b, m_c, p);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "attn_fast_bwd2_kernel launch");
   }
   const int warps = bwd ? kBwdWarps : kFwdWarps;
   const size_t smem = 1024 + (size_t)warps * (bwd ? BwdWarp::kBytes : FwdWarp::kBytes) + tab_bytes(p.heads) +

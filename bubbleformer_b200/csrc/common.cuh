@@ -149,6 +149,22 @@ __device__ __forceinline__ float gelu_tanh_grad(float x) {
 __device__ __forceinline__ float gelu_fwd(float x, int exact) { return exact ? gelu_erf(x) : gelu_tanh(x); }
 __device__ __forceinline__ float gelu_bwd(float x, int exact) { return exact ? gelu_erf_grad(x) : gelu_tanh_grad(x); }
 
+// value and derivative together (the tanh / erf is shared): the forward of the MLP stores gelu'(pre) for its backward
+__device__ __forceinline__ void gelu_both(float x, int exact, float& g, float& d) {
+  if (exact) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+    const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
+    g = x * cdf;
+    d = fmaf(x, pdf, cdf);
+  } else {
+    const float x2 = x * x;
+    const float th = tanh_approx(x * fmaf(0.0356774081f, x2, 0.7978845608f));
+    const float hx = 0.5f * x;
+    g = fmaf(hx, th, hx);
+    d = fmaf(hx * fmaf(0.1070322243f, x2, 0.7978845608f), fmaf(-th, th, 1.0f), fmaf(0.5f, th, 0.5f));
+  }
+}
+
 // 16-bit storage type helpers: T16 is __nv_bfloat16 (blocks) or __half (stem/head)
 template <typename T> struct T16x2;
 template <> struct T16x2<__nv_bfloat16> { using type = __nv_bfloat162; };

@@ -81,8 +81,17 @@ __device__ __forceinline__ void ex_epilogue(const ExGemm& g, int m, int n, float
       }
       break;
     }
-    case BF_EPI_DGELU: {
-      const float v = acc * gelu_bwd(g.aux[(long)m * g.ldo + n], g.gelu_exact);
+    case BF_EPI_GELU_D: {
+      float gv, dv;
+      gelu_both(acc + b, g.gelu_exact, gv, dv);
+      if (g.out_b != nullptr) g.out_b[(long)m * g.ldo + n] = dv;
+      g.out_a[(long)m * g.ldo + n] = gv;
+      break;
+    }
+    case BF_EPI_DGELU:
+    case BF_EPI_DMUL: {
+      const float aux = g.aux[(long)m * g.ldo + n];
+      const float v = acc * (g.epilogue == BF_EPI_DMUL ? aux : gelu_bwd(aux, g.gelu_exact));
       g.out_a[(long)m * g.ldo + n] = v;
       if (g.colsum_out != nullptr) atomicAdd(g.colsum_out + n, v);
       break;
@@ -162,8 +171,9 @@ int launch_gemm_f32(const bf_gemm_args* a, cudaStream_t st) {
     BF_REQUIRE(a->s2d_cin > 0 && a->s2d_hin % 2 == 0 && a->s2d_win % 2 == 0 && a->K == 4 * a->s2d_cin, "bf_gemm (fp32): S2D geometry");
   }
   switch (a->epilogue) {
-    case BF_EPI_STORE16: case BF_EPI_GELU: case BF_EPI_D2S: BF_REQUIRE(a->out16, "bf_gemm (fp32): out16 required"); break;
-    case BF_EPI_DGELU: BF_REQUIRE(a->out16 && a->aux16, "bf_gemm (fp32): DGELU needs out16/aux16"); break;
+    case BF_EPI_STORE16: case BF_EPI_GELU: case BF_EPI_GELU_D: case BF_EPI_D2S:
+      BF_REQUIRE(a->out16, "bf_gemm (fp32): out16 required"); break;
+    case BF_EPI_DGELU: case BF_EPI_DMUL: BF_REQUIRE(a->out16 && a->aux16, "bf_gemm (fp32): DGELU / DMUL need out16/aux16"); break;
     case BF_EPI_RESID: BF_REQUIRE(a->out32 && a->in32 && a->col_gamma, "bf_gemm (fp32): RESID operands"); break;
     case BF_EPI_ACC32: BF_REQUIRE(a->out32 && a->in32, "bf_gemm (fp32): ACC32 operands"); break;
     case BF_EPI_STORE32: case BF_EPI_ATOMIC32: BF_REQUIRE(a->out32, "bf_gemm (fp32): out32 required"); break;

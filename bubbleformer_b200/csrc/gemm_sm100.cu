@@ -380,6 +380,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       if (p.has_out16) tma_prefetch_desc(&map_o16);
       if (p.has_out16b) tma_prefetch_desc(&map_o16b);
       if (p.epilogue != BF_EPI_STORE16 && p.epilogue != BF_EPI_GELU && p.epilogue != BF_EPI_DGELU &&
+          p.epilogue != BF_EPI_GELU_D && p.epilogue != BF_EPI_DMUL &&
           p.epilogue != BF_EPI_D2S && p.epilogue != BF_EPI_QKV_LN)
         tma_prefetch_desc(&map_o32);
     }
@@ -579,16 +580,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             sb ^= 1;
             break;
           }
-          case BF_EPI_GELU: {
+          case BF_EPI_GELU:
+          case BF_EPI_GELU_D: {
             uint8_t* s = slab + (kDouble ? sb * 2048 : 0);
             uint8_t* s2 = slab + (kDouble ? 4096 + sb * 2048 : 2048);
             if (lane == 0) { if (kDouble) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
             __syncwarp();
-            if (p.has_out16b) {
-              if (p.is_f16) st_row_16<__half>(s2, lane, acc); else st_row_16<__nv_bfloat16>(s2, lane, acc);
-            }
+            if (p.epilogue == BF_EPI_GELU_D) {
+              // second output = gelu'(pre): the backward then needs no transcendental (and no second tanh at all)
+              float d[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = gelu_fwd(acc[j], p.gelu_exact);
+              for (int j = 0; j < 32; ++j) gelu_both(acc[j], p.gelu_exact, acc[j], d[j]);
+              if (p.has_out16b) {
+                if (p.is_f16) st_row_16<__half>(s2, lane, d); else st_row_16<__nv_bfloat16>(s2, lane, d);
+              }
+            } else {
+              if (p.has_out16b) {
+                if (p.is_f16) st_row_16<__half>(s2, lane, acc); else st_row_16<__nv_bfloat16>(s2, lane, acc);
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[j] = gelu_fwd(acc[j], p.gelu_exact);
+            }
             if (p.is_f16) st_row_16<__half>(s, lane, acc); else st_row_16<__nv_bfloat16>(s, lane, acc);
             fence_proxy_async();
             __syncwarp();
@@ -616,12 +628,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             sb ^= 1;
             break;
           }
-          case BF_EPI_DGELU: {
+          case BF_EPI_DGELU:
+          case BF_EPI_DMUL: {
             uint8_t* box = in_tile + c * (BM * 64);
             float pre[32];
             if (p.is_f16) ld_row_16<__half>(box, row, pre); else ld_row_16<__nv_bfloat16>(box, row, pre);
+            if (p.epilogue == BF_EPI_DMUL) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] *= gelu_bwd(pre[j], p.gelu_exact);
+              for (int j = 0; j < 32; ++j) acc[j] *= pre[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[j] *= gelu_bwd(pre[j], p.gelu_exact);
+            }
             if (p.is_f16) st_row_16<__half>(box, row, acc); else st_row_16<__nv_bfloat16>(box, row, acc);
             fence_proxy_async();
             __syncwarp();
@@ -852,7 +870,8 @@ static int launch(const Maps& mp, GemmParams& p, cudaStream_t st) {
   const int b_res_bytes = p.b_resident ? p.k_iters * BN * BK * 2 : 0;
   const int stage_bytes = p.b_resident ? BM * BK * 2 : BM * BK * 2 + (BN / CG) * BK * 2;
   const int bar_bytes = (2 * kMaxStages + 9) * 8 + 16;
-  const bool slabs = !(p.epilogue == BF_EPI_DGELU || p.epilogue == BF_EPI_ACC32 || p.epilogue == BF_EPI_D2S);
+  const bool slabs = !(p.epilogue == BF_EPI_DGELU || p.epilogue == BF_EPI_DMUL || p.epilogue == BF_EPI_ACC32 ||
+                       p.epilogue == BF_EPI_D2S);
   const int slab_bytes = slabs ? epi_warps(BN) * slab_bytes_per_warp(BN)
                                : (p.colsum_out != nullptr ? ((p.num_n_blocks * BN * 4 + 1023) / 1024) * 1024 : 0);
   p.in_bytes = p.in_kind == 0 ? 0 : BM * BN * (p.in_kind == 2 ? 4 : 2);
@@ -883,6 +902,11 @@ static int launch(const Maps& mp, GemmParams& p, cudaStream_t st) {
   const int tiles = p.num_m_blocks * p.num_n_blocks * p.split_k;
   int grid = tiles < num_sms() / CG ? tiles * CG : (num_sms() / CG) * CG;   // tiles are per CTA pair when CG = 2
   if (p.b_resident) grid = (num_sms() / p.num_n_blocks) * p.num_n_blocks;   // a CTA keeps one n block for all its tiles
+  {
+    static int gcap = -1;                      // BF_GEMM_GRID=n caps the persistent grid (measurements)
+    if (gcap < 0) { const char* e = getenv("BF_GEMM_GRID"); gcap = e ? atoi(e) : 0; }
+    if (gcap >= CG && grid > gcap) grid = (gcap / CG) * CG;
+  }
   cudaError_t le;
   if constexpr (CG == 2)
     le = launch_k_cluster(kern, dim3(grid), dim3(gemm_threads(BN)), (size_t)total, st, 2u, mp.a, mp.b, mp.in, mp.o16,
@@ -911,7 +935,8 @@ static int resident_bn(const bf_gemm_args& a) {
   if (!resident_enabled() || a.bn != 0) return 0;
   if (a.a_mode != BF_A_ROWMAJOR || a.split_k != 1 || a.K > 6 * BK) return 0;
   const int e = a.epilogue;
-  if (!(e == BF_EPI_STORE16 || e == BF_EPI_GELU || e == BF_EPI_DGELU || e == BF_EPI_RESID || e == BF_EPI_QKV_LN)) return 0;
+  if (!(e == BF_EPI_STORE16 || e == BF_EPI_GELU || e == BF_EPI_GELU_D || e == BF_EPI_DGELU || e == BF_EPI_DMUL ||
+        e == BF_EPI_RESID || e == BF_EPI_QKV_LN)) return 0;
   const int bn = e == BF_EPI_RESID ? 64 : 128;
   if (a.N % bn != 0) return 0;
   const int nnb = a.N / bn, mb = (a.M + BM - 1) / BM;
@@ -940,11 +965,15 @@ static int pick_bn(const bf_gemm_args& a) {
   return best;
 }
 
-// CTA pairs (cta_group::2) for the big row-major GEMMs: BF_GEMM_CG=1 forces the single-CTA kernel, BF_GEMM_CG=2 is the
-// default (pairs wherever the kernel supports the operand layout and the problem has enough row blocks).
+// CTA pairs (cta_group::2) for the big row-major GEMMs are OPT-IN (BF_GEMM_CG=2).  Measured on B200 (round 2,
+// profiles/r2e_gemm_sweep.txt, r2d_gemm_cg{1,2}.csv, same-box A/B of the replayed step): pairs change nothing -- 42.6 vs
+// 49.7 us on the QKV shape, 51.8 vs 52.8 us on fc2, 55.6 vs 54.3 us on fc1, 29.21 vs 29.11 ms per step -- and the L2
+// traffic ncu reports (lts__t_bytes) does not drop either: the peer CTA's half of B reaches the tensor core over the same
+// SM ingress fabric as a TMA load, so the ~112 GB/s per SM (10-12 TB/s per chip) that bounds this kernel's operand feed at
+// 77 FLOP per byte is spent either way.  The residual-epilogue tiles (BN = 128) were ~10 % slower as pairs.
 static int cg_mode() {
   static int m = -1;
-  if (m < 0) { const char* e = getenv("BF_GEMM_CG"); m = (e != nullptr && e[0] == '1') ? 1 : 2; }
+  if (m < 0) { const char* e = getenv("BF_GEMM_CG"); m = (e != nullptr && e[0] == '2') ? 2 : 1; }
   return m;
 }
 static int pick_cg(const bf_gemm_args& a, int bn, int resident) {
@@ -995,13 +1024,14 @@ extern "C" int bf_gemm(const bf_gemm_args* a, void* stream) {
   p.stats_out = a->stats_out;
   p.ln_rstd = a->ln_rstd;
   p.colsum_out = a->colsum_out;
-  BF_REQUIRE(a->colsum_out == nullptr || a->epilogue == BF_EPI_DGELU, "bf_gemm: colsum_out only with BF_EPI_DGELU");
+  BF_REQUIRE(a->colsum_out == nullptr || a->epilogue == BF_EPI_DGELU || a->epilogue == BF_EPI_DMUL,
+             "bf_gemm: colsum_out only with BF_EPI_DGELU / BF_EPI_DMUL");
   for (const float* v : {a->bias, a->col_scale, a->col_shift, a->col_gamma})
     BF_REQUIRE((reinterpret_cast<uintptr_t>(v) & 15) == 0, "bf_gemm: per-column vectors must be 16-byte aligned");
 
   // epilogue operand checks
   switch (a->epilogue) {
-    case BF_EPI_STORE16: case BF_EPI_GELU: BF_REQUIRE(a->out16, "bf_gemm: out16 required"); break;
+    case BF_EPI_STORE16: case BF_EPI_GELU: case BF_EPI_GELU_D: BF_REQUIRE(a->out16, "bf_gemm: out16 required"); break;
     case BF_EPI_QKV_LN:
       BF_REQUIRE(a->out16 && a->ln_rstd, "bf_gemm: QKV_LN needs out16 and ln_rstd");
       BF_REQUIRE(a->ln_head_dim == 64 && a->N % 192 == 0,
@@ -1016,7 +1046,7 @@ extern "C" int bf_gemm(const bf_gemm_args* a, void* stream) {
       BF_REQUIRE(a->stats_out == nullptr || (a->rows_per_group % 32 == 0),
                  "bf_gemm: stats_out needs rows_per_group to be a multiple of 32");
       break;
-    case BF_EPI_DGELU: BF_REQUIRE(a->out16 && a->aux16, "bf_gemm: DGELU needs out16/aux16"); break;
+    case BF_EPI_DGELU: case BF_EPI_DMUL: BF_REQUIRE(a->out16 && a->aux16, "bf_gemm: DGELU / DMUL need out16/aux16"); break;
     case BF_EPI_ACC32: BF_REQUIRE(a->out32 && a->in32, "bf_gemm: ACC32 needs in32/out32"); break;
     case BF_EPI_D2S:
       BF_REQUIRE(a->out16 && a->d2s_h > 0 && a->d2s_w > 0 && a->d2s_cout > 0, "bf_gemm: D2S geometry");
@@ -1108,7 +1138,7 @@ extern "C" int bf_gemm(const bf_gemm_args* a, void* stream) {
   // epilogue tensor maps (unused ones alias the A map: never dereferenced)
   mp.in = mp.a; mp.o16 = mp.a; mp.o16b = mp.a; mp.o32 = mp.a;
   const int e = a->epilogue;
-  if (e == BF_EPI_DGELU) {
+  if (e == BF_EPI_DGELU || e == BF_EPI_DMUL) {
     p.in_kind = 1;
     if ((st = make_epi_map(&mp.in, a->dtype, a->aux16, a->M, a->N, a->ldo, BM))) return st;
   } else if (e == BF_EPI_ACC32 || e == BF_EPI_RESID) {
@@ -1119,7 +1149,7 @@ extern "C" int bf_gemm(const bf_gemm_args* a, void* stream) {
     p.has_out16 = 1;
     if ((st = make_epi_map(&mp.o16, a->dtype, a->out16, a->M, a->N, a->ldo, 32))) return st;
   }
-  if ((e == BF_EPI_GELU || e == BF_EPI_RESID) && a->out16b) {
+  if ((e == BF_EPI_GELU || e == BF_EPI_GELU_D || e == BF_EPI_RESID) && a->out16b) {
     p.has_out16b = 1;
     if ((st = make_epi_map(&mp.o16b, a->dtype, a->out16b, a->M, a->N, a->ldo, 32))) return st;
   }

@@ -28,6 +28,9 @@ from . import ops
 
 F32, BF16, F16 = torch.float32, torch.bfloat16, torch.float16
 EXACT = False
+# A/B switches for same-box measurements (scripts/gpu/ab_env.sh); the defaults are the measured-faster forms
+import os as _os
+MLP_SAVES_DERIVATIVE = _os.environ.get("BF_MLP_DERIV", "1") != "0"     # fc1 stores gelu'(pre); 0: stores pre, dGELU epilogue
 
 
 def set_exact_mode(on: bool) -> None:
@@ -329,7 +332,9 @@ def spatial_forward(X, g: Geom, p, w16, heads: int, attn_scale: bool, feat_scale
         sv["feat"] = (c, c1, c0)
     G = _empty((N, 4 * E), BF16, X)
     Hpre = _empty((N, 4 * E), BF16, X) if save else None
-    ops.gemm(Xb, w16("mlp.fc1.weight"), N, 4 * E, E, epilogue=L.EPI_GELU, bias=p["mlp.fc1.bias"], out16=G, out16b=Hpre)
+    # the second output is gelu'(pre), not pre: the tanh is evaluated once and the backward epilogue is a multiply
+    ops.gemm(Xb, w16("mlp.fc1.weight"), N, 4 * E, E, epilogue=L.EPI_GELU_D if MLP_SAVES_DERIVATIVE else L.EPI_GELU,
+             bias=p["mlp.fc1.bias"], out16=G, out16b=Hpre)
     Y2 = _empty((N, E), BF16, X)
     st3 = _zeros((I, E, 2), X)
     if P % 32 == 0:      # the fc2 epilogue accumulates the statistics of what it stores
@@ -362,7 +367,8 @@ def spatial_backward(dXout, g: Geom, p, w16, heads: int, attn_scale: bool, feat_
                   dbias=grads["mlp_norm.bias"], dcol_scale=grads["gamma_mlp"])
     # fc2 (its bias feeds an InstanceNorm, so its gradient is identically zero and stays zero)
     dH = _empty((N, 4 * E), BF16, dXout)
-    ops.gemm(dY2, w16("mlp.fc2.weight"), N, 4 * E, E, epilogue=L.EPI_DGELU, b_mode=L.B_KN, aux16=Hpre, out16=dH,
+    ops.gemm(dY2, w16("mlp.fc2.weight"), N, 4 * E, E, epilogue=L.EPI_DMUL if MLP_SAVES_DERIVATIVE else L.EPI_DGELU,
+             b_mode=L.B_KN, aux16=Hpre, out16=dH,
              colsum_out=grads["mlp.fc1.bias"])
     ops.gemm(dY2, G, E, 4 * E, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
              split_k=pick_split(N, E, 4 * E), out32=grads["mlp.fc2.weight"])

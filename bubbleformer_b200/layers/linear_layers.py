@@ -26,7 +26,7 @@ class _GeluMLPFn(torch.autograd.Function):
         G = torch.empty(N, Hd, dtype=torch.bfloat16, device=x.device)
         need = any(ctx.needs_input_grad)
         Hpre = torch.empty(N, Hd, dtype=torch.bfloat16, device=x.device) if need else None
-        ops.gemm(xb, w1, N, Hd, E, epilogue=L.EPI_GELU, bias=b1.detach(), out16=G, out16b=Hpre)
+        ops.gemm(xb, w1, N, Hd, E, epilogue=L.EPI_GELU_D, bias=b1.detach(), out16=G, out16b=Hpre)
         out = torch.empty(N, E, dtype=torch.float32, device=x.device)
         ops.gemm(G, w2, N, E, Hd, epilogue=L.EPI_STORE32, bias=b2.detach(), out32=out)
         if need:
@@ -47,7 +47,7 @@ class _GeluMLPFn(torch.autograd.Function):
         dW2 = torch.zeros(E, Hd, dtype=torch.float32, device=dev)
         db2 = torch.zeros(E, dtype=torch.float32, device=dev)
         dH = torch.empty(N, Hd, dtype=torch.bfloat16, device=dev)
-        ops.gemm(dY16, w2, N, Hd, E, epilogue=L.EPI_DGELU, b_mode=L.B_KN, aux16=Hpre, out16=dH, colsum_out=db1)
+        ops.gemm(dY16, w2, N, Hd, E, epilogue=L.EPI_DMUL, b_mode=L.B_KN, aux16=Hpre, out16=dH, colsum_out=db1)
         ops.gemm(dY16, G, E, Hd, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
                  split_k=ctx.pick_split(N, E, Hd), out32=dW2)
         ops.colsum16(dY16, db2)

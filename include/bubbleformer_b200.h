@@ -90,6 +90,9 @@ enum bf_epilogue {
   BF_EPI_D2S = 6,     /* out16 scattered depth-to-space: m = (img, y, x), n = (ky, kx, co) ->
                          out16[((img*2h + 2y+ky)*2w + 2x+kx)*cout + co]  (ConvTranspose2d k2 s2)        */
   BF_EPI_STORE32 = 7, /* out32 = acc + bias                                                            */
+  BF_EPI_GELU_D = 9,  /* pre = acc + bias; out16 = gelu(pre); out16b = gelu'(pre): the forward of fc1 as the training path
+                         runs it -- the tanh / erf is evaluated once and the backward (BF_EPI_DMUL) is a multiply     */
+  BF_EPI_DMUL = 10,   /* out16 = acc * aux16  (aux16 = gelu'(pre) saved by BF_EPI_GELU_D); colsum_out like BF_EPI_DGELU */
   BF_EPI_QKV_LN = 8   /* QKV projection with the per-head LayerNorm of q and k (upstream layers/attention.py:82,
                          214) fused in: columns are head*3d + [q | k | v], d = ln_head_dim = 64.  out16 receives
                          xhat_q = (q - mean)*rstd, xhat_k (no affine part: bf_attention applies it) and v;
@@ -131,7 +134,7 @@ typedef struct bf_gemm_args {
                              the tensor, so the norm that follows needs no separate pass (rows_per_group = tokens per
                              image, multiple of 32)                                                             */
   float* ln_rstd;         /* BF_EPI_QKV_LN only: (M, N / (3*ln_head_dim), 2) fp32                                */
-  float* colsum_out;      /* BF_EPI_DGELU only, may be NULL: [N] += column sums of out16 (gradient of the fc1 bias) */
+  float* colsum_out;      /* BF_EPI_DGELU / BF_EPI_DMUL only, may be NULL: [N] += column sums of out16 (gradient of the fc1 bias) */
 } bf_gemm_args;
 
 BF_API int bf_gemm(const bf_gemm_args* args, void* stream);

@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 
 VARIANTS = [
     "nk_small", "nk_ragged", "nk_bn64", "nk_bn128", "nk_bn192", "nk_bn256", "nk_big", "nk_pair_ragged", "nk_pair_odd",
-    "nk_f16", "gelu", "resid", "resid_stats", "qkv_ln", "dgelu", "acc32", "store32",
+    "nk_f16", "gelu", "gelu_d", "dmul", "gelu_d_big", "dmul_big", "resid", "resid_stats", "qkv_ln", "dgelu", "acc32", "store32",
     "gelu_big", "resid_big", "resid_stats_big", "dgelu_big", "kn_dgrad_res",        # config-2 shapes: the B-resident schedule
     "kn_dgrad", "kn_dgrad_256", "wgrad", "wgrad_split", "wgrad_192",
     "s2d_w128", "s2d_w32", "s2d_c48", "d2s", "d2s_c48", "perf",
@@ -54,10 +54,10 @@ def run_variant(v):
         return (torch.randn(*s, device=dev) * scale).to(dt)
 
     ok = True
-    big = v in ("gelu_big", "resid_big", "resid_stats_big", "dgelu_big")
+    big = v in ("gelu_big", "resid_big", "resid_stats_big", "dgelu_big", "gelu_d_big", "dmul_big")
     if big:
         v = v[:-4]
-    if v.startswith("nk_") or v in ("gelu", "resid", "dgelu", "acc32", "store32"):
+    if v.startswith("nk_") or v in ("gelu", "gelu_d", "dmul", "resid", "dgelu", "acc32", "store32"):
         shapes = {"nk_small": (128, 128, 64), "nk_ragged": (300, 200, 104), "nk_bn64": (256, 64, 128),
                   "nk_bn128": (4096, 384, 384), "nk_bn192": (4096, 1152, 384), "nk_bn256": (4096, 1536, 384),
                   "nk_big": (40960, 1152, 384), "nk_f16": (1024, 96, 384),
@@ -89,6 +89,25 @@ def run_variant(v):
             ops.gemm(A, B, M, N, K, epilogue=L.EPI_GELU, bias=bias, out16=out, out16b=pre)
             ok &= report(v + ".pre", pre, ref, 1e-2)
             ok &= report(v + ".act", out, torch.nn.functional.gelu(ref), 1e-2)
+        elif v == "gelu_d":
+            out = torch.zeros(M, N, device=dev, dtype=dt)
+            der = torch.zeros(M, N, device=dev, dtype=dt)
+            ops.gemm(A, B, M, N, K, epilogue=L.EPI_GELU_D, bias=bias, out16=out, out16b=der)
+            r32 = ref.clone().requires_grad_(True)
+            g = torch.nn.functional.gelu(r32)
+            g.sum().backward()
+            ok &= report(v + ".act", out, g.detach(), 1e-2)
+            ok &= report(v + ".der", der, r32.grad, 1e-2)
+        elif v == "dmul":
+            aux = rnd(M, N)
+            out = torch.zeros(M, N, device=dev, dtype=dt)
+            cs = torch.zeros(N, device=dev)
+            if big:
+                ops.gemm(A, B.t().contiguous(), M, N, K, epilogue=L.EPI_DMUL, b_mode=L.B_KN, aux16=aux, out16=out, colsum_out=cs)
+            else:
+                ops.gemm(A, B, M, N, K, epilogue=L.EPI_DMUL, aux16=aux, out16=out, colsum_out=cs)
+            ok &= report(v + ".colsum", cs[None], out.float().sum(0)[None], 2e-3)
+            ok &= report(v, out, (A.float() @ B.float().t()) * aux.float(), 1e-2)
         elif v == "resid":
             xin = torch.randn(M, N, device=dev)
             cs, ch, cg = torch.randn(N, device=dev), torch.randn(N, device=dev), torch.randn(N, device=dev)

@@ -56,6 +56,14 @@ def gemm(A, B, M, N, K, *, epilogue, a_mode=L.A_ROWMAJOR, b_mode=L.B_NK, split_k
         if out16b is not None:
             out16b.reshape(M, N).copy_(acc)
         out16.reshape(M, N).copy_(F.gelu(acc))
+    elif epilogue == L.EPI_GELU_D:
+        if out16b is not None:
+            out16b.reshape(M, N).copy_(_gelu_grad(acc))
+        out16.reshape(M, N).copy_(F.gelu(acc))
+    elif epilogue == L.EPI_DMUL:
+        out16.reshape(M, N).copy_(acc * aux16.reshape(M, N).float())
+        if colsum_out is not None:
+            colsum_out.add_(out16.reshape(M, N).float().sum(0))
     elif epilogue == L.EPI_RESID:
         if out16b is not None:
             out16b.reshape(M, N).copy_(acc)
