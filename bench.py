@@ -156,6 +156,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)     # torchrun exports 1; this arm runs on rank 0 alone
     steps = max(1, min(args.steps, 12))      # bounded sample: a B=1 micro-batch takes ~2 s on 16 host cores
     warm = max(1, min(args.warmup, 2))
     r = time_cpu_port(steps, warm, train=args.workload == "train")
@@ -368,6 +369,9 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # torchrun exports OMP_NUM_THREADS=1; the host-side legs (parity oracle, CPU baseline) want the box's cores
+    _world = int(os.environ.get("WORLD_SIZE", "1"))
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // _world))
     import torch
     import torch.distributed as dist
     from bubbleformer_b200 import _lib, ops
