@@ -157,7 +157,7 @@ lib.bf_feat_consts.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]
 lib.bf_branch_param_grads.argtypes = [C.POINTER(BranchGradArgs), _vp]
 lib.bf_set_gelu_mode.argtypes = [_i]
 lib.bf_film_fwd.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]
-lib.bf_film_bwd.argtypes = [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]
+lib.bf_film_bwd.argtypes = [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]
 lib.bf_colsum16.argtypes = [_vp, _i, _i64, _i, _i64, _vp, _vp]
 lib.bf_attention_fwd.argtypes = [C.POINTER(AttnArgs), _vp]
 lib.bf_attention_bwd.argtypes = [C.POINTER(AttnArgs), _vp]

@@ -123,50 +123,66 @@ film_fwd_kernel(const float* __restrict__ cond, int F, const float* __restrict__
   }
 }
 
-// one block: d_W[j,f] += sum_b dgb[b,j] c[b,f];  d_bias[j] += sum_b dgb[b,j];  dc[b,f] = sum_j dgb[b,j] W[j,f];
-// LayerNorm backward over F for the affine parameters:  d_lw[f] += sum_b dc*xhat,  d_lb[f] += sum_b dc.
-__global__ void __launch_bounds__(256)
-film_bwd_kernel(const float* __restrict__ dgb, const float* __restrict__ cond, int B, int F,
-                const float* __restrict__ lw, const float* __restrict__ lb, const float* __restrict__ W, int E2,
-                float* __restrict__ d_lw, float* __restrict__ d_lb, float* __restrict__ d_W, float* __restrict__ d_bias) {
+// backward, two tiny launches:
+//  (1) one thread per output j (grid over j): d_W[j,f] += sum_b dgb[b,j] c[b,f], d_bias[j] += sum_b dgb[b,j], and the
+//      block's share of dc[b,f] = sum_j dgb[b,j] W[j,f] reduced through shuffles, one atomic per (b, f) per block
+//  (2) LayerNorm backward over F for the affine parameters: d_lw[f] += sum_b dc*xhat, d_lb[f] += sum_b dc
+__global__ void __launch_bounds__(128)
+film_bwd_w_kernel(const float* __restrict__ dgb, const float* __restrict__ cond, int B, int F,
+                  const float* __restrict__ lw, const float* __restrict__ lb, const float* __restrict__ W, int E2,
+                  float* __restrict__ d_W, float* __restrict__ d_bias, float* __restrict__ dc) {
   pdl_prologue_done();
-  extern __shared__ float sm[];            // c[B][F], xhat[B][F], dc[B][F]
+  extern __shared__ float sm[];            // c[B][F], xhat scratch [F]
   float* s_c = sm;
-  float* s_x = s_c + B * F;
-  float* s_dc = s_x + B * F;
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    float xh[kFilmMaxF];
     float rstd;
-    film_ln_row(cond + (long)b * F, F, lw, lb, s_x + b * F, s_c + b * F, rstd);
+    film_ln_row(cond + (long)b * F, F, lw, lb, xh, s_c + b * F, rstd);
   }
-  for (int i = threadIdx.x; i < B * F; i += blockDim.x) s_dc[i] = 0.f;
   __syncthreads();
-  for (int j = threadIdx.x; j < E2; j += blockDim.x) {
-    float dw[kFilmMaxF];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = j < E2;
+  float w[kFilmMaxF], dw[kFilmMaxF];
 #pragma unroll
-    for (int f = 0; f < kFilmMaxF; ++f) dw[f] = 0.f;
-    float db = 0.f;
-    for (int b = 0; b < B; ++b) {
-      const float g = dgb[(long)b * E2 + j];
-      db += g;
+  for (int f = 0; f < kFilmMaxF; ++f) { w[f] = (live && f < F) ? W[(long)j * F + f] : 0.f; dw[f] = 0.f; }
+  float db = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float g = live ? dgb[(long)b * E2 + j] : 0.f;
+    db += g;
 #pragma unroll
-      for (int f = 0; f < kFilmMaxF; ++f)
-        if (f < F) {
-          dw[f] = fmaf(g, s_c[b * F + f], dw[f]);
-          atomicAdd(s_dc + b * F + f, g * W[(long)j * F + f]);
-        }
+    for (int f = 0; f < kFilmMaxF; ++f) {
+      if (f < F) {
+        dw[f] = fmaf(g, s_c[b * F + f], dw[f]);
+        const float v = warp_sum(g * w[f]);
+        if ((threadIdx.x & 31) == 0) atomicAdd(dc + b * F + f, v);
+      }
     }
+  }
+  if (live) {
     d_bias[j] += db;
 #pragma unroll
     for (int f = 0; f < kFilmMaxF; ++f)
       if (f < F) d_W[(long)j * F + f] += dw[f];
   }
-  __syncthreads();
-  for (int f = threadIdx.x; f < F; f += blockDim.x) {
-    float a = 0.f, c = 0.f;
-    for (int b = 0; b < B; ++b) { a = fmaf(s_dc[b * F + f], s_x[b * F + f], a); c += s_dc[b * F + f]; }
-    d_lw[f] += a;
-    d_lb[f] += c;
+}
+
+__global__ void __launch_bounds__(32)
+film_bwd_ln_kernel(const float* __restrict__ dc, const float* __restrict__ cond, int B, int F,
+                   const float* __restrict__ lw, const float* __restrict__ lb, float* __restrict__ d_lw,
+                   float* __restrict__ d_lb) {
+  pdl_prologue_done();
+  const int f = threadIdx.x;
+  if (f >= F) return;
+  float a = 0.f, c = 0.f;
+  for (int b = 0; b < B; ++b) {
+    float xh[kFilmMaxF], cc[kFilmMaxF];
+    float rstd;
+    film_ln_row(cond + (long)b * F, F, lw, lb, xh, cc, rstd);
+    a = fmaf(dc[b * F + f], xh[f], a);
+    c += dc[b * F + f];
   }
+  d_lw[f] += a;
+  d_lb[f] += c;
 }
 
 }  // namespace bf
@@ -186,18 +202,20 @@ extern "C" int bf_film_fwd(const float* cond, int B, int F, const float* ln_w, c
 
 extern "C" int bf_film_bwd(const float* dgb, const float* cond, int B, int F, const float* ln_w, const float* ln_b,
                            const float* W, int E2, float* d_ln_w, float* d_ln_b, float* d_W, float* d_bias,
-                           void* stream) {
-  BF_REQUIRE(dgb && cond && ln_w && ln_b && W && d_ln_w && d_ln_b && d_W && d_bias, "bf_film_bwd: null pointer");
+                           float* dc_scratch, void* stream) {
+  BF_REQUIRE(dgb && cond && ln_w && ln_b && W && d_ln_w && d_ln_b && d_W && d_bias && dc_scratch, "bf_film_bwd: null pointer");
   BF_REQUIRE(B > 0 && E2 > 0 && F > 0 && F <= kFilmMaxF, "bf_film_bwd: B=%d F=%d (<= %d) E2=%d", B, F, kFilmMaxF, E2);
-  const size_t smem = (size_t)3 * B * F * sizeof(float);
-  BF_REQUIRE(smem <= 48 * 1024, "bf_film_bwd: batch %d too large for one block", B);
-  launch_k(film_bwd_kernel, dim3(1), dim3(256), smem, static_cast<cudaStream_t>(stream), dgb, cond, B, F, ln_w, ln_b, W,
-           E2, d_ln_w, d_ln_b, d_W, d_bias);
-  count_launch();
-  BF_LAUNCH_CHECK("film_bwd_kernel");
+  const size_t smem = (size_t)B * F * sizeof(float);
+  BF_REQUIRE(smem <= 48 * 1024, "bf_film_bwd: batch %d too large", B);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  launch_k(film_bwd_w_kernel, dim3((E2 + 127) / 128), dim3(128), smem, st, dgb, cond, B, F, ln_w, ln_b, W, E2, d_W, d_bias,
+           dc_scratch);
+  launch_k(film_bwd_ln_kernel, dim3(1), dim3(32), (size_t)0, st, (const float*)dc_scratch, cond, B, F, ln_w, ln_b, d_ln_w,
+           d_ln_b);
+  count_launch(2);
+  BF_LAUNCH_CHECK("film_bwd kernels");
   return BF_OK;
 }
-
 extern "C" int bf_feat_consts(const float* W, const float* norm2_bias, const float* out_bias, const float* low,
                               const float* high, int E, float* c, float* c1, float* c0, void* stream) {
   BF_REQUIRE(W && norm2_bias && out_bias && low && high && c && c1 && c0 && E > 0, "bf_feat_consts: bad arguments");

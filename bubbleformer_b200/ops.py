@@ -248,10 +248,11 @@ def film_bwd(dgb, cond, ln_w, ln_b, W, d_ln_w, d_ln_b, d_W, d_bias) -> None:
     """Accumulates the FiLM MLP's parameter gradients from dgb (B, 2E)."""
     B, F = cond.shape
     E2 = W.shape[0]
+    dc = torch.zeros(B * F, dtype=torch.float32, device=dgb.device)
     L.check(L.lib.bf_film_bwd(_f32(dgb, B * E2, "dgb"), _f32(cond, B * F, "cond"), B, F, _f32(ln_w, F, "ln_w"),
                               _f32(ln_b, F, "ln_b"), _f32(W, E2 * F, "W"), E2, _f32(d_ln_w, F, "d_ln_w"),
                               _f32(d_ln_b, F, "d_ln_b"), _f32(d_W, E2 * F, "d_W"), _f32(d_bias, E2, "d_bias"),
-                              _stream()), "bf_film_bwd")
+                              _ptr(dc), _stream()), "bf_film_bwd")
 
 
 def colsum16(x, out) -> None:

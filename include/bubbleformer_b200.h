@@ -236,11 +236,13 @@ BF_API int bf_branch_param_grads(const bf_branch_grad_args* args, void* stream);
  *   gb[b, :] = W * LayerNorm_F(cond[b, :]; ln_w, ln_b) + bias       cond (B, F) fp32, W (2E, F), gb (B, 2E)
  * gamma = gb[:, :E], beta = gb[:, E:] are applied by bf_inorm_apply (film_gamma / film_beta).  F <= 32.
  * bf_film_bwd ACCUMULATES the parameter gradients from dgb (B, 2E) (the caller zeroes them); cond gets no gradient
- * (the fluid parameters are data, dataset.py:170-178).                                                          */
+ * (the fluid parameters are data, dataset.py:170-178).  dc_scratch: (B, F) fp32 workspace, ZEROED by the caller
+ * (receives d LayerNorm-output, reduced over the 2E outputs with one atomic per block).                           */
 BF_API int bf_film_fwd(const float* cond, int B, int F, const float* ln_w, const float* ln_b, const float* W,
                        const float* bias, int E2, float* gb, void* stream);
 BF_API int bf_film_bwd(const float* dgb, const float* cond, int B, int F, const float* ln_w, const float* ln_b,
-                       const float* W, int E2, float* d_ln_w, float* d_ln_b, float* d_W, float* d_bias, void* stream);
+                       const float* W, int E2, float* d_ln_w, float* d_ln_b, float* d_W, float* d_bias,
+                       float* dc_scratch, void* stream);
 
 /* Input pipeline (upstream data/dataset.py:120-186, BubbleForecast.__getitem__): the trajectories are resident in HBM
  * as frames (F, C_src, H*W) fp32; one launch cuts B windows of T frames, selects and normalises the fields and writes

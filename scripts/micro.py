@@ -68,6 +68,8 @@ def main():
         "gemm_acc32": (lambda: ops.gemm(H, W1, N, E, 4 * E, epilogue=L.EPI_ACC32, b_mode=L.B_KN, in32=X32, out32=o32), 2.0 * N * 4 * E * E, N * 4 * E * 2 + N * E * 8),
         "gemm_dgrad_qkv": (lambda: ops.gemm(QKV, Win, N, E, 3 * E, epilogue=L.EPI_STORE16, b_mode=L.B_KN, out16=O), 2.0 * N * 3 * E * E, (N * E + N * 3 * E) * 2),
         "gemm_fc1": (lambda: ops.gemm(Xb, W1, N, 4 * E, E, epilogue=L.EPI_GELU, bias=v4E, out16=out4, out16b=out4b), 2.0 * N * 4 * E * E, (N * E + 2 * N * 4 * E) * 2),
+        "gemm_fc1d": (lambda: ops.gemm(Xb, W1, N, 4 * E, E, epilogue=L.EPI_GELU_D, bias=v4E, out16=out4, out16b=out4b), 2.0 * N * 4 * E * E, (N * E + 2 * N * 4 * E) * 2),
+        "gemm_dmul": (lambda: ops.gemm(Xb, W2, N, 4 * E, E, epilogue=L.EPI_DMUL, b_mode=L.B_KN, aux16=H, out16=out4, colsum_out=v4E), 2.0 * N * 4 * E * E, (N * E + 2 * N * 4 * E) * 2),
         "gemm_fc2": (lambda: ops.gemm(H, W2, N, E, 4 * E, epilogue=L.EPI_STORE16, bias=vE, out16=O), 2.0 * N * 4 * E * E, (N * 4 * E + N * E) * 2),
         "gemm_resid": (lambda: ops.gemm(Xb, Wo, N, E, E, epilogue=L.EPI_RESID, bias=vE, col_gamma=vE, row_scale=rs, rows_per_group=P,
                                         in32=X32, out32=o32, out16=O, out16b=O2), 2.0 * N * E * E, N * E * (2 + 4 + 4 + 2 + 2)),

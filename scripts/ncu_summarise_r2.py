@@ -28,7 +28,7 @@ for r in rows[1:]:
 ids = sorted(per)
 short = lambda n: n.split("(")[0].replace("void ", "").replace("bf::", "")[:72]
 # one replayed step = between the last two weight-mirror casts (cast16 over the 28.9 M parameters: > 20 us)
-casts = [i for i in ids if "cast16_kernel" in per[i]["k"] and per[i].get("gpu__time_duration.sum", 0) > 15000]
+casts = [i for i in ids if "cast16_kernel<__nv_bfloat16>" in per[i]["k"] and per[i].get("gpu__time_duration.sum", 0) > 20000]
 s, e = casts[-2], casts[-1]
 step = [per[i] for i in ids if s <= i < e]
 

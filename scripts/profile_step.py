@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--res", type=int, default=512)
     ap.add_argument("--detail", action="store_true")
+    ap.add_argument("--big", action="store_true", help="film_avit_big (E=768, 12 heads): BASELINE configs[4] with --res 1024 --batch 1")
     args = ap.parse_args()
     import torch
     import bench
@@ -24,7 +25,7 @@ def main():
     from bubbleformer_b200.parallel import GradSink
     from oracle.param_init import fluid_params
     dev = "cuda"
-    model = get_model("filmavit", time_window=5, **bench.CFG).to(dev)
+    model = get_model("filmavit", time_window=5, **(bench.CFG_BIG if args.big else bench.CFG)).to(dev)
     model.train()
     sink = GradSink(model)
     B = args.batch
