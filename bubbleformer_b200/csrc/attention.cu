@@ -690,6 +690,7 @@ static int attn_common(const bf_attn_args* a, AttnParams& p, int& LP, bool bwd) 
 
 namespace bf {
 int launch_attn_fast(const bf_attn_args* a, bool bwd, cudaStream_t st);
+int launch_attn_fast64(const bf_attn_args* a, bool bwd, cudaStream_t st);
 int launch_attn_f32(const bf_attn_args* a, bool bwd, cudaStream_t st);
 }
 
@@ -697,7 +698,9 @@ extern "C" int bf_attention_fwd(const bf_attn_args* a, void* stream) {
   AttnParams p; int LP;
   if (int st = attn_common(a, p, LP, false)) return st;
   if (a->dtype == BF_F32) return launch_attn_f32(a, false, static_cast<cudaStream_t>(stream));
-  if (a->prenorm) return launch_attn_fast(a, false, static_cast<cudaStream_t>(stream));
+  if (a->prenorm)
+    return a->L > 32 ? launch_attn_fast64(a, false, static_cast<cudaStream_t>(stream))
+                     : launch_attn_fast(a, false, static_cast<cudaStream_t>(stream));
   return dispatch_attn<false>(a->head_dim, LP, p, static_cast<cudaStream_t>(stream));
 }
 
@@ -705,6 +708,8 @@ extern "C" int bf_attention_bwd(const bf_attn_args* a, void* stream) {
   AttnParams p; int LP;
   if (int st = attn_common(a, p, LP, true)) return st;
   if (a->dtype == BF_F32) return launch_attn_f32(a, true, static_cast<cudaStream_t>(stream));
-  if (a->prenorm) return launch_attn_fast(a, true, static_cast<cudaStream_t>(stream));
+  if (a->prenorm)
+    return a->L > 32 ? launch_attn_fast64(a, true, static_cast<cudaStream_t>(stream))
+                     : launch_attn_fast(a, true, static_cast<cudaStream_t>(stream));
   return dispatch_attn<true>(a->head_dim, LP, p, static_cast<cudaStream_t>(stream));
 }

@@ -195,9 +195,9 @@ def _attn_branch_fwd(X, g: Geom, p: Dict[str, torch.Tensor], w16, heads: int, ax
     Xn = _empty((N, E), BF16, X)
     ops.inorm_apply(X, Xn, I, P, st1, p["norm1.weight"], p["norm1.bias"])
     QKV = _empty((N, 3 * E), BF16, X)
-    # head_dim 64 and short axes: LayerNorm(q), LayerNorm(k) are computed in the QKV GEMM epilogue (xhat + rstd) and
-    # the attention kernels work on the pre-normalised rows; otherwise the generic kernels normalise in place
-    prenorm = (E // heads == 64) and all(_axis(g, ax)["L_"] <= 32 for ax in axes) and BF16 == torch.bfloat16
+    # head_dim 64 and axes of up to 64 tokens: LayerNorm(q), LayerNorm(k) are computed in the QKV GEMM epilogue (xhat +
+    # rstd) and the attention kernels work on the pre-normalised rows; otherwise the generic kernels normalise in place
+    prenorm = (E // heads == 64) and all(_axis(g, ax)["L_"] <= 64 for ax in axes) and BF16 == torch.bfloat16
     rstd = _empty((N, heads, 2), F32, X) if prenorm else None
     if prenorm:
         ops.gemm(Xn, w16("input_head.weight"), N, 3 * E, E, epilogue=L.EPI_QKV_LN, bias=p["input_head.bias"], out16=QKV,

@@ -302,7 +302,8 @@ typedef struct bf_attn_args {
   float out_scale;
   int32_t prenorm;             /* 1: qkv holds xhat_q | xhat_k | v as written by bf_gemm(BF_EPI_QKV_LN): the kernel
                                   applies the LayerNorm affine itself and the backward returns gradients w.r.t. the
-                                  RAW q / k using `rstd`.  Fast path: head_dim 64, L <= 32.                        */
+                                  RAW q / k using `rstd`.  Fast paths: head_dim 64, L <= 32 (32-row tiles, short
+                                  sequences packed) and 32 < L <= 64 (64-row tiles).                               */
   float* d_qn_w;  float* d_qn_b;  float* d_kn_w;  float* d_kn_b;
   float* d_bias_emb;  float* d_scale_factor;
   const float* rstd;           /* prenorm backward: (tokens, heads, 2) rstd of the raw q / k rows                  */

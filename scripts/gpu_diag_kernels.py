@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 GROUPS = ["params", "stats", "apply", "inorm_bwd", "resid_colsum", "attn_x", "attn_y", "attn_t", "attn_d48", "attn_l64",
-          "attn_noscale", "attn_l128", "patch", "misc", "film", "gelu_modes"]
+          "attn_noscale", "attn_l128", "attn_l64_big", "attn_l40", "patch", "misc", "film", "gelu_modes"]
 
 
 def rel(got, ref):
@@ -164,7 +164,10 @@ def run(group):
         cfg = {"attn_x": dict(I=6, h=8, w=32, E=384, he=6, axis="x"), "attn_y": dict(I=6, h=32, w=8, E=384, he=6, axis="y"),
                "attn_t": dict(I=10, h=4, w=8, E=384, he=6, axis="t", T=5), "attn_d48": dict(I=4, h=4, w=20, E=192, he=4, axis="x"),
                "attn_l64": dict(I=2, h=3, w=64, E=128, he=2, axis="x"), "attn_noscale": dict(I=3, h=12, w=6, E=128, he=2, axis="y", noscale=True),
-               "attn_l128": dict(I=2, h=2, w=128, E=128, he=2, axis="x")}[group]
+               "attn_l128": dict(I=2, h=2, w=128, E=128, he=2, axis="x"),
+               # 64-row fast path: full tiles (12 heads like film_avit_big, y axis), a 40-token axis (masked tail), 3 heads
+               "attn_l64_big": dict(I=2, h=64, w=16, E=768, he=12, axis="y"),
+               "attn_l40": dict(I=3, h=5, w=40, E=192, he=3, axis="x")}[group]
         I, h, w, E, he, axis = cfg["I"], cfg["h"], cfg["w"], cfg["E"], cfg["he"], cfg["axis"]
         d = E // he
         P = h * w
@@ -233,7 +236,7 @@ def run(group):
         ok &= report(f"{group} d_bias_emb", grads["d_bias_emb"], params[4].grad, 1e-2)
         if sf is not None:
             ok &= report(f"{group} d_scale_factor", grads["d_scale_factor"], sfp.grad, 1e-2)
-        if d == 64 and Ls <= 32:
+        if d == 64 and Ls <= 64:
             # pre-normalised fast path: rows hold xhat_q | xhat_k | v (as the QKV GEMM epilogue writes them) + rstd
             x4 = qkv.float().reshape(tokens, he, 3, d)
             qk = x4[:, :, :2]
@@ -253,10 +256,11 @@ def run(group):
             grads = dict(d_qn_w=torch.zeros(d, device=dev), d_qn_b=torch.zeros(d, device=dev), d_kn_w=torch.zeros(d, device=dev),
                          d_kn_b=torch.zeros(d, device=dev), d_bias_emb=torch.zeros(32, he, device=dev),
                          d_scale_factor=torch.zeros(he, device=dev) if sf is not None else None,
-                         d_qkv_bias=torch.zeros(3 * E, device=dev))
+                         d_qkv_bias=torch.zeros(3 * E, device=dev) if Ls <= 32 else None)
             ops.attention(qkvn, dqkv, dout=dout, grads=grads, prenorm=True, rstd=rstd, **common)
             got = dqkv.float().reshape(tokens, he, 3, d)
-            ok &= report(f"{group} prenorm d_qkv_bias (fused column sums)", grads["d_qkv_bias"], dqkv.float().sum(0), 1e-2)
+            if Ls <= 32:
+                ok &= report(f"{group} prenorm d_qkv_bias (fused column sums)", grads["d_qkv_bias"], dqkv.float().sum(0), 1e-2)
             for i, nm in enumerate("qkv"):
                 ok &= report(f"{group} prenorm d{nm}", got[:, :, i], dq_ref[:, :, i], 1e-2)
             ok &= report(f"{group} prenorm d_qn_w", grads["d_qn_w"], params[0].grad, 1e-2)

@@ -35,7 +35,7 @@ def test_gemm(variant):
 
 
 @pytest.mark.parametrize("group", ["params", "stats", "apply", "inorm_bwd", "resid_colsum", "attn_x", "attn_y", "attn_t",
-                                   "attn_d48", "attn_l64", "attn_noscale", "attn_l128", "patch", "misc", "film",
+                                   "attn_d48", "attn_l64", "attn_noscale", "attn_l128", "attn_l64_big", "attn_l40", "patch", "misc", "film",
                                    "gelu_modes"])
 def test_kernels(group):
     import gpu_diag_kernels
