@@ -335,9 +335,15 @@ inorm_bwd_reduce_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, Bw
   float gv[8], xv[8];                                                                   \
   unpack8<TG>(ring + ((st) * NSLOT) * kNT + threadIdx.x, gv);                           \
   unpack8<TX>(ring + ((st) * NSLOT + NG) * kNT + threadIdx.x, xv);                      \
+  if (GELU && p.gelu == 1) {      /* tanh form: derivative of two elements per packed half-precision evaluation */ \
+    _Pragma("unroll") for (int j = 0; j < 8; j += 2) {                                  \
+      const float2 d2 = gelu_grad_h2(fmaf(xv[j], wa[j], wb[j]), fmaf(xv[j + 1], wa[j + 1], wb[j + 1])); \
+      gv[j] *= d2.x; gv[j + 1] *= d2.y;                                                 \
+    }                                                                                   \
+  }                                                                                     \
   _Pragma("unroll") for (int j = 0; j < 8; ++j) {                                       \
     float gg = gv[j];                                                                   \
-    if (GELU) gg *= gelu_bwd(fmaf(xv[j], wa[j], wb[j]), p.gelu == 2);                    \
+    if (GELU && p.gelu != 1) gg *= gelu_bwd(fmaf(xv[j], wa[j], wb[j]), p.gelu == 2);     \
     acc[j] += gg;                                                                       \
     acc[8 + j] = fmaf(gg, xv[j], acc[8 + j]);                                           \
   }
@@ -413,9 +419,15 @@ inorm_bwd_apply_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, TO*
   float gv[8], xv[8], o[8];                                                             \
   unpack8<TG>(ring + ((st) * NSLOT) * kNT + threadIdx.x, gv);                           \
   unpack8<TX>(ring + ((st) * NSLOT + NG) * kNT + threadIdx.x, xv);                      \
+  if (GELU && p.gelu == 1) {                                                            \
+    _Pragma("unroll") for (int j = 0; j < 8; j += 2) {                                  \
+      const float2 d2 = gelu_grad_h2(fmaf(xv[j], wa[j], wb[j]), fmaf(xv[j + 1], wa[j + 1], wb[j + 1])); \
+      gv[j] *= d2.x; gv[j + 1] *= d2.y;                                                 \
+    }                                                                                   \
+  }                                                                                     \
   _Pragma("unroll") for (int j = 0; j < 8; ++j) {                                       \
     float gg = gv[j];                                                                   \
-    if (GELU) gg *= gelu_bwd(fmaf(xv[j], wa[j], wb[j]), p.gelu == 2);                    \
+    if (GELU && p.gelu != 1) gg *= gelu_bwd(fmaf(xv[j], wa[j], wb[j]), p.gelu == 2);     \
     o[j] = fmaf(ka[j], gg, fmaf(kb[j], xv[j], kc[j]));                                  \
   }                                                                                     \
   if (ADD) {                                                                            \

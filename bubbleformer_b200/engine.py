@@ -31,6 +31,7 @@ EXACT = False
 # A/B switches for same-box measurements (scripts/gpu/ab_env.sh); the defaults are the measured-faster forms
 import os as _os
 MLP_SAVES_DERIVATIVE = _os.environ.get("BF_MLP_DERIV", "1") != "0"     # fc1 stores gelu'(pre); 0: stores pre, dGELU epilogue
+DMUL_BN = int(_os.environ.get("BF_DMUL_BN", "0"))                       # N tile of the fc2 input-gradient GEMM (0 = automatic)
 
 
 def set_exact_mode(on: bool) -> None:
@@ -368,7 +369,7 @@ def spatial_backward(dXout, g: Geom, p, w16, heads: int, attn_scale: bool, feat_
     # fc2 (its bias feeds an InstanceNorm, so its gradient is identically zero and stays zero)
     dH = _empty((N, 4 * E), BF16, dXout)
     ops.gemm(dY2, w16("mlp.fc2.weight"), N, 4 * E, E, epilogue=L.EPI_DMUL if MLP_SAVES_DERIVATIVE else L.EPI_DGELU,
-             b_mode=L.B_KN, aux16=Hpre, out16=dH,
+             b_mode=L.B_KN, aux16=Hpre, out16=dH, bn=DMUL_BN,
              colsum_out=grads["mlp.fc1.bias"])
     ops.gemm(dY2, G, E, 4 * E, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
              split_k=pick_split(N, E, 4 * E), out32=grads["mlp.fc2.weight"])
