@@ -5,53 +5,59 @@
 // GELU (patching.py:47,103), FiLM (linear_layers.py:71-77), layer-scale * drop-path + residual
 // (attention.py:317).  Also the residual-branch backward helper and column sums for bias gradients.
 //
-// All kernels are HBM-bound streaming passes built on one pattern: a thread owns 8 consecutive channels and
-// walks down the rows of its image slice; its loads are issued several rows ahead with cp.async (16 B each)
-// into a private ring of shared-memory slots, so tens of KB per SM are in flight without holding registers
-// and without any block-level synchronisation in the loop (a thread only ever reads back what it copied).
-// The grid is sized to exactly one resident wave (3 CTAs per SM); per-(image, channel) partial sums are
-// combined in shared memory and flushed with one fp32 atomic per block.
+// All kernels are HBM-bound streaming passes built on one pattern (measured against the per-thread cp.async ring it
+// replaces -- scripts/exp/stream_exp.cu, profiles/r2o_stream_exp.txt: 30.2 -> 18.6 us for the fp32 -> bf16 apply pass and
+// 58.6 -> 36.2 us for the norm1 backward apply at config 2, i.e. 0.78 / 0.92 of the measured HBM copy rate):
+//   * a block owns a slab of rows of one image (x one column chunk); a dedicated producer warp moves that slab through
+//     a shared-memory ring with TMA 1-D bulk copies (cp.async.bulk, full lines, one instruction per operand and stage
+//     when the rows are contiguous, one per row otherwise), completion on a per-stage mbarrier;
+//   * the 256 consumer threads each own 8 consecutive channels: they read their 16 / 32 bytes per row from shared memory,
+//     keep the per-(image, channel) coefficients in registers and store results straight to global memory (128- or
+//     256-bit stores), then hand the stage back through a second mbarrier -- no block-level synchronisation in the loop;
+//   * the grid is one resident wave (2 blocks per SM, 96 KiB of ring each); per-(image, channel) partial sums are combined
+//     in shared memory and flushed with one fp32 atomic per block.
 // Statistics are kept as raw sums (sum x, sum x^2) per (image, channel) so producers can accumulate them.
 #include "common.cuh"
 
 namespace bf {
 
-constexpr int kNT = 256;                 // threads per block
-constexpr int kRingBytes = 64 * 1024;    // cp.async ring per block
-constexpr int kBlocksPerSM = 3;
+constexpr int kNT = 256;                 // consumer threads per block
+constexpr int kThreads = kNT + 32;       // + the producer warp (warp 8)
+constexpr int kRingBytes = 96 * 1024;    // bulk-copy ring per block
+constexpr int kMaxStages = 8;
+constexpr int kSmemBytes = kRingBytes + 2 * kMaxStages * 8;
+constexpr int kBlocksPerSM = 2;
+constexpr int kStageTarget = 20 * 1024;  // bytes per stage aimed for (all operands)
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// number of 16-byte slots that 8 channels of type T occupy
-template <typename T> struct Slots { static constexpr int N = sizeof(T) * 8 / 16; };
-
+// this thread's 8 channels of one row of an operand staged in shared memory
 template <typename T>
-__device__ __forceinline__ void unpack8(const uint4* slot, float (&v)[8]) {
+__device__ __forceinline__ void ld8(const uint8_t* p, float (&v)[8]) {
   if constexpr (sizeof(T) == 4) {
-    const float4 a = *reinterpret_cast<const float4*>(slot), b = *reinterpret_cast<const float4*>(slot + kNT);
+    const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   } else {
-    const uint4 u = *slot;
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
     const float2 a = unpack2<T>(u.x), b = unpack2<T>(u.y), c = unpack2<T>(u.z), d = unpack2<T>(u.w);
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
   }
 }
-// slot layout: ring[(stage * NSLOT + slot) * kNT + tid]; a fp32 tensor uses two consecutive slot indices
+// 8 results to global memory: one 128-bit store (16-bit types), one 256-bit store (fp32, 32-byte aligned rows) or two
+// 128-bit stores (fp32 at 16-byte alignment; `wide` is block uniform)
 template <typename T>
-__device__ __forceinline__ void issue8(uint4* slot, const T* src) {
-  cp_async16(slot, src);
-  if constexpr (sizeof(T) == 4) cp_async16(slot + kNT, src + 4);
-}
-template <typename T>
-__device__ __forceinline__ void store8(T* p, const float (&v)[8]) {
+__device__ __forceinline__ void store8(T* p, const float (&v)[8], bool wide) {
   if constexpr (sizeof(T) == 4) {
-    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
-    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    if (wide) {
+      asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                   "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+    } else {
+      reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+      reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
   } else {
     uint4 u;
     u.x = pack2<T>(v[0], v[1]); u.y = pack2<T>(v[2], v[3]); u.z = pack2<T>(v[4], v[5]); u.w = pack2<T>(v[6], v[7]);
@@ -59,25 +65,39 @@ __device__ __forceinline__ void store8(T* p, const float (&v)[8]) {
   }
 }
 
-// Geometry shared by all kernels: block = tx_n vector columns x ty_n rows; grid = (splits, images, column chunks)
+// N consecutive floats added to global memory: 128-bit vector reductions (red.global.add.v4.f32: a quarter of the L2
+// atomic operations -- the column sums of one launch all land on the same few addresses) when the destination is
+// 16-byte aligned, scalar atomics otherwise
+template <int N>
+__device__ __forceinline__ void red_add(float* dst, const float (&v)[N]) {
+  static_assert(N % 4 == 0, "red_add");
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+    for (int j = 0; j < N; j += 4)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]),
+                   "f"(v[j + 3]) : "memory");
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; ++j) atomicAdd(dst + j, v[j]);
+  }
+}
+
+// Geometry shared by all kernels: block = tx_n vector columns x ty_n rows of consumers; grid = (splits, images, column
+// chunks); a stage of the ring holds rb = kk * ty_n rows of every input operand
 struct Geom {
   int I, P, C;
-  int vc, tx_n, ty_n, chunks, splits, rows_per_split, n_it;
+  int vc, tx_n, ty_n, chunks, splits, rows_per_split;
+  int kk, rb, ns, stage_bytes;
 };
-static Geom make_geom(int I, int P, int C) {
+// `sum_es`: bytes per element summed over the streamed input operands
+static Geom make_geom(int I, int P, int C, int sum_es) {
   Geom g;
   g.I = I; g.P = P; g.C = C;
   g.vc = C / 8;
-  // column chunking that keeps the most threads busy (tx_n * floor(256 / tx_n)), fewest chunks on ties
-  int best_chunks = 1, best_active = -1;
-  for (int ch = (g.vc + kNT - 1) / kNT; ch <= (g.vc + 31) / 32 || ch == 1; ++ch) {
-    const int tx = (g.vc + ch - 1) / ch;
-    if (tx > kNT) continue;
-    const int active = tx * (kNT / tx);
-    if (active > best_active) { best_active = active; best_chunks = ch; }
-    if (ch > 64) break;
-  }
-  g.chunks = best_chunks;
+  // Fewest column chunks: whole rows (ld == C) are contiguous, so a stage of an operand is ONE bulk copy; splitting the
+  // columns to keep more consumer threads busy would turn it into one copy per row (measured on the 1152-column sums:
+  // 35 vs 27 us), and these passes are bound by the copies, not by the consumers.
+  g.chunks = (g.vc + kNT - 1) / kNT;
   g.tx_n = (g.vc + g.chunks - 1) / g.chunks;
   g.ty_n = kNT / g.tx_n;
   const int target = num_sms() * kBlocksPerSM;                  // one resident wave
@@ -87,7 +107,17 @@ static Geom make_geom(int I, int P, int C) {
   if (splits < 1) splits = 1;
   g.splits = splits;
   g.rows_per_split = (P + splits - 1) / splits;
-  g.n_it = (g.rows_per_split + g.ty_n - 1) / g.ty_n;
+  const int group_bytes = g.ty_n * g.tx_n * 8 * sum_es;         // one row per consumer thread row
+  int kk = kStageTarget / group_bytes;
+  const int kk_max = (g.rows_per_split + g.ty_n - 1) / g.ty_n;
+  if (kk > kk_max) kk = kk_max;
+  if (kk < 1) kk = 1;
+  g.kk = kk;
+  g.rb = kk * g.ty_n;
+  g.stage_bytes = g.rb * g.tx_n * 8 * sum_es;
+  int ns = kRingBytes / g.stage_bytes;
+  if (ns > kMaxStages) ns = kMaxStages;
+  g.ns = ns;
   return g;
 }
 
@@ -103,7 +133,7 @@ __device__ __forceinline__ Ctx make_ctx(const Geom& g) {
   c.img = blockIdx.y;
   c.r0 = blockIdx.x * g.rows_per_split;
   c.r1 = min(g.P, c.r0 + g.rows_per_split);
-  c.active = c.ty < g.ty_n && c.vcol < g.vc;
+  c.active = threadIdx.x < kNT && c.ty < g.ty_n && c.vcol < g.vc;
   return c;
 }
 
@@ -133,56 +163,114 @@ __device__ __forceinline__ void mean_rstd(const float* stats, long idx, float in
   rstd = rsqrtf(var + 1e-5f);
 }
 
-// The streaming loop.  ISSUE(row, stage) copies the thread's operands of one row; BODY(row, stage) consumes them.
-#define BF_STREAM_LOOP(S_, ISSUE, BODY)                                                   \
-  {                                                                                       \
-    _Pragma("unroll") for (int it_ = 0; it_ < (S_); ++it_) {                              \
-      const int row_ = c.r0 + c.ty + it_ * g.ty_n;                                        \
-      if (c.active && it_ < g.n_it && row_ < c.r1) { ISSUE(row_, it_) }                   \
-      cp_async_commit();                                                                  \
-    }                                                                                     \
-    int stage_ = 0;                                                                       \
-    for (int it_ = 0; it_ < g.n_it; ++it_) {                                              \
-      cp_async_wait<(S_) - 1>();                                                          \
-      const int row_ = c.r0 + c.ty + it_ * g.ty_n;                                        \
-      if (c.active && row_ < c.r1) { BODY(row_, stage_) }                                 \
-      const int nrow_ = row_ + (S_) * g.ty_n;                                             \
-      if (c.active && it_ + (S_) < g.n_it && nrow_ < c.r1) { ISSUE(nrow_, stage_) }       \
-      cp_async_commit();                                                                  \
-      if (++stage_ == (S_)) stage_ = 0;                                                   \
-    }                                                                                     \
-    cp_async_wait<0>();                                                                   \
-  }
+// Up to three streamed input operands of a kernel.  base: first row of this block's image at the block's first channel;
+// pitch: row pitch in bytes; es: element size.  Offsets inside a stage follow from the geometry.
+struct StreamOps {
+  const uint8_t* base[3];
+  long pitch[3];
+  int es[3];
+  int n;
+};
 
-template <int NSLOT> struct Stages { static constexpr int S = (kRingBytes / (NSLOT * kNT * 16)) > 8 ? 8 : (kRingBytes / (NSLOT * kNT * 16)); };
+// Barrier set-up.  Runs BEFORE griddepcontrol.wait, i.e. while the previous kernel of the stream still drains.
+#define BF_STREAM_SETUP()                                                                  \
+  extern __shared__ __align__(128) uint8_t ring[];                                         \
+  uint64_t* full_ = reinterpret_cast<uint64_t*>(ring + kRingBytes);                        \
+  uint64_t* empty_ = full_ + kMaxStages;                                                   \
+  if (threadIdx.x == 0) {                                                                  \
+    for (int s_ = 0; s_ < kMaxStages; ++s_) { mbar_init(full_ + s_, 1); mbar_init(empty_ + s_, kNT / 32); } \
+    fence_mbar_init();                                                                     \
+  }                                                                                        \
+  __syncthreads();                                                                         \
+  pdl_prologue_done();
+
+// The streaming loop.  `ops_` describes the inputs; BODY(row, s0, s1, s2) consumes one row: s0..s2 point at this thread's
+// 8 channels of each operand in shared memory.  The producer warp falls through to whatever follows the loop.
+#define BF_STREAM_LOOP(ops_, BODY)                                                         \
+  {                                                                                        \
+    const int cw_ = g.tx_n * 8;                           /* channels per block row */     \
+    const int nblk_ = c.r1 > c.r0 ? (c.r1 - c.r0 + g.rb - 1) / g.rb : 0;                   \
+    int off_[3];                                                                           \
+    off_[0] = 0;                                                                           \
+    off_[1] = g.rb * cw_ * (ops_).es[0];                                                   \
+    off_[2] = off_[1] + g.rb * cw_ * ((ops_).n > 1 ? (ops_).es[1] : 0);                    \
+    const int sum_es_ = (ops_).es[0] + (ops_).es[1] + (ops_).es[2];   /* unused operands have es = 0 */ \
+    if (threadIdx.x >= kNT) {                                                              \
+      const int lane_ = threadIdx.x & 31;                                                  \
+      int st_ = 0; uint32_t ph_ = 0;                                                       \
+      for (int b_ = 0; b_ < nblk_; ++b_) {                                                 \
+        const int row_ = c.r0 + b_ * g.rb;                                                 \
+        const int rows_ = min(g.rb, c.r1 - row_);                                          \
+        if (lane_ == 0) {                                                                  \
+          mbar_wait(empty_ + st_, ph_ ^ 1u);                                               \
+          mbar_arrive_expect_tx(full_ + st_, (uint32_t)(rows_ * cw_ * sum_es_));           \
+        }                                                                                  \
+        __syncwarp();                                                                      \
+        uint8_t* sp_ = ring + st_ * g.stage_bytes;                                         \
+        _Pragma("unroll") for (int k_ = 0; k_ < 3; ++k_) {                                 \
+          if (k_ >= (ops_).n) break;                                                       \
+          const int rowb_ = cw_ * (ops_).es[k_];                                           \
+          const uint8_t* src_ = (ops_).base[k_] + (long)row_ * (ops_).pitch[k_];           \
+          if ((ops_).pitch[k_] == rowb_) {                                                 \
+            if (lane_ == k_) bulk_g2s(sp_ + off_[k_], src_, (uint32_t)(rows_ * rowb_), full_ + st_); \
+          } else {                                                                         \
+            for (int r_ = lane_; r_ < rows_; r_ += 32)                                     \
+              bulk_g2s(sp_ + off_[k_] + r_ * rowb_, src_ + (long)r_ * (ops_).pitch[k_], (uint32_t)rowb_, full_ + st_); \
+          }                                                                                \
+        }                                                                                  \
+        if (++st_ == g.ns) { st_ = 0; ph_ ^= 1u; }                                         \
+      }                                                                                    \
+    } else {                                                                               \
+      int st_ = 0; uint32_t ph_ = 0;                                                       \
+      for (int b_ = 0; b_ < nblk_; ++b_) {                                                 \
+        mbar_wait(full_ + st_, ph_);                                                       \
+        if (c.active) {                                                                    \
+          const uint8_t* sp_ = ring + st_ * g.stage_bytes;                                 \
+          for (int k_ = 0; k_ < g.kk; ++k_) {                                              \
+            const int rl_ = c.ty + k_ * g.ty_n;                                            \
+            const int row_ = c.r0 + b_ * g.rb + rl_;                                       \
+            if (row_ < c.r1) {                                                             \
+              const int e_ = rl_ * cw_ + c.tx * 8;                                         \
+              BODY(row_, (sp_ + off_[0] + e_ * (ops_).es[0]), (sp_ + off_[1] + e_ * (ops_).es[1]), \
+                   (sp_ + off_[2] + e_ * (ops_).es[2]))                                    \
+            }                                                                              \
+          }                                                                                \
+        }                                                                                  \
+        __syncwarp();                                                                      \
+        if ((threadIdx.x & 31) == 0) mbar_arrive(empty_ + st_);                            \
+        if (++st_ == g.ns) { st_ = 0; ph_ ^= 1u; }                                         \
+      }                                                                                    \
+    }                                                                                      \
+  }
 
 // ---------------------------------------------------------------------------------------------
 // statistics: stats[img][c] += (sum x, sum x^2)
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(kNT, kBlocksPerSM)
+__global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 inorm_stats_kernel(const T* __restrict__ x, long ldx, Geom g, float* __restrict__ stats) {
-  pdl_prologue_done();
-  constexpr int NSLOT = Slots<T>::N, S = Stages<NSLOT>::S;
-  extern __shared__ __align__(16) uint4 ring[];
+  BF_STREAM_SETUP()
   const Ctx c = make_ctx(g);
-  const T* xb = x + ((long)c.img * g.P) * ldx + (long)c.vcol * 8;
+  StreamOps ops{};
+  ops.n = 1;
+  ops.base[0] = reinterpret_cast<const uint8_t*>(x + ((long)c.img * g.P) * ldx + (long)blockIdx.z * g.tx_n * 8);
+  ops.pitch[0] = ldx * (long)sizeof(T); ops.es[0] = sizeof(T);
   float acc[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-#define ISSUE(row, st) issue8<T>(ring + ((st) * NSLOT) * kNT + threadIdx.x, xb + (long)(row) * ldx);
-#define BODY(row, st)                                                        \
+#define BODY(row, s0, s1, s2)                                                \
   float v[8];                                                                \
-  unpack8<T>(ring + ((st) * NSLOT) * kNT + threadIdx.x, v);                  \
+  ld8<T>(s0, v);                                                             \
   _Pragma("unroll") for (int j = 0; j < 8; ++j) { acc[j] += v[j]; acc[8 + j] = fmaf(v[j], v[j], acc[8 + j]); }
-  BF_STREAM_LOOP(S, ISSUE, BODY)
-#undef ISSUE
+  BF_STREAM_LOOP(ops, BODY)
 #undef BODY
   reduce_over_ty<16>(acc, reinterpret_cast<float*>(ring), g, c);
   if (c.active && c.ty == 0) {
     float* dst = stats + ((long)c.img * g.C + (long)c.vcol * 8) * 2;
+    float il[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { atomicAdd(dst + 2 * j, acc[j]); atomicAdd(dst + 2 * j + 1, acc[8 + j]); }
+    for (int j = 0; j < 8; ++j) { il[2 * j] = acc[j]; il[2 * j + 1] = acc[8 + j]; }
+    red_add<16>(dst, il);
   }
 }
 
@@ -204,14 +292,13 @@ struct ApplyParams {
   const float* row_scale;    // [I] or null
   const float* col_gamma;    // [C] (with resid_in)
   float* stats_out;          // [I][C][2] or null: += (sum, sum^2) of the values written
+  int wide;                  // fp32 output rows are 32-byte aligned (256-bit stores)
 };
 
 template <typename TI, typename TO, bool RESID>
-__global__ void __launch_bounds__(kNT, kBlocksPerSM)
+__global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 inorm_apply_kernel(const TI* __restrict__ x, TO* __restrict__ out, ApplyParams p) {
-  pdl_prologue_done();
-  constexpr int NX = Slots<TI>::N, NSLOT = NX + (RESID ? 2 : 0), S = Stages<NSLOT>::S;
-  extern __shared__ __align__(16) uint4 ring[];
+  BF_STREAM_SETUP()
   const Geom& g = p.g;
   const Ctx c = make_ctx(g);
   const int c0 = c.vcol * 8;
@@ -243,38 +330,44 @@ inorm_apply_kernel(const TI* __restrict__ x, TO* __restrict__ out, ApplyParams p
     }
   }
   const bool post_film = p.gelu && p.film_gamma != nullptr;
-  const TI* xb = x + ((long)c.img * g.P) * p.ldx + c0;
+  const long cb = (long)blockIdx.z * g.tx_n * 8;        // first channel of this block's column chunk
+  StreamOps ops{};
+  ops.n = RESID ? 2 : 1;
+  ops.base[0] = reinterpret_cast<const uint8_t*>(x + ((long)c.img * g.P) * p.ldx + cb);
+  ops.pitch[0] = p.ldx * (long)sizeof(TI); ops.es[0] = sizeof(TI);
+  if (RESID) {
+    ops.base[1] = reinterpret_cast<const uint8_t*>(p.resid_in + ((long)c.img * g.P) * p.ldo + cb);
+    ops.pitch[1] = p.ldo * 4; ops.es[1] = 4;
+  }
   TO* ob = out + ((long)c.img * g.P) * p.ldo + c0;
-  const float* rb = RESID ? p.resid_in + ((long)c.img * g.P) * p.ldo + c0 : nullptr;
   float acc[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) acc[j] = 0.f;
   const bool want_stats = p.stats_out != nullptr;
-#define ISSUE(row, st)                                                                   \
-  issue8<TI>(ring + ((st) * NSLOT) * kNT + threadIdx.x, xb + (long)(row) * p.ldx);       \
-  if (RESID) issue8<float>(ring + ((st) * NSLOT + NX) * kNT + threadIdx.x, rb + (long)(row) * p.ldo);
-#define BODY(row, st)                                                                    \
+  const bool wide = p.wide != 0;
+#define BODY(row, s0, s1, s2)                                                            \
   float v[8];                                                                            \
-  unpack8<TI>(ring + ((st) * NSLOT) * kNT + threadIdx.x, v);                             \
+  ld8<TI>(s0, v);                                                                        \
   _Pragma("unroll") for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], a[j], b[j]);          \
   if (p.gelu) { _Pragma("unroll") for (int j = 0; j < 8; ++j) v[j] = gelu_fwd(v[j], p.gelu == 2); }  \
   if (post_film) { _Pragma("unroll") for (int j = 0; j < 8; ++j) v[j] = fmaf(fg[j], v[j], fb[j]); } \
   if (RESID) {                                                                           \
     float xr[8];                                                                         \
-    unpack8<float>(ring + ((st) * NSLOT + NX) * kNT + threadIdx.x, xr);                  \
+    ld8<float>(s1, xr);                                                                  \
     _Pragma("unroll") for (int j = 0; j < 8; ++j) v[j] += xr[j];                         \
   }                                                                                      \
   if (want_stats) { _Pragma("unroll") for (int j = 0; j < 8; ++j) { acc[j] += v[j]; acc[8 + j] = fmaf(v[j], v[j], acc[8 + j]); } } \
-  store8<TO>(ob + (long)(row) * p.ldo, v);
-  BF_STREAM_LOOP(S, ISSUE, BODY)
-#undef ISSUE
+  store8<TO>(ob + (long)(row) * p.ldo, v, wide);
+  BF_STREAM_LOOP(ops, BODY)
 #undef BODY
   if (want_stats) {
     reduce_over_ty<16>(acc, reinterpret_cast<float*>(ring), g, c);
     if (c.active && c.ty == 0) {
       float* dst = p.stats_out + ((long)c.img * g.C + c0) * 2;
+      float il[16];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { atomicAdd(dst + 2 * j, acc[j]); atomicAdd(dst + 2 * j + 1, acc[8 + j]); }
+      for (int j = 0; j < 8; ++j) { il[2 * j] = acc[j]; il[2 * j + 1] = acc[8 + j]; }
+      red_add<16>(dst, il);
     }
   }
 }
@@ -299,14 +392,13 @@ struct BwdParams {
   const float* add32;        // fp32 tensor added to the result (residual-stream gradient), ld = ldo
   // pass 2, optional: parameter gradients from `red` (fp32 atomics by the first row split of every image)
   float* dweight; float* dbias; float* dcol_scale; float* dfilm_gamma; float* dfilm_beta;
+  int wide;                  // fp32 output rows are 32-byte aligned (256-bit stores)
 };
 
 template <typename TG, typename TX, bool GELU>
-__global__ void __launch_bounds__(kNT, kBlocksPerSM)
+__global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 inorm_bwd_reduce_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, BwdParams p) {
-  pdl_prologue_done();
-  constexpr int NG = Slots<TG>::N, NSLOT = NG + Slots<TX>::N, S = Stages<NSLOT>::S;
-  extern __shared__ __align__(16) uint4 ring[];
+  BF_STREAM_SETUP()
   const Geom& g = p.g;
   const Ctx c = make_ctx(g);
   const int c0 = c.vcol * 8;
@@ -323,18 +415,20 @@ inorm_bwd_reduce_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, Bw
       }
     }
   }
-  const TG* gb = gin + ((long)c.img * g.P) * p.ldg + c0;
-  const TX* xb = x + ((long)c.img * g.P) * p.ldx + c0;
+  const long cb = (long)blockIdx.z * g.tx_n * 8;
+  StreamOps ops{};
+  ops.n = 2;
+  ops.base[0] = reinterpret_cast<const uint8_t*>(gin + ((long)c.img * g.P) * p.ldg + cb);
+  ops.pitch[0] = p.ldg * (long)sizeof(TG); ops.es[0] = sizeof(TG);
+  ops.base[1] = reinterpret_cast<const uint8_t*>(x + ((long)c.img * g.P) * p.ldx + cb);
+  ops.pitch[1] = p.ldx * (long)sizeof(TX); ops.es[1] = sizeof(TX);
   float acc[16];                                  // [0..8): sum g, [8..16): sum g*x
 #pragma unroll
   for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-#define ISSUE(row, st)                                                                  \
-  issue8<TG>(ring + ((st) * NSLOT) * kNT + threadIdx.x, gb + (long)(row) * p.ldg);      \
-  issue8<TX>(ring + ((st) * NSLOT + NG) * kNT + threadIdx.x, xb + (long)(row) * p.ldx);
-#define BODY(row, st)                                                                   \
+#define BODY(row, s0, s1, s2)                                                           \
   float gv[8], xv[8];                                                                   \
-  unpack8<TG>(ring + ((st) * NSLOT) * kNT + threadIdx.x, gv);                           \
-  unpack8<TX>(ring + ((st) * NSLOT + NG) * kNT + threadIdx.x, xv);                      \
+  ld8<TG>(s0, gv);                                                                      \
+  ld8<TX>(s1, xv);                                                                      \
   if (GELU && p.gelu == 1) {      /* tanh form: derivative of two elements per packed half-precision evaluation */ \
     _Pragma("unroll") for (int j = 0; j < 8; j += 2) {                                  \
       const float2 d2 = gelu_grad_h2(fmaf(xv[j], wa[j], wb[j]), fmaf(xv[j + 1], wa[j + 1], wb[j + 1])); \
@@ -347,28 +441,27 @@ inorm_bwd_reduce_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, Bw
     acc[j] += gg;                                                                       \
     acc[8 + j] = fmaf(gg, xv[j], acc[8 + j]);                                           \
   }
-  BF_STREAM_LOOP(S, ISSUE, BODY)
-#undef ISSUE
+  BF_STREAM_LOOP(ops, BODY)
 #undef BODY
   reduce_over_ty<16>(acc, reinterpret_cast<float*>(ring), g, c);
   if (c.active && c.ty == 0) {
     float* dst = p.red + ((long)c.img * g.C + c0) * 2;
+    float il[16];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       // sum g*xhat = rstd * (sum g*x - mean * sum g)
-      atomicAdd(dst + 2 * j, acc[j]);
-      atomicAdd(dst + 2 * j + 1, rstd[j] * (acc[8 + j] - mean[j] * acc[j]));
+      il[2 * j] = acc[j];
+      il[2 * j + 1] = rstd[j] * (acc[8 + j] - mean[j] * acc[j]);
     }
+    red_add<16>(dst, il);
   }
 }
 
 // backward, pass 2: dx = rstd*w*cs*(g - R1/P - xhat*R2/P) [+ add32]   ( = A*g + B*x + C0 per channel )
 template <typename TG, typename TX, typename TO, bool GELU, bool ADD>
-__global__ void __launch_bounds__(kNT, kBlocksPerSM)
+__global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 inorm_bwd_apply_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, TO* __restrict__ out, BwdParams p) {
-  pdl_prologue_done();
-  constexpr int NG = Slots<TG>::N, NX = Slots<TX>::N, NSLOT = NG + NX + (ADD ? 2 : 0), S = Stages<NSLOT>::S;
-  extern __shared__ __align__(16) uint4 ring[];
+  BF_STREAM_SETUP()
   const Geom& g = p.g;
   const Ctx c = make_ctx(g);
   const int c0 = c.vcol * 8;
@@ -407,18 +500,23 @@ inorm_bwd_apply_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, TO*
       }
     }
   }
-  const TG* gb = gin + ((long)c.img * g.P) * p.ldg + c0;
-  const TX* xb = x + ((long)c.img * g.P) * p.ldx + c0;
+  const long cb = (long)blockIdx.z * g.tx_n * 8;
+  StreamOps ops{};
+  ops.n = ADD ? 3 : 2;
+  ops.base[0] = reinterpret_cast<const uint8_t*>(gin + ((long)c.img * g.P) * p.ldg + cb);
+  ops.pitch[0] = p.ldg * (long)sizeof(TG); ops.es[0] = sizeof(TG);
+  ops.base[1] = reinterpret_cast<const uint8_t*>(x + ((long)c.img * g.P) * p.ldx + cb);
+  ops.pitch[1] = p.ldx * (long)sizeof(TX); ops.es[1] = sizeof(TX);
+  if (ADD) {
+    ops.base[2] = reinterpret_cast<const uint8_t*>(p.add32 + ((long)c.img * g.P) * p.ldo + cb);
+    ops.pitch[2] = p.ldo * 4; ops.es[2] = 4;
+  }
   TO* ob = out + ((long)c.img * g.P) * p.ldo + c0;
-  const float* ab = ADD ? p.add32 + ((long)c.img * g.P) * p.ldo + c0 : nullptr;
-#define ISSUE(row, st)                                                                  \
-  issue8<TG>(ring + ((st) * NSLOT) * kNT + threadIdx.x, gb + (long)(row) * p.ldg);      \
-  issue8<TX>(ring + ((st) * NSLOT + NG) * kNT + threadIdx.x, xb + (long)(row) * p.ldx); \
-  if (ADD) issue8<float>(ring + ((st) * NSLOT + NG + NX) * kNT + threadIdx.x, ab + (long)(row) * p.ldo);
-#define BODY(row, st)                                                                   \
+  const bool wide = p.wide != 0;
+#define BODY(row, s0, s1, s2)                                                           \
   float gv[8], xv[8], o[8];                                                             \
-  unpack8<TG>(ring + ((st) * NSLOT) * kNT + threadIdx.x, gv);                           \
-  unpack8<TX>(ring + ((st) * NSLOT + NG) * kNT + threadIdx.x, xv);                      \
+  ld8<TG>(s0, gv);                                                                      \
+  ld8<TX>(s1, xv);                                                                      \
   if (GELU && p.gelu == 1) {                                                            \
     _Pragma("unroll") for (int j = 0; j < 8; j += 2) {                                  \
       const float2 d2 = gelu_grad_h2(fmaf(xv[j], wa[j], wb[j]), fmaf(xv[j + 1], wa[j + 1], wb[j + 1])); \
@@ -432,12 +530,11 @@ inorm_bwd_apply_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, TO*
   }                                                                                     \
   if (ADD) {                                                                            \
     float av[8];                                                                        \
-    unpack8<float>(ring + ((st) * NSLOT + NG + NX) * kNT + threadIdx.x, av);            \
+    ld8<float>(s2, av);                                                                 \
     _Pragma("unroll") for (int j = 0; j < 8; ++j) o[j] += av[j];                        \
   }                                                                                     \
-  store8<TO>(ob + (long)(row) * p.ldo, o);
-  BF_STREAM_LOOP(S, ISSUE, BODY)
-#undef ISSUE
+  store8<TO>(ob + (long)(row) * p.ldo, o, wide);
+  BF_STREAM_LOOP(ops, BODY)
 #undef BODY
 }
 
@@ -507,13 +604,12 @@ struct ResidBwdParams {
   const float* coef;         // [C]
   void* dz16;                // out, ld = ldz, may be null
   float* S0; float* S1;      // [I][C] per-image sums
+  int wide;                  // fp32 validation backend: dz rows are 32-byte aligned
 };
 template <typename T16, bool HASZ>
-__global__ void __launch_bounds__(kNT, kBlocksPerSM)
+__global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 resid_bwd_kernel(ResidBwdParams p) {
-  pdl_prologue_done();
-  constexpr int NSLOT = 2 + (HASZ ? Slots<T16>::N : 0), S = Stages<NSLOT>::S;
-  extern __shared__ __align__(16) uint4 ring[];
+  BF_STREAM_SETUP()
   const Geom& g = p.g;
   const Ctx c = make_ctx(g);
   const int c0 = c.vcol * 8;
@@ -523,62 +619,63 @@ resid_bwd_kernel(ResidBwdParams p) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) cf[j] = p.coef[c0 + j] * rs;
   }
-  const float* db = p.dx + ((long)c.img * g.P) * p.lddx + c0;
-  const T16* zb = HASZ ? reinterpret_cast<const T16*>(p.z16) + ((long)c.img * g.P) * p.ldz + c0 : nullptr;
+  const long cb = (long)blockIdx.z * g.tx_n * 8;
+  StreamOps ops{};
+  ops.n = HASZ ? 2 : 1;
+  ops.base[0] = reinterpret_cast<const uint8_t*>(p.dx + ((long)c.img * g.P) * p.lddx + cb);
+  ops.pitch[0] = p.lddx * 4; ops.es[0] = 4;
+  if (HASZ) {
+    ops.base[1] = reinterpret_cast<const uint8_t*>(reinterpret_cast<const T16*>(p.z16) + ((long)c.img * g.P) * p.ldz + cb);
+    ops.pitch[1] = p.ldz * (long)sizeof(T16); ops.es[1] = sizeof(T16);
+  }
   T16* ob = p.dz16 ? reinterpret_cast<T16*>(p.dz16) + ((long)c.img * g.P) * p.ldz + c0 : nullptr;
   float acc[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-#define ISSUE(row, st)                                                                  \
-  issue8<float>(ring + ((st) * NSLOT) * kNT + threadIdx.x, db + (long)(row) * p.lddx);  \
-  if (HASZ) issue8<T16>(ring + ((st) * NSLOT + 2) * kNT + threadIdx.x, zb + (long)(row) * p.ldz);
-#define BODY(row, st)                                                                   \
+#define BODY(row, s0, s1, s2)                                                           \
   float dv[8], o[8];                                                                    \
-  unpack8<float>(ring + ((st) * NSLOT) * kNT + threadIdx.x, dv);                        \
+  ld8<float>(s0, dv);                                                                   \
   if (HASZ) {                                                                           \
     float zv[8];                                                                        \
-    unpack8<T16>(ring + ((st) * NSLOT + 2) * kNT + threadIdx.x, zv);                    \
+    ld8<T16>(s1, zv);                                                                   \
     _Pragma("unroll") for (int j = 0; j < 8; ++j) acc[8 + j] = fmaf(dv[j], zv[j], acc[8 + j]); \
   }                                                                                     \
   _Pragma("unroll") for (int j = 0; j < 8; ++j) { acc[j] += dv[j]; o[j] = cf[j] * dv[j]; } \
-  if (ob != nullptr) store8<T16>(ob + (long)(row) * p.ldz, o);
-  BF_STREAM_LOOP(S, ISSUE, BODY)
-#undef ISSUE
+  if (ob != nullptr) store8<T16>(ob + (long)(row) * p.ldz, o, p.wide != 0);
+  BF_STREAM_LOOP(ops, BODY)
 #undef BODY
   reduce_over_ty<16>(acc, reinterpret_cast<float*>(ring), g, c);
   if (c.active && c.ty == 0) {
+    float s0[8], s1[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(p.S0 + (long)c.img * g.C + c0 + j, rs * acc[j]);
-      if (HASZ) atomicAdd(p.S1 + (long)c.img * g.C + c0 + j, rs * acc[8 + j]);
-    }
+    for (int j = 0; j < 8; ++j) { s0[j] = rs * acc[j]; s1[j] = rs * acc[8 + j]; }
+    red_add<8>(p.S0 + (long)c.img * g.C + c0, s0);
+    if (HASZ) red_add<8>(p.S1 + (long)c.img * g.C + c0, s1);
   }
 }
 
 // column sums of a 16-bit matrix: out[c] += sum_rows x[r, c]   (bias gradients)
 template <typename T16>
-__global__ void __launch_bounds__(kNT, kBlocksPerSM)
+__global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 colsum16_kernel(const T16* __restrict__ x, long ldx, Geom g, float* __restrict__ out) {
-  pdl_prologue_done();
-  constexpr int NSLOT = Slots<T16>::N, S = Stages<NSLOT>::S;
-  extern __shared__ __align__(16) uint4 ring[];
+  BF_STREAM_SETUP()
   const Ctx c = make_ctx(g);
-  const T16* xb = x + ((long)c.img * g.P) * ldx + (long)c.vcol * 8;
+  StreamOps ops{};
+  ops.n = 1;
+  ops.base[0] = reinterpret_cast<const uint8_t*>(x + ((long)c.img * g.P) * ldx + (long)blockIdx.z * g.tx_n * 8);
+  ops.pitch[0] = ldx * (long)sizeof(T16); ops.es[0] = sizeof(T16);
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#define ISSUE(row, st) issue8<T16>(ring + (st) * NSLOT * kNT + threadIdx.x, xb + (long)(row) * ldx);
-#define BODY(row, st)                                                \
+#define BODY(row, s0, s1, s2)                                        \
   float v[8];                                                        \
-  unpack8<T16>(ring + (st) * NSLOT * kNT + threadIdx.x, v);          \
+  ld8<T16>(s0, v);                                                   \
   _Pragma("unroll") for (int j = 0; j < 8; ++j) acc[j] += v[j];
-  BF_STREAM_LOOP(S, ISSUE, BODY)
-#undef ISSUE
+  BF_STREAM_LOOP(ops, BODY)
 #undef BODY
   reduce_over_ty<8>(acc, reinterpret_cast<float*>(ring), g, c);
   if (c.active && c.ty == 0) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(out + (long)c.vcol * 8 + j, acc[j]);
+    red_add<8>(out + (long)c.vcol * 8, acc);
   }
 }
 
@@ -591,17 +688,21 @@ static int check_common(const char* fn, int I, int P, int C, long ld, const void
   return BF_OK;
 }
 
+static inline int es_of(int dtype) { return dtype == BF_F32 ? 4 : 2; }
+// fp32 rows that start on 32-byte boundaries take 256-bit stores
+static inline int wide_ok(const void* out, long ld) { return ((reinterpret_cast<uintptr_t>(out) & 31) == 0 && ld % 8 == 0) ? 1 : 0; }
+
 template <typename K>
 static int set_smem(K kern) {
-  return check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes),
+  return check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes),
                     "cudaFuncSetAttribute(norm)");
 }
-// launch with the 64 KiB ring; the attribute is set once per kernel instantiation
+// launch with the bulk-copy ring; the attribute is set once per kernel instantiation
 #define BF_NORM_LAUNCH(kern, grid, stream, ...)                                   \
   do {                                                                            \
     static bool done_ = false;                                                    \
     if (!done_) { if (int e_ = set_smem(kern)) return e_; done_ = true; }         \
-    launch_k(kern, dim3(grid), dim3(kNT), (size_t)(kRingBytes), stream, __VA_ARGS__);                         \
+    launch_k(kern, dim3(grid), dim3(kThreads), (size_t)(kSmemBytes), stream, __VA_ARGS__);                    \
   } while (0)
 
 }  // namespace bf
@@ -613,7 +714,7 @@ extern "C" int bf_inorm_stats(const void* x, int x_dtype, int I, int P, int C, i
   BF_REQUIRE(x && stats, "bf_inorm_stats: null pointer");
   BF_REQUIRE(x_dtype == BF_BF16 || x_dtype == BF_F16 || x_dtype == BF_F32, "bf_inorm_stats: dtype %d", x_dtype);
   if (int st = check_common("bf_inorm_stats", I, P, C, ldx, x)) return st;
-  const Geom g = make_geom(I, P, C);
+  const Geom g = make_geom(I, P, C, es_of(x_dtype));
   dim3 grid(g.splits, I, g.chunks);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (x_dtype == BF_F32) BF_NORM_LAUNCH(inorm_stats_kernel<float>, grid, s, (const float*)x, (long)ldx, g, stats);
@@ -634,7 +735,8 @@ extern "C" int bf_inorm_apply(const bf_inorm_apply_args* a, void* stream) {
   BF_REQUIRE(a->resid_in == nullptr || (a->out_dtype == BF_F32 && a->col_gamma), "bf_inorm_apply: residual needs f32 out");
   BF_REQUIRE(!(a->resid_in != nullptr && a->gelu), "bf_inorm_apply: gelu and the residual epilogue are exclusive");
   ApplyParams p{};
-  p.g = make_geom(a->I, a->P, a->C);
+  p.g = make_geom(a->I, a->P, a->C, es_of(a->x_dtype) + (a->resid_in != nullptr ? 4 : 0));
+  p.wide = wide_ok(a->out, a->ldo);
   p.ldx = a->ldx; p.ldo = a->ldo;
   p.stats = a->stats; p.weight = a->weight; p.bias = a->bias; p.gelu = a->gelu ? (gelu_exact() ? 2 : 1) : 0;
   p.film_gamma = a->film_gamma; p.film_beta = a->film_beta; p.film_T = a->film_T > 0 ? a->film_T : 1;
@@ -672,7 +774,8 @@ extern "C" int bf_inorm_bwd(const bf_inorm_bwd_args* a, void* stream) {
   BF_REQUIRE((reinterpret_cast<uintptr_t>(a->gin) & 15) == 0, "bf_inorm_bwd: gin must be 16-byte aligned");
   BF_REQUIRE(a->phase == 1 || a->phase == 2, "bf_inorm_bwd: phase %d", a->phase);
   BwdParams p{};
-  p.g = make_geom(a->I, a->P, a->C);
+  p.g = make_geom(a->I, a->P, a->C, es_of(a->g_dtype) + es_of(a->x_dtype) + ((a->phase == 2 && a->add32 != nullptr) ? 4 : 0));
+  p.wide = (a->phase == 2 && a->out != nullptr) ? wide_ok(a->out, a->ldo) : 0;
   p.ldg = a->ldg; p.ldx = a->ldx; p.ldo = a->ldo;
   p.stats = a->stats; p.weight = a->weight; p.bias = a->bias; p.gelu = a->gelu ? (gelu_exact() ? 2 : 1) : 0; p.red = a->red;
   p.row_scale = a->row_scale; p.col_scale = a->col_scale; p.film_gamma = a->film_gamma;
@@ -757,7 +860,8 @@ extern "C" int bf_resid_bwd(const float* dx, int64_t lddx, const void* z16, void
   if (int st = check_common("bf_resid_bwd", I, P, C, lddx, dx)) return st;
   BF_REQUIRE((z16 == nullptr && dz16 == nullptr) || (ldz >= C && ldz % 8 == 0), "bf_resid_bwd: ldz");
   ResidBwdParams p{};
-  p.g = make_geom(I, P, C);
+  p.g = make_geom(I, P, C, 4 + (z16 != nullptr ? es_of(dtype) : 0));
+  p.wide = dz16 != nullptr ? wide_ok(dz16, ldz) : 0;
   p.lddx = lddx; p.ldz = ldz;
   p.dx = dx; p.z16 = z16; p.row_scale = row_scale; p.coef = coef; p.dz16 = dz16; p.S0 = S0; p.S1 = S1;
   dim3 grid(p.g.splits, I, p.g.chunks);
@@ -782,7 +886,7 @@ extern "C" int bf_colsum16(const void* x, int dtype, int64_t rows, int C, int64_
   BF_REQUIRE(dtype == BF_BF16 || dtype == BF_F16 || dtype == BF_F32, "bf_colsum16: dtype");
   BF_REQUIRE(rows > 0 && rows < (1ll << 31), "bf_colsum16: rows");
   if (int st = check_common("bf_colsum16", 1, (int)rows, C, ldx, x)) return st;
-  const Geom g = make_geom(1, (int)rows, C);
+  const Geom g = make_geom(1, (int)rows, C, es_of(dtype));
   dim3 grid(g.splits, 1, g.chunks);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == BF_BF16) BF_NORM_LAUNCH(colsum16_kernel<__nv_bfloat16>, grid, s, (const __nv_bfloat16*)x, (long)ldx, g, out);
