@@ -77,6 +77,7 @@ class InormApplyArgs(C.Structure):
         ("film_T", C.c_int32), ("film_ld", C.c_int32),
         ("resid_in", C.c_void_p), ("row_scale", C.c_void_p), ("col_gamma", C.c_void_p),
         ("out", C.c_void_p), ("stats_out", C.c_void_p),
+        ("compute_stats", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 

@@ -26,6 +26,11 @@ constexpr int kThreads = kNT + 32;       // + the producer warp (warp 8)
 constexpr int kRingBytes = 96 * 1024;    // bulk-copy ring per block
 constexpr int kMaxStages = 8;
 constexpr int kSmemBytes = kRingBytes + 2 * kMaxStages * 8;
+// fused two-phase kernels (thread-block clusters): a smaller ring plus this block's per-channel partial sums
+constexpr int kFusedRingBytes = 80 * 1024;
+constexpr int kFusedMaxC = 1024;
+constexpr int kFusedSmemBytes = kRingBytes + 2 * kMaxStages * 8;   // ring (88 KiB) + partials (8 KiB) + barriers
+static_assert(kFusedRingBytes + 2 * kFusedMaxC * 2 * 4 <= kRingBytes, "fused layout");   // partials + totals
 constexpr int kBlocksPerSM = 2;
 constexpr int kStageTarget = 20 * 1024;  // bytes per stage aimed for (all operands)
 
@@ -90,7 +95,7 @@ struct Geom {
   int kk, rb, ns, stage_bytes;
 };
 // `sum_es`: bytes per element summed over the streamed input operands
-static Geom make_geom(int I, int P, int C, int sum_es) {
+static Geom make_geom(int I, int P, int C, int sum_es, int ring_bytes = kRingBytes, int max_splits_cap = 1 << 30) {
   Geom g;
   g.I = I; g.P = P; g.C = C;
   g.vc = C / 8;
@@ -104,6 +109,7 @@ static Geom make_geom(int I, int P, int C, int sum_es) {
   int splits = target / (I * g.chunks);
   const int max_splits = (P + g.ty_n - 1) / g.ty_n;             // at least one row per thread row
   if (splits > max_splits) splits = max_splits;
+  if (splits > max_splits_cap) splits = max_splits_cap;
   if (splits < 1) splits = 1;
   g.splits = splits;
   g.rows_per_split = (P + splits - 1) / splits;
@@ -115,7 +121,7 @@ static Geom make_geom(int I, int P, int C, int sum_es) {
   g.kk = kk;
   g.rb = kk * g.ty_n;
   g.stage_bytes = g.rb * g.tx_n * 8 * sum_es;
-  int ns = kRingBytes / g.stage_bytes;
+  int ns = ring_bytes / g.stage_bytes;
   if (ns > kMaxStages) ns = kMaxStages;
   g.ns = ns;
   return g;
@@ -182,11 +188,15 @@ struct StreamOps {
     fence_mbar_init();                                                                     \
   }                                                                                        \
   __syncthreads();                                                                         \
+  int st_ = 0; uint32_t ph_ = 0;        /* ring position: continues across consecutive loops */ \
   pdl_prologue_done();
 
 // The streaming loop.  `ops_` describes the inputs; BODY(row, s0, s1, s2) consumes one row: s0..s2 point at this thread's
 // 8 channels of each operand in shared memory.  The producer warp falls through to whatever follows the loop.
-#define BF_STREAM_LOOP(ops_, BODY)                                                         \
+#define BF_STREAM_LOOP(ops_, BODY) BF_STREAM_LOOP_(ops_, BODY, false)
+// REV_: walk the slab from its last row block to its first (second pass of a fused kernel: the rows read last in the
+// first pass are the most likely to still be in L2)
+#define BF_STREAM_LOOP_(ops_, BODY, REV_)                                                  \
   {                                                                                        \
     const int cw_ = g.tx_n * 8;                           /* channels per block row */     \
     const int nblk_ = c.r1 > c.r0 ? (c.r1 - c.r0 + g.rb - 1) / g.rb : 0;                   \
@@ -197,8 +207,8 @@ struct StreamOps {
     const int sum_es_ = (ops_).es[0] + (ops_).es[1] + (ops_).es[2];   /* unused operands have es = 0 */ \
     if (threadIdx.x >= kNT) {                                                              \
       const int lane_ = threadIdx.x & 31;                                                  \
-      int st_ = 0; uint32_t ph_ = 0;                                                       \
-      for (int b_ = 0; b_ < nblk_; ++b_) {                                                 \
+      for (int bb_ = 0; bb_ < nblk_; ++bb_) {                                              \
+        const int b_ = (REV_) ? nblk_ - 1 - bb_ : bb_;                                     \
         const int row_ = c.r0 + b_ * g.rb;                                                 \
         const int rows_ = min(g.rb, c.r1 - row_);                                          \
         if (lane_ == 0) {                                                                  \
@@ -221,8 +231,8 @@ struct StreamOps {
         if (++st_ == g.ns) { st_ = 0; ph_ ^= 1u; }                                         \
       }                                                                                    \
     } else {                                                                               \
-      int st_ = 0; uint32_t ph_ = 0;                                                       \
-      for (int b_ = 0; b_ < nblk_; ++b_) {                                                 \
+      for (int bb_ = 0; bb_ < nblk_; ++bb_) {                                              \
+        const int b_ = (REV_) ? nblk_ - 1 - bb_ : bb_;                                     \
         mbar_wait(full_ + st_, ph_);                                                       \
         if (c.active) {                                                                    \
           const uint8_t* sp_ = ring + st_ * g.stage_bytes;                                 \
@@ -538,6 +548,195 @@ inorm_bwd_apply_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, TO*
 #undef BODY
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fused two-phase kernels.  The slabs of ONE image form a thread-block cluster (<= 8 blocks, co-scheduled by the
+// hardware): every block reduces its slab, leaves its per-channel partial sums in its own shared memory, the cluster
+// synchronises, every block adds up all partials through distributed shared memory and streams its slab a second time
+// (back to front: out of L2, not HBM) to apply the result.  One launch, no global atomics, no zeroed buffers; the
+// reduced values are also written to global memory (by the first block of the cluster) for later consumers.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld_cluster_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// acc[16] of the ty == 0 threads -> this block's partial table -> sums over the cluster in tot[16] of every active thread.
+// Only the ty == 0 threads read the peers' tables (distributed shared memory); the block's other threads pick the totals
+// up from local shared memory (every thread reading every peer directly cost 25 us per launch at config 2).
+__device__ __forceinline__ void cluster_total16(float (&acc)[16], float (&tot)[16], float* part, const Geom& g, const Ctx& c) {
+  fence_proxy_async();        // the ring was used as reduction scratch (generic proxy); bulk copies refill it next
+  float* mine = part + c.tx * 16;
+  float* total = part + g.tx_n * 16 + c.tx * 16;
+  if (c.active && c.ty == 0) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4)
+      *reinterpret_cast<float4*>(mine + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+  }
+  cluster_sync_all();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) tot[j] = 0.f;
+  if (c.active && c.ty == 0) {
+    const uint32_t local = smem_u32(mine);
+    for (int r = 0; r < g.splits; ++r) {
+      const uint32_t remote = mapa_shared(local, (uint32_t)r);
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 v = ld_cluster_f4(remote + j * 4);
+        tot[j] += v.x; tot[j + 1] += v.y; tot[j + 2] += v.z; tot[j + 3] += v.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j += 4)
+      *reinterpret_cast<float4*>(total + j) = make_float4(tot[j], tot[j + 1], tot[j + 2], tot[j + 3]);
+  }
+  __syncthreads();
+  if (c.active && c.ty != 0) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(total + j);
+      tot[j] = v.x; tot[j + 1] = v.y; tot[j + 2] = v.z; tot[j + 3] = v.w;
+    }
+  }
+}
+
+// forward: statistics of x, then out = IN(x) * weight + bias
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(kThreads, kBlocksPerSM)
+inorm_fwd_fused_kernel(const TI* __restrict__ x, TO* __restrict__ out, ApplyParams p, float* __restrict__ stats_w) {
+  BF_STREAM_SETUP()
+  float* part = reinterpret_cast<float*>(ring + kFusedRingBytes);
+  const Geom& g = p.g;
+  const Ctx c = make_ctx(g);
+  const int c0 = c.vcol * 8;
+  StreamOps ops{};
+  ops.n = 1;
+  ops.base[0] = reinterpret_cast<const uint8_t*>(x + ((long)c.img * g.P) * p.ldx);
+  ops.pitch[0] = p.ldx * (long)sizeof(TI); ops.es[0] = sizeof(TI);
+  float acc[16], tot[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#define BODY(row, s0, s1, s2)                                                \
+  float v[8];                                                                \
+  ld8<TI>(s0, v);                                                            \
+  _Pragma("unroll") for (int j = 0; j < 8; ++j) { acc[j] += v[j]; acc[8 + j] = fmaf(v[j], v[j], acc[8 + j]); }
+  BF_STREAM_LOOP(ops, BODY)
+#undef BODY
+  reduce_over_ty<16>(acc, reinterpret_cast<float*>(ring), g, c);
+  cluster_total16(acc, tot, part, g, c);
+  const float inv_p = 1.f / (float)g.P;
+  float a[8], b[8];
+  if (c.active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float mean = tot[j] * inv_p;
+      const float rstd = rsqrtf(fmaxf(tot[8 + j] * inv_p - mean * mean, 0.f) + 1e-5f);
+      const float w = p.weight[c0 + j];
+      a[j] = rstd * w;
+      b[j] = p.bias[c0 + j] - mean * rstd * w;
+    }
+    if (blockIdx.x == 0 && c.ty == 0) {            // raw sums for the backward pass: [img][c][2]
+      float4* dst = reinterpret_cast<float4*>(stats_w + ((long)c.img * g.C + c0) * 2);
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) dst[j / 2] = make_float4(tot[j], tot[8 + j], tot[j + 1], tot[9 + j]);
+    }
+  }
+  TO* ob = out + ((long)c.img * g.P) * p.ldo + c0;
+  const bool wide = p.wide != 0;
+#define BODY(row, s0, s1, s2)                                                \
+  float v[8];                                                                \
+  ld8<TI>(s0, v);                                                            \
+  _Pragma("unroll") for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], a[j], b[j]); \
+  store8<TO>(ob + (long)(row) * p.ldo, v, wide);
+  BF_STREAM_LOOP_(ops, BODY, true)
+#undef BODY
+  cluster_sync_all();                              // nobody leaves while a peer may still read its partials
+}
+
+// backward: (sum g, sum g*xhat) per (image, channel), then dx = rstd*w*cs*(g - R1/P - xhat*R2/P) [+ add32]
+template <typename TG, typename TX, typename TO, bool ADD>
+__global__ void __launch_bounds__(kThreads, kBlocksPerSM)
+inorm_bwd_fused_kernel(const TG* __restrict__ gin, const TX* __restrict__ x, TO* __restrict__ out, BwdParams p) {
+  BF_STREAM_SETUP()
+  float* part = reinterpret_cast<float*>(ring + kFusedRingBytes);
+  const Geom& g = p.g;
+  const Ctx c = make_ctx(g);
+  const int c0 = c.vcol * 8;
+  StreamOps ops{};
+  ops.n = 2;
+  ops.base[0] = reinterpret_cast<const uint8_t*>(gin + ((long)c.img * g.P) * p.ldg);
+  ops.pitch[0] = p.ldg * (long)sizeof(TG); ops.es[0] = sizeof(TG);
+  ops.base[1] = reinterpret_cast<const uint8_t*>(x + ((long)c.img * g.P) * p.ldx);
+  ops.pitch[1] = p.ldx * (long)sizeof(TX); ops.es[1] = sizeof(TX);
+  float acc[16], tot[16];                          // [0..8): sum g, [8..16): sum g*x
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#define BODY(row, s0, s1, s2)                                                \
+  float gv[8], xv[8];                                                        \
+  ld8<TG>(s0, gv);                                                           \
+  ld8<TX>(s1, xv);                                                           \
+  _Pragma("unroll") for (int j = 0; j < 8; ++j) { acc[j] += gv[j]; acc[8 + j] = fmaf(gv[j], xv[j], acc[8 + j]); }
+  BF_STREAM_LOOP(ops, BODY)
+#undef BODY
+  reduce_over_ty<16>(acc, reinterpret_cast<float*>(ring), g, c);
+  cluster_total16(acc, tot, part, g, c);
+  const float inv_p = 1.f / (float)g.P;
+  float ka[8], kb[8], kc[8];
+  if (c.active) {
+    float r1v[8], r2v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const long idx = (long)c.img * g.C + c0 + j;
+      float mean, rstd;
+      mean_rstd(p.stats, idx, inv_p, mean, rstd);
+      const float R1 = tot[j], R2 = rstd * (tot[8 + j] - mean * tot[j]);
+      r1v[j] = R1; r2v[j] = R2;
+      const float w = p.weight[c0 + j];
+      float cs = 1.f;
+      if (p.row_scale != nullptr) cs *= p.row_scale[c.img];
+      if (p.col_scale != nullptr) cs *= p.col_scale[c0 + j];
+      const float k = rstd * w * cs;
+      const float m1 = R1 * inv_p, m2 = R2 * inv_p;
+      ka[j] = k;
+      kb[j] = -k * m2 * rstd;
+      kc[j] = -k * m1 + k * m2 * rstd * mean;
+      if (blockIdx.x == 0 && c.ty == 0 && p.dweight != nullptr) {
+        const float b = p.bias[c0 + j];
+        atomicAdd(p.dweight + c0 + j, cs * R2);
+        atomicAdd(p.dbias + c0 + j, cs * R1);
+        if (p.dcol_scale != nullptr)
+          atomicAdd(p.dcol_scale + c0 + j, (p.row_scale != nullptr ? p.row_scale[c.img] : 1.f) * fmaf(w, R2, b * R1));
+      }
+    }
+    if (blockIdx.x == 0 && c.ty == 0) {
+      float4* dst = reinterpret_cast<float4*>(p.red + ((long)c.img * g.C + c0) * 2);
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) dst[j / 2] = make_float4(r1v[j], r2v[j], r1v[j + 1], r2v[j + 1]);
+    }
+  }
+  if (ADD) {
+    ops.n = 3;
+    ops.base[2] = reinterpret_cast<const uint8_t*>(p.add32 + ((long)c.img * g.P) * p.ldo);
+    ops.pitch[2] = p.ldo * 4; ops.es[2] = 4;
+  }
+  TO* ob = out + ((long)c.img * g.P) * p.ldo + c0;
+  const bool wide = p.wide != 0;
+#define BODY(row, s0, s1, s2)                                                \
+  float gv[8], xv[8], o[8];                                                  \
+  ld8<TG>(s0, gv);                                                           \
+  ld8<TX>(s1, xv);                                                           \
+  _Pragma("unroll") for (int j = 0; j < 8; ++j) o[j] = fmaf(ka[j], gv[j], fmaf(kb[j], xv[j], kc[j])); \
+  if (ADD) {                                                                 \
+    float av[8];                                                             \
+    ld8<float>(s2, av);                                                      \
+    _Pragma("unroll") for (int j = 0; j < 8; ++j) o[j] += av[j];             \
+  }                                                                          \
+  store8<TO>(ob + (long)(row) * p.ldo, o, wide);
+  BF_STREAM_LOOP_(ops, BODY, true)
+#undef BODY
+  cluster_sync_all();
+}
+
 // parameter gradients from the per-(image, channel) reductions: 32 channels x 8 image lanes per block
 struct BwdParamArgs {
   const float* red; const float* stats;
@@ -705,6 +904,68 @@ static int set_smem(K kern) {
     launch_k(kern, dim3(grid), dim3(kThreads), (size_t)(kSmemBytes), stream, __VA_ARGS__);                    \
   } while (0)
 
+// same, as one thread-block cluster per image (fused two-phase kernels)
+template <typename K>
+static void debug_cluster_occupancy(K kern, dim3 grid, unsigned cluster_x) {
+  if (getenv("BF_DEBUG_OCC") == nullptr) return;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster_x; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = -1;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+  int per_sm = -1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, kSmemBytes);
+  cudaFuncAttributes fa{};
+  cudaFuncGetAttributes(&fa, kern);
+  fprintf(stderr, "[bf] cluster kernel: grid %u x %u cluster %u -> max active clusters %d (%s), blocks/SM %d, regs %d\n", grid.x, grid.y,
+          cluster_x, n, cudaGetErrorString(e), per_sm, fa.numRegs);
+}
+#define BF_NORM_LAUNCH_CLUSTER(kern, grid, cluster_x, stream, ...)                \
+  do {                                                                            \
+    static bool done_ = false;                                                    \
+    if (!done_) { if (int e_ = set_smem(kern)) return e_; done_ = true; debug_cluster_occupancy(kern, dim3(grid), cluster_x); } \
+    launch_k_cluster(kern, dim3(grid), dim3(kThreads), (size_t)(kSmemBytes), stream, (unsigned)(cluster_x), __VA_ARGS__); \
+  } while (0)
+
+// How many clusters of `cs` fused-kernel blocks the device can hold at once (cudaOccupancyMaxActiveClusters; all fused
+// instantiations share block size, shared memory and the 2-blocks-per-SM register bound).  Cached per cluster size.
+static int max_active_clusters(int cs) {
+  static int cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (cs < 1 || cs > 8) return 0;
+  if (cache[cs] == 0) {
+    auto kern = inorm_fwd_fused_kernel<__nv_bfloat16, __nv_bfloat16>;
+    if (set_smem(kern) != BF_OK) return 0;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(cs, 64, 1); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = -1; }
+    cache[cs] = n > 0 ? n : -1;
+  }
+  return cache[cs] > 0 ? cache[cs] : 0;
+}
+
+// The fused kernels need the whole image in one cluster (<= 8 slabs), one column chunk, ALL clusters resident at once
+// (a second wave of a few clusters doubles the time: measured with 7-block clusters, 37 of 40 fit) and enough blocks to
+// fill the machine (otherwise two launches of a full wave are faster).  BF_NORM_FUSED=0 forces the two-launch form.
+static bool fused_geom(int I, int P, int C, int sum_es, Geom* g) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("BF_NORM_FUSED"); on = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  if (!on || C > kFusedMaxC || C / 8 > kNT) return false;
+  int cs = 8;
+  while (cs >= 2 && max_active_clusters(cs) < I) --cs;
+  if (cs < 2) return false;
+  *g = make_geom(I, P, C, sum_es, kFusedRingBytes, cs);
+  if (g->chunks != 1 || g->ns < 2) return false;
+  return (long)I * g->splits >= num_sms();
+}
+
 }  // namespace bf
 
 using namespace bf;
@@ -734,6 +995,37 @@ extern "C" int bf_inorm_apply(const bf_inorm_apply_args* a, void* stream) {
   BF_REQUIRE(a->film_gamma == nullptr || (a->film_T > 0 && a->I % a->film_T == 0), "bf_inorm_apply: film_T");
   BF_REQUIRE(a->resid_in == nullptr || (a->out_dtype == BF_F32 && a->col_gamma), "bf_inorm_apply: residual needs f32 out");
   BF_REQUIRE(!(a->resid_in != nullptr && a->gelu), "bf_inorm_apply: gelu and the residual epilogue are exclusive");
+  if (a->compute_stats) {
+    // `stats` is an output here: one fused launch when the shape allows it, otherwise statistics pass + this call again
+    const bool plain = !a->gelu && a->film_gamma == nullptr && a->resid_in == nullptr && a->stats_out == nullptr;
+    Geom fg;
+    const int xi = a->x_dtype, xo = a->out_dtype;
+    const bool types = (xi == BF_BF16 && xo == BF_BF16) || (xi == BF_F32 && xo == BF_BF16) || (xi == BF_F32 && xo == BF_F32) ||
+                       (xi == BF_F16 && xo == BF_F16);
+    if (plain && types && fused_geom(a->I, a->P, a->C, es_of(xi), &fg)) {
+      ApplyParams p{};
+      p.g = fg;
+      p.wide = wide_ok(a->out, a->ldo);
+      p.ldx = a->ldx; p.ldo = a->ldo;
+      p.weight = a->weight; p.bias = a->bias;
+      dim3 grid(fg.splits, a->I, 1);
+      cudaStream_t s = static_cast<cudaStream_t>(stream);
+      float* sw = const_cast<float*>(a->stats);
+      if (xi == BF_BF16) BF_NORM_LAUNCH_CLUSTER((inorm_fwd_fused_kernel<__nv_bfloat16, __nv_bfloat16>), grid, fg.splits, s, (const __nv_bfloat16*)a->x, (__nv_bfloat16*)a->out, p, sw);
+      else if (xi == BF_F16) BF_NORM_LAUNCH_CLUSTER((inorm_fwd_fused_kernel<__half, __half>), grid, fg.splits, s, (const __half*)a->x, (__half*)a->out, p, sw);
+      else if (xo == BF_BF16) BF_NORM_LAUNCH_CLUSTER((inorm_fwd_fused_kernel<float, __nv_bfloat16>), grid, fg.splits, s, (const float*)a->x, (__nv_bfloat16*)a->out, p, sw);
+      else BF_NORM_LAUNCH_CLUSTER((inorm_fwd_fused_kernel<float, float>), grid, fg.splits, s, (const float*)a->x, (float*)a->out, p, sw);
+      count_launch();
+      BF_LAUNCH_CHECK("inorm_fwd_fused_kernel");
+      return BF_OK;
+    }
+    if (int st = check_cuda(cudaMemsetAsync(const_cast<float*>(a->stats), 0, (size_t)a->I * a->C * 2 * sizeof(float),
+                                            static_cast<cudaStream_t>(stream)), "cudaMemsetAsync(stats)")) return st;
+    if (int st = bf_inorm_stats(a->x, a->x_dtype, a->I, a->P, a->C, a->ldx, const_cast<float*>(a->stats), stream)) return st;
+    bf_inorm_apply_args b = *a;
+    b.compute_stats = 0;
+    return bf_inorm_apply(&b, stream);
+  }
   ApplyParams p{};
   p.g = make_geom(a->I, a->P, a->C, es_of(a->x_dtype) + (a->resid_in != nullptr ? 4 : 0));
   p.wide = wide_ok(a->out, a->ldo);
@@ -772,7 +1064,52 @@ extern "C" int bf_inorm_bwd(const bf_inorm_bwd_args* a, void* stream) {
   if (int st = check_common("bf_inorm_bwd", a->I, a->P, a->C, a->ldx, a->x)) return st;
   BF_REQUIRE(a->ldg >= a->C && a->ldg % 8 == 0, "bf_inorm_bwd: ldg");
   BF_REQUIRE((reinterpret_cast<uintptr_t>(a->gin) & 15) == 0, "bf_inorm_bwd: gin must be 16-byte aligned");
-  BF_REQUIRE(a->phase == 1 || a->phase == 2, "bf_inorm_bwd: phase %d", a->phase);
+  BF_REQUIRE(a->phase == 1 || a->phase == 2 || a->phase == 3, "bf_inorm_bwd: phase %d", a->phase);
+  if (a->phase == 3) {
+    // both phases; `red` is an output (no zeroing by the caller).  One fused launch when the shape allows it.
+    BF_REQUIRE(a->out, "bf_inorm_bwd: out required in phase 3");
+    BF_REQUIRE(a->ldo >= a->C && a->ldo % 8 == 0, "bf_inorm_bwd: ldo");
+    BF_REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "bf_inorm_bwd: out must be 16-byte aligned");
+    const int gd = a->g_dtype, xd = a->x_dtype, od = a->out_dtype;
+    const bool add = a->add32 != nullptr;
+    const bool plain = !a->gelu && a->film_gamma == nullptr && a->dfilm_gamma == nullptr;
+    const int combo = (gd == BF_BF16 && xd == BF_BF16 && od == BF_BF16 && !add) ? 1
+                    : (gd == BF_BF16 && xd == BF_F32 && od == BF_F32) ? 2
+                    : (gd == BF_F32 && xd == BF_BF16 && od == BF_BF16 && !add) ? 3
+                    : (gd == BF_F32 && xd == BF_F32 && od == BF_F32) ? 4 : 0;
+    Geom fg;
+    if (plain && combo != 0 && fused_geom(a->I, a->P, a->C, es_of(gd) + es_of(xd) + (add ? 4 : 0), &fg)) {
+      BwdParams p{};
+      p.g = fg;
+      p.wide = wide_ok(a->out, a->ldo);
+      p.ldg = a->ldg; p.ldx = a->ldx; p.ldo = a->ldo;
+      p.stats = a->stats; p.weight = a->weight; p.bias = a->bias; p.red = a->red;
+      p.row_scale = a->row_scale; p.col_scale = a->col_scale; p.add32 = a->add32;
+      p.film_T = 1; p.film_ld = a->C;
+      p.dweight = a->dweight; p.dbias = a->dbias; p.dcol_scale = a->dcol_scale;
+      BF_REQUIRE((a->dweight == nullptr) == (a->dbias == nullptr), "bf_inorm_bwd: dweight / dbias pair");
+      BF_REQUIRE(a->dweight != nullptr || a->dcol_scale == nullptr, "bf_inorm_bwd: dcol_scale needs dweight / dbias as well");
+      dim3 grid(fg.splits, a->I, 1);
+      cudaStream_t s = static_cast<cudaStream_t>(stream);
+      typedef __nv_bfloat16 bf16;
+#define BF_FUSED(TG, TX, TO, ADD_) BF_NORM_LAUNCH_CLUSTER((inorm_bwd_fused_kernel<TG, TX, TO, ADD_>), grid, fg.splits, s, (const TG*)a->gin, (const TX*)a->x, (TO*)a->out, p)
+      if (combo == 1) BF_FUSED(bf16, bf16, bf16, false);
+      else if (combo == 2) { if (add) BF_FUSED(bf16, float, float, true); else BF_FUSED(bf16, float, float, false); }
+      else if (combo == 3) BF_FUSED(float, bf16, bf16, false);
+      else { if (add) BF_FUSED(float, float, float, true); else BF_FUSED(float, float, float, false); }
+#undef BF_FUSED
+      count_launch();
+      BF_LAUNCH_CHECK("inorm_bwd_fused_kernel");
+      return BF_OK;
+    }
+    if (int st = check_cuda(cudaMemsetAsync(a->red, 0, (size_t)a->I * a->C * 2 * sizeof(float), static_cast<cudaStream_t>(stream)),
+                            "cudaMemsetAsync(red)")) return st;
+    bf_inorm_bwd_args b = *a;
+    b.phase = 1;
+    if (int st = bf_inorm_bwd(&b, stream)) return st;
+    b.phase = 2;
+    return bf_inorm_bwd(&b, stream);
+  }
   BwdParams p{};
   p.g = make_geom(a->I, a->P, a->C, es_of(a->g_dtype) + es_of(a->x_dtype) + ((a->phase == 2 && a->add32 != nullptr) ? 4 : 0));
   p.wide = (a->phase == 2 && a->out != nullptr) ? wide_ok(a->out, a->ldo) : 0;

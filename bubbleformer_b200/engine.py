@@ -32,6 +32,11 @@ EXACT = False
 import os as _os
 MLP_SAVES_DERIVATIVE = _os.environ.get("BF_MLP_DERIV", "1") != "0"     # fc1 stores gelu'(pre); 0: stores pre, dGELU epilogue
 DMUL_BN = int(_os.environ.get("BF_DMUL_BN", "0"))                       # N tile of the fc2 input-gradient GEMM (0 = automatic)
+# Cluster-fused InstanceNorm calls (statistics + apply, reduce + apply in ONE launch; csrc/norm.cu).  Measured on B200 at
+# config 2 (same-box A/B of the replayed step, gpurun_out/r2t_*): 26.22 vs 26.22 ms -- the second launch of the two-launch
+# form already finds its operands in L2 and overlaps its prologue with the first through PDL, so the fusion buys nothing,
+# and 40 six-block clusters leave fewer blocks in flight than a full wave.  Opt-in.
+NORM_FUSED = _os.environ.get("BF_NORM_FUSED", "0") == "1"
 
 
 def set_exact_mode(on: bool) -> None:
@@ -174,6 +179,30 @@ def _take_stats(X: torch.Tensor) -> Optional[torch.Tensor]:
     return None
 
 
+def _norm_fwd(x, out, I, P, weight, bias) -> torch.Tensor:
+    """out = InstanceNorm(x) * weight + bias; returns the raw statistics (I, C, 2) for the backward pass."""
+    C_ = x.shape[1]
+    if NORM_FUSED:
+        st = _empty((I, C_, 2), F32, x)
+        ops.inorm_apply(x, out, I, P, st, weight, bias, compute_stats=True)
+    else:
+        st = _zeros((I, C_, 2), x)
+        ops.inorm_stats(x, I, P, st)
+        ops.inorm_apply(x, out, I, P, st, weight, bias)
+    return st
+
+
+def _norm_bwd(gin, x, I, P, stats, weight, bias, **kw) -> None:
+    """InstanceNorm backward (reduce + apply, parameter gradients accumulated by the apply launch)."""
+    C_ = x.shape[1]
+    if NORM_FUSED:
+        ops.inorm_bwd(3, gin, x, I, P, stats, weight, bias, _empty((I, C_, 2), F32, x), **kw)
+    else:
+        red = _zeros((I, C_, 2), x)
+        ops.inorm_bwd(1, gin, x, I, P, stats, weight, bias, red)
+        ops.inorm_bwd(2, gin, x, I, P, stats, weight, bias, red, **kw)
+
+
 def _axis(g: Geom, axis: str) -> dict:
     P = g.P
     if axis == "t":
@@ -190,11 +219,11 @@ def _attn_branch_fwd(X, g: Geom, p: Dict[str, torch.Tensor], w16, heads: int, ax
                      mask_img, col_scale, col_shift, gamma, want_x16: bool, save: bool, want_stats: bool = False):
     I, P, N, E = g.I, g.P, g.N, X.shape[1]
     st1 = _take_stats(X)
-    if st1 is None:
-        st1 = _zeros((I, E, 2), X)
-        ops.inorm_stats(X, I, P, st1)
     Xn = _empty((N, E), BF16, X)
-    ops.inorm_apply(X, Xn, I, P, st1, p["norm1.weight"], p["norm1.bias"])
+    if st1 is None:      # no producer accumulated them
+        st1 = _norm_fwd(X, Xn, I, P, p["norm1.weight"], p["norm1.bias"])
+    else:
+        ops.inorm_apply(X, Xn, I, P, st1, p["norm1.weight"], p["norm1.bias"])
     QKV = _empty((N, 3 * E), BF16, X)
     # head_dim 64 and axes of up to 64 tokens: LayerNorm(q), LayerNorm(k) are computed in the QKV GEMM epilogue (xhat +
     # rstd) and the attention kernels work on the pre-normalised rows; otherwise the generic kernels normalise in place
@@ -214,10 +243,8 @@ def _attn_branch_fwd(X, g: Geom, p: Dict[str, torch.Tensor], w16, heads: int, ax
                       kn_b=p["knorm.bias"], bias_emb=p["rel_pos_bias.relative_attention_bias.weight"],
                       bucket=relpos_bucket_vector(geo["L_"], X.device), scale_factor=sf, out_scale=oscale,
                       accumulate=i > 0, prenorm=prenorm, **geo)
-    st2 = _zeros((I, E, 2), X)
-    ops.inorm_stats(O, I, P, st2)
     On = _empty((N, E), BF16, X)
-    ops.inorm_apply(O, On, I, P, st2, p["norm2.weight"], p["norm2.bias"])
+    st2 = _norm_fwd(O, On, I, P, p["norm2.weight"], p["norm2.bias"])
     Xout = _empty((N, E), F32, X)
     Z = _empty((N, E), BF16, X) if save else None
     X16 = _empty((N, E), BF16, X) if want_x16 else None
@@ -250,11 +277,9 @@ def _attn_branch_bwd(dXout, g: Geom, p, w16, heads: int, axes, scale_keys, mask_
     ops.gemm(dZ, On, E, E, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN, split_k=pick_split(N, E, E),
              out32=grads["output_head.weight"].view(E, E))
     # norm2
-    red2 = _zeros((I, E, 2), dXout)
-    ops.inorm_bwd(1, dOn, O, I, P, st2, p["norm2.weight"], p["norm2.bias"], red2)
     dO = _empty((N, E), BF16, dXout)
-    ops.inorm_bwd(2, dOn, O, I, P, st2, p["norm2.weight"], p["norm2.bias"], red2, out=dO,
-                  dweight=grads["norm2.weight"], dbias=grads["norm2.bias"])
+    _norm_bwd(dOn, O, I, P, st2, p["norm2.weight"], p["norm2.bias"], out=dO,
+              dweight=grads["norm2.weight"], dbias=grads["norm2.bias"])
     # attention(s)
     dQKV = _empty((N, 3 * E), BF16, dXout)
     oscale = 1.0 / len(axes)
@@ -283,11 +308,9 @@ def _attn_branch_bwd(dXout, g: Geom, p, w16, heads: int, axes, scale_keys, mask_
     ops.gemm(dQKV, Xn, 3 * E, E, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
              split_k=pick_split(N, 3 * E, E), out32=grads["input_head.weight"].view(3 * E, E))
     # norm1 (+ the identity path of the residual)
-    red1 = _zeros((I, E, 2), dXout)
-    ops.inorm_bwd(1, dXn, X, I, P, st1, p["norm1.weight"], p["norm1.bias"], red1)
     dX = _empty((N, E), F32, dXout)
-    ops.inorm_bwd(2, dXn, X, I, P, st1, p["norm1.weight"], p["norm1.bias"], red1, out=dX, add32=dXout,
-                  dweight=grads["norm1.weight"], dbias=grads["norm1.bias"])
+    _norm_bwd(dXn, X, I, P, st1, p["norm1.weight"], p["norm1.bias"], out=dX, add32=dXout,
+              dweight=grads["norm1.weight"], dbias=grads["norm1.bias"])
     return dX, S01
 
 
@@ -360,10 +383,8 @@ def spatial_backward(dXout, g: Geom, p, w16, heads: int, attn_scale: bool, feat_
     E = dXout.shape[1]
     Xb, G, Hpre, Y2, st3 = (sv[k] for k in ("Xb", "G", "Hpre", "Y2", "st3"))
     # ---- MLP branch: X_out = X_mid + mask*gamma_mlp*IN(Y2) ----
-    red3 = _zeros((I, E, 2), dXout)
-    ops.inorm_bwd(1, dXout, Y2, I, P, st3, p["mlp_norm.weight"], p["mlp_norm.bias"], red3)
     dY2 = _empty((N, E), BF16, dXout)
-    ops.inorm_bwd(2, dXout, Y2, I, P, st3, p["mlp_norm.weight"], p["mlp_norm.bias"], red3, out=dY2,
+    _norm_bwd(dXout, Y2, I, P, st3, p["mlp_norm.weight"], p["mlp_norm.bias"], out=dY2,
                   row_scale=mask_mlp, col_scale=p["gamma_mlp"], dweight=grads["mlp_norm.weight"],
                   dbias=grads["mlp_norm.bias"], dcol_scale=grads["gamma_mlp"])
     # fc2 (its bias feeds an InstanceNorm, so its gradient is identically zero and stays zero)

@@ -127,7 +127,9 @@ def _film_ptrs(film_gb: torch.Tensor, C_: int):
 
 
 def inorm_apply(x, out, I, P, stats, weight, bias, *, gelu=False, film_gamma=None, film_beta=None, film_T=0,
-                film_gb=None, resid_in=None, row_scale=None, col_gamma=None, stats_out=None) -> None:
+                film_gb=None, resid_in=None, row_scale=None, col_gamma=None, stats_out=None,
+                compute_stats=False) -> None:
+    """compute_stats: `stats` is an output (any contents on entry): statistics pass and apply in one call / launch."""
     _mat(x, "x"); _mat(out, "out")
     C_ = x.shape[1]
     a = L.InormApplyArgs()
@@ -149,6 +151,7 @@ def inorm_apply(x, out, I, P, stats, weight, bias, *, gelu=False, film_gamma=Non
     a.col_gamma = _f32(col_gamma, C_, "col_gamma")
     a.out = _ptr(out)
     a.stats_out = _f32(stats_out, I * C_ * 2, "stats_out")
+    a.compute_stats = int(compute_stats)
     L.check(L.lib.bf_inorm_apply(C.byref(a), _stream()), "bf_inorm_apply")
 
 

@@ -166,13 +166,21 @@ typedef struct bf_inorm_apply_args {
   void* out;
   float* stats_out;           /* [I][C][2] or NULL: += (sum, sum^2) of the values written to `out`, i.e. the raw
                                  statistics the NEXT InstanceNorm needs (saves its separate pass)               */
+  int32_t compute_stats;      /* 1: `stats` is an OUTPUT (no zeroing needed): the call first computes the statistics of
+                                 x and then applies them.  For plain calls (no gelu / film / residual) on block-sized
+                                 tensors this is ONE launch: the slabs of an image form a thread-block cluster, exchange
+                                 their partial sums through distributed shared memory and re-read x from L2.        */
+  int32_t reserved_;
 } bf_inorm_apply_args;
 BF_API int bf_inorm_apply(const bf_inorm_apply_args* args, void* stream);
 
 /* Backward of y = [gelu](IN(x)) given gin = dL/dy (times an optional per-(image, channel) scale
  * cs = row_scale[img]*col_scale[c]*film_gamma[img/film_T][c] that sat between y and the consumer).
  * phase 1: red[img][c] += (sum g, sum g*xhat), g = gin [* gelu'(.)]         (red zeroed by the caller)
- * phase 2: out = rstd*w*cs*(g - R1/P - xhat*R2/P) [+ add32]                                            */
+ * phase 2: out = rstd*w*cs*(g - R1/P - xhat*R2/P) [+ add32]
+ * phase 3: both; `red` is an output and need not be zeroed.  Without gelu / film on block-sized tensors this is ONE
+ *          launch (one thread-block cluster per image, partial sums exchanged through distributed shared memory,
+ *          second read of gin / x out of L2); otherwise it runs phase 1 and phase 2 back to back.             */
 typedef struct bf_inorm_bwd_args {
   int32_t phase;  int32_t gelu;
   const void* gin;  int32_t g_dtype;  int32_t x_dtype;

@@ -11,7 +11,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-GROUPS = ["params", "stats", "apply", "inorm_bwd", "resid_colsum", "attn_x", "attn_y", "attn_t", "attn_d48", "attn_l64",
+GROUPS = ["params", "stats", "apply", "inorm_bwd", "inorm_fused", "resid_colsum", "attn_x", "attn_y", "attn_t", "attn_d48", "attn_l64",
           "attn_noscale", "attn_l128", "attn_l64_big", "attn_l40", "patch", "misc", "film", "gelu_modes"]
 
 
@@ -142,6 +142,55 @@ def run(group):
             if fg is not None:
                 ok &= report(f"   dfilm_gamma", dfg, fg.grad, 1e-2)
                 ok &= report(f"   dfilm_beta", dfb, fb.grad, 1e-2)
+    elif group == "inorm_fused":
+        # statistics + apply (compute_stats) and reduce + apply (phase 3) in one call: (40, 256, 128) and (40, 1024, 384)
+        # take the cluster-fused kernels (one cluster of 7 slabs per image), (3, 64, 96) the two-launch fallback
+        for (I, P, Cn) in [(40, 256, 128), (40, 1024, 384), (3, 64, 96), (20, 640, 768)]:
+            w, b = torch.randn(Cn, device=dev), torch.randn(Cn, device=dev)
+            for (din, dout) in [(torch.bfloat16, torch.bfloat16), (torch.float32, torch.bfloat16), (torch.float32, torch.float32)]:
+                x = (torch.randn(I * P, Cn, device=dev) * 1.7 + 0.3).to(din)
+                st = torch.full((I, Cn, 2), float("nan"), device=dev)          # an output: any contents on entry
+                out = torch.zeros(I * P, Cn, device=dev, dtype=dout)
+                ops.inorm_apply(x, out, I, P, st, w, b, compute_stats=True)
+                xi = x.float().reshape(I, P, Cn)
+                ok &= report(f"fused stats {I}x{P}x{Cn} {din}", st, torch.stack([xi.sum(1), (xi * xi).sum(1)], dim=-1), 1e-5)
+                ok &= report(f"fused apply {I}x{P}x{Cn} {din}->{dout}", out, inorm_ref(x, I, P, w, b),
+                             1e-5 if dout == torch.float32 else 6e-3)
+            for (dx_, dg_, dout_, mode) in [(torch.bfloat16, torch.bfloat16, torch.bfloat16, "plain"),
+                                            (torch.float32, torch.bfloat16, torch.float32, "add"),
+                                            (torch.float32, torch.bfloat16, torch.float32, "plain"),
+                                            (torch.bfloat16, torch.float32, torch.bfloat16, "scale"),
+                                            (torch.float32, torch.float32, torch.float32, "add")]:
+                x = (torch.randn(I * P, Cn, device=dev) * 1.5 + 0.2).to(dx_)
+                wg = (1 + 0.1 * torch.randn(Cn, device=dev)).requires_grad_(True)
+                bg = (0.1 * torch.randn(Cn, device=dev)).requires_grad_(True)
+                gin = torch.randn(I * P, Cn, device=dev).to(dg_)
+                x32 = x.float().requires_grad_(True)
+                y = inorm_ref(x32, I, P, wg, bg)
+                kw = {}
+                cs = None
+                if mode == "scale":
+                    rs = torch.rand(I, device=dev)
+                    cs = torch.randn(Cn, device=dev).requires_grad_(True)
+                    y = rs.repeat_interleave(P)[:, None] * cs * y
+                    kw.update(row_scale=rs, col_scale=cs.detach())
+                (y * gin.float()).sum().backward()
+                st = torch.zeros(I, Cn, 2, device=dev)
+                ops.inorm_stats(x, I, P, st)
+                red = torch.full((I, Cn, 2), float("nan"), device=dev)
+                out = torch.zeros(I * P, Cn, device=dev, dtype=dout_)
+                add = torch.randn(I * P, Cn, device=dev) if mode == "add" else None
+                dw, db, dcs = (torch.zeros(Cn, device=dev) for _ in range(3))
+                ops.inorm_bwd(3, gin, x, I, P, st, wg.detach(), bg.detach(), red, out=out, add32=add, dweight=dw, dbias=db,
+                              dcol_scale=dcs if cs is not None else None, **kw)
+                want = x32.grad + (add if add is not None else 0)
+                tol = 1e-4 if dout_ == torch.float32 and dx_ == torch.float32 and dg_ == torch.float32 else 1e-2
+                ok &= report(f"fused bwd {I}x{P}x{Cn} x={dx_} g={dg_} {mode}", out, want, tol)
+                ok &= report(f"   dweight", dw, wg.grad, 1e-2)
+                ok &= report(f"   dbias", db, bg.grad, 1e-2)
+                if cs is not None:
+                    ok &= report(f"   dcol_scale", dcs, cs.grad, 1e-2)
+                ok &= report(f"   red finite", red, torch.nan_to_num(red), 1e-9)
     elif group == "resid_colsum":
         I, P, Cn = 5, 1024, 384
         dx = torch.randn(I * P, Cn, device=dev)

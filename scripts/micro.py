@@ -103,6 +103,11 @@ def main():
         "inorm_bwd1": (lambda: ops.inorm_bwd(1, Xb, O, I, P, st, vE, vE, red), 0, N * E * 4),
         "inorm_bwd2": (lambda: ops.inorm_bwd(2, Xb, O, I, P, st, vE, vE, red, out=O2), 0, N * E * 6),
         "inorm_bwd2_add": (lambda: ops.inorm_bwd(2, Xb, X32, I, P, st, vE, vE, red, out=o32, add32=X32), 0, N * E * 14),
+        "inorm_fwd_fused": (lambda: ops.inorm_apply(Xb, O, I, P, st, vE, vE, compute_stats=True), 0, N * E * 6),
+        "inorm_fwd_fused32": (lambda: ops.inorm_apply(X32, O, I, P, st, vE, vE, compute_stats=True), 0, N * E * 10),
+        "inorm_bwd3": (lambda: ops.inorm_bwd(3, Xb, O, I, P, st, vE, vE, red, out=O2), 0, N * E * 10),
+        "inorm_bwd3_add": (lambda: ops.inorm_bwd(3, Xb, X32, I, P, st, vE, vE, red, out=o32, add32=X32), 0, N * E * 20),
+        "inorm_bwd3_mlp": (lambda: ops.inorm_bwd(3, X32, Xb, I, P, st, vE, vE, red, out=O2), 0, N * E * 14),
         "resid_bwd": (lambda: ops.resid_bwd(X32, Xb, O, I, P, rs, vE, torch.zeros(I, E, device=dev), torch.zeros(I, E, device=dev)), 0, N * E * 8),
         "colsum": (lambda: ops.colsum16(QKV, torch.zeros(3 * E, device=dev)), 0, N * 3 * E * 2),
     }

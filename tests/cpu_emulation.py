@@ -109,8 +109,11 @@ def _mean_rstd(stats, P):
 
 
 def inorm_apply(x, out, I, P, stats, weight, bias, *, gelu=False, film_gamma=None, film_beta=None, film_T=0,
-                film_gb=None, resid_in=None, row_scale=None, col_gamma=None, stats_out=None):
+                film_gb=None, resid_in=None, row_scale=None, col_gamma=None, stats_out=None, compute_stats=False):
     C = x.shape[1]
+    if compute_stats:                # `stats` is an output
+        stats.zero_()
+        inorm_stats(x, I, P, stats)
     if film_gb is not None:          # (B, 2C) = [gamma | beta], the layout bf_film_fwd writes
         film_gamma, film_beta = film_gb[:, :C], film_gb[:, C:]
     mean, rstd = _mean_rstd(stats, P)
@@ -142,9 +145,12 @@ def inorm_bwd(phase, gin, x, I, P, stats, weight, bias, red, *, gelu=False, out=
     g = gin.float().reshape(I, P, C)
     if gelu:
         g = g * _gelu_grad(xh * weight + bias)
-    if phase == 1:
+    if phase == 3:                   # both phases, `red` is an output
+        red.zero_()
+    if phase in (1, 3):
         red.add_(torch.stack([g.sum(1), (g * xh).sum(1)], dim=-1))
-        return
+        if phase == 1:
+            return
     cs = torch.ones(I, C)
     if row_scale is not None:
         cs = cs * row_scale[:, None]

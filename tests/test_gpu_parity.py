@@ -34,7 +34,7 @@ def test_gemm(variant):
     assert _native_loaded()
 
 
-@pytest.mark.parametrize("group", ["params", "stats", "apply", "inorm_bwd", "resid_colsum", "attn_x", "attn_y", "attn_t",
+@pytest.mark.parametrize("group", ["params", "stats", "apply", "inorm_bwd", "inorm_fused", "resid_colsum", "attn_x", "attn_y", "attn_t",
                                    "attn_d48", "attn_l64", "attn_noscale", "attn_l128", "attn_l64_big", "attn_l40", "patch", "misc", "film",
                                    "gelu_modes"])
 def test_kernels(group):
