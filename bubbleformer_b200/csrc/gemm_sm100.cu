@@ -779,9 +779,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     u[k].z = pack2<__nv_bfloat16>(acc[8 * k + 4], acc[8 * k + 5]); u[k].w = pack2<__nv_bfloat16>(acc[8 * k + 6], acc[8 * k + 7]);
                   }
                 }
-                uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out16) + pix * co + c0);
+                uint16_t* dst16 = reinterpret_cast<uint16_t*>(p.out16) + pix * co + c0;
+                if ((reinterpret_cast<uintptr_t>(dst16) & 31) == 0) {
+                  // 64 bytes per thread as two 256-bit stores: whole 32-byte sectors (the lanes of a warp are 2 pixels apart)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) dst[k] = u[k];
+                  for (int k = 0; k < 4; k += 2)
+                    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst16 + 8 * k), "r"(u[k].x),
+                                 "r"(u[k].y), "r"(u[k].z), "r"(u[k].w), "r"(u[k + 1].x), "r"(u[k + 1].y), "r"(u[k + 1].z),
+                                 "r"(u[k + 1].w) : "memory");
+                } else {
+                  uint4* dst = reinterpret_cast<uint4*>(dst16);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) dst[k] = u[k];
+                }
               } else {
                 uint16_t* out = reinterpret_cast<uint16_t*>(p.out16);
 #pragma unroll
@@ -963,11 +973,17 @@ static bool resident_enabled() {
   return on != 0;
 }
 static int resident_bn(const bf_gemm_args& a) {
-  if (!resident_enabled() || a.bn != 0) return 0;
+  // Depth-to-space GEMMs of the stem / head (K = 96, M = 160 K ... 655 K rows, 32 KB of weights per CTA) re-fetch B for
+  // each of their 10 240 tiles, but keeping it resident does not help either (measured 264 vs 245 us on the
+  // 655360 x 384 x 96 shape): the scatter epilogue bounds them.  BF_GEMM_D2S_RESIDENT=1 enables it for measurements.
+  static int d2s_res = -1;
+  if (d2s_res < 0) { const char* e = getenv("BF_GEMM_D2S_RESIDENT"); d2s_res = (e != nullptr && e[0] == '1') ? 1 : 0; }
+  const bool small_k_d2s = d2s_res && a.epilogue == BF_EPI_D2S && a.K <= 2 * BK;
+  if (!(resident_enabled() || small_k_d2s) || a.bn != 0) return 0;
   if (a.a_mode != BF_A_ROWMAJOR || a.split_k != 1 || a.K > 6 * BK) return 0;
   const int e = a.epilogue;
   if (!(e == BF_EPI_STORE16 || e == BF_EPI_GELU || e == BF_EPI_GELU_D || e == BF_EPI_DGELU || e == BF_EPI_DMUL ||
-        e == BF_EPI_RESID || e == BF_EPI_QKV_LN)) return 0;
+        e == BF_EPI_RESID || e == BF_EPI_QKV_LN || small_k_d2s)) return 0;
   const int bn = e == BF_EPI_RESID ? 64 : 128;
   if (a.N % bn != 0) return 0;
   const int nnb = a.N / bn, mb = (a.M + BM - 1) / BM;

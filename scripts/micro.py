@@ -51,6 +51,9 @@ def main():
               d_scale_factor=torch.zeros(he, device=dev))
 
     rstd = torch.rand(N, he, 2, device=dev) + 0.5
+    A96 = torch.randn(655360, 96, device=dev).half()
+    W96 = (torch.randn(96, 384, device=dev) / 10).half()
+    Z96 = torch.empty(4 * 655360, 96, device=dev, dtype=torch.float16)
 
     def attn(axis, bwd):
         geo = engine._axis(g, axis)
@@ -85,6 +88,8 @@ def main():
                            2.0 * N * 3 * E * E, (N * E + N * 3 * E) * 2),
         "gemm_resid_noz": (lambda: ops.gemm(Xb, Wo, N, E, E, epilogue=L.EPI_RESID, bias=vE, col_gamma=vE, row_scale=rs, rows_per_group=P,
                                           in32=X32, out32=o32), 2.0 * N * E * E, N * E * (2 + 4 + 4)),
+        "gemm_d2s": (lambda: ops.gemm(A96, W96, 655360, 384, 96, epilogue=L.EPI_D2S, b_mode=L.B_KN, d2s=(128, 128, 96), out16=Z96, ldo=384),
+                     2.0 * 655360 * 384 * 96, 655360 * (96 + 384) * 2),
         "gemm_wgrad_qkv": (lambda: ops.gemm(QKV, Xb, 3 * E, E, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
                                             split_k=engine.pick_split(N, 3 * E, E), out32=torch.zeros(3 * E, E, device=dev)), 2.0 * N * 3 * E * E, (N * 4 * E) * 2),
         "gemm_wgrad_out": (lambda: ops.gemm(Xb, Xb, E, E, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
