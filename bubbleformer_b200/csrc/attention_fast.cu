@@ -290,18 +290,44 @@ __device__ __forceinline__ void ln_bwd16(float (&acc)[8][4], float pre, const ui
   }
 }
 
-// column sums of a 16-row tile held in C fragments -> shared accumulators
+// Column sums of a 16-row (or, two tiles at once, 32-row) tile held in C fragments -> the WARP's private accumulators in
+// shared memory.  A warp keeps one head for the whole launch, every column of its table is owned by exactly one lane
+// (t, nt, e), so the update is a plain read-modify-write: no atomics (shared fp32 atomics are compare-and-swap loops,
+// and twelve warps contending on one table cost +45 us per launch in the first version of this fusion).
 __device__ __forceinline__ void colsum_frag1(float* s_dst, const float (&o)[8][4], int lane) {
   const int t = lane & 3;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
+    float v0 = o[nt][0] + o[nt][2], v1 = o[nt][1] + o[nt][3];
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      float v = o[nt][e] + o[nt][2 + e];
-      v += __shfl_xor_sync(0xffffffffu, v, 4);
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if ((lane >> 2) == 0) atomicAdd(s_dst + nt * 8 + 2 * t + e, v);
+    for (int sh = 4; sh < 32; sh <<= 1) {
+      v0 += __shfl_xor_sync(0xffffffffu, v0, sh);
+      v1 += __shfl_xor_sync(0xffffffffu, v1, sh);
+    }
+    if ((lane >> 2) == 0) {
+      float2* d = reinterpret_cast<float2*>(s_dst + nt * 8 + 2 * t);
+      float2 c = *d;
+      c.x += v0; c.y += v1;
+      *d = c;
+    }
+  }
+}
+__device__ __forceinline__ void colsum_frag2(float* s_dst, const float (&o)[2][8][4], int lane) {
+  const int t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    float v0 = (o[0][nt][0] + o[0][nt][2]) + (o[1][nt][0] + o[1][nt][2]);
+    float v1 = (o[0][nt][1] + o[0][nt][3]) + (o[1][nt][1] + o[1][nt][3]);
+#pragma unroll
+    for (int sh = 4; sh < 32; sh <<= 1) {
+      v0 += __shfl_xor_sync(0xffffffffu, v0, sh);
+      v1 += __shfl_xor_sync(0xffffffffu, v1, sh);
+    }
+    if ((lane >> 2) == 0) {
+      float2* d = reinterpret_cast<float2*>(s_dst + nt * 8 + 2 * t);
+      float2 c = *d;
+      c.x += v0; c.y += v1;
+      *d = c;
     }
   }
 }
@@ -324,8 +350,9 @@ attn_fast_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
   float* s_dkw = s_dqb + FD;
   float* s_demb = s_dkw + FD;           // [32 * heads]
   float* s_dsf = s_demb + 32 * p.heads; // [heads]
-  float* s_dbias = s_dsf + p.heads;     // [heads * 3 * 64] column sums of dq | dk | dv (input_head bias gradient)
-  const int n_acc = 3 * FD + 33 * p.heads + (p.d_qkv_bias != nullptr ? 3 * FD * p.heads : 0);
+  // [warps][3 * 64] column sums of dq | dk | dv of each warp's head (input_head bias gradient), 8-byte aligned
+  float* s_dbias = s_dsf + ((p.heads + 1) & ~1);
+  const int n_acc = 3 * FD + 33 * p.heads + 2 + (p.d_qkv_bias != nullptr ? 3 * FD * kBwdWarps : 0);
   for (int i = threadIdx.x; i < n_acc; i += blockDim.x) s_acc[i] = 0.f;
   uint8_t* my = smem + warp * BwdWarp::kBytes;
   uint8_t* sQ = my + BwdWarp::kQ;
@@ -497,8 +524,8 @@ attn_fast_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
           for (int e = 0; e < 4; ++e) o[mt][nt][e] *= p.out_scale;
         }
         stage16(sdo, mt * 16, o[mt], lane);
-        if (p.d_qkv_bias != nullptr) colsum_frag1(s_dbias + head * 3 * FD + 2 * FD, o[mt], lane);
       }
+      if (p.d_qkv_bias != nullptr) colsum_frag2(s_dbias + warp * 3 * FD + 2 * FD, o, lane);
       store_tile(&map_dqkv, sdo, head * 3 * FD + 2 * FD, it, p.accumulate, lane);
     }
     // ---- dK' = dS^T Q'  -> LayerNorm backward -> d(raw k) ----
@@ -535,8 +562,8 @@ attn_fast_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         stage16(sdo, mt * 16, o[mt], lane);
-        if (p.d_qkv_bias != nullptr) colsum_frag1(s_dbias + head * 3 * FD + FD, o[mt], lane);
       }
+      if (p.d_qkv_bias != nullptr) colsum_frag2(s_dbias + warp * 3 * FD + FD, o, lane);
       store_tile(&map_dqkv, sdo, head * 3 * FD + FD, it, p.accumulate, lane);
     }
     // ---- dQ' = dS K'  -> LayerNorm backward -> d(raw q), staged over the (dead) q rows it was derived from ----
@@ -564,7 +591,7 @@ attn_fast_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
       ln_bwd16<true, true>(o, qscale, sQ, rstd_s, 0, mt * 16, wq, dwq, dbq, lane);
       __syncwarp();                     // all lanes have read the xhat rows of this m tile
       stage16(sQ, mt * 16, o, lane);
-      if (p.d_qkv_bias != nullptr) colsum_frag1(s_dbias + head * 3 * FD, o, lane);
+      if (p.d_qkv_bias != nullptr) colsum_frag1(s_dbias + warp * 3 * FD, o, lane);
     }
     store_tile(&map_dqkv, sQ, head * 3 * FD, it, p.accumulate, lane);
   }
@@ -611,8 +638,16 @@ attn_fast_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
     for (int i = threadIdx.x; i < 32 * p.heads; i += blockDim.x) atomicAdd(p.d_bias_emb + i, s_demb[i]);
   if (p.d_scale_factor != nullptr)
     for (int i = threadIdx.x; i < p.heads; i += blockDim.x) atomicAdd(p.d_scale_factor + i, s_dsf[i]);
-  if (p.d_qkv_bias != nullptr)
-    for (int i = threadIdx.x; i < 3 * FD * p.heads; i += blockDim.x) atomicAdd(p.d_qkv_bias + i, s_dbias[i]);
+  if (p.d_qkv_bias != nullptr) {
+    // the launch guarantees gridDim * warps % heads == 0: warp w of this block worked on head (block * warps + w) % heads
+    for (int i = threadIdx.x; i < 3 * FD * p.heads; i += blockDim.x) {
+      const int h = i / (3 * FD), col = i - h * 3 * FD;
+      float v = 0.f;
+      for (int w = 0; w < kBwdWarps; ++w)
+        if ((int)(((long)blockIdx.x * kBwdWarps + w) % p.heads) == h) v += s_dbias[w * 3 * FD + col];
+      if (v != 0.f) atomicAdd(p.d_qkv_bias + i, v);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1129,7 +1164,7 @@ int launch_attn_fast(const bf_attn_args* a, bool bwd, cudaStream_t st) {
   }
   const int warps = bwd ? kBwdWarps : kFwdWarps;
   const size_t smem = 1024 + (size_t)warps * (bwd ? BwdWarp::kBytes : FwdWarp::kBytes) + tab_bytes(p.heads) +
-                      (bwd ? (size_t)(3 * FD + 33 * p.heads + 3 * FD * p.heads) * sizeof(float) : 0);
+                      (bwd ? (size_t)(3 * FD + 33 * p.heads + 2 + 3 * FD * kBwdWarps) * sizeof(float) : 0);
   BF_REQUIRE(smem <= 227 * 1024, "bf_attention (prenorm): shared memory %zu too large (heads=%d)", smem, p.heads);
   static bool attr_done[4] = {false, false, false, false};
   const int ki = (bwd ? 2 : 0) + (packed ? 1 : 0);
@@ -1145,7 +1180,7 @@ int launch_attn_fast(const bf_attn_args* a, bool bwd, cudaStream_t st) {
   const long n_work = p.n_tiles * p.heads;
   long blocks = (n_work + warps - 1) / warps;
   if (blocks > num_sms()) blocks = num_sms();
-  if (bwd && !packed) {
+  if (bwd && (!packed || p.d_qkv_bias != nullptr)) {
     // a warp must keep one head for the whole launch (work item wi -> head wi % heads, stride gridDim * warps)
     while (blocks > 1 && (blocks * warps) % p.heads != 0) --blocks;
     BF_REQUIRE((blocks * warps) % p.heads == 0, "bf_attention_bwd (prenorm): heads=%d does not divide %d warps", p.heads, warps);

@@ -37,6 +37,10 @@ DMUL_BN = int(_os.environ.get("BF_DMUL_BN", "0"))                       # N tile
 # form already finds its operands in L2 and overlaps its prologue with the first through PDL, so the fusion buys nothing,
 # and 40 six-block clusters leave fewer blocks in flight than a full wave.  Opt-in.
 NORM_FUSED = _os.environ.get("BF_NORM_FUSED", "0") == "1"
+# input_head bias gradient (column sums of d qkv) inside the attention backward instead of a separate pass.  With per-warp
+# private tables (no shared atomics) the fusion is correct and cheap per tile, but the attention backward is bound by its
+# instruction count and the separate pass finds d qkv in L2: 26.29 vs 26.08 ms per step (same-box A/B, r2v).  Opt-in.
+ATTN_FUSED_BIAS = _os.environ.get("BF_ATTN_FUSED_BIAS", "0") == "1"
 
 
 def set_exact_mode(on: bool) -> None:
@@ -283,10 +287,9 @@ def _attn_branch_bwd(dXout, g: Geom, p, w16, heads: int, axes, scale_keys, mask_
     # attention(s)
     dQKV = _empty((N, 3 * E), BF16, dXout)
     oscale = 1.0 / len(axes)
-    # The pre-normalised attention backward can also accumulate the column sums of the d qkv it writes (input_head bias
-    # gradient, `d_qkv_bias`), but its per-tile shared-memory atomics cost more (+45 us per launch at config 2) than the
-    # separate 28 us column-sum pass over dQKV, so that fusion stays off.
-    fused_bias = False
+    # The pre-normalised attention backward (axes of up to 32 tokens) can accumulate the column sums of the d qkv it
+    # writes (input_head bias gradient, `d_qkv_bias`) in per-warp private shared-memory tables; see ATTN_FUSED_BIAS.
+    fused_bias = ATTN_FUSED_BIAS and sv["rstd"] is not None and all(_axis(g, ax)["L_"] <= 32 for ax in axes)
     for i, ax in enumerate(axes):
         geo = _axis(g, ax)
         sf = p[scale_keys[i]].reshape(-1) if scale_keys is not None else None
