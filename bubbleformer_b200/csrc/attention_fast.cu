@@ -596,20 +596,37 @@ attn_fast_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
     store_tile(&map_dqkv, sQ, head * 3 * FD, it, p.accumulate, lane);
   }
   if (lane == 0) tma_store_wait_all();
+  __syncwarp();
+  // ---- parameter gradients.  The warp's tiles are dead: their first 1 KiB + becomes the warp's PRIVATE table
+  //      [0:64) d qnorm.weight, [64:128) d qnorm.bias, [128:192) d knorm.weight, [192:255) bias gradient per relative
+  //      position (rel + 31), [256] d scale factor.  No shared-memory atomics (fp32 shared atomics are compare-and-swap
+  //      loops: twelve warps contending on the block-level tables were 15 % of this kernel's samples); the block's
+  //      tables are added up after one __syncthreads and leave as one global atomic per entry and block. ----
+  float* wtab = reinterpret_cast<float*>(my);
+  wtab[192 + lane] = 0.f;
+  wtab[224 + lane] = 0.f;
+  if (lane == 0) wtab[256] = 0.f;
+  __syncwarp();
   if (!PACKED) {
     if (p.d_bias_emb != nullptr) {
+      // rel = 8*q + 2t + e - g: for a fixed k the lanes that share a rel differ in t, so four rounds (one per t) never
+      // have two lanes on the same entry
 #pragma unroll
       for (int k = 0; k < 14; ++k) {
         const int rel = 8 * ((k >> 1) - 3) + 2 * t + (k & 1) - g8;
-        atomicAdd(s_demb + __ldg(p.bucket + rel + FLP - 1) * p.heads + my_head, dacc[k]);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          if (t == r) wtab[192 + rel + FLP - 1] += dacc[k];
+          __syncwarp();
+        }
       }
     }
     if (p.d_scale_factor != nullptr) {
       dsf_acc = warp_sum(dsf_acc);
-      if (lane == 0) atomicAdd(s_dsf + my_head, dsf_acc);
+      if (lane == 0) wtab[256] = dsf_acc;
     }
   }
-  // ---- LayerNorm parameter gradients: lanes with equal t hold partial sums of the same columns ----
+  // LayerNorm parameter gradients: lanes with equal t hold partial sums of the same columns
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
@@ -622,24 +639,48 @@ attn_fast_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
         c += __shfl_xor_sync(0xffffffffu, c, o);
       }
       if (g8 == 0) {
-        atomicAdd(s_dqw + nt * 8 + 2 * t + e, a);
-        atomicAdd(s_dqb + nt * 8 + 2 * t + e, b);
-        atomicAdd(s_dkw + nt * 8 + 2 * t + e, c);
+        wtab[nt * 8 + 2 * t + e] = a;
+        wtab[FD + nt * 8 + 2 * t + e] = b;
+        wtab[2 * FD + nt * 8 + 2 * t + e] = c;
       }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < FD; i += blockDim.x) {
-    atomicAdd(p.d_qn_w + i, s_dqw[i]);
-    atomicAdd(p.d_qn_b + i, s_dqb[i]);
-    atomicAdd(p.d_kn_w + i, s_dkw[i]);
+  const float* wt0 = reinterpret_cast<const float*>(smem);
+  constexpr int kWStride = BwdWarp::kBytes / 4;          // floats between two warps' tables
+  for (int i = threadIdx.x; i < 3 * FD; i += blockDim.x) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < kBwdWarps; ++w) v += wt0[w * kWStride + i];
+    float* dst = i < FD ? p.d_qn_w + i : (i < 2 * FD ? p.d_qn_b + (i - FD) : p.d_kn_w + (i - 2 * FD));
+    atomicAdd(dst, v);
   }
-  if (p.d_bias_emb != nullptr)
-    for (int i = threadIdx.x; i < 32 * p.heads; i += blockDim.x) atomicAdd(p.d_bias_emb + i, s_demb[i]);
-  if (p.d_scale_factor != nullptr)
-    for (int i = threadIdx.x; i < p.heads; i += blockDim.x) atomicAdd(p.d_scale_factor + i, s_dsf[i]);
-  if (p.d_qkv_bias != nullptr) {
+  if (!PACKED) {
     // the launch guarantees gridDim * warps % heads == 0: warp w of this block worked on head (block * warps + w) % heads
+    if (p.d_bias_emb != nullptr) {
+      for (int i = threadIdx.x; i < (2 * FLP - 1) * p.heads; i += blockDim.x) {
+        const int h = i / (2 * FLP - 1), r = i - h * (2 * FLP - 1);
+        float v = 0.f;
+        for (int w = 0; w < kBwdWarps; ++w)
+          if ((int)(((long)blockIdx.x * kBwdWarps + w) % p.heads) == h) v += wt0[w * kWStride + 192 + r];
+        if (v != 0.f) atomicAdd(p.d_bias_emb + __ldg(p.bucket + r) * p.heads + h, v);
+      }
+    }
+    if (p.d_scale_factor != nullptr) {
+      for (int h = threadIdx.x; h < p.heads; h += blockDim.x) {
+        float v = 0.f;
+        for (int w = 0; w < kBwdWarps; ++w)
+          if ((int)(((long)blockIdx.x * kBwdWarps + w) % p.heads) == h) v += wt0[w * kWStride + 256];
+        atomicAdd(p.d_scale_factor + h, v);
+      }
+    }
+  } else {
+    if (p.d_bias_emb != nullptr)
+      for (int i = threadIdx.x; i < 32 * p.heads; i += blockDim.x) atomicAdd(p.d_bias_emb + i, s_demb[i]);
+    if (p.d_scale_factor != nullptr)
+      for (int i = threadIdx.x; i < p.heads; i += blockDim.x) atomicAdd(p.d_scale_factor + i, s_dsf[i]);
+  }
+  if (p.d_qkv_bias != nullptr) {
     for (int i = threadIdx.x; i < 3 * FD * p.heads; i += blockDim.x) {
       const int h = i / (3 * FD), col = i - h * 3 * FD;
       float v = 0.f;
