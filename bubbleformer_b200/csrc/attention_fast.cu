@@ -474,24 +474,23 @@ attn_fast_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
     // ---- bias-embedding and scale-factor gradients ----
     if (PACKED) {
       if (p.d_bias_emb != nullptr) {
-        for (int r = lane; r < 2 * L - 1; r += 32) {
-          float s = 0.f;
-          for (int gq = 0; gq < G; ++gq) {
-            for (int i = 0; i < L; ++i) {
-              const int j = i + r - (L - 1);
-              if (j >= 0 && j < L) s += __bfloat162float(*reinterpret_cast<const bf16*>(sV + swz(gq * L + i, 32 + gq * L + j)));
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {   // lane owns relative positions lane and lane + 32 for the whole launch (one head per warp)
+          const int r = lane + 32 * rr;
+          if (r < 2 * L - 1) {
+            float s = 0.f;
+            for (int gq = 0; gq < G; ++gq) {
+              for (int i = 0; i < L; ++i) {
+                const int j = i + r - (L - 1);
+                if (j >= 0 && j < L) s += __bfloat162float(*reinterpret_cast<const bf16*>(sV + swz(gq * L + i, 32 + gq * L + j)));
+              }
             }
+            dacc[rr] += s;
           }
-          atomicAdd(s_demb + __ldg(p.bucket + r) * p.heads + head, s);
         }
       }
-      if (p.d_scale_factor != nullptr) {
-        dsf = warp_sum(dsf);
-        if (lane == 0) atomicAdd(s_dsf + head, dsf);
-      }
-    } else {
-      dsf_acc += dsf;
     }
+    dsf_acc += dsf;
     // ---- dV = P'^T dO' ----
     {
       float o[2][8][4];
@@ -607,8 +606,11 @@ attn_fast_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
   wtab[224 + lane] = 0.f;
   if (lane == 0) wtab[256] = 0.f;
   __syncwarp();
-  if (!PACKED) {
-    if (p.d_bias_emb != nullptr) {
+  if (p.d_bias_emb != nullptr) {
+    if (PACKED) {
+      if (lane < 2 * L - 1) wtab[192 + lane] = dacc[0];
+      if (lane + 32 < 2 * L - 1) wtab[224 + lane] = dacc[1];
+    } else {
       // rel = 8*q + 2t + e - g: for a fixed k the lanes that share a rel differ in t, so four rounds (one per t) never
       // have two lanes on the same entry
 #pragma unroll
@@ -621,10 +623,10 @@ attn_fast_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
         }
       }
     }
-    if (p.d_scale_factor != nullptr) {
-      dsf_acc = warp_sum(dsf_acc);
-      if (lane == 0) wtab[256] = dsf_acc;
-    }
+  }
+  if (p.d_scale_factor != nullptr) {
+    dsf_acc = warp_sum(dsf_acc);
+    if (lane == 0) wtab[256] = dsf_acc;
   }
   // LayerNorm parameter gradients: lanes with equal t hold partial sums of the same columns
 #pragma unroll
@@ -655,30 +657,24 @@ attn_fast_bwd_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_c
     float* dst = i < FD ? p.d_qn_w + i : (i < 2 * FD ? p.d_qn_b + (i - FD) : p.d_kn_w + (i - 2 * FD));
     atomicAdd(dst, v);
   }
-  if (!PACKED) {
-    // the launch guarantees gridDim * warps % heads == 0: warp w of this block worked on head (block * warps + w) % heads
-    if (p.d_bias_emb != nullptr) {
-      for (int i = threadIdx.x; i < (2 * FLP - 1) * p.heads; i += blockDim.x) {
-        const int h = i / (2 * FLP - 1), r = i - h * (2 * FLP - 1);
-        float v = 0.f;
-        for (int w = 0; w < kBwdWarps; ++w)
-          if ((int)(((long)blockIdx.x * kBwdWarps + w) % p.heads) == h) v += wt0[w * kWStride + 192 + r];
-        if (v != 0.f) atomicAdd(p.d_bias_emb + __ldg(p.bucket + r) * p.heads + h, v);
-      }
+  // the launch guarantees gridDim * warps % heads == 0: warp w of this block worked on head (block * warps + w) % heads
+  if (p.d_bias_emb != nullptr) {
+    const int nrel = 2 * L - 1;                 // table index = rel + L - 1
+    for (int i = threadIdx.x; i < nrel * p.heads; i += blockDim.x) {
+      const int h = i / nrel, r = i - h * nrel;
+      float v = 0.f;
+      for (int w = 0; w < kBwdWarps; ++w)
+        if ((int)(((long)blockIdx.x * kBwdWarps + w) % p.heads) == h) v += wt0[w * kWStride + 192 + r];
+      if (v != 0.f) atomicAdd(p.d_bias_emb + __ldg(p.bucket + r) * p.heads + h, v);
     }
-    if (p.d_scale_factor != nullptr) {
-      for (int h = threadIdx.x; h < p.heads; h += blockDim.x) {
-        float v = 0.f;
-        for (int w = 0; w < kBwdWarps; ++w)
-          if ((int)(((long)blockIdx.x * kBwdWarps + w) % p.heads) == h) v += wt0[w * kWStride + 256];
-        atomicAdd(p.d_scale_factor + h, v);
-      }
+  }
+  if (p.d_scale_factor != nullptr) {
+    for (int h = threadIdx.x; h < p.heads; h += blockDim.x) {
+      float v = 0.f;
+      for (int w = 0; w < kBwdWarps; ++w)
+        if ((int)(((long)blockIdx.x * kBwdWarps + w) % p.heads) == h) v += wt0[w * kWStride + 256];
+      atomicAdd(p.d_scale_factor + h, v);
     }
-  } else {
-    if (p.d_bias_emb != nullptr)
-      for (int i = threadIdx.x; i < 32 * p.heads; i += blockDim.x) atomicAdd(p.d_bias_emb + i, s_demb[i]);
-    if (p.d_scale_factor != nullptr)
-      for (int i = threadIdx.x; i < p.heads; i += blockDim.x) atomicAdd(p.d_scale_factor + i, s_dsf[i]);
   }
   if (p.d_qkv_bias != nullptr) {
     for (int i = threadIdx.x; i < 3 * FD * p.heads; i += blockDim.x) {
@@ -1221,7 +1217,7 @@ int launch_attn_fast(const bf_attn_args* a, bool bwd, cudaStream_t st) {
   const long n_work = p.n_tiles * p.heads;
   long blocks = (n_work + warps - 1) / warps;
   if (blocks > num_sms()) blocks = num_sms();
-  if (bwd && (!packed || p.d_qkv_bias != nullptr)) {
+  if (bwd) {
     // a warp must keep one head for the whole launch (work item wi -> head wi % heads, stride gridDim * warps)
     while (blocks > 1 && (blocks * warps) % p.heads != 0) --blocks;
     BF_REQUIRE((blocks * warps) % p.heads == 0, "bf_attention_bwd (prenorm): heads=%d does not divide %d warps", p.heads, warps);
