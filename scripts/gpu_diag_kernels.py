@@ -58,6 +58,22 @@ def run(group):
             xi = x.float().reshape(I, P, Cn)
             ref = torch.stack([xi.sum(1), (xi * xi).sum(1)], dim=-1)
             ok &= report(f"stats {I}x{P}x{Cn} {dt}", st, ref, 1e-5)
+        # row pitch > C (a column slice of a wider matrix): the bulk-copy ring moves such rows one copy per row
+        for (I, P, Cn, dt) in [(3, 200, 96, torch.bfloat16), (2, 333, 384, torch.float32)]:
+            wide = (torch.randn(I * P, 2 * Cn + 8, device=dev) * 2 + 0.5).to(dt)
+            x = wide[:, 8:8 + Cn]
+            st = torch.zeros(I, Cn, 2, device=dev)
+            ops.inorm_stats(x, I, P, st)
+            xi = x.float().reshape(I, P, Cn)
+            ok &= report(f"stats strided {I}x{P}x{Cn} {dt}", st, torch.stack([xi.sum(1), (xi * xi).sum(1)], dim=-1), 1e-5)
+            w, b = torch.randn(Cn, device=dev), torch.randn(Cn, device=dev)
+            owide = torch.zeros(I * P, Cn + 16, device=dev, dtype=torch.float32)
+            out = owide[:, 8:8 + Cn]
+            ops.inorm_apply(x, out, I, P, st, w, b)
+            ok &= report(f"apply strided {I}x{P}x{Cn} {dt}", out, inorm_ref(x, I, P, w, b), 1e-5)
+            untouched = bool((owide[:, :8] == 0).all()) and bool((owide[:, 8 + Cn:] == 0).all())
+            print(f"[apply strided: columns outside the slice untouched] {'OK' if untouched else 'MISMATCH'}")
+            ok &= untouched
     elif group == "apply":
         I, P, Cn, T = 4, 1024, 384, 2
         w, b = torch.randn(Cn, device=dev), torch.randn(Cn, device=dev)
