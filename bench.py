@@ -387,7 +387,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # the gradient all-reduce moves 115 MB per ~28 ms step (4 GB/s): a few NCCL CTAs are plenty, and every SM they
         # do not occupy stays with the persistent GEMM grids they overlap with
-        os.environ.setdefault("NCCL_MAX_CTAS", "8")
+        os.environ.setdefault("NCCL_MAX_CTAS", "4")
         dist.init_process_group("nccl", device_id=dev)
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
@@ -465,7 +465,7 @@ def main():
     # is read back to the host per step.  Like a data loader with one batch of prefetch, the copy of step i+1 is
     # issued on a copy stream while step i computes, and the loss read lags one step so it never stalls the GPU.
     xh, th, ch = (t.cpu().pin_memory() for t in (x, tgt, cond))
-    Ke = max(3, min(K, 10))
+    Ke = max(3, min(K, 20))
     copy_stream = torch.cuda.Stream(device=dev)
 
     def fetch():
@@ -583,7 +583,11 @@ def main():
                        "parallelism": f"dp{world}", "cuda_graph": (not args.no_graph) if train else True,
                        "l2_policy": "per-step working set (>10 GB of activations) far exceeds the 126 MB L2",
                        "precision": "bf16 block GEMMs / attention, fp16 patch embed+unembed forward, fp32 residual stream, statistics and gradients",
-                       "weights": "identical on every rank (one seed); per-rank data and drop-path masks"},
+                       "weights": "identical on every rank (one seed); per-rank data and drop-path masks",
+                       "comm": ("NCCL all-reduce (AVG) of the flat fp32 gradient buffer in 8 MB buckets on a side stream, "
+                                "NCCL_MAX_CTAS=%s, %s SMs reserved for it (kernel grids sized for the rest)"
+                                % (os.environ.get("NCCL_MAX_CTAS", "default"),
+                                   os.environ.get("BF_RESERVED_SMS", os.environ.get("NCCL_MAX_CTAS", "0")))) if world > 1 else "none"},
             "e2e": {"value": e2e_value, "unit": "samples/s" if train else "steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": Ke},
             "gpu_launches": launches, "gpu_launches_per_step": launches / K,

@@ -138,7 +138,7 @@ class BranchGradArgs(C.Structure):
     ]
 
 
-EXPORTS = ["bf_set_gelu_mode", "bf_get_gelu_mode", "bf_film_fwd", "bf_film_bwd", "bf_window_gather", "bf_eikonal_sums", "bf_heatflux_rows", "bf_optim_step", "bf_feat_consts", "bf_branch_param_grads", "bf_last_error", "bf_version", "bf_launch_count", "bf_gemm", "bf_inorm_stats", "bf_inorm_apply",
+EXPORTS = ["bf_set_gelu_mode", "bf_get_gelu_mode", "bf_set_reserved_sms", "bf_film_fwd", "bf_film_bwd", "bf_window_gather", "bf_eikonal_sums", "bf_heatflux_rows", "bf_optim_step", "bf_feat_consts", "bf_branch_param_grads", "bf_last_error", "bf_version", "bf_launch_count", "bf_gemm", "bf_inorm_stats", "bf_inorm_apply",
            "bf_inorm_bwd", "bf_inorm_bwd_params", "bf_resid_bwd", "bf_colsum16", "bf_attention_fwd",
            "bf_attention_bwd", "bf_lploss_sums", "bf_lploss_bwd", "bf_patch_in", "bf_patch_out", "bf_patch_wgrad", "bf_s2d_gather", "bf_cast16", "bf_convert16"]
 

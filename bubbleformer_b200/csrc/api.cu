@@ -24,6 +24,10 @@ int check_cuda(cudaError_t e, const char* what) {
   return BF_ERR_CUDA;
 }
 
+static std::atomic<int> g_reserved_sms{0};
+
+// SMs the kernels size their one-wave / persistent grids for: the device's SM count minus the SMs set aside with
+// bf_set_reserved_sms (for the NCCL kernels of the gradient all-reduce that run next to the backward pass).
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -31,7 +35,8 @@ int num_sms() {
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   }
-  return n;
+  const int r = g_reserved_sms.load(std::memory_order_relaxed);
+  return n - r > 0 ? n - r : 1;
 }
 
 bool pdl_enabled() {
@@ -66,3 +71,8 @@ extern "C" int bf_set_gelu_mode(int exact_erf) {
   return BF_OK;
 }
 extern "C" int bf_get_gelu_mode(void) { return bf::gelu_exact() ? 1 : 0; }
+extern "C" int bf_set_reserved_sms(int n) {
+  if (n < 0 || n > 64) { bf::set_error("bf_set_reserved_sms: %d is outside [0, 64]", n); return BF_ERR_INVALID; }
+  bf::g_reserved_sms.store(n, std::memory_order_relaxed);
+  return BF_OK;
+}

@@ -37,6 +37,13 @@ class GradSink:
             self._sync_parameters()
         self.bucket_elems = bucket_bytes // 4
         self.comm_stream = torch.cuda.Stream(device=dev) if (self.world > 1 and dev.type == "cuda") else None
+        if self.comm_stream is not None:
+            # The all-reduce kernels run beside the backward kernels: leave them their SMs (include/bubbleformer_b200.h,
+            # bf_set_reserved_sms).  BF_RESERVED_SMS overrides; default = NCCL_MAX_CTAS when that is set, else 0.
+            import os
+            from . import _lib
+            n = os.environ.get("BF_RESERVED_SMS", os.environ.get("NCCL_MAX_CTAS", "0"))
+            _lib.check(_lib.lib.bf_set_reserved_sms(int(n or 0)), "bf_set_reserved_sms")
         self._pending: List = []
         self._lo: Optional[int] = None
         self._hi: Optional[int] = None

@@ -54,6 +54,14 @@ BF_API int64_t bf_launch_count(void);
 BF_API int bf_set_gelu_mode(int exact_erf);
 BF_API int bf_get_gelu_mode(void);
 
+/* SMs set aside for other work that runs NEXT TO these kernels: the NCCL all-reduce kernels of data-parallel training
+ * (upstream: Lightning strategy="ddp", scripts/train.py:163).  Every kernel here sizes its grid as one resident wave /
+ * one persistent CTA per SM with a static tile order; a CTA that cannot become resident because an NCCL CTA holds its SM
+ * only starts when another CTA has finished, i.e. the whole launch takes twice as long.  With n SMs reserved the grids
+ * are sized for (SM count - n), so they stay resident beside n communication CTAs (NCCL_MAX_CTAS=n).  Process-wide,
+ * read at launch time (set it before capturing a CUDA graph); 0 <= n <= 64, default 0.                           */
+BF_API int bf_set_reserved_sms(int n);
+
 /* fp32 validation.  The north star asks for parity within rel-L2 1e-4 "for the fp32 path" (upstream runs fp32 / TF32,
  * scripts/train.py:72).  The production kernels store operands in 16 bits and cannot reach that by construction, so every
  * entry point that moves 16-bit activations also accepts dtype = BF_F32: bf_gemm, bf_attention_fwd/bwd (args->dtype),
