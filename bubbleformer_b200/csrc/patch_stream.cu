@@ -195,8 +195,8 @@ patch_wgrad_mma_kernel(const T16* __restrict__ a, long lda, const float* __restr
 // ---------------------------------------------------------------------------------------------
 template <typename T16, int NT>
 __global__ void __launch_bounds__(kPsWarps * 32, 2)
-patch_out_mma_kernel(const T16* __restrict__ a, const float* __restrict__ Wck, float* __restrict__ out,
-                     int F, int h, int w, int C, int tiles_per_block) {
+patch_out_mma_kernel(const T16* __restrict__ a, int lda, const float* __restrict__ Wck, float* __restrict__ out,
+                     int F, int h, int w, int C, int accumulate, int tiles_per_block) {
   pdl_prologue_done();
   extern __shared__ __align__(16) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -208,7 +208,7 @@ patch_out_mma_kernel(const T16* __restrict__ a, const float* __restrict__ Wck, f
   const int img = blockIdx.y;
   const int tile0 = blockIdx.x * tiles_per_block, tile1 = min(n_tiles, tile0 + tiles_per_block);
   const int kts = C >> 4;                                // 16-channel k steps (<= kPsMT)
-  const T16* aimg = a + (long)img * h * w * C;
+  const T16* aimg = a + (long)img * h * w * lda;      // C channels of this pass out of lda per pixel
   float* oimg = out + (long)img * F * (2 * h) * (2 * w);
 
   // B fragments for k step ks, n tile j: b0 = (channel 16ks+2t, +1; column 8j+g), b1 = channels +8
@@ -234,7 +234,7 @@ patch_out_mma_kernel(const T16* __restrict__ a, const float* __restrict__ Wck, f
   int buf = 0;
   auto issue = [&](int tile, int bf_) {
     const int y = tile / tiles_x, x0 = (tile - y * tiles_x) * 16;
-    issue_act_tile<T16>(my + bf_ * a_bytes, aimg + ((long)y * w + x0) * C, C, C, w - x0, lane);
+    issue_act_tile<T16>(my + bf_ * a_bytes, aimg + ((long)y * w + x0) * lda, lda, C, w - x0, lane);
   };
   if (tile0 + warp < tile1) issue(tile0 + warp, 0);
   cp_commit();
@@ -269,6 +269,10 @@ patch_out_mma_kernel(const T16* __restrict__ a, const float* __restrict__ Wck, f
       const int f = 2 * j + (t >> 1), ky = t & 1;
       if (f < F) {
         float* op = oimg + ((long)f * (2 * h) + 2 * y + ky) * (2 * w) + 2 * (x0 + g);
+        if (accumulate) {             // a later channel pass of the same output (more than 96 channels)
+          if (x0 + g < w) { const float2 o = *reinterpret_cast<const float2*>(op); c[j][0] += o.x; c[j][1] += o.y; }
+          if (x0 + g + 8 < w) { const float2 o = *reinterpret_cast<const float2*>(op + 16); c[j][2] += o.x; c[j][3] += o.y; }
+        }
         if (x0 + g < w) *reinterpret_cast<float2*>(op) = make_float2(c[j][0], c[j][1]);
         if (x0 + g + 8 < w) *reinterpret_cast<float2*>(op + 16) = make_float2(c[j][2], c[j][3]);
       }
@@ -287,7 +291,8 @@ static int plan_blocks(int tiles, int I, int& tpb) {
 }
 
 bool patch_wgrad_mma_ok(int F, int W, int N) { return F >= 1 && F <= 8 && W % 4 == 0 && N % 16 == 0; }
-bool patch_out_mma_ok(int F, int C) { return F >= 1 && F <= 8 && C % 16 == 0 && C <= 16 * kPsMT; }
+// more than 96 channels (film_avit_big: 192) run as passes of 96 that accumulate into the output
+bool patch_out_mma_ok(int F, int C) { return F >= 1 && F <= 8 && C % 16 == 0 && C <= 8 * 16 * kPsMT; }
 
 int launch_patch_wgrad_mma(const void* a, int dtype, const float* x, float* dW, int I, int F, int H, int W, int N,
                            cudaStream_t s) {
@@ -338,14 +343,18 @@ int launch_patch_out_mma(const void* a, int dtype, const float* Wck, float* out,
                                                    64 * 1024), "cudaFuncSetAttribute(patch_out)")) return e_;     \
       done_ = true;                                                                                               \
     }                                                                                                             \
-    launch_k(patch_out_mma_kernel<T, NT_>, grid, dim3(kPsWarps * 32), sm, s, (const T*)a, Wck, out, F, h, w, C, tpb); \
+    launch_k(patch_out_mma_kernel<T, NT_>, grid, dim3(kPsWarps * 32), sm, s, (const T*)a + c_off, C, Wck + (long)c_off * 4 * F, \
+             out, F, h, w, cp, c_off > 0 ? 1 : 0, tpb);                                                           \
   } while (0)
 #define BF_PO(T) do { if (NT == 1) BF_PO_(T, 1); else if (NT == 2) BF_PO_(T, 2); else BF_PO_(T, 4); } while (0)
-  if (dtype == BF_BF16) BF_PO(__nv_bfloat16); else BF_PO(__half);
+  for (int c_off = 0; c_off < C; c_off += 16 * kPsMT) {
+    const int cp = C - c_off < 16 * kPsMT ? C - c_off : 16 * kPsMT;
+    if (dtype == BF_BF16) BF_PO(__nv_bfloat16); else BF_PO(__half);
+    count_launch();
+    BF_LAUNCH_CHECK("patch_out_mma_kernel");
+  }
 #undef BF_PO
 #undef BF_PO_
-  count_launch();
-  BF_LAUNCH_CHECK("patch_out_mma_kernel");
   return BF_OK;
 }
 

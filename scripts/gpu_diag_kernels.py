@@ -340,7 +340,8 @@ def run(group):
     elif group == "patch":
         for (I, Fd, H, W, N, dt) in [(2, 4, 64, 64, 96, torch.float16), (3, 2, 32, 48, 24, torch.float16),
                                      (1, 1, 16, 16, 384, torch.bfloat16), (2, 4, 32, 40, 96, torch.bfloat16),
-                                     (1, 3, 16, 24, 48, torch.float16), (3, 4, 128, 128, 96, torch.bfloat16)]:
+                                     (1, 3, 16, 24, 48, torch.float16), (3, 4, 128, 128, 96, torch.bfloat16),
+                                     (2, 4, 64, 48, 192, torch.float16)]:      # film_avit_big stem: two 96-channel passes
             x = torch.randn(I, Fd, H, W, device=dev)
             Wc = torch.randn(N, Fd, 2, 2, device=dev) / (4 * Fd) ** 0.5
             out = torch.zeros(I, H // 2, W // 2, N, device=dev, dtype=dt)
@@ -353,7 +354,7 @@ def run(group):
             # conv-transpose out: a (I,h,w,C) -> (I,F,2h,2w)
             a = torch.randn(I, H // 2, W // 2, N, device=dev).to(dt)
             Wt = torch.randn(N, Fd, 2, 2, device=dev) / N ** 0.5
-            o2 = torch.zeros(I, Fd, H, W, device=dev)
+            o2 = torch.full((I, Fd, H, W), float("nan"), device=dev)      # an output: any contents on entry
             ops.patch_out(a, Wt.reshape(N, 4 * Fd).contiguous(), o2)
             ref2 = F.conv_transpose2d(a.float().permute(0, 3, 1, 2), Wt, stride=2)
             ok &= report(f"patch_out {N}->{Fd}", o2, ref2, 1e-5)
