@@ -88,6 +88,11 @@ def main():
                            2.0 * N * 3 * E * E, (N * E + N * 3 * E) * 2),
         "gemm_resid_noz": (lambda: ops.gemm(Xb, Wo, N, E, E, epilogue=L.EPI_RESID, bias=vE, col_gamma=vE, row_scale=rs, rows_per_group=P,
                                           in32=X32, out32=o32), 2.0 * N * E * E, N * E * (2 + 4 + 4)),
+        "gemm_fc2_bn128": (lambda: ops.gemm(H, W2, N, E, 4 * E, epilogue=L.EPI_STORE16, bias=vE, out16=O, bn=128), 2.0 * N * 4 * E * E, (N * 4 * E + N * E) * 2),
+        "gemm_dgrad_qkv_bn128": (lambda: ops.gemm(QKV, Win, N, E, 3 * E, epilogue=L.EPI_STORE16, b_mode=L.B_KN, out16=O, bn=128), 2.0 * N * 3 * E * E, (N * E + N * 3 * E) * 2),
+        "gemm_acc32_bn128": (lambda: ops.gemm(H, W1, N, E, 4 * E, epilogue=L.EPI_ACC32, b_mode=L.B_KN, in32=X32, out32=o32, bn=128), 2.0 * N * 4 * E * E, N * 4 * E * 2 + N * E * 8),
+        "gemm_dgrad_out_bn128": (lambda: ops.gemm(Xb, Wo, N, E, E, epilogue=L.EPI_STORE16, b_mode=L.B_KN, out16=O, bn=128), 2.0 * N * E * E, N * E * 4),
+        "gemm_dgrad_out": (lambda: ops.gemm(Xb, Wo, N, E, E, epilogue=L.EPI_STORE16, b_mode=L.B_KN, out16=O), 2.0 * N * E * E, N * E * 4),
         "gemm_d2s": (lambda: ops.gemm(A96, W96, 655360, 384, 96, epilogue=L.EPI_D2S, b_mode=L.B_KN, d2s=(128, 128, 96), out16=Z96, ldo=384),
                      2.0 * 655360 * 384 * 96, 655360 * (96 + 384) * 2),
         "gemm_wgrad_qkv": (lambda: ops.gemm(QKV, Xb, 3 * E, E, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
