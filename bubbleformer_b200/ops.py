@@ -90,6 +90,15 @@ def gemm(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, *, epilogue: 
         a.ln_head_dim = ln_head_dim
         a.ln_rstd = _f32(ln_rstd, 2 * M * (N // (3 * max(ln_head_dim, 1))), "ln_rstd")
     L.check(L.lib.bf_gemm(C.byref(a), _stream()), "bf_gemm")
+    if GEMM_RECORD is not None:       # bench.py: replay exactly these launches back to back (the tensors stay referenced)
+        GEMM_RECORD.append((a, 2.0 * M * N * K, (A, B, bias, col_scale, col_shift, col_gamma, row_scale, in32, aux16, out16,
+                                                 out16b, out32, stats_out, ln_rstd, colsum_out)))
+
+
+def gemm_replay(record) -> None:
+    """Issue the launches recorded in GEMM_RECORD again, in order, on the current stream."""
+    for a, _, _ in record:
+        L.check(L.lib.bf_gemm(C.byref(a), _stream()), "bf_gemm")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -383,6 +392,7 @@ def lploss_bwd(pred, tgt, coef, dpred) -> None:
 # optional per-launch timing (bench.py roofline, scripts/profile_step.py); zero overhead when off
 # ---------------------------------------------------------------------------------------------
 GEMM_TIMING = None      # list of (start_event, end_event, flops) when enabled
+GEMM_RECORD = None      # list of (args struct, flops, referenced tensors) when enabled
 PROFILE = None          # list of (name, tag, start_event, end_event) when enabled
 
 
