@@ -204,3 +204,23 @@ def test_gelu_mlp_standalone_forward_backward():
     assert rel(y, yr) < 1e-2
     for g, r in zip(got, [xr.grad] + [p.grad for p in ps]):
         assert g is not None and rel(g, r) < 1e-2, rel(g, r)
+
+
+@pytest.mark.parametrize("reserved", [4, 11])
+def test_reserved_sms_keep_results(reserved):
+    """bf_set_reserved_sms (grids sized for SM count - n: what data-parallel training runs with beside NCCL) must not
+    change any result: the kernel groups and the config-2 whole-model case pass with SMs set aside (11: an odd SM count,
+    so every 'one wave' / head-divisibility rule is exercised off its usual value)."""
+    import gpu_diag_gemm
+    import gpu_diag_kernels
+    import gpu_diag_model
+    from bubbleformer_b200 import _lib
+    _lib.check(_lib.lib.bf_set_reserved_sms(reserved), "bf_set_reserved_sms")
+    try:
+        for v in ("nk_big", "resid_stats_big", "qkv_ln", "wgrad_split", "d2s"):
+            assert gpu_diag_gemm.run_variant(v)
+        for g in ("stats", "apply", "inorm_bwd", "inorm_fused", "resid_colsum", "attn_x", "attn_t", "attn_l64", "patch"):
+            assert gpu_diag_kernels.run(g)
+        assert gpu_diag_model.run_case("oracle_cfg2")
+    finally:
+        _lib.check(_lib.lib.bf_set_reserved_sms(0), "bf_set_reserved_sms")
