@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libbubbleformer_b200.so")
 
 BF_BF16, BF_F16 = 0, 1
 A_ROWMAJOR, A_S2D, A_KM = 0, 1, 2
-B_NK, B_KN = 0, 1
+B_NK, B_KN, B_KN_S2D = 0, 1, 2
 EPI_STORE16, EPI_GELU, EPI_RESID, EPI_DGELU, EPI_ACC32, EPI_ATOMIC32, EPI_D2S, EPI_STORE32, EPI_QKV_LN = range(9)
 EPI_GELU_D, EPI_DMUL = 9, 10
 

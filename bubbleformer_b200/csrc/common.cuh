@@ -458,6 +458,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 
 // Instruction descriptor for kind::f16: fp32 accumulate, A/B format (0 = fp16, 1 = bf16), majors, N, M.
+// (A and B carry their own format fields, but they must agree: fp16 x bf16 is an illegal instruction on sm_100a.)
 __host__ __device__ constexpr uint32_t make_idesc_f16(int fmt, int a_mn_major, int b_mn_major, int M, int N) {
   return (1u << 4) | (static_cast<uint32_t>(fmt) << 7) | (static_cast<uint32_t>(fmt) << 10) |
          (static_cast<uint32_t>(a_mn_major) << 15) | (static_cast<uint32_t>(b_mn_major) << 16) |

@@ -49,6 +49,8 @@ struct GemmParams {
   int s2d;            // 1: A coords are 4-D (k, xo, ky, row), B coords 3-D (k, ky, n)
   int s2d_box_w;      // xo extent of the A box (divides 128)
   int s2d_wo;         // output width
+  int b_s2d;          // 1: B (MN-major, K = output pixels) is the implicit patch gather: 4-D coords (n in segment, xo, ky, row)
+  int b_seg;          // B_S2D: elements per ky segment (2 * cin)
   uint32_t idesc;
   int is_f16;
   int gelu_exact;     // GELU / DGELU epilogues: 1 = exact erf (bf_set_gelu_mode), 0 = tanh form
@@ -311,9 +313,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             if (res) {
               // B is already resident
             } else if (B_MN) {
+              if (p.b_s2d) {
+                // k0 .. k0+63 are 64 consecutive output pixels of one image row; each 64-column block lies in one ky segment
+                const int xo0 = k0 % p.s2d_wo, r0 = k0 / p.s2d_wo;
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j)
-                tma_load_2d(sb + j * (64 * BK * 2), &map_b, full_bar + stage, n0 + 64 * j, k0);
+                for (int j = 0; j < BN / 64; ++j) {
+                  const int n = n0 + 64 * j;
+                  const int ky = n / p.b_seg;
+                  tma_load_4d(sb + j * (64 * BK * 2), &map_b, full_bar + stage, n - ky * p.b_seg, xo0, ky, r0);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j)
+                  tma_load_2d(sb + j * (64 * BK * 2), &map_b, full_bar + stage, n0 + 64 * j, k0);
+              }
             } else {
               tma_load_2d(sb, &map_b, full_bar + stage, k0, n0);
             }
@@ -1053,8 +1066,11 @@ extern "C" int bf_gemm(const bf_gemm_args* a, void* stream) {
   BF_REQUIRE((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->B) & 15) == 0,
              "bf_gemm: operands must be 16-byte aligned");
   const bool a_mn = a->a_mode == BF_A_KM;
-  const bool b_mn = a->b_mode == BF_B_KN;
+  const bool b_s2d = a->b_mode == BF_B_KN_S2D;
+  const bool b_mn = a->b_mode == BF_B_KN || b_s2d;
   const bool s2d = a->a_mode == BF_A_S2D;
+  const int b_dtype = a->dtype;
+  BF_REQUIRE(!b_s2d || (a_mn && a->split_k >= 1), "bf_gemm: B_KN_S2D is the wgrad form (needs a_mode BF_A_KM)");
   BF_REQUIRE(!(a_mn && !b_mn), "bf_gemm: A_KM requires B_KN (wgrad form)");
   BF_REQUIRE(a->split_k >= 1, "bf_gemm: split_k %d", a->split_k);
   BF_REQUIRE(a->split_k == 1 || a->epilogue == BF_EPI_ATOMIC32, "bf_gemm: split_k > 1 needs BF_EPI_ATOMIC32");
@@ -1175,18 +1191,30 @@ extern "C" int bf_gemm(const bf_gemm_args* a, void* stream) {
       uint32_t box[2] = {BK, BM};
       if ((st = make_map(&mp.a, a->dtype, a->A, 2, dims, str, box, SW128))) return st;
     }
-    if (b_mn) {   // (K, N) row-major: inner dim N
+    if (b_s2d) {  // implicit patch gather, K = output pixels: (n in ky segment = 2C, xo = Wo, ky = 2, row = I*Ho)
+      const int C = a->s2d_cin, Hin = a->s2d_hin, Win = a->s2d_win, I = a->s2d_images;
+      BF_REQUIRE(C > 0 && Hin > 0 && Win > 0 && I > 0 && Hin % 2 == 0 && Win % 2 == 0, "bf_gemm: B_KN_S2D geometry");
+      const int Ho = Hin / 2, Wo = Win / 2, seg = 2 * C;
+      BF_REQUIRE(a->N == 4 * C && (long)a->K == (long)I * Ho * Wo, "bf_gemm: B_KN_S2D needs N == 4*cin and K == images*ho*wo");
+      BF_REQUIRE(Wo % 64 == 0 && seg % 64 == 0, "bf_gemm: B_KN_S2D needs wo %% 64 == 0 and (2*cin) %% 64 == 0 (wo=%d cin=%d)", Wo, C);
+      BF_REQUIRE(cg == 1 && !p.b_resident, "bf_gemm: B_KN_S2D runs on the single-CTA streaming schedule");
+      p.b_s2d = 1; p.b_seg = seg; p.s2d_wo = Wo;
+      uint64_t dims[4] = {(uint64_t)seg, (uint64_t)Wo, 2, (uint64_t)I * Ho};
+      uint64_t str[3] = {(uint64_t)seg * 2, (uint64_t)Win * C * 2, (uint64_t)2 * Win * C * 2};
+      uint32_t box[4] = {64, BK, 1, 1};
+      if ((st = make_map(&mp.b, b_dtype, a->B, 4, dims, str, box, SW128))) return st;
+    } else if (b_mn) {   // (K, N) row-major: inner dim N
       BF_REQUIRE(a->ldb >= a->N, "bf_gemm: ldb < N");
       uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->K};
       uint64_t str[1] = {(uint64_t)a->ldb * 2};
       uint32_t box[2] = {64, BK};
-      if ((st = make_map(&mp.b, a->dtype, a->B, 2, dims, str, box, SW128))) return st;
+      if ((st = make_map(&mp.b, b_dtype, a->B, 2, dims, str, box, SW128))) return st;
     } else {
       BF_REQUIRE(a->ldb >= a->K, "bf_gemm: ldb < K");
       uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
       uint64_t str[1] = {(uint64_t)a->ldb * 2};
       uint32_t box[2] = {BK, (uint32_t)(bn / cg)};
-      if ((st = make_map(&mp.b, a->dtype, a->B, 2, dims, str, box, SW128))) return st;
+      if ((st = make_map(&mp.b, b_dtype, a->B, 2, dims, str, box, SW128))) return st;
     }
   }
 

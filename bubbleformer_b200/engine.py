@@ -41,6 +41,7 @@ NORM_FUSED = _os.environ.get("BF_NORM_FUSED", "0") == "1"
 # private tables (no shared atomics) the fusion is correct and cheap per tile, but the attention backward is bound by its
 # instruction count and the separate pass finds d qkv in L2: 26.29 vs 26.08 ms per step (same-box A/B, r2v).  Opt-in.
 ATTN_FUSED_BIAS = _os.environ.get("BF_ATTN_FUSED_BIAS", "0") == "1"
+IMPLICIT_GATHER = _os.environ.get("BF_IMPLICIT_GATHER", "1") != "0"     # head backward reads dZ in place (no s2d_gather copy)
 
 
 def set_exact_mode(on: bool) -> None:
@@ -596,21 +597,33 @@ def debed_backward(dOut, g: Geom, p, n_layers: int, sv, grads):
         dZ = _empty((4 * M, Cout), BF16, dOut)
         ops.inorm_bwd(2, gin, Z, I, 4 * h_ * w_, st, nw, nb, red, gelu=True, out=dZ,
                       dweight=grads[f"out_proj.{3 * i + 1}.weight"], dbias=grads[f"out_proj.{3 * i + 1}.bias"])
-        # gather dZ (I, 2h, 2w, Cout) into (M, (ky, kx, co)): A operand of the dgrad and B operand of the wgrad
-        dZg = _empty((M, 4 * Cout), BF16, dOut)
-        ops.s2d_gather(dZ.view(I, 2 * h_, 2 * w_, Cout), dZg)
+        # dZ (I, 2h, 2w, Cout) enters both GEMMs as the 2x2 patch gather (M, (ky, kx, co)): the A operand of the dgrad and
+        # the B operand of the wgrad.  With 64-pixel row segments both read it in place through 4-D tensor maps
+        # (BF_A_S2D / BF_B_KN_S2D); otherwise one gathered copy is made.
+        implicit = IMPLICIT_GATHER and not EXACT and _s2d_ok(w_) and w_ % 64 == 0 and (2 * Cout) % 64 == 0
         Ab = _empty(tuple(A.shape), BF16, dOut)
         ops.convert16(A, Ab)
         dWp = _zeros((Cin, 4 * Cout), dOut)
-        ops.gemm(Ab, dZg, Cin, 4 * Cout, M, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
-                 split_k=pick_split(M, Cin, 4 * Cout), out32=dWp)
-        grads[f"out_proj.{3 * i}.weight"] += dWp.view(Cin, 2, 2, Cout).permute(0, 3, 1, 2)
         Wb = _convT_w(wt, BF16)                                   # (Cin, 4*Cout) = (N, K) of the dgrad
+        if implicit:
+            s2d = (I, 2 * h_, 2 * w_, Cout)
+            dZ2 = dZ.view(-1, Cout)
+            ops.gemm(Ab, dZ2, Cin, 4 * Cout, M, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN_S2D, s2d=s2d,
+                     split_k=pick_split(M, Cin, 4 * Cout), out32=dWp)
+            akw = dict(a_mode=L.A_S2D, s2d=s2d, ldb=4 * Cout)
+            dZg = dZ2
+        else:
+            dZg = _empty((M, 4 * Cout), BF16, dOut)
+            ops.s2d_gather(dZ.view(I, 2 * h_, 2 * w_, Cout), dZg)
+            ops.gemm(Ab, dZg, Cin, 4 * Cout, M, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
+                     split_k=pick_split(M, Cin, 4 * Cout), out32=dWp)
+            akw = {}
+        grads[f"out_proj.{3 * i}.weight"] += dWp.view(Cin, 2, 2, Cout).permute(0, 3, 1, 2)
         if i == 0:
             dX = _empty((M, Cin), F32, dOut)
-            ops.gemm(dZg, Wb, M, Cin, 4 * Cout, epilogue=L.EPI_STORE32, out32=dX)
+            ops.gemm(dZg, Wb, M, Cin, 4 * Cout, epilogue=L.EPI_STORE32, out32=dX, **akw)
             return dX
         dA = _empty((M, Cin), BF16, dOut)
-        ops.gemm(dZg, Wb, M, Cin, 4 * Cout, epilogue=L.EPI_STORE16, out16=dA)
+        ops.gemm(dZg, Wb, M, Cin, 4 * Cout, epilogue=L.EPI_STORE16, out16=dA, **akw)
         gin = dA
     return dX

@@ -84,7 +84,13 @@ enum bf_a_mode {
 };
 enum bf_b_mode {
   BF_B_NK = 0, /* B is (N, K) row-major: a weight matrix as PyTorch stores it                         */
-  BF_B_KN = 1  /* B is (K, N) row-major: dgrad reads the same weight without a transposed copy; wgrad  */
+  BF_B_KN = 1, /* B is (K, N) row-major: dgrad reads the same weight without a transposed copy; wgrad  */
+  BF_B_KN_S2D = 2 /* wgrad of a 2x2/stride-2 conv stage without a gathered copy: B[k, n] is the implicit patch gather of
+                     a channels-last image tensor (s2d_* geometry), k = output pixel (img, yo, xo) -- the contraction
+                     index, K = images*hin/2*win/2 -- and n = (ky, kx, ci), N = 4*cin.  Needs a_mode BF_A_KM,
+                     (win/2) % 64 == 0 and (2*cin) % 64 == 0; A and B have the same 16-bit type (tcgen05 kind::f16 with an
+                     fp16 operand against a bf16 one is an illegal instruction on sm_100a: measured).
+                     layers/patching.py:37-44, 93-99 (autograd wgrad)                                            */
 };
 enum bf_epilogue {
   BF_EPI_STORE16 = 0, /* out16 = acc + bias                                                            */

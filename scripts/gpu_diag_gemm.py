@@ -16,7 +16,7 @@ VARIANTS = [
     "nk_f16", "gelu", "gelu_d", "dmul", "gelu_d_big", "dmul_big", "resid", "resid_stats", "qkv_ln", "dgelu", "acc32", "store32",
     "gelu_big", "resid_big", "resid_stats_big", "dgelu_big", "kn_dgrad_res",        # config-2 shapes: the B-resident schedule
     "kn_dgrad", "kn_dgrad_256", "wgrad", "wgrad_split", "wgrad_192",
-    "s2d_w128", "s2d_w32", "s2d_c48", "d2s", "d2s_c48", "perf",
+    "s2d_w128", "s2d_w32", "s2d_c48", "d2s", "d2s_c48", "bs2d", "bs2d_split", "bs2d_c192", "perf",
 ]
 
 
@@ -186,6 +186,20 @@ def run_variant(v):
                  split_k=8 if v == "wgrad_split" else 1, out32=out,
                  bn=192 if v == "wgrad_192" else 0)
         ok &= report(v, out, dY.float().t() @ X.float(), 1e-4)
+    elif v.startswith("bs2d"):
+        # weight gradient of a 2x2/s2 conv stage: dW[co, (ky,kx,ci)] = sum_pixels dY[pix, co] * patch[pix, (ky,kx,ci)] with
+        # B = the implicit patch gather of the image tensor (no gathered copy)
+        I, Hin, Win, Cin, Co, tA, sk = {"bs2d": (2, 8, 256, 96, 96, torch.bfloat16, 1),
+                                        "bs2d_split": (3, 16, 128, 96, 96, torch.bfloat16, 5),
+                                        "bs2d_c192": (1, 8, 128, 192, 192, torch.float16, 3)}[v]
+        img = (torch.randn(I, Hin, Win, Cin, device=dev)).to(tA)
+        M = I * (Hin // 2) * (Win // 2)
+        dY = (torch.randn(M, Co, device=dev) * M ** -0.5).to(tA)
+        out = torch.zeros(Co, 4 * Cin, device=dev)
+        ops.gemm(dY, img.view(-1, Cin), Co, 4 * Cin, M, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN_S2D,
+                 s2d=(I, Hin, Win, Cin), split_k=sk, out32=out)
+        g = img.float().reshape(I, Hin // 2, 2, Win // 2, 2, Cin).permute(0, 1, 3, 2, 4, 5).reshape(M, 4 * Cin)
+        ok &= report(v, out, dY.float().t() @ g, 1e-4)
     elif v.startswith("s2d"):
         I, Hin, Win, Cin, N = {"s2d_w128": (2, 8, 256, 96, 96), "s2d_w32": (3, 64, 64, 96, 384),
                                "s2d_c48": (2, 16, 32, 48, 48)}[v]

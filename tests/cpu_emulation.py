@@ -32,7 +32,11 @@ def gemm(A, B, M, N, K, *, epilogue, a_mode=L.A_ROWMAJOR, b_mode=L.B_NK, split_k
     else:
         a = a.reshape(M, K)
     b = B.float()
-    b = b.reshape(K, N) if b_mode == L.B_KN else b.reshape(N, K).t()
+    if b_mode == L.B_KN_S2D:          # implicit patch gather, K = output pixels
+        I, Hin, Win, Cin = s2d
+        b = b.reshape(I, Hin // 2, 2, Win // 2, 2, Cin).permute(0, 1, 3, 2, 4, 5).reshape(K, N)
+    else:
+        b = b.reshape(K, N) if b_mode == L.B_KN else b.reshape(N, K).t()
     acc = a @ b
     if bias is not None:
         acc = acc + bias

@@ -26,7 +26,7 @@ def _native_loaded():
 @pytest.mark.parametrize("variant", [
     "nk_small", "nk_ragged", "nk_bn64", "nk_bn128", "nk_bn192", "nk_bn256", "nk_big", "nk_pair_ragged", "nk_pair_odd", "nk_f16", "gelu", "gelu_d", "dmul", "gelu_d_big", "dmul_big", "resid", "resid_stats", "qkv_ln",
     "dgelu", "acc32", "store32", "kn_dgrad", "kn_dgrad_256", "wgrad", "wgrad_split", "wgrad_192", "s2d_w128",
-    "s2d_w32", "s2d_c48", "d2s", "d2s_c48",
+    "s2d_w32", "s2d_c48", "d2s", "d2s_c48", "bs2d", "bs2d_split", "bs2d_c192",
     "gelu_big", "resid_big", "resid_stats_big", "dgelu_big", "kn_dgrad_res"])     # config-2 shapes: B-resident schedule
 def test_gemm(variant):
     import gpu_diag_gemm
