@@ -154,7 +154,7 @@ lib.bf_eikonal_sums.argtypes = [_vp, _vp, _i64, _i, _i, C.c_float, _vp]
 lib.bf_heatflux_rows.argtypes = [_vp, _vp, _vp, _i64, _i64, _i, C.c_float, C.c_float, C.c_float, C.c_float, _vp]
 lib.bf_optim_step.argtypes = [_i, _vp, _vp, _vp, _vp, _vp, _i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                               _i64, _vp]
-lib.bf_feat_consts.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]
+lib.bf_feat_consts.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]
 lib.bf_branch_param_grads.argtypes = [C.POINTER(BranchGradArgs), _vp]
 lib.bf_set_gelu_mode.argtypes = [_i]
 lib.bf_film_fwd.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]

@@ -13,8 +13,8 @@ namespace bf {
 // one block per output channel j: c[j] = sum_i W[j,i]*nb[i] + b[j]
 __global__ void __launch_bounds__(128)
 feat_consts_kernel(const float* __restrict__ W, const float* __restrict__ nb, const float* __restrict__ bout,
-                   const float* __restrict__ lo, const float* __restrict__ hi, int E, float* __restrict__ c,
-                   float* __restrict__ c1, float* __restrict__ c0) {
+                   const float* __restrict__ lo, const float* __restrict__ hi, const float* __restrict__ gamma, int E,
+                   float* __restrict__ c, float* __restrict__ c1, float* __restrict__ c0, float* __restrict__ coef) {
   pdl_prologue_done();
   __shared__ float sh[4];
   const int j = blockIdx.x;
@@ -28,6 +28,7 @@ feat_consts_kernel(const float* __restrict__ W, const float* __restrict__ nb, co
     c[j] = cj;
     c1[j] = 1.f + hi[j];
     c0[j] = cj * (lo[j] - hi[j]);
+    if (coef != nullptr) coef[j] = gamma[j] * (1.f + hi[j]);
   }
 }
 
@@ -217,10 +218,12 @@ extern "C" int bf_film_bwd(const float* dgb, const float* cond, int B, int F, co
   return BF_OK;
 }
 extern "C" int bf_feat_consts(const float* W, const float* norm2_bias, const float* out_bias, const float* low,
-                              const float* high, int E, float* c, float* c1, float* c0, void* stream) {
+                              const float* high, const float* gamma, int E, float* c, float* c1, float* c0, float* coef,
+                              void* stream) {
   BF_REQUIRE(W && norm2_bias && out_bias && low && high && c && c1 && c0 && E > 0, "bf_feat_consts: bad arguments");
+  BF_REQUIRE((gamma == nullptr) == (coef == nullptr), "bf_feat_consts: gamma and coef go together");
   launch_k(feat_consts_kernel, dim3(E), dim3(128), (size_t)0, static_cast<cudaStream_t>(stream), W, norm2_bias, out_bias,
-           low, high, E, c, c1, c0);
+           low, high, gamma, E, c, c1, c0, coef);
   count_launch();
   BF_LAUNCH_CHECK("feat_consts_kernel");
   return BF_OK;

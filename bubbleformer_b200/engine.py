@@ -130,7 +130,7 @@ class _ZeroArena:
     issues a handful of fill kernels instead of one per buffer.  A region is handed out once and never reused;
     `reset()` (called at the start of every model forward) drops the chunk, which also keeps CUDA-graph captures
     self-contained (the fill of the chunk is recorded inside the capture)."""
-    CHUNK = 1 << 20          # floats
+    CHUNK = 1 << 22          # floats (16 MiB: a config-2 forward + backward takes ~4 M floats of statistics / reductions)
 
     def __init__(self):
         self.buf = None
@@ -346,18 +346,18 @@ def _feat_consts(p, feat_scale: bool):
     IN has zero mean per image and channel), so the op is the per-channel affine z*(1+high) + c*(low-high).
     """
     if not feat_scale:
-        return None, None, None
+        return None, None, None, None
     return ops.feat_consts(p["output_head.weight"], p["norm2.bias"], p["output_head.bias"], p["low_freq_scalar"],
-                           p["high_freq_scalar"])
+                           p["high_freq_scalar"], gamma=p["gamma_att"])
 
 
 def spatial_forward(X, g: Geom, p, w16, heads: int, attn_scale: bool, feat_scale: bool, mask_att, mask_mlp, save: bool):
     I, P, N, E = g.I, g.P, g.N, X.shape[1]
     keys = ["attn_scale_factor_x", "attn_scale_factor_y"] if attn_scale else None
-    c, c1, c0 = _feat_consts(p, feat_scale)
+    c, c1, c0, coef = _feat_consts(p, feat_scale)
     Xmid, Xb, sv = _attn_branch_fwd(X, g, p, w16, heads, ["x", "y"], keys, mask_att, c1, c0, p["gamma_att"], True, save)
     if save:
-        sv["feat"] = (c, c1, c0)
+        sv["feat"] = (c, c1, c0, coef)
     G = _empty((N, 4 * E), BF16, X)
     Hpre = _empty((N, 4 * E), BF16, X) if save else None
     # the second output is gelu'(pre), not pre: the tanh is evaluated once and the backward epilogue is a multiply
@@ -405,9 +405,10 @@ def spatial_backward(dXout, g: Geom, p, w16, heads: int, attn_scale: bool, feat_
              split_k=pick_split(N, 4 * E, E), out32=grads["mlp.fc1.weight"])
     # ---- attention branch ----
     keys = ["attn_scale_factor_x", "attn_scale_factor_y"] if attn_scale else None
-    c, c1, c0 = sv["feat"] if "feat" in sv else _feat_consts(p, feat_scale)
+    c, c1, c0, coef = sv["feat"] if "feat" in sv else _feat_consts(p, feat_scale)
     ga = p["gamma_att"]
-    coef = (ga * c1).contiguous() if feat_scale else ga
+    if not feat_scale:
+        coef = ga
     dX, S01 = _attn_branch_bwd(dXmid, g, p, w16, heads, ["x", "y"], keys, mask_att, coef, sv, grads)
     feat = None
     if feat_scale:

@@ -222,14 +222,16 @@ def resid_bwd(dx, z16, dz16, I, P, row_scale, coef, S0, S1) -> None:
                                _f32(S1, I * Cn, "S1"), _stream()), "bf_resid_bwd")
 
 
-def feat_consts(W, norm2_bias, out_bias, low, high):
-    """(c, c1, c0) of the axial block's feature scaling; W: output_head.weight viewed (E, E) fp32."""
+def feat_consts(W, norm2_bias, out_bias, low, high, gamma=None):
+    """(c, c1, c0) of the axial block's feature scaling -- plus coef = gamma*c1 when `gamma` is given; W: output_head.weight
+    viewed (E, E) fp32."""
     E = W.shape[0]
-    out = torch.empty(3, E, dtype=torch.float32, device=W.device)
+    out = torch.empty(4 if gamma is not None else 3, E, dtype=torch.float32, device=W.device)
     L.check(L.lib.bf_feat_consts(_f32(W, E * E, "W"), _f32(norm2_bias, E, "norm2_bias"), _f32(out_bias, E, "out_bias"),
-                                 _f32(low, E, "low"), _f32(high, E, "high"), E, _ptr(out[0]), _ptr(out[1]), _ptr(out[2]),
+                                 _f32(low, E, "low"), _f32(high, E, "high"), _f32(gamma, E, "gamma"), E, _ptr(out[0]),
+                                 _ptr(out[1]), _ptr(out[2]), _ptr(out[3]) if gamma is not None else None,
                                  _stream()), "bf_feat_consts")
-    return out[0], out[1], out[2]
+    return tuple(out[i] for i in range(out.shape[0]))
 
 
 def branch_param_grads(S01, gamma, d_gamma, d_out_bias, feat=None) -> None:

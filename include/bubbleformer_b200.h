@@ -235,9 +235,11 @@ BF_API int bf_resid_bwd(const float* dx, int64_t lddx, const void* z16, void* dz
 
 /* Feature-scaling constants of the axial block (upstream layers/attention.py:302-307).  The per-image mean of
  * z = IN(o) W^T + b is exactly c = W b_norm2 + b_out, so  z + mean(z)*low + (z - mean(z))*high == z*c1 + c0  with
- * c1 = 1 + high, c0 = c*(low - high).  W: output_head.weight (E, E) fp32; all outputs [E].                     */
+ * c1 = 1 + high, c0 = c*(low - high).  W: output_head.weight (E, E) fp32; all outputs [E].  gamma / coef (both or
+ * neither, may be NULL): coef = gamma*c1, the factor between dX_out and dZ that the backward pass needs.        */
 BF_API int bf_feat_consts(const float* W, const float* norm2_bias, const float* out_bias, const float* low,
-                          const float* high, int E, float* c, float* c1, float* c0, void* stream);
+                          const float* high, const float* gamma, int E, float* c, float* c1, float* c0, float* coef,
+                          void* stream);
 
 /* Parameter gradients of one residual branch  X_out = X + mask*gamma*(Z*c1 + c0)  from the per-image sums of
  * bf_resid_bwd (S01 = (2, I, E): S0 = sum mask*dX_out, S1 = sum mask*dX_out*Z), accumulated in place:

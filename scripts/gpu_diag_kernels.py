@@ -372,9 +372,10 @@ def run(group):
             ga, lo, hi, nb, bo = (torch.randn(E, device=dev) for _ in range(5))
             W = torch.randn(E, E, 1, 1, device=dev) / E ** 0.5
             if fs:
-                c, c1, c0 = ops.feat_consts(W, nb, bo, lo, hi)
-                rc, rc1, rc0 = emu.feat_consts(W, nb, bo, lo, hi)
-                for nm, a_, b_ in (("c", c, rc), ("c1", c1, rc1), ("c0", c0, rc0)):
+                c, c1, c0, cf = ops.feat_consts(W, nb, bo, lo, hi, gamma=ga)
+                rc, rc1, rc0, rcf = emu.feat_consts(W, nb, bo, lo, hi, gamma=ga)
+                assert len(ops.feat_consts(W, nb, bo, lo, hi)) == 3
+                for nm, a_, b_ in (("c", c, rc), ("c1", c1, rc1), ("c0", c0, rc0), ("coef", cf, rcf)):
                     ok &= report(f"feat_consts {nm} E={E}", a_, b_, 1e-5)
             names = ["d_gamma", "d_out_bias", "d_low", "d_high", "d_W", "d_norm2_bias"]
             got = {n: torch.randn(E * E if n == "d_W" else E, device=dev) for n in names}

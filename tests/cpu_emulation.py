@@ -207,9 +207,11 @@ def resid_bwd(dx, z16, dz16, I, P, row_scale, coef, S0, S1):
         S1.reshape(I, C).add_((rs * dx * z16.float()).reshape(I, P, C).sum(1))
 
 
-def feat_consts(W, norm2_bias, out_bias, low, high):
+def feat_consts(W, norm2_bias, out_bias, low, high, gamma=None):
     Wm = W.reshape(W.shape[0], -1)
     c = (Wm * norm2_bias[None, :]).sum(dim=1) + out_bias
+    if gamma is not None:
+        return c, 1.0 + high, c * (low - high), gamma * (1.0 + high)
     return c, 1.0 + high, c * (low - high)
 
 
