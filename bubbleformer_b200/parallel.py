@@ -43,7 +43,11 @@ class GradSink:
             import os
             from . import _lib
             n = os.environ.get("BF_RESERVED_SMS", os.environ.get("NCCL_MAX_CTAS", "0"))
-            _lib.check(_lib.lib.bf_set_reserved_sms(int(n or 0)), "bf_set_reserved_sms")
+            try:
+                n = min(max(int(n or 0), 0), 32)     # a large NCCL_MAX_CTAS must not take a fifth of the machine away
+            except ValueError:
+                n = 0
+            _lib.check(_lib.lib.bf_set_reserved_sms(n), "bf_set_reserved_sms")
         self._pending: List = []
         self._lo: Optional[int] = None
         self._hi: Optional[int] = None
