@@ -40,7 +40,10 @@ class _SlabRatio(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         pred, tgt, sums = ctx.saved_tensors
-        coef = (g.reshape(-1).float() * torch.rsqrt(sums[:, 0] * sums[:, 1])).contiguous()
+        # d ratio / d pred = (pred - tgt) / (||pred - tgt|| ||tgt||); a slab with pred == tgt has the sub-gradient 0 (not
+        # rsqrt(0) * 0 = NaN), which is also what upstream's torch.norm backward returns at zero
+        prod = sums[:, 0] * sums[:, 1]
+        coef = torch.where(prod > 0, g.reshape(-1).float() * torch.rsqrt(prod), torch.zeros_like(prod)).contiguous()
         dpred = torch.empty_like(pred)
         H, W = pred.shape[-2:]
         ops.lploss_bwd(pred.view(1, 1, -1, H, W), tgt.view(1, 1, -1, H, W), coef, dpred.view(1, 1, -1, H, W))

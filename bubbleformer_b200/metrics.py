@@ -24,7 +24,11 @@ def _check(t: torch.Tensor, nd: int, name: str) -> torch.Tensor:
 
 
 def eikonal_loss(phi: torch.Tensor, dx: float = 1.0 / 32) -> torch.Tensor:
-    """phi: SDF (B, T, H, W).  Scalar tensor."""
+    """phi: SDF (B, T, H, W).  Scalar tensor.  A rollout metric (upstream evaluates it under no_grad, inference.py):
+    the kernel has no backward, so a gradient request fails loudly instead of returning a silently detached value."""
+    if phi.requires_grad and torch.is_grad_enabled():
+        raise NotImplementedError("bubbleformer_b200.eikonal_loss is a no-grad rollout metric (call it under "
+                                  "torch.no_grad() or on a detached tensor); it has no backward kernel")
     phi = _check(phi, 4, "phi")
     B, T, H, W = phi.shape
     sums = torch.zeros(B * T, dtype=torch.float32, device=phi.device)
