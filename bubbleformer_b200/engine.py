@@ -125,6 +125,51 @@ def _empty(shape, dtype, like):
     return torch.empty(shape, dtype=dtype, device=like.device)
 
 
+# The block weight-gradient GEMMs have no consumer inside the backward pass (only the optimiser / the gradient
+# all-reduce read them), so they leave the dependent chain: each is issued on a second stream that forks from the
+# current one at the point of issue and is joined before the block's backward returns (every operand is still
+# referenced until then, and GradSink's bucket logic sees a finished block exactly as before).  Their CTAs fill the
+# partial last waves of the input-gradient / norm kernels on the main chain; inside a CUDA-graph capture the fork and
+# join become graph edges.  Measured on B200 (same-box A/B of the replayed config-2 step, gpurun_out/r6_*): 25.08 ->
+# 24.78 ms per step.  Also moving the bias column sums, the per-channel parameter kernels and the stem / head weight
+# gradients there, or forking before the input-gradient GEMM, measured neutral (r6b_*) and is not kept.
+# BF_WGRAD_STREAM=0 keeps everything on one stream.
+WGRAD_STREAM = _os.environ.get("BF_WGRAD_STREAM", "1") != "0"
+_SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+_SIDE_DIRTY = False
+
+
+class _WgradStream:
+    def __enter__(self):
+        global _SIDE_DIRTY
+        self.on = WGRAD_STREAM and not EXACT and torch.cuda.is_available()   # (the CPU emulation of tests/ has no streams)
+        if not self.on:
+            return self
+        main = torch.cuda.current_stream()
+        dev = main.device.index
+        side = _SIDE_STREAMS.get(dev)
+        if side is None:
+            side = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=main.device)
+        side.wait_stream(main)
+        self._ctx = torch.cuda.stream(side)
+        self._ctx.__enter__()
+        _SIDE_DIRTY = True
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self._ctx.__exit__(*exc)
+        return False
+
+
+def _wgrad_join() -> None:
+    global _SIDE_DIRTY
+    if _SIDE_DIRTY:
+        main = torch.cuda.current_stream()
+        main.wait_stream(_SIDE_STREAMS[main.device.index])
+        _SIDE_DIRTY = False
+
+
 class _ZeroArena:
     """Small zero-initialised fp32 buffers (statistics, reductions) carved from one zero-filled chunk, so a step
     issues a handful of fill kernels instead of one per buffer.  A region is handed out once and never reused;
@@ -279,8 +324,9 @@ def _attn_branch_bwd(dXout, g: Geom, p, w16, heads: int, axes, scale_keys, mask_
     # output_head: dgrad reads W (E_out, E_in) as the (K, N) operand, wgrad contracts over tokens
     dOn = _empty((N, E), BF16, dXout)
     ops.gemm(dZ, w16("output_head.weight"), N, E, E, epilogue=L.EPI_STORE16, b_mode=L.B_KN, out16=dOn)
-    ops.gemm(dZ, On, E, E, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN, split_k=pick_split(N, E, E),
-             out32=grads["output_head.weight"].view(E, E))
+    with _WgradStream():
+        ops.gemm(dZ, On, E, E, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN, split_k=pick_split(N, E, E),
+                 out32=grads["output_head.weight"].view(E, E))
     # norm2
     dO = _empty((N, E), BF16, dXout)
     _norm_bwd(dOn, O, I, P, st2, p["norm2.weight"], p["norm2.bias"], out=dO,
@@ -309,8 +355,9 @@ def _attn_branch_bwd(dXout, g: Geom, p, w16, heads: int, axes, scale_keys, mask_
     # input_head
     dXn = _empty((N, E), BF16, dXout)
     ops.gemm(dQKV, w16("input_head.weight"), N, E, 3 * E, epilogue=L.EPI_STORE16, b_mode=L.B_KN, out16=dXn)
-    ops.gemm(dQKV, Xn, 3 * E, E, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
-             split_k=pick_split(N, 3 * E, E), out32=grads["input_head.weight"].view(3 * E, E))
+    with _WgradStream():
+        ops.gemm(dQKV, Xn, 3 * E, E, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
+                 split_k=pick_split(N, 3 * E, E), out32=grads["input_head.weight"].view(3 * E, E))
     # norm1 (+ the identity path of the residual)
     dX = _empty((N, E), F32, dXout)
     _norm_bwd(dXn, X, I, P, st1, p["norm1.weight"], p["norm1.bias"], out=dX, add32=dXout,
@@ -333,6 +380,7 @@ def temporal_backward(dXout, g: Geom, p, w16, heads: int, attn_scale: bool, mask
     dX, S01 = _attn_branch_bwd(dXout, g, p, w16, heads, ["t"], keys, mask_img, p["gamma"], sv, grads)
     # d_gamma += S1 (d/dgamma of mask*gamma*Z), d_output_head.bias += gamma*S0
     ops.branch_param_grads(S01, p["gamma"], grads["gamma"], grads["output_head.bias"])
+    _wgrad_join()
     return dX
 
 
@@ -396,13 +444,15 @@ def spatial_backward(dXout, g: Geom, p, w16, heads: int, attn_scale: bool, feat_
     ops.gemm(dY2, w16("mlp.fc2.weight"), N, 4 * E, E, epilogue=L.EPI_DMUL if MLP_SAVES_DERIVATIVE else L.EPI_DGELU,
              b_mode=L.B_KN, aux16=Hpre, out16=dH, bn=DMUL_BN,
              colsum_out=grads["mlp.fc1.bias"])
-    ops.gemm(dY2, G, E, 4 * E, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
-             split_k=pick_split(N, E, 4 * E), out32=grads["mlp.fc2.weight"])
+    with _WgradStream():
+        ops.gemm(dY2, G, E, 4 * E, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
+                 split_k=pick_split(N, E, 4 * E), out32=grads["mlp.fc2.weight"])
     # fc1: the input gradient joins the residual-stream gradient in the epilogue
     dXmid = _empty((N, E), F32, dXout)
     ops.gemm(dH, w16("mlp.fc1.weight"), N, E, 4 * E, epilogue=L.EPI_ACC32, b_mode=L.B_KN, in32=dXout, out32=dXmid)
-    ops.gemm(dH, Xb, 4 * E, E, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
-             split_k=pick_split(N, 4 * E, E), out32=grads["mlp.fc1.weight"])
+    with _WgradStream():
+        ops.gemm(dH, Xb, 4 * E, E, N, epilogue=L.EPI_ATOMIC32, a_mode=L.A_KM, b_mode=L.B_KN,
+                 split_k=pick_split(N, 4 * E, E), out32=grads["mlp.fc1.weight"])
     # ---- attention branch ----
     keys = ["attn_scale_factor_x", "attn_scale_factor_y"] if attn_scale else None
     c, c1, c0, coef = sv["feat"] if "feat" in sv else _feat_consts(p, feat_scale)
@@ -418,6 +468,7 @@ def spatial_backward(dXout, g: Geom, p, w16, heads: int, attn_scale: bool, feat_
                     norm2_bias=p["norm2.bias"], d_low=grads["low_freq_scalar"], d_high=grads["high_freq_scalar"],
                     d_W=grads["output_head.weight"], d_norm2_bias=grads["norm2.bias"])
     ops.branch_param_grads(S01, ga, grads["gamma_att"], grads["output_head.bias"], feat)
+    _wgrad_join()
     return dX
 
 
