@@ -379,8 +379,8 @@ def temporal_backward(dXout, g: Geom, p, w16, heads: int, attn_scale: bool, mask
     keys = ["attn_scale_factor"] if attn_scale else None
     dX, S01 = _attn_branch_bwd(dXout, g, p, w16, heads, ["t"], keys, mask_img, p["gamma"], sv, grads)
     # d_gamma += S1 (d/dgamma of mask*gamma*Z), d_output_head.bias += gamma*S0
-    ops.branch_param_grads(S01, p["gamma"], grads["gamma"], grads["output_head.bias"])
     _wgrad_join()
+    ops.branch_param_grads(S01, p["gamma"], grads["gamma"], grads["output_head.bias"])
     return dX
 
 
@@ -467,8 +467,10 @@ def spatial_backward(dXout, g: Geom, p, w16, heads: int, attn_scale: bool, feat_
         feat = dict(c=c, c1=c1, c0=c0, low=p["low_freq_scalar"], high=p["high_freq_scalar"], W=p["output_head.weight"],
                     norm2_bias=p["norm2.bias"], d_low=grads["low_freq_scalar"], d_high=grads["high_freq_scalar"],
                     d_W=grads["output_head.weight"], d_norm2_bias=grads["norm2.bias"])
-    ops.branch_param_grads(S01, ga, grads["gamma_att"], grads["output_head.bias"], feat)
+    # (joined first: branch_param_grads adds the feature-scale term to d output_head.weight with plain read-modify-writes,
+    # which must not run beside the weight-gradient GEMM's reduce-adds into the same buffer)
     _wgrad_join()
+    ops.branch_param_grads(S01, ga, grads["gamma_att"], grads["output_head.bias"], feat)
     return dX
 
 
