@@ -13,6 +13,7 @@ parameters (:170-183), and the returned layouts (T, C, H, W) per sample.
 from __future__ import annotations
 
 import json
+import warnings
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -50,17 +51,20 @@ class DeviceForecastWindows:
         data = arrays if arrays is not None else [read_hdf5(f, self.fields) for f in filenames]   # only the fields used
         self.traj_lens = [int(d[self.input_fields[0]].shape[0]) for d in data]
         self.num_trajs = [1] * len(data)
-        self.host = [{k: np.asarray(d[k], dtype=np.float32) for k in self.fields} for d in data]
-        shapes = {d[k].shape[1:] for d in self.host for k in self.fields}
+        host = [{k: np.asarray(d[k], dtype=np.float32) for k in self.fields} for d in data]
+        shapes = {d[k].shape[1:] for d in host for k in self.fields}
         if len(shapes) != 1:
             raise ValueError("all fields of all trajectories must share one (H, W)")
         self.H, self.W = shapes.pop()
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("bubbleformer_b200 runs on CUDA only (no CPU fallback)")
-        stacked = np.concatenate([np.stack([d[k] for k in self.fields], axis=1) for d in self.host], axis=0)
-        self.frames = torch.from_numpy(np.ascontiguousarray(stacked)).to(dev)          # (sum frames, C, H, W)
-        del stacked, data                   # the raw file mapping is dropped; self.host keeps the fields for normalize()
+        # Host memory: one copy of the fields at a time.  Each field goes straight into its channel of the resident
+        # (sum frames, C, H, W) tensor (no stacked host copy), the per-file normalisation terms are taken now, and
+        # the host arrays / the raw file buffer are dropped.
+        self.frames = self._upload(host, self.fields, dev)
+        self._file_terms = [{k: self._field_terms(d[k], norm) for k in self.fields} for d in host]
+        del host, data
         self.downsample_factor = int(downsample_factor)
         if self.downsample_factor < 1:
             raise ValueError("downsample_factor must be >= 1")
@@ -86,6 +90,36 @@ class DeviceForecastWindows:
         self._upload_terms()
 
     @staticmethod
+    def _upload(host: List[Dict[str, np.ndarray]], fields: List[str], dev) -> torch.Tensor:
+        """(sum frames, C, H, W) fp32 on `dev`: trajectory after trajectory, field k in channel k."""
+        first = host[0][fields[0]]
+        total = sum(int(d[fields[0]].shape[0]) for d in host)
+        frames = torch.empty((total, len(fields)) + tuple(first.shape[1:]), dtype=torch.float32, device=dev)
+        base = 0
+        for d in host:
+            n = int(d[fields[0]].shape[0])
+            for c, k in enumerate(fields):
+                if d[k].shape[0] != n:
+                    raise ValueError(f"field {k} has {d[k].shape[0]} frames, expected {n}")
+                with warnings.catch_warnings():          # the reader hands out read-only views of the file buffer;
+                    warnings.simplefilter("ignore")      # they are only read here
+                    src = torch.from_numpy(np.ascontiguousarray(d[k]))
+                frames[base:base + n, c].copy_(src)
+            base += n
+        return frames
+
+    @staticmethod
+    def _field_terms(x: np.ndarray, norm: str):
+        """(subtract, divide) of one field of one file, as upstream's normalize() takes them (dataset.py:86-107)."""
+        if norm == "std":
+            return x.mean(), x.std()
+        if norm == "minmax":
+            return x.min(), x.max() - x.min()
+        if norm == "tanh":
+            return (x.max() + x.min()) / 2.0, (x.max() - x.min()) / 2.0
+        return 0.0, 1.0
+
+    @staticmethod
     def _nearest_index(n_in: int, factor: int) -> torch.Tensor:
         """Source indices of F.interpolate(mode="nearest") to n_in // factor: min(floor(dst * scale), n_in - 1), the
         scale n_in / n_out evaluated in float32 like ATen."""
@@ -103,19 +137,8 @@ class DeviceForecastWindows:
         if diff_terms is None and div_terms is None:
             diff_terms, div_terms = {}, {}
             for k in self.fields:
-                dl, vl = [], []
-                for d in self.host:
-                    x = d[k]
-                    if self.norm == "std":
-                        dl.append(x.mean()); vl.append(x.std())
-                    elif self.norm == "minmax":
-                        dl.append(x.min()); vl.append(x.max() - x.min())
-                    elif self.norm == "tanh":
-                        dl.append((x.max() + x.min()) / 2.0); vl.append((x.max() - x.min()) / 2.0)
-                    else:
-                        dl.append(0.0); vl.append(1.0)
-                diff_terms[k] = np.mean(dl).item()
-                div_terms[k] = np.mean(vl).item() + 1e-8
+                diff_terms[k] = np.mean([t[k][0] for t in self._file_terms]).item()
+                div_terms[k] = np.mean([t[k][1] for t in self._file_terms]).item() + 1e-8
         self.diff_terms, self.div_terms = diff_terms, div_terms
         self._upload_terms()
         return self.diff_terms, self.div_terms

@@ -213,3 +213,24 @@ def test_device_windows_downsample_and_fields_match_pinned_oracle(tmp_path):
             assert tuple(inp[b].shape) == ri.shape and tuple(tgt[b].shape) == ro.shape
             assert float((inp[b].cpu() - torch.from_numpy(ri)).abs().max()) < 1e-5 * max(1.0, float(np.abs(ri).max()))
             assert float((tgt[b].cpu() - torch.from_numpy(ro)).abs().max()) < 1e-5 * max(1.0, float(np.abs(ro).max()))
+
+
+@pytest.mark.parametrize("norm", ["none", "std", "minmax", "tanh"])
+def test_device_windows_host_side_pieces(norm):
+    """The host-side pieces of DeviceForecastWindows that need no GPU: the per-file normalisation terms (taken at
+    construction, so the host copies of the fields can be dropped) average to the oracle's constants, and the
+    channel-by-channel upload lays the trajectories out as (sum frames, C, H, W) like the stacked copy it replaced."""
+    import torch
+    from bubbleformer_b200.data import DeviceForecastWindows as D
+    from oracle import data_oracle as O
+    rng = np.random.default_rng(3)
+    fields = ["dfun", "temperature", "velx", "vely"]
+    arrays = [{k: (rng.standard_normal((n, 6, 8)) * (1 + i) + i).astype(np.float32) for i, k in enumerate(fields)} for n in (7, 5)]
+    terms = [{k: D._field_terms(a[k], norm) for k in fields} for a in arrays]
+    rd, rv = O.norm_terms(arrays, fields, norm)
+    for k in fields:
+        assert abs(np.mean([t[k][0] for t in terms]).item() - rd[k]) < 1e-6
+        assert abs(np.mean([t[k][1] for t in terms]).item() + 1e-8 - rv[k]) < 1e-6 * rv[k]
+    frames = D._upload(arrays, fields, torch.device("cpu"))
+    ref = np.concatenate([np.stack([a[k] for k in fields], axis=1) for a in arrays], axis=0)
+    assert frames.shape == (12, 4, 6, 8) and np.array_equal(frames.numpy(), ref)
