@@ -74,6 +74,29 @@ def shard_trajectories(n_traj: int, rank: int, world: int) -> Sequence[int]:
     return range(rank, n_traj, world)
 
 
+def gather_trajectories(local: torch.Tensor, n_traj: int, rank: int, world: int, group=None) -> torch.Tensor:
+    """Reassemble per-trajectory results after a sharded rollout (the optional gather at the end; the rollout itself
+    has no collective).  `local`: (this rank's trajectories in `shard_trajectories` order, ...).  Returns
+    (n_traj, ...) in trajectory order on every rank.  Shards are padded to the largest one for the all-gather."""
+    if world == 1:
+        return local
+    import torch.distributed as dist
+    mine = len(shard_trajectories(n_traj, rank, world))
+    if local.shape[0] != mine:
+        raise ValueError(f"rank {rank} holds {local.shape[0]} trajectories, its shard has {mine}")
+    per = -(-n_traj // world)
+    pad = local.new_zeros((per,) + tuple(local.shape[1:]))
+    pad[:mine] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    out = local.new_empty((n_traj,) + tuple(local.shape[1:]))
+    for r in range(world):
+        idx = list(shard_trajectories(n_traj, r, world))
+        if idx:
+            out[idx] = bufs[r][:len(idx)]
+    return out
+
+
 def evaluate_rollout(preds: torch.Tensor, targets: torch.Tensor, sdf_channel: int = 0) -> dict:
     """Metrics of one trajectory on the device: preds / targets (frames, C, H, W) as `scripts/inference.py:254-255`
     concatenates them.  Relative L2 per field (the criterion inference.py prints) and the eikonal residual of the
