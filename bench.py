@@ -475,22 +475,30 @@ def main():
             ev.record(copy_stream)
         return bufs, ev
 
+    loss_host = torch.empty(2, dtype=torch.float32).pin_memory()          # two slots: the read lags one step
+    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+
     def run_e2e(n):
         nxt = fetch()
-        prev = None
         host = 0.0
-        for _ in range(n):
+        for i in range(n):
             (xd, td, cd), ev = nxt
             nxt = fetch()                                    # prefetch the next step's inputs
             torch.cuda.current_stream().wait_event(ev)
             for t_ in (xd, td, cd):
                 t_.record_stream(torch.cuda.current_stream())
             r = step(xd, td, cd)
-            r = r.detach() if train else r[0, 0, 0, 0, :1].clone()
-            if prev is not None:
-                host = float(prev)                           # D2H read of the previous step's result
-            prev = r
-        host = float(prev)
+            r = r.detach() if train else r[0, 0, 0, 0, :1]
+            # D2H read of this step's result: an asynchronous copy into pinned memory behind the step (the step's result
+            # is a static buffer of the captured graph, so it is copied out before the next replay can overwrite it) ...
+            slot = i & 1
+            loss_host[slot:slot + 1].copy_(r.reshape(1), non_blocking=True)
+            loss_ev[slot].record()
+            if i > 0:                                        # ... consumed on the host one step later
+                loss_ev[slot ^ 1].synchronize()
+                host = float(loss_host[slot ^ 1])
+        loss_ev[(n - 1) & 1].synchronize()
+        host = float(loss_host[(n - 1) & 1])
         torch.cuda.synchronize()
         return host
 
