@@ -130,10 +130,12 @@ def _empty(shape, dtype, like):
 # current one at the point of issue and is joined before the block's backward returns (every operand is still
 # referenced until then, and GradSink's bucket logic sees a finished block exactly as before).  Their CTAs fill the
 # partial last waves of the input-gradient / norm kernels on the main chain; inside a CUDA-graph capture the fork and
-# join become graph edges.  Measured on B200 (same-box A/B of the replayed config-2 step, gpurun_out/r6_*): 25.08 ->
-# 24.78 ms per step.  Also moving the bias column sums, the per-channel parameter kernels and the stem / head weight
-# gradients there, or forking before the input-gradient GEMM, measured neutral (r6b_*) and is not kept.
-# BF_WGRAD_STREAM=0 keeps everything on one stream.
+# join become graph edges.  Measured on B200 (same-box A/B of the replayed config-2 step, profiles/r6_wgrad_stream.txt):
+# 25.08 -> 24.78 ms per step.  Also moving the bias column sums, the per-channel parameter kernels and the stem / head
+# weight gradients there, or forking before the input-gradient GEMM, measured neutral and is not kept.  The join comes
+# BEFORE the block's branch_param_grads launch, the one main-stream kernel that also writes a weight-gradient buffer.
+# BF_WGRAD_STREAM=0 keeps everything on one stream.  (Module-level state: one backward pass per device at a time, which
+# is how the autograd engine runs a device's nodes.)
 WGRAD_STREAM = _os.environ.get("BF_WGRAD_STREAM", "1") != "0"
 _SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
 _SIDE_DIRTY = False
